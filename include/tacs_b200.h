@@ -1,0 +1,191 @@
+/*
+ * tacs_b200.h -- C ABI of libtacs_b200.so, the B200-native drop-in for the TACS
+ * finite-element assembly + Krylov-operator hot path.
+ *
+ * The reference has no FFI on this path: callers bind to C++ virtual classes in
+ * libtacs.so (C++ drivers directly, Python through Cython, tacs/TACS.pyx).  Each entry
+ * point below is the flat-C form of the reference member function it replaces (cited as
+ * file:line under /root/reference); INTEGRATION.md shows the C++ shim and the Cython
+ * stub a maintainer would add on the reference side.  All pointers are host pointers
+ * unless a name says `device`; sizes are element counts; arrays are copied, never kept.
+ *
+ * Conventions (the reference's own, src/TACSAssembler.cpp:513-581, src/TACSObject.h:106-135):
+ *   - objects are opaque, reference-counted handles; every *_create returns a handle
+ *     holding one reference (NULL on failure); drop it with tacsb200_release
+ *   - int-returning calls return 0 on success, non-zero on failure after printing a
+ *     message to stderr; nothing throws across this boundary
+ *   - there is no CPU execution path: every compute call fails loudly without a GPU
+ *   - one process drives one GPU; calls are synchronous with respect to the host unless
+ *     documented otherwise (the work is enqueued on the library's stream and the call
+ *     returns after the result it hands back is complete)
+ */
+#ifndef TACS_B200_H
+#define TACS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *tacsb200_handle;
+
+int tacsb200_abi_version(void);
+/* Select the GPU (device < 0: cudaSetDevice(LOCAL_RANK or 0)). Called implicitly by the first
+   object that needs the device. */
+int tacsb200_init(int device);
+/* One process per GPU: rank/size of this process and the 128-byte ncclUniqueId created on rank 0
+   (tacsb200_comm_unique_id) and distributed by the caller (torch.distributed, MPI, a file...).
+   Replaces the MPI_Comm every reference object carries (src/TACSObject.h:39). */
+int tacsb200_comm_unique_id(unsigned char id[128]);
+int tacsb200_comm_init(int rank, int size, const unsigned char id[128]);
+int tacsb200_comm_rank(void);
+int tacsb200_comm_size(void);
+int tacsb200_synchronize(void);
+/* number of tacs_b200 kernels launched since the last call with reset != 0 */
+long tacsb200_kernel_launches(int reset);
+void tacsb200_release(tacsb200_handle h);
+
+/* ---- constitutive: src/constitutive ------------------------------------------------------ */
+/* TACSMaterialProperties(rho, specific_heat, E, nu, ys, alpha, kappa)  TACSMaterialProperties.h:44 */
+tacsb200_handle tacsb200_material_properties_create(double rho, double specific_heat, double E, double nu,
+                                                    double ys, double alpha, double kappa);
+/* orthotropic constructor, TACSMaterialProperties.h:47 */
+tacsb200_handle tacsb200_material_properties_create_ortho(double rho, double specific_heat, double E1,
+                                                          double E2, double E3, double nu12, double nu13,
+                                                          double nu23, double G12, double G13, double G23);
+/* TACSOrthotropicPly(plyThickness, properties)  TACSMaterialProperties.h:174 */
+tacsb200_handle tacsb200_orthotropic_ply_create(double ply_thickness, tacsb200_handle props);
+/* TACSIsoShellConstitutive(props, t, tNum=-1, tlb, tub, tOffset, kcorr)  TACSIsoShellConstitutive.h:33 */
+tacsb200_handle tacsb200_iso_shell_constitutive_create(tacsb200_handle props, double t, double tOffset,
+                                                       double kcorr);
+/* TACSCompositeShellConstitutive(num_plies, ply_props, thickness, angles, kcorr, tOffset)
+   TACSCompositeShellConstitutive.h:27 */
+tacsb200_handle tacsb200_composite_shell_constitutive_create(int num_plies, tacsb200_handle *plies,
+                                                             const double *ply_thickness,
+                                                             const double *ply_angles, double kcorr,
+                                                             double tOffset);
+/* TACSSolidConstitutive(properties, t)  TACSSolidConstitutive.h:34 */
+tacsb200_handle tacsb200_solid_constitutive_create(tacsb200_handle props, double t);
+/* TACSShellConstitutive::setDrillingRegularization  TACSShellConstitutive.cpp:66 */
+void tacsb200_shell_set_drilling_regularization(double k);
+/* TACSConstitutive::evalTangentStiffness  TACSConstitutive.h:340 (22 values shell, 21 solid) */
+int tacsb200_constitutive_eval_tangent_stiffness(tacsb200_handle con, double *C);
+/* TACSShellConstitutive::evalMassMoments  TACSShellConstitutive.h */
+int tacsb200_shell_constitutive_eval_mass_moments(tacsb200_handle con, double *moments);
+
+/* ---- transforms and elements: src/elements ---------------------------------------------------- */
+/* TACSShellNaturalTransform / TACSShellRefAxisTransform  shell/TACSShellElementTransform.h:21,95 */
+tacsb200_handle tacsb200_shell_natural_transform_create(void);
+tacsb200_handle tacsb200_shell_ref_axis_transform_create(const double axis[3]);
+/* TACSQuad4Shell / TACSQuad9Shell (transform, constitutive)  shell/TACSShellElementDefs.h:19-25 */
+tacsb200_handle tacsb200_quad4_shell_create(tacsb200_handle transform, tacsb200_handle con);
+tacsb200_handle tacsb200_quad9_shell_create(tacsb200_handle transform, tacsb200_handle con);
+/* TACSLinearHexaBasis / TACSQuadraticHexaBasis  basis/TACSHexaBasis.h */
+tacsb200_handle tacsb200_linear_hexa_basis_create(void);
+tacsb200_handle tacsb200_quadratic_hexa_basis_create(void);
+/* TACSLinearElasticity3D(con, TACS_LINEAR_STRAIN)  TACSLinearElasticity.h:178 */
+tacsb200_handle tacsb200_linear_elasticity3d_create(tacsb200_handle con);
+/* TACSElement3D(model, basis)  TACSElement3D.h:26 */
+tacsb200_handle tacsb200_element3d_create(tacsb200_handle model, tacsb200_handle basis);
+/* TACSElement::getNumNodes / getVarsPerNode  TACSElement.h:98-105 */
+int tacsb200_element_num_nodes(tacsb200_handle e);
+int tacsb200_element_vars_per_node(tacsb200_handle e);
+/* TACSElement::addJacobian (TACSElement.h:450) / addResidual (:422) for a batch of `count` elements
+   sharing this descriptor, evaluated by the device element kernel. Element-major arrays:
+   Xpts[count][3*nn], vars/dvars/ddvars[count][nv] (dvars, ddvars may be NULL),
+   res[count][nv], mat[count][nv*nv] row-major; res and mat are overwritten. */
+int tacsb200_element_add_jacobian(tacsb200_handle e, int count, double alpha, double beta, double gamma,
+                                  const double *Xpts, const double *vars, const double *dvars,
+                                  const double *ddvars, double *res, double *mat);
+int tacsb200_element_add_residual(tacsb200_handle e, int count, const double *Xpts, const double *vars,
+                                  const double *dvars, const double *ddvars, double *res);
+
+/* ---- TACSCreator: src/TACSCreator.h:46-120 --------------------------------------------------- */
+/* Every rank passes the same global mesh (the reference reads it on the root rank only and
+   scatters it, TACSCreator.cpp:548-747; here the scatter is a local selection). */
+tacsb200_handle tacsb200_creator_create(int vars_per_node);
+int tacsb200_creator_set_global_connectivity(tacsb200_handle c, int num_nodes, int num_elements,
+                                             const int *ptr, const int *conn, const int *elem_id_nums);
+int tacsb200_creator_set_boundary_conditions(tacsb200_handle c, int num_bcs, const int *bc_nodes,
+                                             const int *bc_ptr, const int *bc_vars, const double *bc_vals);
+int tacsb200_creator_set_nodes(tacsb200_handle c, const double *Xpts);
+int tacsb200_creator_set_elements(tacsb200_handle c, int num_elems, tacsb200_handle *elems);
+/* partitionMesh(split_size, part): part == NULL runs METIS exactly as TACSCreator.cpp:1104-1125 */
+int tacsb200_creator_partition_mesh(tacsb200_handle c, int split_size, const int *part);
+int tacsb200_creator_get_node_nums(tacsb200_handle c, int *new_nodes);
+int tacsb200_creator_get_element_partition(tacsb200_handle c, int *partition);
+tacsb200_handle tacsb200_creator_create_tacs(tacsb200_handle c);
+
+/* ---- TACSAssembler: src/TACSAssembler.h:61-523 ------------------------------------------------ */
+int tacsb200_assembler_get_vars_per_node(tacsb200_handle a);
+int tacsb200_assembler_get_num_nodes(tacsb200_handle a);
+int tacsb200_assembler_get_num_owned_nodes(tacsb200_handle a);
+int tacsb200_assembler_get_num_elements(tacsb200_handle a);
+int tacsb200_assembler_get_owner_range(tacsb200_handle a, int *lo, int *hi);
+/* getElementConnectivity (:90): local elements, global node numbers; returns conn length */
+int tacsb200_assembler_get_element_connectivity(tacsb200_handle a, int *ptr, int *conn);
+/* getGlobalNodeNum (:328) for every local node */
+int tacsb200_assembler_get_local_to_global(tacsb200_handle a, int *global);
+tacsb200_handle tacsb200_assembler_create_vec(tacsb200_handle a);      /* createVec :179 */
+tacsb200_handle tacsb200_assembler_create_node_vec(tacsb200_handle a); /* createNodeVec :163 */
+tacsb200_handle tacsb200_assembler_create_mat(tacsb200_handle a);      /* createMat :206 */
+int tacsb200_assembler_get_nodes(tacsb200_handle a, tacsb200_handle X);
+int tacsb200_assembler_set_nodes(tacsb200_handle a, tacsb200_handle X);
+int tacsb200_assembler_set_variables(tacsb200_handle a, tacsb200_handle q, tacsb200_handle qdot,
+                                     tacsb200_handle qddot); /* :197 */
+int tacsb200_assembler_zero_variables(tacsb200_handle a);
+int tacsb200_assembler_apply_bcs_vec(tacsb200_handle a, tacsb200_handle v); /* applyBCs(TACSVec*) :182 */
+int tacsb200_assembler_apply_bcs_mat(tacsb200_handle a, tacsb200_handle m); /* applyBCs(TACSMat*) :183 */
+int tacsb200_assembler_set_bcs(tacsb200_handle a, tacsb200_handle v);       /* setBCs :187 */
+int tacsb200_assembler_set_num_threads(tacsb200_handle a, int t); /* accepted and ignored (:317) */
+/* assembleRes(residual, lambda = 1, applyBCs = true)  :221 */
+int tacsb200_assembler_assemble_res(tacsb200_handle a, tacsb200_handle res);
+/* assembleJacobian(alpha, beta, gamma, residual, A, TACS_MAT_NORMAL, lambda = 1, applyBCs = true) :224 */
+int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double beta, double gamma,
+                                         tacsb200_handle res, tacsb200_handle mat);
+
+/* ---- TACSBVec: src/bpmat/TACSBVec.h:67-163 (TACSVec interface KSM.h:91-115) ---------------------- */
+int tacsb200_vec_get_size(tacsb200_handle v);                /* length of getArray(): bs * owned nodes */
+int tacsb200_vec_get_array(tacsb200_handle v, double *out);  /* device -> host copy */
+int tacsb200_vec_set_array(tacsb200_handle v, const double *in);
+double *tacsb200_vec_device_ptr(tacsb200_handle v);          /* owned entries in HBM */
+double tacsb200_vec_norm(tacsb200_handle v);
+double tacsb200_vec_dot(tacsb200_handle x, tacsb200_handle y);
+int tacsb200_vec_mdot(tacsb200_handle x, int n, tacsb200_handle *ys, double *out);
+int tacsb200_vec_axpy(tacsb200_handle y, double alpha, tacsb200_handle x);
+int tacsb200_vec_axpby(tacsb200_handle y, double alpha, double beta, tacsb200_handle x);
+int tacsb200_vec_scale(tacsb200_handle y, double alpha);
+int tacsb200_vec_copy_values(tacsb200_handle y, tacsb200_handle x);
+int tacsb200_vec_zero_entries(tacsb200_handle y);
+
+/* ---- TACSParallelMat / BCSRMat: src/bpmat/TACSParallelMat.h:52-136, BCSRMat.h:34-206 ---------- */
+/* which: 0 = Aloc, 1 = Bext (getBCSRMat :103, BCSRMat::getArrays BCSRMat.h:82) */
+int tacsb200_mat_get_sizes(tacsb200_handle m, int which, int *bsize, int *nrows, int *ncols, int *nnzb);
+int tacsb200_mat_get_pattern(tacsb200_handle m, int which, int *rowp, int *cols);
+int tacsb200_mat_get_values(tacsb200_handle m, int which, double *out);
+double *tacsb200_mat_device_values(tacsb200_handle m, int which);
+int tacsb200_mat_get_ext_col_nodes(tacsb200_handle m, int *nodes); /* getExtColMap :107 */
+int tacsb200_mat_zero_entries(tacsb200_handle m);
+int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y); /* mult :248 */
+/* asynchronous variant for benchmarking: enqueue only, pair with tacsb200_synchronize */
+int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y);
+tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m); /* TACSMat::createVec KSM.h */
+
+/* ---- GMRES: src/bpmat/KSM.h:392-440, KSM.cpp:547-956 -------------------------------------------- */
+tacsb200_handle tacsb200_gmres_create(tacsb200_handle mat, int m, int nrestart);
+int tacsb200_gmres_set_tolerances(tacsb200_handle k, double rtol, double atol);
+int tacsb200_gmres_solve(tacsb200_handle k, tacsb200_handle b, tacsb200_handle x, int zero_guess);
+int tacsb200_gmres_get_iter_count(tacsb200_handle k);
+double tacsb200_gmres_get_residual_norm(tacsb200_handle k);
+
+/* ---- device-timed helpers for bench.py (CUDA events on the library's stream) ------------------------ */
+/* Run `reps` back-to-back assembleJacobian / assembleRes / mult calls and return the elapsed device
+   time in milliseconds (cudaEvent pair on the launching stream); < 0 on failure. */
+double tacsb200_time_assemble_jacobian(tacsb200_handle a, double alpha, double beta, double gamma,
+                                       tacsb200_handle res, tacsb200_handle mat, int reps);
+double tacsb200_time_assemble_res(tacsb200_handle a, tacsb200_handle res, int reps);
+double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y, int reps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACS_B200_H */

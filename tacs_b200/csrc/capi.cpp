@@ -1,0 +1,504 @@
+// extern "C" boundary of libtacs_b200.so (declared in include/tacs_b200.h).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/tacs_b200.h"
+#include "tb2_host.h"
+
+using namespace tb2;
+
+namespace tb2 {
+int comm_unique_id(unsigned char id[128]);
+int comm_init(int rank, int size, const unsigned char id[128]);
+}  // namespace tb2
+
+template <class T>
+static T *as(tacsb200_handle h) {
+  T *p = h ? dynamic_cast<T *>(static_cast<Object *>(h)) : nullptr;
+  return p;
+}
+static tacsb200_handle keep(Object *o) {
+  if (o) o->incref();
+  return static_cast<tacsb200_handle>(o);
+}
+#define REQUIRE(ptr, what)                                              \
+  if (!(ptr)) {                                                         \
+    fprintf(stderr, "tacs_b200: %s: invalid %s handle\n", __func__, what); \
+    return 1;                                                           \
+  }
+#define REQUIRE_H(ptr, what)                                            \
+  if (!(ptr)) {                                                         \
+    fprintf(stderr, "tacs_b200: %s: invalid %s handle\n", __func__, what); \
+    return nullptr;                                                     \
+  }
+
+template <class F>
+static double timed(int reps, F fn) {
+  if (ctx().device < 0) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaStreamSynchronize(ctx().stream);
+  cudaEventRecord(e0, ctx().stream);
+  int fail = 0;
+  for (int i = 0; i < reps && !fail; i++) fail = fn();
+  cudaEventRecord(e1, ctx().stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (fail || cudaGetLastError() != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+extern "C" {
+
+int tacsb200_abi_version(void) { return 1; }
+
+int tacsb200_init(int device) {
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) : 0;
+  }
+  return ctx_init(device);
+}
+int tacsb200_comm_unique_id(unsigned char id[128]) { return comm_unique_id(id); }
+int tacsb200_comm_init(int rank, int size, const unsigned char id[128]) { return comm_init(rank, size, id); }
+int tacsb200_comm_rank(void) { return ctx().rank; }
+int tacsb200_comm_size(void) { return ctx().size; }
+int tacsb200_synchronize(void) {
+  if (ctx().device < 0) return 1;
+  return cuda_ok(cudaStreamSynchronize(ctx().stream), "synchronize") ? 0 : 1;
+}
+long tacsb200_kernel_launches(int reset) {
+  long n = ctx().kernel_launches;
+  if (reset) ctx().kernel_launches = 0;
+  return n;
+}
+void tacsb200_release(tacsb200_handle h) {
+  if (h) static_cast<Object *>(h)->decref();
+}
+
+/* ---- constitutive ---------------------------------------------------------------------- */
+tacsb200_handle tacsb200_material_properties_create(double rho, double cp, double E, double nu, double ys,
+                                                    double alpha, double kappa) {
+  return keep(new TACSMaterialProperties(rho, cp, E, nu, ys, alpha, kappa));
+}
+tacsb200_handle tacsb200_material_properties_create_ortho(double rho, double cp, double E1, double E2,
+                                                          double E3, double nu12, double nu13, double nu23,
+                                                          double G12, double G13, double G23) {
+  return keep(new TACSMaterialProperties(rho, cp, E1, E2, E3, nu12, nu13, nu23, G12, G13, G23));
+}
+tacsb200_handle tacsb200_orthotropic_ply_create(double t, tacsb200_handle props) {
+  TACSMaterialProperties *p = as<TACSMaterialProperties>(props);
+  REQUIRE_H(p, "material properties");
+  return keep(new TACSOrthotropicPly(t, p));
+}
+tacsb200_handle tacsb200_iso_shell_constitutive_create(tacsb200_handle props, double t, double tOffset,
+                                                       double kcorr) {
+  TACSMaterialProperties *p = as<TACSMaterialProperties>(props);
+  REQUIRE_H(p, "material properties");
+  return keep(new TACSIsoShellConstitutive(p, t, tOffset, kcorr));
+}
+tacsb200_handle tacsb200_composite_shell_constitutive_create(int n, tacsb200_handle *plies, const double *thick,
+                                                             const double *angles, double kcorr,
+                                                             double tOffset) {
+  std::vector<TACSOrthotropicPly *> p(n);
+  for (int i = 0; i < n; i++) {
+    p[i] = as<TACSOrthotropicPly>(plies[i]);
+    REQUIRE_H(p[i], "orthotropic ply");
+  }
+  return keep(new TACSCompositeShellConstitutive(n, p.data(), thick, angles, kcorr, tOffset));
+}
+tacsb200_handle tacsb200_solid_constitutive_create(tacsb200_handle props, double t) {
+  TACSMaterialProperties *p = as<TACSMaterialProperties>(props);
+  REQUIRE_H(p, "material properties");
+  return keep(new TACSSolidConstitutive(p, t));
+}
+void tacsb200_shell_set_drilling_regularization(double k) { TACSShellConstitutive::setDrillingRegularization(k); }
+int tacsb200_constitutive_eval_tangent_stiffness(tacsb200_handle con, double *C) {
+  TACSConstitutive *c = as<TACSConstitutive>(con);
+  REQUIRE(c, "constitutive");
+  c->evalTangentStiffness(C);
+  return 0;
+}
+int tacsb200_shell_constitutive_eval_mass_moments(tacsb200_handle con, double *m) {
+  TACSShellConstitutive *c = as<TACSShellConstitutive>(con);
+  REQUIRE(c, "shell constitutive");
+  c->evalMassMoments(m);
+  return 0;
+}
+
+/* ---- transforms / elements -------------------------------------------------------------- */
+tacsb200_handle tacsb200_shell_natural_transform_create(void) { return keep(new TACSShellNaturalTransform()); }
+tacsb200_handle tacsb200_shell_ref_axis_transform_create(const double axis[3]) {
+  return keep(new TACSShellRefAxisTransform(axis));
+}
+static tacsb200_handle make_shell(int order, tacsb200_handle transform, tacsb200_handle con) {
+  TACSShellTransform *t = as<TACSShellTransform>(transform);
+  TACSShellConstitutive *c = as<TACSShellConstitutive>(con);
+  if (!t || !c) {
+    fprintf(stderr, "tacs_b200: shell element needs a recognised transform and shell constitutive object\n");
+    return nullptr;
+  }
+  return keep(new TACSShellElement(order, t, c));
+}
+tacsb200_handle tacsb200_quad4_shell_create(tacsb200_handle t, tacsb200_handle c) { return make_shell(2, t, c); }
+tacsb200_handle tacsb200_quad9_shell_create(tacsb200_handle t, tacsb200_handle c) { return make_shell(3, t, c); }
+tacsb200_handle tacsb200_linear_hexa_basis_create(void) { return keep(new TACSLinearHexaBasis()); }
+tacsb200_handle tacsb200_quadratic_hexa_basis_create(void) { return keep(new TACSQuadraticHexaBasis()); }
+tacsb200_handle tacsb200_linear_elasticity3d_create(tacsb200_handle con) {
+  TACSSolidConstitutive *c = as<TACSSolidConstitutive>(con);
+  REQUIRE_H(c, "solid constitutive");
+  return keep(new TACSLinearElasticity3D(c));
+}
+tacsb200_handle tacsb200_element3d_create(tacsb200_handle model, tacsb200_handle basis) {
+  TACSElementModel *m = as<TACSElementModel>(model);
+  TACSElementBasis *b = as<TACSElementBasis>(basis);
+  if (!m || !b || !dynamic_cast<TACSLinearElasticity3D *>(m)) {
+    fprintf(stderr, "tacs_b200: TACSElement3D needs TACSLinearElasticity3D and a hexahedral basis\n");
+    return nullptr;
+  }
+  return keep(new TACSElement3D(m, b));
+}
+int tacsb200_element_num_nodes(tacsb200_handle e) {
+  TACSElement *el = as<TACSElement>(e);
+  return el ? el->getNumNodes() : -1;
+}
+int tacsb200_element_vars_per_node(tacsb200_handle e) {
+  TACSElement *el = as<TACSElement>(e);
+  return el ? el->getVarsPerNode() : -1;
+}
+int tacsb200_element_add_jacobian(tacsb200_handle e, int count, double alpha, double beta, double gamma,
+                                  const double *Xpts, const double *vars, const double *dvars,
+                                  const double *ddvars, double *res, double *mat) {
+  TACSElement *el = as<TACSElement>(e);
+  REQUIRE(el, "element");
+  return el->addJacobianBatch(count, alpha, beta, gamma, Xpts, vars, dvars, ddvars, res, mat);
+}
+int tacsb200_element_add_residual(tacsb200_handle e, int count, const double *Xpts, const double *vars,
+                                  const double *dvars, const double *ddvars, double *res) {
+  TACSElement *el = as<TACSElement>(e);
+  REQUIRE(el, "element");
+  return el->addJacobianBatch(count, 1.0, 0.0, 0.0, Xpts, vars, dvars, ddvars, res, nullptr);
+}
+
+/* ---- creator ------------------------------------------------------------------------------ */
+tacsb200_handle tacsb200_creator_create(int vars_per_node) { return keep(new TACSCreator(vars_per_node)); }
+int tacsb200_creator_set_global_connectivity(tacsb200_handle c, int nn, int ne, const int *ptr, const int *conn,
+                                             const int *ids) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE(cr, "creator");
+  cr->setGlobalConnectivity(nn, ne, ptr, conn, ids);
+  return 0;
+}
+int tacsb200_creator_set_boundary_conditions(tacsb200_handle c, int nb, const int *nodes, const int *ptr,
+                                             const int *vars, const double *vals) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE(cr, "creator");
+  cr->setBoundaryConditions(nb, nodes, ptr, vars, vals);
+  return 0;
+}
+int tacsb200_creator_set_nodes(tacsb200_handle c, const double *X) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE(cr, "creator");
+  cr->setNodes(X);
+  return 0;
+}
+int tacsb200_creator_set_elements(tacsb200_handle c, int n, tacsb200_handle *elems) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE(cr, "creator");
+  std::vector<TACSElement *> e(n);
+  for (int i = 0; i < n; i++) {
+    e[i] = as<TACSElement>(elems[i]);
+    REQUIRE(e[i], "element");
+  }
+  cr->setElements(n, e.data());
+  return 0;
+}
+int tacsb200_creator_partition_mesh(tacsb200_handle c, int split, const int *part) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE(cr, "creator");
+  return cr->partitionMesh(split, part);
+}
+int tacsb200_creator_get_node_nums(tacsb200_handle c, int *out) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  if (!cr) return 0;
+  const int *nn = nullptr;
+  int n = cr->getNodeNums(&nn);
+  if (out && nn) memcpy(out, nn, n * sizeof(int));
+  return n;
+}
+int tacsb200_creator_get_element_partition(tacsb200_handle c, int *out) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  if (!cr) return 0;
+  const int *p = nullptr;
+  int n = cr->getElementPartition(&p);
+  if (out && p) memcpy(out, p, n * sizeof(int));
+  return n;
+}
+tacsb200_handle tacsb200_creator_create_tacs(tacsb200_handle c) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE_H(cr, "creator");
+  return keep(cr->createTACS());
+}
+
+/* ---- assembler ------------------------------------------------------------------------------ */
+#define ASM(a)                           \
+  TACSAssembler *t = as<TACSAssembler>(a); \
+  REQUIRE(t, "assembler")
+int tacsb200_assembler_get_vars_per_node(tacsb200_handle a) { ASM(a); return t->getVarsPerNode(); }
+int tacsb200_assembler_get_num_nodes(tacsb200_handle a) { ASM(a); return t->getNumNodes(); }
+int tacsb200_assembler_get_num_owned_nodes(tacsb200_handle a) { ASM(a); return t->getNumOwnedNodes(); }
+int tacsb200_assembler_get_num_elements(tacsb200_handle a) { ASM(a); return t->getNumElements(); }
+int tacsb200_assembler_get_owner_range(tacsb200_handle a, int *lo, int *hi) {
+  ASM(a);
+  *lo = t->owner_range[t->rank];
+  *hi = t->owner_range[t->rank + 1];
+  return 0;
+}
+int tacsb200_assembler_get_element_connectivity(tacsb200_handle a, int *ptr, int *conn) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  if (!t) return -1;
+  if (ptr) memcpy(ptr, t->elem_ptr.data(), t->elem_ptr.size() * sizeof(int));
+  if (conn) memcpy(conn, t->elem_conn_global.data(), t->elem_conn_global.size() * sizeof(int));
+  return (int)t->elem_conn_global.size();
+}
+int tacsb200_assembler_get_local_to_global(tacsb200_handle a, int *global) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  if (!t) return -1;
+  const int lo = t->owner_range[t->rank];
+  for (int l = 0; l < t->nlocal; l++) {
+    if (l < t->ext_before) global[l] = t->ext_nodes[l];
+    else if (l < t->ext_before + t->nowned) global[l] = lo + (l - t->ext_before);
+    else global[l] = t->ext_nodes[l - t->nowned];
+  }
+  return t->nlocal;
+}
+tacsb200_handle tacsb200_assembler_create_vec(tacsb200_handle a) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  REQUIRE_H(t, "assembler");
+  return keep(t->createVec());
+}
+tacsb200_handle tacsb200_assembler_create_node_vec(tacsb200_handle a) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  REQUIRE_H(t, "assembler");
+  return keep(t->createNodeVec());
+}
+tacsb200_handle tacsb200_assembler_create_mat(tacsb200_handle a) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  REQUIRE_H(t, "assembler");
+  return keep(t->createMat());
+}
+int tacsb200_assembler_get_nodes(tacsb200_handle a, tacsb200_handle X) {
+  ASM(a);
+  TACSBVec *v = as<TACSBVec>(X);
+  REQUIRE(v, "vector");
+  t->getNodes(v);
+  return 0;
+}
+int tacsb200_assembler_set_nodes(tacsb200_handle a, tacsb200_handle X) {
+  ASM(a);
+  TACSBVec *v = as<TACSBVec>(X);
+  REQUIRE(v, "vector");
+  t->setNodes(v);
+  return 0;
+}
+int tacsb200_assembler_set_variables(tacsb200_handle a, tacsb200_handle q, tacsb200_handle qd, tacsb200_handle qdd) {
+  ASM(a);
+  t->setVariables(as<TACSBVec>(q), as<TACSBVec>(qd), as<TACSBVec>(qdd));
+  return 0;
+}
+int tacsb200_assembler_zero_variables(tacsb200_handle a) { ASM(a); t->zeroVariables(); return 0; }
+int tacsb200_assembler_apply_bcs_vec(tacsb200_handle a, tacsb200_handle v) {
+  ASM(a);
+  TACSBVec *x = as<TACSBVec>(v);
+  REQUIRE(x, "vector");
+  t->applyBCs(x);
+  return 0;
+}
+int tacsb200_assembler_apply_bcs_mat(tacsb200_handle a, tacsb200_handle m) {
+  ASM(a);
+  TACSParallelMat *A = as<TACSParallelMat>(m);
+  REQUIRE(A, "matrix");
+  t->applyBCs(A);
+  return 0;
+}
+int tacsb200_assembler_set_bcs(tacsb200_handle a, tacsb200_handle v) {
+  ASM(a);
+  TACSBVec *x = as<TACSBVec>(v);
+  REQUIRE(x, "vector");
+  t->setBCs(x);
+  return 0;
+}
+int tacsb200_assembler_set_num_threads(tacsb200_handle a, int n) { ASM(a); (void)n; return 0; }
+int tacsb200_assembler_assemble_res(tacsb200_handle a, tacsb200_handle res) {
+  ASM(a);
+  TACSBVec *r = as<TACSBVec>(res);
+  REQUIRE(r, "vector");
+  if (t->assembleRes(r, 1.0)) return 1;
+  return tacsb200_synchronize();
+}
+int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double beta, double gamma,
+                                         tacsb200_handle res, tacsb200_handle mat) {
+  ASM(a);
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE(A, "matrix");
+  if (t->assembleJacobian(alpha, beta, gamma, as<TACSBVec>(res), A, 1.0)) return 1;
+  return tacsb200_synchronize();
+}
+
+/* ---- vectors ---------------------------------------------------------------------------------- */
+#define VEC(v, name)              \
+  TACSBVec *name = as<TACSBVec>(v); \
+  REQUIRE(name, "vector")
+int tacsb200_vec_get_size(tacsb200_handle v) { VEC(v, x); return (int)x->ownedSize(); }
+int tacsb200_vec_get_array(tacsb200_handle v, double *out) { VEC(v, x); return x->getArray(out); }
+int tacsb200_vec_set_array(tacsb200_handle v, const double *in) { VEC(v, x); return x->setArray(in); }
+double *tacsb200_vec_device_ptr(tacsb200_handle v) {
+  TACSBVec *x = as<TACSBVec>(v);
+  return x ? x->owned() : nullptr;
+}
+double tacsb200_vec_norm(tacsb200_handle v) {
+  TACSBVec *x = as<TACSBVec>(v);
+  return x ? x->norm() : -1.0;
+}
+double tacsb200_vec_dot(tacsb200_handle a, tacsb200_handle b) {
+  TACSBVec *x = as<TACSBVec>(a), *y = as<TACSBVec>(b);
+  return (x && y) ? x->dot(y) : 0.0;
+}
+int tacsb200_vec_mdot(tacsb200_handle v, int n, tacsb200_handle *ys, double *out) {
+  VEC(v, x);
+  std::vector<TACSBVec *> y(n);
+  for (int i = 0; i < n; i++) {
+    y[i] = as<TACSBVec>(ys[i]);
+    REQUIRE(y[i], "vector");
+  }
+  x->mdot(y.data(), out, n);
+  return 0;
+}
+int tacsb200_vec_axpy(tacsb200_handle yv, double alpha, tacsb200_handle xv) {
+  VEC(yv, y); VEC(xv, x);
+  y->axpy(alpha, x);
+  return 0;
+}
+int tacsb200_vec_axpby(tacsb200_handle yv, double alpha, double beta, tacsb200_handle xv) {
+  VEC(yv, y); VEC(xv, x);
+  y->axpby(alpha, beta, x);
+  return 0;
+}
+int tacsb200_vec_scale(tacsb200_handle yv, double alpha) { VEC(yv, y); y->scale(alpha); return 0; }
+int tacsb200_vec_copy_values(tacsb200_handle yv, tacsb200_handle xv) {
+  VEC(yv, y); VEC(xv, x);
+  y->copyValues(x);
+  return 0;
+}
+int tacsb200_vec_zero_entries(tacsb200_handle yv) { VEC(yv, y); y->zeroEntries(); return 0; }
+
+/* ---- matrix ------------------------------------------------------------------------------------ */
+#define MAT(m)                                  \
+  TACSParallelMat *A = as<TACSParallelMat>(m); \
+  REQUIRE(A, "matrix")
+int tacsb200_mat_get_sizes(tacsb200_handle m, int which, int *bsize, int *nrows, int *ncols, int *nnzb) {
+  MAT(m);
+  BCSRPattern &P = which ? A->Bext : A->Aloc;
+  *bsize = P.bsize; *nrows = P.nrows; *ncols = P.ncols; *nnzb = (int)P.nnzb();
+  return 0;
+}
+int tacsb200_mat_get_pattern(tacsb200_handle m, int which, int *rowp, int *cols) {
+  MAT(m);
+  BCSRPattern &P = which ? A->Bext : A->Aloc;
+  memcpy(rowp, P.rowp.data(), P.rowp.size() * sizeof(int));
+  memcpy(cols, P.cols.data(), P.cols.size() * sizeof(int));
+  return 0;
+}
+int tacsb200_mat_get_values(tacsb200_handle m, int which, double *out) {
+  MAT(m);
+  BCSRPattern &P = which ? A->Bext : A->Aloc;
+  return P.d_vals.download(out, P.d_vals.count) ? 0 : 1;
+}
+double *tacsb200_mat_device_values(tacsb200_handle m, int which) {
+  TACSParallelMat *A = as<TACSParallelMat>(m);
+  if (!A) return nullptr;
+  return which ? A->Bext.d_vals.ptr : A->Aloc.d_vals.ptr;
+}
+int tacsb200_mat_get_ext_col_nodes(tacsb200_handle m, int *nodes) {
+  TACSParallelMat *A = as<TACSParallelMat>(m);
+  if (!A) return -1;
+  if (nodes) memcpy(nodes, A->ext_col_nodes.data(), A->ext_col_nodes.size() * sizeof(int));
+  return (int)A->ext_col_nodes.size();
+}
+int tacsb200_mat_zero_entries(tacsb200_handle m) { MAT(m); A->zeroEntries(); return 0; }
+int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
+  MAT(m);
+  VEC(xv, x); VEC(yv, y);
+  A->mult(x, y);
+  return 0;
+}
+int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
+  if (tacsb200_mat_mult_async(m, xv, yv)) return 1;
+  return tacsb200_synchronize();
+}
+tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m) {
+  TACSParallelMat *A = as<TACSParallelMat>(m);
+  REQUIRE_H(A, "matrix");
+  return keep(A->createVec());
+}
+
+/* ---- GMRES --------------------------------------------------------------------------------------- */
+tacsb200_handle tacsb200_gmres_create(tacsb200_handle mat, int m, int nrestart) {
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE_H(A, "matrix");
+  return keep(new GMRES(A, m, nrestart));
+}
+int tacsb200_gmres_set_tolerances(tacsb200_handle k, double rtol, double atol) {
+  GMRES *g = as<GMRES>(k);
+  REQUIRE(g, "GMRES");
+  g->setTolerances(rtol, atol);
+  return 0;
+}
+int tacsb200_gmres_solve(tacsb200_handle k, tacsb200_handle b, tacsb200_handle x, int zero_guess) {
+  GMRES *g = as<GMRES>(k);
+  TACSBVec *bv = as<TACSBVec>(b), *xv = as<TACSBVec>(x);
+  if (!g || !bv || !xv) return -1;
+  return g->solve(bv, xv, zero_guess);
+}
+int tacsb200_gmres_get_iter_count(tacsb200_handle k) {
+  GMRES *g = as<GMRES>(k);
+  return g ? g->getIterCount() : -1;
+}
+double tacsb200_gmres_get_residual_norm(tacsb200_handle k) {
+  GMRES *g = as<GMRES>(k);
+  return g ? g->getResidualNorm() : -1.0;
+}
+
+/* ---- device-timed helpers --------------------------------------------------------------------------- */
+double tacsb200_time_assemble_jacobian(tacsb200_handle a, double alpha, double beta, double gamma,
+                                       tacsb200_handle res, tacsb200_handle mat, int reps) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  TACSBVec *r = as<TACSBVec>(res);
+  if (!t || !A) return -1.0;
+  return timed(reps, [&]() { return t->assembleJacobian(alpha, beta, gamma, r, A, 1.0); });
+}
+double tacsb200_time_assemble_res(tacsb200_handle a, tacsb200_handle res, int reps) {
+  TACSAssembler *t = as<TACSAssembler>(a);
+  TACSBVec *r = as<TACSBVec>(res);
+  if (!t || !r) return -1.0;
+  return timed(reps, [&]() { return t->assembleRes(r, 1.0); });
+}
+double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv, int reps) {
+  TACSParallelMat *A = as<TACSParallelMat>(m);
+  TACSBVec *x = as<TACSBVec>(xv), *y = as<TACSBVec>(yv);
+  if (!A || !x || !y) return -1.0;
+  return timed(reps, [&]() {
+    A->mult(x, y);
+    return 0;
+  });
+}
+
+}  // extern "C"

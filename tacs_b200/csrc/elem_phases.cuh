@@ -1,0 +1,543 @@
+// Element mathematics of the assembly hot path, written as *team phases*.
+//
+// One element is evaluated by a team of threads that share a work area in shared memory. The
+// evaluation is a fixed sequence of phases; inside a phase every task is independent, tasks are
+// dealt round-robin to the team's threads, and a team barrier separates phases. Every function
+// here is a single task of a phase (TB2_HD: compiled for the device by nvcc, and for the host by
+// the CPU emulation harness in tests/emul/ that replays the same phases sequentially).
+//
+// What is computed (citations into /root/reference/src/elements):
+//   shell  TACSShellElement<...>::addJacobian / addResidual   shell/TACSShellElement.h:294-641
+//          node normals  TacsShellComputeNodeNormals             shell/TACSShellUtilities.h:301-342
+//          drill strain  TacsShellComputeDrillStrain             shell/TACSShellUtilities.h:649-693
+//          director      TACSLinearizedRotation                  shell/TACSDirector.h:14-610
+//          tying strain  TACSShellLinearModel::computeTyingStrain  shell/TACSShellElementModel.h:28-73
+//          disp. gradient  TacsShellComputeDispGrad              shell/TACSShellUtilities.h:361-421
+//          strain / stress  evalStrain Model.h:717-732, computeStress constitutive/TACSShellConstitutive.h:133-155
+//          transforms    shell/TACSShellElementTransform.h:21-215
+//   solid  TACSElement3D::addJacobian / addResidual           TACSElement3D.cpp:139-224
+//          TACSLinearElasticity3D (linear strain)               TACSLinearElasticity.cpp:875-947, 1158-1342
+//          getFieldGradient                                     basis/TACSElementBasis.cpp:266-326
+//
+// Formulation. Both models are linear, so the element tangent is state independent and equals
+// K = sum_q w_q det_q B_q^T C B_q with B_q the strain-displacement rows at quadrature point q
+// (for the shell: MITC-interpolated membrane/shear rows, bending rows through the director
+// d = q x n, and the nodal drill rows interpolated to q). The residual is B^T C B u plus the
+// inertial terms; the Jacobian is alpha*K + gamma*M. This is the reference's bilinear form
+// evaluated directly instead of through its first/second-derivative back-propagation chain.
+#pragma once
+
+#include "elem_tables.h"
+
+namespace tb2 {
+
+// ------------------------------------------------------------------------------------------
+// small dense helpers
+// ------------------------------------------------------------------------------------------
+TB2_HD void cross3(const double *x, const double *y, double *o) {
+  o[0] = x[1] * y[2] - x[2] * y[1];
+  o[1] = x[2] * y[0] - x[0] * y[2];
+  o[2] = x[0] * y[1] - x[1] * y[0];
+}
+
+TB2_HD double inv3x3(const double *A, double *Ai) {
+  double det = (A[8] * (A[0] * A[4] - A[3] * A[1]) - A[7] * (A[0] * A[5] - A[3] * A[2]) +
+                A[6] * (A[1] * A[5] - A[2] * A[4]));
+  double di = 1.0 / det;
+  Ai[0] = (A[4] * A[8] - A[5] * A[7]) * di;
+  Ai[1] = -(A[1] * A[8] - A[2] * A[7]) * di;
+  Ai[2] = (A[1] * A[5] - A[2] * A[4]) * di;
+  Ai[3] = -(A[3] * A[8] - A[5] * A[6]) * di;
+  Ai[4] = (A[0] * A[8] - A[2] * A[6]) * di;
+  Ai[5] = -(A[0] * A[5] - A[2] * A[3]) * di;
+  Ai[6] = (A[3] * A[7] - A[4] * A[6]) * di;
+  Ai[7] = -(A[0] * A[7] - A[1] * A[6]) * di;
+  Ai[8] = (A[0] * A[4] - A[1] * A[3]) * di;
+  return det;
+}
+
+TB2_HD void mat3mul(const double *A, const double *B, double *C) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+// Local shell frame T = [t1 t2 n] (columns). kind 0: natural transform, which removes the normal
+// component from t1[0] only (the reference repeats one line three times, Transform.h:42-44);
+// kind 1: reference-axis transform with a pre-normalised axis.
+TB2_HD void shell_frame(int kind, const double *axis, const double *Xxi, const double *n0, double *T) {
+  double n[3] = {n0[0], n0[1], n0[2]};
+  double inv = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  n[0] *= inv;
+  n[1] *= inv;
+  n[2] *= inv;
+  double t1[3], t2[3];
+  if (kind == 0) {
+    t1[0] = Xxi[0];
+    t1[1] = Xxi[2];
+    t1[2] = Xxi[4];
+    double d = n[0] * t1[0] + n[1] * t1[1] + n[2] * t1[2];
+    t1[0] = t1[0] - d * n[0];
+    t1[0] = t1[0] - d * n[0];
+    t1[0] = t1[0] - d * n[0];
+  } else {
+    double an = axis[0] * n[0] + axis[1] * n[1] + axis[2] * n[2];
+    t1[0] = axis[0] - an * n[0];
+    t1[1] = axis[1] - an * n[1];
+    t1[2] = axis[2] - an * n[2];
+  }
+  inv = 1.0 / sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+  t1[0] *= inv;
+  t1[1] *= inv;
+  t1[2] *= inv;
+  cross3(n, t1, t2);
+  T[0] = t1[0]; T[3] = t1[1]; T[6] = t1[2];
+  T[1] = t2[0]; T[4] = t2[1]; T[7] = t2[2];
+  T[2] = n[0];  T[5] = n[1];  T[8] = n[2];
+}
+
+// Per-descriptor constants of an element (one row of the device descriptor table, 32 doubles):
+//   shell: [0..21] tangent stiffness A(6) B(6) D(6) As(3) drill, [22..24] mass moments,
+//          [25] transform kind, [26..28] reference axis
+//   solid: [0..20] C (upper triangle by rows), [21] density
+static constexpr int kDescStride = 32;
+
+// ------------------------------------------------------------------------------------------
+// shell work area and phases
+// ------------------------------------------------------------------------------------------
+template <int O, int QC>
+struct ShellWork {
+  using D = ShellDims<O>;
+  static constexpr int n = D::n, nd = D::nd, nq = D::nq, nty = D::nty;
+  static constexpr int NS = 9;          // strain rows per quadrature point
+  static constexpr int TR = 6, TC = 6;  // K tile of one thread = one node pair
+  static constexpr int ntiles = n * n;
+  double X[3 * n];
+  double u[nd];
+  double acc[nd];  // second time derivative of the state
+  double desc[kDescStride];
+  double fn[3 * n];
+  double Bdr[n][nd];
+  double Bty[nty][nd];
+  double T[nq][9], A[nq][9], Az[nq][9];
+  double wdet[nq];
+  double W[nq][5][nty];
+  double B[QC][NS][nd];
+  double CB[QC][NS][nd];
+  double rpart[ntiles][6];
+};
+
+// phase 1, task i in [0,n): node normal, nodal frame, nodal drill-strain row
+template <int O, int QC>
+TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
+  double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = 0; j < n; j++) {
+    const double d0 = tab.dNn[i][j][0], d1 = tab.dNn[i][j][1];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      Xxi[2 * c] += d0 * w.X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * w.X[3 * j + c];
+    }
+  }
+  double a[3] = {Xxi[0], Xxi[2], Xxi[4]}, b[3] = {Xxi[1], Xxi[3], Xxi[5]}, f[3];
+  cross3(a, b, f);
+  double nrm = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+  if (nrm != 0.0) {
+    double inv = 1.0 / nrm;
+    f[0] *= inv;
+    f[1] *= inv;
+    f[2] *= inv;
+  }
+  w.fn[3 * i] = f[0];
+  w.fn[3 * i + 1] = f[1];
+  w.fn[3 * i + 2] = f[2];
+  double Xd[9], T[9], Xdinv[9], XdinvT[9];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    Xd[3 * c] = Xxi[2 * c];
+    Xd[3 * c + 1] = Xxi[2 * c + 1];
+    Xd[3 * c + 2] = f[c];
+  }
+  shell_frame((int)w.desc[25], &w.desc[26], Xxi, f, T);
+  inv3x3(Xd, Xdinv);
+  mat3mul(Xdinv, T, XdinvT);
+  for (int j = 0; j < n; j++) {
+    const double d0 = tab.dNn[i][j][0], d1 = tab.dNn[i][j][1];
+    const double g0 = d0 * XdinvT[0] + d1 * XdinvT[3];
+    const double g1 = d0 * XdinvT[1] + d1 * XdinvT[4];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      w.Bdr[i][6 * j + c] = 0.5 * (T[3 * c + 1] * g0 - T[3 * c] * g1);
+      w.Bdr[i][6 * j + 3 + c] = 0.0;
+    }
+  }
+  double t1[3] = {T[0], T[3], T[6]}, t2[3] = {T[1], T[4], T[7]}, t12[3];
+  cross3(t1, t2, t12);
+  w.Bdr[i][6 * i + 3] = -t12[0];
+  w.Bdr[i][6 * i + 4] = -t12[1];
+  w.Bdr[i][6 * i + 5] = -t12[2];
+  (void)nd;
+}
+
+// phase 2, task ty in [0,nty): tying-strain row
+template <int O, int QC>
+TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+  constexpr int n = ShellDims<O>::n;
+  const int field = shell_ty_field<O>(ty);
+  double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
+  for (int j = 0; j < n; j++) {
+    const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      Xxi[2 * c] += d0 * w.X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * w.X[3 * j + c];
+      n0[c] += N * w.fn[3 * j + c];
+    }
+  }
+  for (int j = 0; j < n; j++) {
+    const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
+    double du[3], dd[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (field == 0) {
+        du[c] = d0 * Xxi[2 * c];
+      } else if (field == 1) {
+        du[c] = d1 * Xxi[2 * c + 1];
+      } else if (field == 2) {
+        du[c] = 0.5 * (d0 * Xxi[2 * c + 1] + d1 * Xxi[2 * c]);
+      } else if (field == 3) {
+        du[c] = 0.5 * n0[c] * d1;
+        dd[c] = 0.5 * N * Xxi[2 * c + 1];
+      } else {
+        du[c] = 0.5 * n0[c] * d0;
+        dd[c] = 0.5 * N * Xxi[2 * c];
+      }
+    }
+    double dq[3];
+    cross3(&w.fn[3 * j], dd, dq);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      w.Bty[ty][6 * j + c] = du[c];
+      w.Bty[ty][6 * j + 3 + c] = dq[c];
+    }
+  }
+}
+
+// phase 2 (same barrier interval), task q in [0,nq): geometry at a quadrature point and the weights
+// that turn tying-point strains into the membrane / transverse-shear strain rows
+template <int O, int QC>
+TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+  constexpr int n = ShellDims<O>::n, nty = ShellDims<O>::nty;
+  double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
+  double nxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = 0; j < n; j++) {
+    const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      Xxi[2 * c] += d0 * w.X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * w.X[3 * j + c];
+      n0[c] += N * w.fn[3 * j + c];
+      nxi[2 * c] += d0 * w.fn[3 * j + c];
+      nxi[2 * c + 1] += d1 * w.fn[3 * j + c];
+    }
+  }
+  double T[9], Xd[9], Xdz[9], Xdinv[9], A[9], Az[9], tmp[9];
+  shell_frame((int)w.desc[25], &w.desc[26], Xxi, n0, T);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    Xd[3 * c] = Xxi[2 * c];
+    Xd[3 * c + 1] = Xxi[2 * c + 1];
+    Xd[3 * c + 2] = n0[c];
+    Xdz[3 * c] = nxi[2 * c];
+    Xdz[3 * c + 1] = nxi[2 * c + 1];
+    Xdz[3 * c + 2] = 0.0;
+  }
+  const double det = inv3x3(Xd, Xdinv);
+  mat3mul(Xdinv, Xdz, tmp);
+#pragma unroll
+  for (int k = 0; k < 9; k++) tmp[k] = -tmp[k];
+  mat3mul(Xdinv, T, A);
+  mat3mul(tmp, A, Az);
+  w.wdet[q] = det * tab.wq[q];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    w.T[q][k] = T[k];
+    w.A[q][k] = A[k];
+    w.Az[q][k] = Az[k];
+  }
+  // e0ty(a,b) = sum_cd A(c,a) G(c,d) A(d,b); rows of the strain vector fed by e0ty:
+  //   m=0: e0 = e0ty(0,0)  m=1: e1 = e0ty(1,1)  m=2: e2 = 2 e0ty(0,1)  m=3: e6 = 2 e0ty(1,2)  m=4: e7 = 2 e0ty(0,2)
+  for (int ty = 0; ty < nty; ty++) {
+    const int f = shell_ty_field<O>(ty);
+    const int c = (f == 1 || f == 3) ? 1 : 0;            // g11,g12,g13 -> 0 ; g22,g23 -> 1
+    const int d = (f == 0) ? 0 : ((f == 1 || f == 2) ? 1 : 2);
+    const double Nt = tab.Ntq[q][ty];
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      const int a = (m == 1 || m == 3) ? 1 : 0;
+      const int b = (m == 0) ? 0 : ((m == 1 || m == 2) ? 1 : 2);
+      double coef = (c == d) ? A[3 * c + a] * A[3 * c + b]
+                             : A[3 * c + a] * A[3 * d + b] + A[3 * d + a] * A[3 * c + b];
+      w.W[q][m][ty] = ((m >= 2) ? 2.0 : 1.0) * Nt * coef;
+    }
+  }
+}
+
+// phase 3, task (ql, j, r): six entries of strain row r for node j at quadrature point q0+ql
+template <int O, int QC>
+TB2_HD void shell_p3_brow(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+  constexpr int n = ShellDims<O>::n, nty = ShellDims<O>::nty;
+  const int r = task % 9, j = (task / 9) % n, ql = task / (9 * n);
+  const int q = q0 + ql;
+  double out[6];
+  if (r == 8) {
+    // drill strain: nodal values interpolated with the nodal shape functions
+#pragma unroll
+    for (int c = 0; c < 6; c++) out[c] = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double N = tab.Nq[q][i];
+#pragma unroll
+      for (int c = 0; c < 6; c++) out[c] += N * w.Bdr[i][6 * j + c];
+    }
+  } else if (r >= 3 && r < 6) {
+    // bending strains from u1x = T^T (u1d XdinvT + u0d XdinvzT)
+    const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
+    const double *T = w.T[q], *A = w.A[q], *Az = w.Az[q];
+    double hz0 = d0 * Az[0] + d1 * Az[3], hz1 = d0 * Az[1] + d1 * Az[4];
+    double h0 = d0 * A[0] + d1 * A[3] + N * Az[6], h1 = d0 * A[1] + d1 * A[4] + N * Az[7];
+    double rd[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (r == 3) {
+        out[c] = T[3 * c] * hz0;
+        rd[c] = T[3 * c] * h0;
+      } else if (r == 4) {
+        out[c] = T[3 * c + 1] * hz1;
+        rd[c] = T[3 * c + 1] * h1;
+      } else {
+        out[c] = T[3 * c] * hz1 + T[3 * c + 1] * hz0;
+        rd[c] = T[3 * c] * h1 + T[3 * c + 1] * h0;
+      }
+    }
+    cross3(&w.fn[3 * j], rd, &out[3]);
+  } else {
+    const int m = (r < 3) ? r : r - 3;  // rows 0,1,2,6,7 -> m = 0..4
+#pragma unroll
+    for (int c = 0; c < 6; c++) out[c] = 0.0;
+    for (int ty = 0; ty < nty; ty++) {
+      const double wt = w.W[q][m][ty];
+#pragma unroll
+      for (int c = 0; c < 6; c++) out[c] += wt * w.Bty[ty][6 * j + c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 6; c++) w.B[ql][r][6 * j + c] = out[c];
+}
+
+// phase 4, task (ql, j, r): CB = w det C B for six entries
+template <int O, int QC>
+TB2_HD void shell_p4_cbrow(int task, int q0, ShellWork<O, QC> &w) {
+  constexpr int n = ShellDims<O>::n;
+  const int r = task % 9, j = (task / 9) % n, ql = task / (9 * n);
+  const double wd = w.wdet[q0 + ql];
+  const double *Cs = w.desc;
+  double coef[6];
+  int first = 0, cnt = 0;
+  if (r < 3) {
+    // [A | B] row r of the symmetric packing [0 1 2; 1 3 4; 2 4 5]
+    const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
+              i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
+    coef[0] = Cs[i0]; coef[1] = Cs[i1]; coef[2] = Cs[i2];
+    coef[3] = Cs[6 + i0]; coef[4] = Cs[6 + i1]; coef[5] = Cs[6 + i2];
+    first = 0; cnt = 6;
+  } else if (r < 6) {
+    const int rr = r - 3;
+    const int i0 = (rr == 0) ? 0 : ((rr == 1) ? 1 : 2), i1 = (rr == 0) ? 1 : ((rr == 1) ? 3 : 4),
+              i2 = (rr == 0) ? 2 : ((rr == 1) ? 4 : 5);
+    coef[0] = Cs[6 + i0]; coef[1] = Cs[6 + i1]; coef[2] = Cs[6 + i2];
+    coef[3] = Cs[12 + i0]; coef[4] = Cs[12 + i1]; coef[5] = Cs[12 + i2];
+    first = 0; cnt = 6;
+  } else if (r == 6) {
+    coef[0] = Cs[18]; coef[1] = Cs[19]; first = 6; cnt = 2;
+  } else if (r == 7) {
+    coef[0] = Cs[19]; coef[1] = Cs[20]; first = 6; cnt = 2;
+  } else {
+    coef[0] = Cs[21]; first = 8; cnt = 1;
+  }
+  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int k = 0; k < cnt; k++) {
+    const double ck = coef[k];
+#pragma unroll
+    for (int c = 0; c < 6; c++) out[c] += ck * w.B[ql][first + k][6 * j + c];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; c++) w.CB[ql][r][6 * j + c] = wd * out[c];
+}
+
+// phase 5 (all families): one TRxTC tile of K accumulates B^T (CB) over the rows of this chunk
+template <int NROWS, int LD, int TR, int TC>
+TB2_HD void tile_accumulate(const double *B, const double *CB, int row0, int col0, double *acc) {
+#pragma unroll 3
+  for (int r = 0; r < NROWS; r++) {
+    double bi[TR], cj[TC];
+#pragma unroll
+    for (int a = 0; a < TR; a++) bi[a] = B[r * LD + row0 + a];
+#pragma unroll
+    for (int b = 0; b < TC; b++) cj[b] = CB[r * LD + col0 + b];
+#pragma unroll
+    for (int a = 0; a < TR; a++)
+#pragma unroll
+      for (int b = 0; b < TC; b++) acc[a * TC + b] += bi[a] * cj[b];
+  }
+}
+
+// phase 6, task tile (i,j): inertial block, residual partials; Kt = alpha*acc + gamma*M is left in acc
+template <int O, int QC>
+TB2_HD void shell_p6_finish(int tile, ShellWork<O, QC> &w, const ShellTables<O> &tab, double alpha,
+                            double gamma, double *acc) {
+  constexpr int n = ShellDims<O>::n, nq = ShellDims<O>::nq;
+  const int i = tile / n, j = tile % n;
+  double S = 0.0;
+  for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][i] * tab.Nq[q][j];
+  const double m0 = w.desc[22], m1 = w.desc[23], m2 = w.desc[24];
+  // d = D q with D(c,e) = eps_{cef} t_f  (director d = q x t)
+  const double *ti = &w.fn[3 * i], *tj = &w.fn[3 * j];
+  const double Di[9] = {0.0, ti[2], -ti[1], -ti[2], 0.0, ti[0], ti[1], -ti[0], 0.0};
+  const double Dj[9] = {0.0, tj[2], -tj[1], -tj[2], 0.0, tj[0], tj[1], -tj[0], 0.0};
+  double M[36];
+#pragma unroll
+  for (int k = 0; k < 36; k++) M[k] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    M[6 * c + c] = S * m0;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      M[6 * c + 3 + e] = S * m1 * Dj[3 * c + e];
+      M[6 * (3 + e) + c] = S * m1 * Di[3 * c + e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) v += Di[3 * c + e] * Dj[3 * c + f];
+      M[6 * (3 + e) + 3 + f] = S * m2 * v;
+    }
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    double rp = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; b++) rp += acc[6 * a + b] * w.u[6 * j + b] + M[6 * a + b] * w.acc[6 * j + b];
+    w.rpart[tile][a] = rp;
+  }
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = alpha * acc[k] + gamma * M[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// solid work area and phases
+// ------------------------------------------------------------------------------------------
+template <int O, int QC>
+struct SolidWork {
+  using D = SolidDims<O>;
+  static constexpr int n = D::n, nd = D::nd, nq = D::nq;
+  static constexpr int NS = 6;
+  static constexpr int TR = (O == 2) ? 6 : 9, TC = (O == 2) ? 6 : 9;
+  static constexpr int ntiles = (nd / TR) * (nd / TC);
+  static constexpr int LD = nd;
+  double X[3 * n];
+  double u[nd];
+  double acc[nd];
+  double desc[kDescStride];
+  double J[nq][9];
+  double wdet[nq];
+  double B[QC][NS][nd];
+  double CB[QC][NS][nd];
+  double rpart[ntiles][TR];
+};
+
+// phase 1, task q: Jacobian inverse and weighted determinant
+template <int O, int QC>
+TB2_HD void solid_p1_qgeom(int q, SolidWork<O, QC> &w, const SolidTables<O> &tab) {
+  constexpr int n = SolidDims<O>::n;
+  double Xd[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, J[9];
+  for (int a = 0; a < n; a++) {
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) Xd[3 * c + k] += tab.dNq[q][a][k] * w.X[3 * a + c];
+  }
+  const double det = inv3x3(Xd, J);
+  w.wdet[q] = det * tab.wq[q];
+#pragma unroll
+  for (int k = 0; k < 9; k++) w.J[q][k] = J[k];
+}
+
+// phase 3, task (ql, a): strain rows and C-weighted rows for the three dofs of node a
+template <int O, int QC>
+TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTables<O> &tab) {
+  constexpr int n = SolidDims<O>::n;
+  const int a = task % n, ql = task / n, q = q0 + ql;
+  const double *J = w.J[q];
+  const double x0 = tab.dNq[q][a][0], x1 = tab.dNq[q][a][1], x2 = tab.dNq[q][a][2];
+  const double gx = x0 * J[0] + x1 * J[3] + x2 * J[6];
+  const double gy = x0 * J[1] + x1 * J[4] + x2 * J[7];
+  const double gz = x0 * J[2] + x1 * J[5] + x2 * J[8];
+  // strain order xx,yy,zz,yz,xz,xy with engineering shears (TACSLinearElasticity.cpp:1186-1192)
+  const double Ba[6][3] = {{gx, 0.0, 0.0}, {0.0, gy, 0.0}, {0.0, 0.0, gz},
+                           {0.0, gz, gy},  {gz, 0.0, gx},  {gy, gx, 0.0}};
+  const double *C = w.desc;
+  // symmetric 6x6 from the upper triangle stored by rows
+  const int idx[6][6] = {{0, 1, 2, 3, 4, 5},     {1, 6, 7, 8, 9, 10},    {2, 7, 11, 12, 13, 14},
+                         {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
+  const double wd = w.wdet[q];
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      w.B[ql][r][3 * a + c] = Ba[r][c];
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += C[idx[r][k]] * Ba[k][c];
+      w.CB[ql][r][3 * a + c] = wd * s;
+    }
+}
+
+// phase 6, task tile: consistent mass block, residual partials; acc <- alpha*acc + gamma*M
+template <int O, int QC>
+TB2_HD void solid_p6_finish(int tile, SolidWork<O, QC> &w, const SolidTables<O> &tab, double alpha,
+                            double gamma, double *acc) {
+  using WK = SolidWork<O, QC>;
+  constexpr int TR = WK::TR, TC = WK::TC, nq = WK::nq, ntc = WK::nd / TC;
+  const int row0 = (tile / ntc) * TR, col0 = (tile % ntc) * TC;
+  const double rho = w.desc[21];
+  double M[TR * TC];
+#pragma unroll
+  for (int k = 0; k < TR * TC; k++) M[k] = 0.0;
+#pragma unroll
+  for (int an = 0; an < TR / 3; an++)
+#pragma unroll
+    for (int bn = 0; bn < TC / 3; bn++) {
+      const int na = row0 / 3 + an, nb = col0 / 3 + bn;
+      double S = 0.0;
+      for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][na] * tab.Nq[q][nb];
+#pragma unroll
+      for (int c = 0; c < 3; c++) M[(3 * an + c) * TC + 3 * bn + c] = rho * S;
+    }
+#pragma unroll
+  for (int a = 0; a < TR; a++) {
+    double rp = 0.0;
+#pragma unroll
+    for (int b = 0; b < TC; b++) rp += acc[a * TC + b] * w.u[col0 + b] + M[a * TC + b] * w.acc[col0 + b];
+    w.rpart[tile][a] = rp;
+  }
+#pragma unroll
+  for (int k = 0; k < TR * TC; k++) acc[k] = alpha * acc[k] + gamma * M[k];
+}
+
+}  // namespace tb2

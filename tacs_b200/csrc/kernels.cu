@@ -1,0 +1,683 @@
+// sm_100a kernels of the assembly + Krylov-operator hot path and their launchers.
+//
+//   element kernels   one *team* of threads per element (elem_phases.cuh), element matrices and
+//                     residuals written to a per-element staging area in HBM
+//   gather kernels    owner-computes, atomic-free and colour-free: every BCSR block (and every
+//                     residual entry) sums its precomputed list of staging slots in ascending
+//                     element order -- the order TACSAssembler's serial loop adds them
+//                     (/root/reference/src/TACSAssembler.cpp:4352-4380, BCSRMat.cpp:1800-1848)
+//   boundary conditions  TACSParallelMat::applyBCs / TACSBVec::applyBCs
+//                     (/root/reference/src/bpmat/TACSParallelMat.cpp:343-374, TACSBVec.cpp:546-596)
+//   block-CSR SpMV    BCSRMatVecMult6 / BCSRMatVecMult3 (+ the multAdd forms used for Bext)
+//                     (/root/reference/src/bpmat/BCSRMatMult6.cpp:82-169, BCSRMatMult3.cpp:27-77)
+//   vector kernels    TACSBVec norm/dot/mdot/axpy/axpby/scale/copy/zero
+//                     (/root/reference/src/bpmat/TACSBVec.cpp:196-428)
+//   halo pack/unpack  TACSBVecDistribute forward gather / reverse add
+//                     (/root/reference/src/bpmat/TACSBVecDistribute.cpp:543-743, 980-1326)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "elem_phases.cuh"
+#include "kernels.h"
+
+namespace tb2 {
+
+// ------------------------------------------------------------------------------------------
+// bulk async copy (TMA, non-tensor form) of the family tables into shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void stage_tables(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             uint64_t *mbar) {
+  if (threadIdx.x == 0) {
+    const uint32_t bar = smem_addr(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(bar)
+        : "memory");
+  }
+  __syncthreads();  // barrier initialised and armed before anyone polls it
+  const uint32_t bar = smem_addr(mbar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+  }
+}
+
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+  if (TEAM <= 32) {
+    __syncwarp();
+  } else {
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// element kernels
+// ------------------------------------------------------------------------------------------
+template <int O>
+struct ShellFamily {
+  static constexpr int QC = (O == 2) ? 2 : 3;
+  using Work = ShellWork<O, QC>;
+  using Tables = ShellTables<O>;
+  static constexpr int TEAM = (O == 2) ? 16 : 96;
+  static constexpr int TEAMS = (O == 2) ? 8 : 1;
+  static constexpr int BS = 6;
+};
+
+template <int O>
+struct SolidFamily {
+  static constexpr int QC = (O == 2) ? 4 : 3;
+  using Work = SolidWork<O, QC>;
+  using Tables = SolidTables<O>;
+  static constexpr int TEAM = (O == 2) ? 16 : 96;
+  static constexpr int TEAMS = (O == 2) ? 8 : 1;
+  static constexpr int BS = 3;
+};
+
+template <class Work, int BS>
+__device__ __forceinline__ void team_load(Work &w, const ElemGroupArgs &g, long e, int tid, int team) {
+  constexpr int n = Work::n, nd = Work::nd;
+  const int *conn = g.conn + e * n;
+  for (int k = tid; k < 3 * n; k += team) w.X[k] = g.Xpts[3 * (long)conn[k / 3] + k % 3];
+  for (int k = tid; k < nd; k += team) {
+    const long src = (long)BS * conn[k / BS] + k % BS;
+    w.u[k] = g.vars ? g.vars[src] : 0.0;
+    w.acc[k] = g.ddvars ? g.ddvars[src] : 0.0;
+  }
+  const double *d = g.desc_table + (long)kDescStride * g.desc_index[e];
+  for (int k = tid; k < kDescStride; k += team) w.desc[k] = d[k];
+}
+
+template <int O>
+__global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS)
+    shell_element_kernel(ElemGroupArgs g) {
+  using F = ShellFamily<O>;
+  using Work = typename F::Work;
+  constexpr int TEAM = F::TEAM, TEAMS = F::TEAMS, QC = F::QC;
+  constexpr int n = Work::n, nd = Work::nd, nq = Work::nq, nty = Work::nty;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typename F::Tables &tab = *reinterpret_cast<typename F::Tables *>(smem_raw);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(typename F::Tables));
+  Work *works = reinterpret_cast<Work *>(smem_raw + sizeof(typename F::Tables) + 16);
+  stage_tables(&tab, g.tables, (uint32_t)sizeof(typename F::Tables), mbar);
+
+  const int team_in_cta = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+  Work &w = works[team_in_cta];
+  const long nteams = (long)gridDim.x * TEAMS;
+  const long nelem = g.nelem;
+  // uniform trip count inside a CTA so that barriers are reached by every thread
+  for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
+    const bool live = (base + team_in_cta) < nelem;
+    const long e = live ? base + team_in_cta : nelem - 1;
+    team_load<Work, 6>(w, g, e, tid, TEAM);
+    team_sync<TEAM>();
+    for (int t = tid; t < n; t += TEAM) shell_p1_node<O, QC>(t, w, tab);
+    team_sync<TEAM>();
+    for (int t = tid; t < nty + nq; t += TEAM) {
+      if (t < nty) shell_p2_tying<O, QC>(t, w, tab);
+      else shell_p2_qgeom<O, QC>(t - nty, w, tab);
+    }
+    team_sync<TEAM>();
+    double acc[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] = 0.0;
+    const bool has_tile = tid < n * n;
+    const int ti = tid / n, tj = tid % n;
+    for (int q0 = 0; q0 < nq; q0 += QC) {
+      for (int t = tid; t < QC * n * 9; t += TEAM) shell_p3_brow<O, QC>(t, q0, w, tab);
+      team_sync<TEAM>();
+      for (int t = tid; t < QC * n * 9; t += TEAM) shell_p4_cbrow<O, QC>(t, q0, w);
+      team_sync<TEAM>();
+      if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
+      team_sync<TEAM>();
+    }
+    if (has_tile) {
+      shell_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, acc);
+      if (live && g.Ke) {
+        double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
+#pragma unroll
+        for (int k = 0; k < 18; k++) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+      }
+    }
+    team_sync<TEAM>();
+    if (live && g.Re) {
+      for (int k = tid; k < nd; k += TEAM) {
+        const int i = k / 6, a = k % 6;
+        double s = 0.0;
+        for (int j = 0; j < n; j++) s += w.rpart[i * n + j][a];
+        g.Re[e * nd + k] = s;
+      }
+    }
+    team_sync<TEAM>();
+  }
+}
+
+template <int O>
+__global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
+    solid_element_kernel(ElemGroupArgs g) {
+  using F = SolidFamily<O>;
+  using Work = typename F::Work;
+  constexpr int TEAM = F::TEAM, TEAMS = F::TEAMS, QC = F::QC;
+  constexpr int n = Work::n, nd = Work::nd, nq = Work::nq, TR = Work::TR, TC = Work::TC;
+  constexpr int ntc = nd / TC, ntiles = Work::ntiles;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typename F::Tables &tab = *reinterpret_cast<typename F::Tables *>(smem_raw);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(typename F::Tables));
+  Work *works = reinterpret_cast<Work *>(smem_raw + sizeof(typename F::Tables) + 16);
+  stage_tables(&tab, g.tables, (uint32_t)sizeof(typename F::Tables), mbar);
+
+  const int team_in_cta = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+  Work &w = works[team_in_cta];
+  const long nteams = (long)gridDim.x * TEAMS;
+  const long nelem = g.nelem;
+  for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
+    const bool live = (base + team_in_cta) < nelem;
+    const long e = live ? base + team_in_cta : nelem - 1;
+    team_load<Work, 3>(w, g, e, tid, TEAM);
+    team_sync<TEAM>();
+    for (int t = tid; t < nq; t += TEAM) solid_p1_qgeom<O, QC>(t, w, tab);
+    team_sync<TEAM>();
+    double acc[TR * TC];
+#pragma unroll
+    for (int k = 0; k < TR * TC; k++) acc[k] = 0.0;
+    const bool has_tile = tid < ntiles;
+    const int ti = tid / ntc, tj = tid % ntc;
+    for (int q0 = 0; q0 < nq; q0 += QC) {
+      for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
+      team_sync<TEAM>();
+      if (has_tile)
+        tile_accumulate<QC * 6, nd, TR, TC>(&w.B[0][0][0], &w.CB[0][0][0], TR * ti, TC * tj, acc);
+      team_sync<TEAM>();
+    }
+    if (has_tile) {
+      solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, acc);
+      if (live && g.Ke) {
+        // the tile covers (TR/3)x(TC/3) node pairs; staging is node-pair-major, 3x3 row-major inside
+#pragma unroll
+        for (int an = 0; an < TR / 3; an++)
+#pragma unroll
+          for (int bn = 0; bn < TC / 3; bn++) {
+            const long na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
+            double *dst = g.Ke + ((e * n + na) * n + nb) * 9;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+          }
+      }
+    }
+    team_sync<TEAM>();
+    if (live && g.Re) {
+      for (int k = tid; k < nd; k += TEAM) {
+        const int ri = k / TR, a = k % TR;
+        double s = 0.0;
+        for (int j = 0; j < ntc; j++) s += w.rpart[ri * ntc + j][a];
+        g.Re[e * nd + k] = s;
+      }
+    }
+    team_sync<TEAM>();
+  }
+}
+
+template <class F>
+static size_t family_smem() {
+  return sizeof(typename F::Tables) + 16 + sizeof(typename F::Work) * F::TEAMS;
+}
+
+size_t elem_tables_bytes(int kind) {
+  switch (kind) {
+    case ELEM_QUAD4_SHELL: return sizeof(ShellTables<2>);
+    case ELEM_QUAD9_SHELL: return sizeof(ShellTables<3>);
+    case ELEM_HEX8: return sizeof(SolidTables<2>);
+    case ELEM_HEX27: return sizeof(SolidTables<3>);
+  }
+  return 0;
+}
+
+void elem_tables_build(int kind, void *host_dst) {
+  switch (kind) {
+    case ELEM_QUAD4_SHELL: build_shell_tables<2>(*static_cast<ShellTables<2> *>(host_dst)); break;
+    case ELEM_QUAD9_SHELL: build_shell_tables<3>(*static_cast<ShellTables<3> *>(host_dst)); break;
+    case ELEM_HEX8: build_solid_tables<2>(*static_cast<SolidTables<2> *>(host_dst)); break;
+    case ELEM_HEX27: build_solid_tables<3>(*static_cast<SolidTables<3> *>(host_dst)); break;
+  }
+}
+
+template <class F, class K>
+static cudaError_t launch_family(K kernel, const ElemGroupArgs &g, int num_sms, cudaStream_t s) {
+  const size_t smem = family_smem<F>();
+  static bool configured = false;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, F::TEAM * F::TEAMS, smem);
+    if (err != cudaSuccess) return err;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    configured = true;
+  }
+  long want = (g.nelem + F::TEAMS - 1) / F::TEAMS;
+  long grid = (long)num_sms * ctas_per_sm;  // persistent: a whole number of CTAs per SM
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  kernel<<<(unsigned)grid, F::TEAM * F::TEAMS, smem, s>>>(g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream_t s) {
+  if (g.nelem <= 0) return cudaSuccess;
+  switch (g.kind) {
+    case ELEM_QUAD4_SHELL: return launch_family<ShellFamily<2>>(shell_element_kernel<2>, g, num_sms, s);
+    case ELEM_QUAD9_SHELL: return launch_family<ShellFamily<3>>(shell_element_kernel<3>, g, num_sms, s);
+    case ELEM_HEX8: return launch_family<SolidFamily<2>>(solid_element_kernel<2>, g, num_sms, s);
+    case ELEM_HEX27: return launch_family<SolidFamily<3>>(solid_element_kernel<3>, g, num_sms, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
+// gather: staging -> BCSR values / residual
+// ------------------------------------------------------------------------------------------
+// One thread per scalar entry of a block; the threads of a block read consecutive staging
+// addresses (coalesced) and every block is written exactly once.
+template <int B2>
+__global__ void gather_blocks_kernel(long nblocks, const int *__restrict__ ptr, const int *__restrict__ src,
+                                     const double *__restrict__ Ke, double *__restrict__ A) {
+  const long total = nblocks * B2;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long b = g / B2;
+    const int entry = (int)(g - b * B2);
+    const int beg = ptr[b], end = ptr[b + 1];
+    double s = 0.0;
+    for (int k = beg; k < end; k++) s += Ke[(long)src[k] * B2 + entry];
+    A[g] = s;
+  }
+}
+
+template <int BS>
+__global__ void gather_residual_kernel(long nnodes, const int *__restrict__ ptr, const int *__restrict__ src,
+                                       const double *__restrict__ Re, double *__restrict__ res) {
+  const long total = nnodes * BS;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long node = g / BS;
+    const int dof = (int)(g - node * BS);
+    const int beg = ptr[node], end = ptr[node + 1];
+    double s = 0.0;
+    for (int k = beg; k < end; k++) s += Re[(long)src[k] * BS + dof];
+    res[g] = s;
+  }
+}
+
+static inline unsigned grid_for(long total, int block, int num_sms) {
+  long want = (total + block - 1) / block;
+  long cap = (long)num_sms * 16;  // a whole number of CTAs per SM, grid-stride beyond that
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (unsigned)want;
+}
+
+cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int *src, const double *Ke,
+                                 double *A, int num_sms, cudaStream_t s) {
+  if (nblocks <= 0) return cudaSuccess;
+  const int block = 256;
+  if (bs == 6)
+    gather_blocks_kernel<36><<<grid_for(nblocks * 36, block, num_sms), block, 0, s>>>(nblocks, ptr, src, Ke, A);
+  else if (bs == 3)
+    gather_blocks_kernel<9><<<grid_for(nblocks * 9, block, num_sms), block, 0, s>>>(nblocks, ptr, src, Ke, A);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_residual(int bs, long nnodes, const int *ptr, const int *src, const double *Re,
+                                   double *res, int num_sms, cudaStream_t s) {
+  if (nnodes <= 0) return cudaSuccess;
+  const int block = 256;
+  if (bs == 6)
+    gather_residual_kernel<6><<<grid_for(nnodes * 6, block, num_sms), block, 0, s>>>(nnodes, ptr, src, Re, res);
+  else if (bs == 3)
+    gather_residual_kernel<3><<<grid_for(nnodes * 3, block, num_sms), block, 0, s>>>(nnodes, ptr, src, Re, res);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// boundary conditions
+// ------------------------------------------------------------------------------------------
+// one thread per (bc, block of its row, constrained dof): zero the row, unit diagonal
+__global__ void mat_apply_bcs_kernel(int bs, int nbcs, const int *__restrict__ bc_rows,
+                                     const int *__restrict__ bc_vars, const int *__restrict__ rowp,
+                                     const int *__restrict__ cols, double *__restrict__ A, int diag_offset) {
+  const int b2 = bs * bs;
+  for (int i = blockIdx.x; i < nbcs; i += gridDim.x) {
+    const int row = bc_rows[i];
+    if (row < 0) continue;
+    const int mask = bc_vars[i];
+    const int beg = rowp[row], end = rowp[row + 1];
+    for (int t = threadIdx.x; t < (end - beg) * b2; t += blockDim.x) {
+      const int k = beg + t / b2, ii = (t % b2) / bs, jj = t % bs;
+      if (mask & (1 << ii)) {
+        double v = 0.0;
+        if (diag_offset >= 0 && cols[k] == row + diag_offset && ii == jj) v = 1.0;
+        A[(long)b2 * k + bs * ii + jj] = v;
+      }
+    }
+  }
+}
+
+// x[dof] = u[dof] - lambda*value (u given) or 0
+__global__ void vec_apply_bcs_kernel(int bs, int nbcs, const int *__restrict__ bc_rows,
+                                     const int *__restrict__ bc_vars, const double *__restrict__ bc_vals,
+                                     const double *__restrict__ u, double lambda, double *__restrict__ x) {
+  const int total = nbcs * bs;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int i = g / bs, k = g % bs;
+    const int row = bc_rows[i];
+    if (row < 0) continue;
+    if (bc_vars[i] & (1 << k)) {
+      const long idx = (long)bs * row + k;
+      x[idx] = u ? u[idx] - lambda * bc_vals[g] : 0.0;
+    }
+  }
+}
+
+// x[dof] = value on constrained dofs (TACSBVec::setBCs, TACSBVec.cpp:601-640)
+__global__ void vec_set_bcs_kernel(int bs, int nbcs, const int *__restrict__ bc_rows,
+                                   const int *__restrict__ bc_vars, const double *__restrict__ bc_vals,
+                                   double lambda, double *__restrict__ x) {
+  const int total = nbcs * bs;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int i = g / bs, k = g % bs;
+    const int row = bc_rows[i];
+    if (row < 0) continue;
+    if (bc_vars[i] & (1 << k)) x[(long)bs * row + k] = lambda * bc_vals[g];
+  }
+}
+
+cudaError_t launch_mat_apply_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars, const int *rowp,
+                                 const int *cols, double *A, int diag_offset, cudaStream_t s) {
+  if (nbcs <= 0) return cudaSuccess;
+  int grid = nbcs < 4096 ? nbcs : 4096;
+  mat_apply_bcs_kernel<<<grid, 128, 0, s>>>(bs, nbcs, bc_rows, bc_vars, rowp, cols, A, diag_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vec_apply_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars,
+                                 const double *bc_vals, const double *u, double lambda, double *x,
+                                 cudaStream_t s) {
+  if (nbcs <= 0) return cudaSuccess;
+  int total = nbcs * bs;
+  vec_apply_bcs_kernel<<<(total + 255) / 256, 256, 0, s>>>(bs, nbcs, bc_rows, bc_vars, bc_vals, u, lambda, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vec_set_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars, const double *bc_vals,
+                               double lambda, double *x, cudaStream_t s) {
+  if (nbcs <= 0) return cudaSuccess;
+  int total = nbcs * bs;
+  vec_set_bcs_kernel<<<(total + 255) / 256, 256, 0, s>>>(bs, nbcs, bc_rows, bc_vars, bc_vals, lambda, x);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// block-CSR SpMV
+// ------------------------------------------------------------------------------------------
+// One thread per scalar row: the BS threads of a block row read one contiguous block per step
+// with 128-bit loads (bs 6) and the matching x block; blocks are visited in ascending column
+// order and each row's BS-term product is summed left to right before it is added, which is the
+// summation order of BCSRMatVecMult6/3. ADD selects y = A x (0) or y += A x (1, Bext multAdd).
+__device__ __forceinline__ double2 ldg2(const double *p) {
+  return __ldg(reinterpret_cast<const double2 *>(p));
+}
+
+template <int ADD>
+__global__ void __launch_bounds__(256) spmv6_kernel(int nrows, const int *__restrict__ rowp,
+                                                   const int *__restrict__ cols, const double *__restrict__ A,
+                                                   const double *__restrict__ x, double *__restrict__ y) {
+  const long total = (long)nrows * 6;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(g / 6), r = (int)(g - (long)row * 6);
+    const int beg = rowp[row], end = rowp[row + 1];
+    double acc = ADD ? y[g] : 0.0;
+    const double *a = A + (long)36 * beg + 6 * r;
+    int k = beg;
+    for (; k + 1 < end; k += 2, a += 72) {
+      const int c0 = cols[k], c1 = cols[k + 1];
+      const double2 a0 = ldg2(a), a1 = ldg2(a + 2), a2 = ldg2(a + 4);
+      const double2 b0 = ldg2(a + 36), b1 = ldg2(a + 38), b2 = ldg2(a + 40);
+      const double *xp = x + (long)6 * c0, *xq = x + (long)6 * c1;
+      const double2 x0 = ldg2(xp), x1 = ldg2(xp + 2), x2 = ldg2(xp + 4);
+      const double2 z0 = ldg2(xq), z1 = ldg2(xq + 2), z2 = ldg2(xq + 4);
+      double s = a0.x * x0.x;
+      s += a0.y * x0.y; s += a1.x * x1.x; s += a1.y * x1.y; s += a2.x * x2.x; s += a2.y * x2.y;
+      acc += s;
+      double t = b0.x * z0.x;
+      t += b0.y * z0.y; t += b1.x * z1.x; t += b1.y * z1.y; t += b2.x * z2.x; t += b2.y * z2.y;
+      acc += t;
+    }
+    if (k < end) {
+      const int c0 = cols[k];
+      const double2 a0 = ldg2(a), a1 = ldg2(a + 2), a2 = ldg2(a + 4);
+      const double *xp = x + (long)6 * c0;
+      const double2 x0 = ldg2(xp), x1 = ldg2(xp + 2), x2 = ldg2(xp + 4);
+      double s = a0.x * x0.x;
+      s += a0.y * x0.y; s += a1.x * x1.x; s += a1.y * x1.y; s += a2.x * x2.x; s += a2.y * x2.y;
+      acc += s;
+    }
+    y[g] = acc;
+  }
+}
+
+template <int ADD>
+__global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__restrict__ rowp,
+                                                   const int *__restrict__ cols, const double *__restrict__ A,
+                                                   const double *__restrict__ x, double *__restrict__ y) {
+  const long total = (long)nrows * 3;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(g / 3), r = (int)(g - (long)row * 3);
+    const int beg = rowp[row], end = rowp[row + 1];
+    double acc = ADD ? y[g] : 0.0;
+    const double *a = A + (long)9 * beg + 3 * r;
+    int k = beg;
+#pragma unroll 4
+    for (; k < end; k++, a += 9) {
+      const double *xp = x + (long)3 * cols[k];
+      double s = __ldg(a) * __ldg(xp);
+      s += __ldg(a + 1) * __ldg(xp + 1);
+      s += __ldg(a + 2) * __ldg(xp + 2);
+      acc += s;
+    }
+    y[g] = acc;
+  }
+}
+
+cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
+                        double *y, int add, int num_sms, cudaStream_t s) {
+  if (nrows <= 0) return cudaSuccess;
+  const int block = 256;
+  long want = ((long)nrows * bs + block - 1) / block;
+  long cap = (long)num_sms * 8 * 64;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (bs == 6) {
+    if (add) spmv6_kernel<1><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
+    else spmv6_kernel<0><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
+  } else if (bs == 3) {
+    if (add) spmv3_kernel<1><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
+    else spmv3_kernel<0><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// vector kernels
+// ------------------------------------------------------------------------------------------
+__global__ void axpy_kernel(long n, double alpha, const double *__restrict__ x, double *__restrict__ y) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] += alpha * x[i];
+}
+__global__ void axpby_kernel(long n, double alpha, double beta, const double *__restrict__ x,
+                             double *__restrict__ y) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = alpha * x[i] + beta * y[i];
+}
+__global__ void scale_kernel(long n, double alpha, double *__restrict__ y) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] *= alpha;
+}
+
+static inline unsigned vec_grid(long n, int num_sms) {
+  long want = (n + 255) / 256;
+  long cap = (long)num_sms * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (unsigned)want;
+}
+
+cudaError_t launch_axpy(long n, double alpha, const double *x, double *y, int num_sms, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  axpy_kernel<<<vec_grid(n, num_sms), 256, 0, s>>>(n, alpha, x, y);
+  return cudaGetLastError();
+}
+cudaError_t launch_axpby(long n, double alpha, double beta, const double *x, double *y, int num_sms,
+                         cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  axpby_kernel<<<vec_grid(n, num_sms), 256, 0, s>>>(n, alpha, beta, x, y);
+  return cudaGetLastError();
+}
+cudaError_t launch_scale(long n, double alpha, double *y, int num_sms, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  scale_kernel<<<vec_grid(n, num_sms), 256, 0, s>>>(n, alpha, y);
+  return cudaGetLastError();
+}
+
+// dot products: NV right-hand vectors against one x in a single sweep (mdot / classical
+// Gram-Schmidt); deterministic two-stage reduction (fixed grid, fixed tree), no atomics.
+constexpr int kDotBlock = 256;
+constexpr int kDotMaxVecs = 8;
+
+struct DotPtrs {
+  const double *y[kDotMaxVecs];
+};
+
+template <int NV>
+__global__ void __launch_bounds__(kDotBlock) dot_partial_kernel(long n, const double *__restrict__ x, DotPtrs ys,
+                                                               double *__restrict__ partial) {
+  double s[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) s[v] = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double xi = x[i];
+#pragma unroll
+    for (int v = 0; v < NV; v++) s[v] += xi * ys.y[v][i];
+  }
+  __shared__ double sh[NV][kDotBlock / 32];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double t = s[v];
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+    if ((threadIdx.x & 31) == 0) sh[v][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+    for (int k = 0; k < kDotBlock / 32; k++) t += sh[threadIdx.x][k];
+    partial[(long)threadIdx.x * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kDotBlock) dot_final_kernel(int nv, int nparts, const double *__restrict__ partial,
+                                                             double *__restrict__ out) {
+  __shared__ double sh[kDotBlock / 32];
+  for (int v = 0; v < nv; v++) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) t += partial[(long)v * nparts + k];
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int k = 0; k < kDotBlock / 32; k++) r += sh[k];
+      out[v] = r;
+    }
+    __syncthreads();
+  }
+}
+
+int dot_num_partials(int num_sms) { return num_sms * 4; }
+
+cudaError_t launch_mdot(long n, const double *x, int nv, const double *const *ys, double *partial, double *out,
+                        int num_sms, cudaStream_t s) {
+  if (nv < 1 || nv > kDotMaxVecs) return cudaErrorInvalidValue;
+  DotPtrs p;
+  for (int v = 0; v < kDotMaxVecs; v++) p.y[v] = ys[v < nv ? v : 0];
+  const int grid = dot_num_partials(num_sms);
+  switch (nv) {
+    case 1: dot_partial_kernel<1><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 2: dot_partial_kernel<2><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 3: dot_partial_kernel<3><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 4: dot_partial_kernel<4><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 5: dot_partial_kernel<5><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 6: dot_partial_kernel<6><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 7: dot_partial_kernel<7><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+    case 8: dot_partial_kernel<8><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
+  }
+  dot_final_kernel<<<1, kDotBlock, 0, s>>>(nv, grid, partial, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// halo pack / unpack (block-size generic: a block is bs doubles)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_blocks_kernel(int bs, long count, const int *__restrict__ idx, const double *__restrict__ x,
+                                   double *__restrict__ buf) {
+  const long total = count * bs;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long i = g / bs;
+    buf[g] = x[(long)bs * idx[i] + (g - i * bs)];
+  }
+}
+
+// add == 0: x[idx] = buf ; add == 1: x[idx] += buf (indices are unique within one call)
+__global__ void unpack_blocks_kernel(int bs, long count, const int *__restrict__ idx, const double *__restrict__ buf,
+                                     double *__restrict__ x, int add) {
+  const long total = count * bs;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long i = g / bs;
+    const long dst = (long)bs * idx[i] + (g - i * bs);
+    x[dst] = add ? x[dst] + buf[g] : buf[g];
+  }
+}
+
+cudaError_t launch_pack_blocks(int bs, long count, const int *idx, const double *x, double *buf, int num_sms,
+                               cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  pack_blocks_kernel<<<vec_grid(count * bs, num_sms), 256, 0, s>>>(bs, count, idx, x, buf);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_blocks(int bs, long count, const int *idx, const double *buf, double *x, int add,
+                                 int num_sms, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  unpack_blocks_kernel<<<vec_grid(count * bs, num_sms), 256, 0, s>>>(bs, count, idx, buf, x, add);
+  return cudaGetLastError();
+}
+
+}  // namespace tb2

@@ -1,0 +1,71 @@
+// Launchers of the sm_100a kernels (kernels.cu). Plain C++ interface used by the host objects.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace tb2 {
+
+enum ElemKind { ELEM_QUAD4_SHELL = 1, ELEM_QUAD9_SHELL = 2, ELEM_HEX8 = 3, ELEM_HEX27 = 4 };
+
+inline int elem_kind_nodes(int kind) {
+  switch (kind) {
+    case ELEM_QUAD4_SHELL: return 4;
+    case ELEM_QUAD9_SHELL: return 9;
+    case ELEM_HEX8: return 8;
+    case ELEM_HEX27: return 27;
+  }
+  return 0;
+}
+inline int elem_kind_bs(int kind) { return (kind == ELEM_QUAD4_SHELL || kind == ELEM_QUAD9_SHELL) ? 6 : 3; }
+
+// One homogeneous group of elements (same family); all pointers are device pointers.
+struct ElemGroupArgs {
+  int kind;
+  long nelem;
+  const int *conn;           // [nelem][nn] local node numbers
+  const int *desc_index;     // [nelem] row of desc_table
+  const double *desc_table;  // [ndesc][32] constitutive / transform constants
+  const void *tables;        // family shape-function tables
+  const double *Xpts;        // [nlocal][3]
+  const double *vars;        // [nlocal][bs] or null (zero state)
+  const double *ddvars;      // [nlocal][bs] or null
+  double alpha, gamma;
+  double *Ke;                // staging [nelem][nn][nn][bs*bs] or null (residual only)
+  double *Re;                // staging [nelem][nn*bs] or null
+};
+
+size_t elem_tables_bytes(int kind);
+void elem_tables_build(int kind, void *host_dst);
+cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream_t s);
+
+cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int *src, const double *Ke,
+                                 double *A, int num_sms, cudaStream_t s);
+cudaError_t launch_gather_residual(int bs, long nnodes, const int *ptr, const int *src, const double *Re,
+                                   double *res, int num_sms, cudaStream_t s);
+
+cudaError_t launch_mat_apply_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars, const int *rowp,
+                                 const int *cols, double *A, int diag_offset, cudaStream_t s);
+cudaError_t launch_vec_apply_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars,
+                                 const double *bc_vals, const double *u, double lambda, double *x,
+                                 cudaStream_t s);
+cudaError_t launch_vec_set_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars, const double *bc_vals,
+                               double lambda, double *x, cudaStream_t s);
+
+cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
+                        double *y, int add, int num_sms, cudaStream_t s);
+
+cudaError_t launch_axpy(long n, double alpha, const double *x, double *y, int num_sms, cudaStream_t s);
+cudaError_t launch_axpby(long n, double alpha, double beta, const double *x, double *y, int num_sms,
+                         cudaStream_t s);
+cudaError_t launch_scale(long n, double alpha, double *y, int num_sms, cudaStream_t s);
+int dot_num_partials(int num_sms);
+// out[v] = x . ys[v] for v < nv <= 8; partial has nv*dot_num_partials doubles
+cudaError_t launch_mdot(long n, const double *x, int nv, const double *const *ys, double *partial, double *out,
+                        int num_sms, cudaStream_t s);
+
+cudaError_t launch_pack_blocks(int bs, long count, const int *idx, const double *x, double *buf, int num_sms,
+                               cudaStream_t s);
+cudaError_t launch_unpack_blocks(int bs, long count, const int *idx, const double *buf, double *x, int add,
+                                 int num_sms, cudaStream_t s);
+
+}  // namespace tb2

@@ -3,9 +3,10 @@
  * /root/reference/src/TACSCreator.cpp:1105-1124, TACSAssembler.cpp:1620-1624)
  * and the CUDA toolkit's libmetis_static.a (64-bit idx_t).  The toolkit archive
  * is partially linked into one object and its four entry points renamed to
- * metis64_* (see Makefile: objcopy --redefine-sym), so these 32-bit wrappers can
- * carry the original names.  Used by BOTH oracle/_ref and the product library so
- * that the two sides consume the partition of one and the same METIS binary.
+ * metis64_* (objcopy --redefine-sym in the build), so these 32-bit wrappers can
+ * carry the original names.  The product library links this adapter for
+ * TACSCreator-style element partitioning; oracle/Makefile compiles the same file
+ * into oracle/_ref so both sides consume the partition of one METIS binary.
  */
 #include <stdint.h>
 #include <stdlib.h>

@@ -1,0 +1,1302 @@
+// Host objects of tacs_b200 (see tb2_host.h): constitutive constants, mesh partition / numbering,
+// sparsity and gather plans, and the drivers that launch the sm_100a kernels.
+#include "tb2_host.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <thread>
+
+#include "metis_shim/metis.h"
+
+namespace tb2 {
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+static Context g_ctx;
+Context &ctx() { return g_ctx; }
+
+bool cuda_ok(cudaError_t err, const char *what) {
+  if (err == cudaSuccess) return true;
+  fprintf(stderr, "tacs_b200: CUDA error in %s: %s\n", what, cudaGetErrorString(err));
+  return false;
+}
+
+int ctx_init(int device) {
+  Context &c = g_ctx;
+  if (c.device >= 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "tacs_b200: no CUDA device is visible; this library has no CPU path\n");
+    return 1;
+  }
+  if (device < 0) device = 0;
+  if (device >= ndev) device = device % ndev;
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return 1;
+  cudaDeviceProp prop;
+  if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return 1;
+  if (prop.major < 10) {
+    fprintf(stderr, "tacs_b200: device %d (%s, sm_%d%d) is not a Blackwell sm_100 part\n", device, prop.name,
+            prop.major, prop.minor);
+    return 1;
+  }
+  c.num_sms = prop.multiProcessorCount;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  c.device = device;
+  return 0;
+}
+
+static void parallel_for(long n, const std::function<void(long, long)> &fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  long nt = hw ? hw : 4;
+  if (nt > 64) nt = 64;
+  if (n < 4096 || nt <= 1) {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  long chunk = (n + nt - 1) / nt;
+  for (long t = 0; t < nt; t++) {
+    long lo = t * chunk, hi = std::min(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back(fn, lo, hi);
+  }
+  for (auto &t : th) t.join();
+}
+
+// ---------------------------------------------------------------------------------------------
+// constitutive objects
+// ---------------------------------------------------------------------------------------------
+TACSMaterialProperties::TACSMaterialProperties(double _rho, double _cp, double _E, double _nu, double _ys,
+                                               double _alpha, double _kappa) {
+  isotropic = true;
+  rho = _rho; specific_heat = _cp; E = _E; nu = _nu; ys = _ys; alpha = _alpha; kappa = _kappa;
+  G = 0.5 * E / (1.0 + nu);
+  E1 = E2 = E3 = E;
+  nu12 = nu13 = nu23 = nu;
+  G12 = G13 = G23 = G;
+}
+
+TACSMaterialProperties::TACSMaterialProperties(double _rho, double _cp, double _E1, double _E2, double _E3,
+                                               double _nu12, double _nu13, double _nu23, double _G12,
+                                               double _G13, double _G23) {
+  isotropic = false;
+  rho = _rho; specific_heat = _cp;
+  E = nu = G = 0.0; ys = alpha = kappa = 0.0;
+  E1 = _E1; E2 = _E2; E3 = _E3;
+  nu12 = _nu12; nu13 = _nu13; nu23 = _nu23;
+  G12 = _G12; G13 = _G13; G23 = _G23;
+}
+
+// TACSMaterialProperties.cpp:323-341
+void TACSMaterialProperties::evalTangentStiffness2D(double C[6]) const {
+  if (isotropic) {
+    double D = E / (1.0 - nu * nu);
+    C[0] = D; C[1] = nu * D; C[2] = 0.0; C[3] = D; C[4] = 0.0; C[5] = G;
+  } else {
+    double nu21 = nu12 * E2 / E1;
+    C[0] = E1 / (1.0 - nu12 * nu21);
+    C[1] = nu12 * E2 / (1.0 - nu12 * nu21);
+    C[2] = 0.0;
+    C[3] = E2 / (1.0 - nu12 * nu21);
+    C[4] = 0.0;
+    C[5] = G12;
+  }
+}
+
+// TACSMaterialProperties.cpp:270-321
+void TACSMaterialProperties::evalTangentStiffness3D(double C[21]) const {
+  for (int i = 0; i < 21; i++) C[i] = 0.0;
+  if (isotropic) {
+    double D = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+    C[0] = (1.0 - nu) * D; C[1] = nu * D; C[2] = nu * D;
+    C[6] = (1.0 - nu) * D; C[7] = nu * D;
+    C[11] = (1.0 - nu) * D;
+    C[15] = G; C[18] = G; C[20] = G;
+  } else {
+    double nu21 = (E2 / E1) * nu12, nu31 = (E3 / E1) * nu13, nu32 = (E3 / E2) * nu23;
+    double D = 1.0 / (1.0 - nu12 * nu21 - nu13 * nu31 - nu23 * nu32 - 2.0 * nu21 * nu32 * nu13);
+    C[0] = (1.0 - nu23 * nu32) * E1 * D;
+    C[1] = (nu21 + nu31 * nu23) * E1 * D;
+    C[2] = (nu31 + nu21 * nu32) * E1 * D;
+    C[6] = (1.0 - nu13 * nu31) * E2 * D;
+    C[7] = (nu32 + nu12 * nu31) * E2 * D;
+    C[11] = (1.0 - nu12 * nu21) * E3 * D;
+    C[15] = G23; C[18] = G13; C[20] = G12;
+  }
+}
+
+// TACSMaterialProperties.cpp:523-545
+TACSOrthotropicPly::TACSOrthotropicPly(double t, TACSMaterialProperties *p) {
+  plyThickness = t;
+  properties = p;
+  properties->incref();
+  rho = p->getDensity();
+  double E1 = p->E1, E2 = p->E2, nu12 = p->nu12;
+  double nu21 = nu12 * E2 / E1;
+  Q11 = E1 / (1.0 - nu12 * nu21);
+  Q22 = E2 / (1.0 - nu12 * nu21);
+  Q12 = nu12 * E2 / (1.0 - nu12 * nu21);
+  Q44 = p->G23; Q55 = p->G13; Q66 = p->G12;
+  C12 = (Q11 + Q22 - 4.0 * Q66);
+  C16 = (Q11 - Q12 - 2.0 * Q66);
+  C26 = (Q12 - Q22 + 2.0 * Q66);
+  C66 = (Q11 + Q22 - 2.0 * Q12 - 2.0 * Q66);
+}
+TACSOrthotropicPly::~TACSOrthotropicPly() { properties->decref(); }
+
+// TACSMaterialProperties.cpp:752-773 (Jones, Mechanics of Composite Materials p.51)
+void TACSOrthotropicPly::calculateQbar(double angle, double Qbar[6]) const {
+  double cos1 = cos(angle), sin1 = sin(angle);
+  double cos2 = cos1 * cos1, sin2 = sin1 * sin1, cos4 = cos2 * cos2, sin4 = sin2 * sin2;
+  Qbar[0] = Q11 * cos4 + 2.0 * (Q12 + 2.0 * Q66) * sin2 * cos2 + Q22 * sin4;
+  Qbar[1] = C12 * sin2 * cos2 + Q12 * (sin4 + cos4);
+  Qbar[2] = C16 * sin1 * cos2 * cos1 + C26 * sin2 * sin1 * cos1;
+  Qbar[3] = Q11 * sin4 + 2.0 * (Q12 + 2.0 * Q66) * sin2 * cos2 + Q22 * cos4;
+  Qbar[4] = C16 * sin2 * sin1 * cos1 + C26 * sin1 * cos2 * cos1;
+  Qbar[5] = C66 * sin2 * cos2 + Q66 * (sin4 + cos4);
+}
+
+// TACSMaterialProperties.cpp:724-734
+void TACSOrthotropicPly::calculateAbar(double angle, double Abar[3]) const {
+  double cos1 = cos(angle), sin1 = sin(angle);
+  double cos2 = cos1 * cos1, sin2 = sin1 * sin1;
+  Abar[0] = cos2 * Q44 + sin2 * Q55;
+  Abar[1] = cos1 * sin1 * (Q55 - Q44);
+  Abar[2] = sin2 * Q44 + cos2 * Q55;
+}
+
+double TACSShellConstitutive::DRILLING_REGULARIZATION = 0.1;  // TACSShellConstitutive.cpp:61
+
+void TACSShellConstitutive::fillDescriptor(double d[]) {
+  evalTangentStiffness(d);
+  evalMassMoments(d + 22);
+}
+
+TACSIsoShellConstitutive::TACSIsoShellConstitutive(TACSMaterialProperties *props, double _t, double _tOffset,
+                                                   double _kcorr) {
+  properties = props;
+  if (properties) properties->incref();
+  t = _t; tOffset = _tOffset; kcorr = _kcorr;
+}
+TACSIsoShellConstitutive::~TACSIsoShellConstitutive() {
+  if (properties) properties->decref();
+}
+
+// TACSIsoShellConstitutive.cpp:192-226
+void TACSIsoShellConstitutive::evalTangentStiffness(double C[]) {
+  if (!properties) {
+    memset(C, 0, 22 * sizeof(double));
+    return;
+  }
+  double *A = &C[0], *B = &C[6], *D = &C[12], *As = &C[18];
+  properties->evalTangentStiffness2D(A);
+  for (int i = 0; i < 6; i++) B[i] = 0.0;
+  double I = t * t * t / 12.0;
+  for (int i = 0; i < 6; i++) {
+    D[i] = I * A[i];
+    A[i] *= t;
+    B[i] += -tOffset * t * A[i];
+    D[i] += tOffset * tOffset * t * t * A[i];
+  }
+  As[0] = As[2] = kcorr * A[5];
+  As[1] = 0.0;
+  C[21] = 0.5 * DRILLING_REGULARIZATION * (As[0] + As[2]);
+}
+
+// TACSIsoShellConstitutive.cpp:120-129
+void TACSIsoShellConstitutive::evalMassMoments(double m[3]) {
+  m[0] = m[1] = m[2] = 0.0;
+  if (properties) {
+    double rho = properties->getDensity();
+    m[0] = rho * t;
+    m[1] = -rho * t * t * tOffset;
+    m[2] = rho * t * t * t * (tOffset * tOffset + 1.0 / 12.0);
+  }
+}
+
+TACSCompositeShellConstitutive::TACSCompositeShellConstitutive(int n, TACSOrthotropicPly **plies,
+                                                               const double *thick, const double *angles,
+                                                               double _kcorr, double _tOffset) {
+  for (int i = 0; i < n; i++) {
+    plies[i]->incref();
+    ply_props.push_back(plies[i]);
+    ply_thickness.push_back(thick[i]);
+    ply_angles.push_back(angles[i]);
+  }
+  kcorr = _kcorr;
+  tOffset = _tOffset;
+}
+TACSCompositeShellConstitutive::~TACSCompositeShellConstitutive() {
+  for (auto p : ply_props) p->decref();
+}
+
+// TACSCompositeShellConstitutive.cpp:249-301
+void TACSCompositeShellConstitutive::evalTangentStiffness(double C[]) {
+  double *A = &C[0], *B = &C[6], *D = &C[12], *As = &C[18];
+  for (int k = 0; k < 6; k++) A[k] = B[k] = D[k] = 0.0;
+  for (int k = 0; k < 3; k++) As[k] = 0.0;
+  double t = 0.0;
+  const int np = (int)ply_props.size();
+  for (int i = 0; i < np; i++) t += ply_thickness[i];
+  double t0 = -(0.5 + tOffset) * t;
+  for (int k = 0; k < np; k++) {
+    double Qbar[6], Abar[3];
+    ply_props[k]->calculateQbar(ply_angles[k], Qbar);
+    ply_props[k]->calculateAbar(ply_angles[k], Abar);
+    double t1 = t0 + ply_thickness[k];
+    double a = (t1 - t0), b = 0.5 * (t1 * t1 - t0 * t0), d = 1.0 / 3.0 * (t1 * t1 * t1 - t0 * t0 * t0);
+    for (int i = 0; i < 6; i++) {
+      A[i] += a * Qbar[i];
+      B[i] += b * Qbar[i];
+      D[i] += d * Qbar[i];
+    }
+    for (int i = 0; i < 3; i++) As[i] += kcorr * a * Abar[i];
+    t0 = t1;
+  }
+  C[21] = 0.5 * DRILLING_REGULARIZATION * (As[0] + As[2]);
+}
+
+// TACSCompositeShellConstitutive.cpp:70-100
+void TACSCompositeShellConstitutive::evalMassMoments(double m[3]) {
+  m[0] = m[1] = m[2] = 0.0;
+  double t = 0.0;
+  const int np = (int)ply_props.size();
+  for (int i = 0; i < np; i++) t += ply_thickness[i];
+  double t0 = -(0.5 + tOffset) * t;
+  for (int i = 0; i < np; i++) {
+    double rho_ply = ply_props[i]->getDensity();
+    double t1 = t0 + ply_thickness[i];
+    double a = (t1 - t0), b = 0.5 * (t1 * t1 - t0 * t0), d = 1.0 / 3.0 * (t1 * t1 * t1 - t0 * t0 * t0);
+    m[0] += a * rho_ply;
+    m[1] += b * rho_ply;
+    m[2] += d * rho_ply;
+    t0 = t1;
+  }
+}
+
+TACSSolidConstitutive::TACSSolidConstitutive(TACSMaterialProperties *props, double _t) {
+  properties = props;
+  if (properties) properties->incref();
+  t = _t;
+}
+TACSSolidConstitutive::~TACSSolidConstitutive() {
+  if (properties) properties->decref();
+}
+// TACSSolidConstitutive.cpp:166-178
+void TACSSolidConstitutive::evalTangentStiffness(double C[]) {
+  if (!properties) {
+    memset(C, 0, 21 * sizeof(double));
+    return;
+  }
+  properties->evalTangentStiffness3D(C);
+  for (int i = 0; i < 21; i++) C[i] *= t;
+}
+void TACSSolidConstitutive::fillDescriptor(double d[]) {
+  evalTangentStiffness(d);
+  d[21] = properties ? evalDensity() : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transforms and elements
+// ---------------------------------------------------------------------------------------------
+TACSShellNaturalTransform::TACSShellNaturalTransform() {
+  kind = 0;
+  axis[0] = axis[1] = axis[2] = 0.0;
+}
+// TACSShellElementTransform.h:97-108: the axis is normalised once in the constructor
+TACSShellRefAxisTransform::TACSShellRefAxisTransform(const double a[3]) {
+  kind = 1;
+  axis[0] = a[0]; axis[1] = a[1]; axis[2] = a[2];
+  double norm = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  double inv = 0.0;
+  if (norm != 0.0) inv = 1.0 / norm;
+  axis[0] *= inv; axis[1] *= inv; axis[2] *= inv;
+}
+
+TACSLinearElasticity3D::TACSLinearElasticity3D(TACSSolidConstitutive *con) {
+  stiff = con;
+  stiff->incref();
+}
+TACSLinearElasticity3D::~TACSLinearElasticity3D() { stiff->decref(); }
+
+TACSShellElement::TACSShellElement(int o, TACSShellTransform *t, TACSShellConstitutive *c) {
+  order = o; transform = t; con = c;
+  transform->incref();
+  con->incref();
+}
+TACSShellElement::~TACSShellElement() {
+  transform->decref();
+  con->decref();
+}
+void TACSShellElement::fillDescriptor(double d[]) {
+  for (int i = 0; i < 32; i++) d[i] = 0.0;
+  con->fillDescriptor(d);
+  d[25] = (double)transform->kind;
+  d[26] = transform->axis[0]; d[27] = transform->axis[1]; d[28] = transform->axis[2];
+}
+
+TACSElement3D::TACSElement3D(TACSElementModel *m, TACSElementBasis *b) {
+  model = dynamic_cast<TACSLinearElasticity3D *>(m);
+  basis = b;
+  if (model) model->incref();
+  basis->incref();
+}
+TACSElement3D::~TACSElement3D() {
+  if (model) model->decref();
+  basis->decref();
+}
+void TACSElement3D::fillDescriptor(double d[]) {
+  for (int i = 0; i < 32; i++) d[i] = 0.0;
+  model->stiff->fillDescriptor(d);
+}
+
+// Staging layout is node-pair-major with a row-major bs x bs block inside; convert to the dense
+// row-major element matrix mat[nv*row + col] of TACSElement::addJacobian.
+int TACSElement::addJacobianBatch(int count, double alpha, double beta, double gamma, const double *Xpts,
+                                  const double *vars, const double *dvars, const double *ddvars, double *res,
+                                  double *mat) {
+  (void)beta; (void)dvars;
+  if (ctx_init(-1)) return 1;
+  const int nn = getNumNodes(), bs = getVarsPerNode(), nv = nn * bs, kind = kernelKind();
+  std::vector<int> conn((size_t)count * nn), desc(count, 0);
+  for (size_t k = 0; k < conn.size(); k++) conn[k] = (int)k;
+  double drow[32];
+  fillDescriptor(drow);
+  std::vector<unsigned char> tab(elem_tables_bytes(kind));
+  elem_tables_build(kind, tab.data());
+  DeviceArray<int> d_conn, d_desc;
+  DeviceArray<double> d_table, d_X, d_u, d_a, d_Ke, d_Re;
+  DeviceArray<unsigned char> d_tab;
+  if (!d_conn.upload(conn) || !d_desc.upload(desc) || !d_table.upload(drow, 32) ||
+      !d_tab.upload(tab.data(), tab.size()) || !d_X.upload(Xpts, (size_t)count * 3 * nn) ||
+      !d_u.upload(vars, (size_t)count * nv))
+    return 1;
+  if (ddvars && !d_a.upload(ddvars, (size_t)count * nv)) return 1;
+  if (mat && !d_Ke.alloc((size_t)count * nv * nv)) return 1;
+  if (!d_Re.alloc((size_t)count * nv)) return 1;
+  ElemGroupArgs g;
+  g.kind = kind; g.nelem = count; g.conn = d_conn.ptr; g.desc_index = d_desc.ptr; g.desc_table = d_table.ptr;
+  g.tables = d_tab.ptr; g.Xpts = d_X.ptr; g.vars = d_u.ptr; g.ddvars = ddvars ? d_a.ptr : nullptr;
+  g.alpha = alpha; g.gamma = gamma; g.Ke = mat ? d_Ke.ptr : nullptr; g.Re = d_Re.ptr;
+  if (!cuda_ok(launch_element_group(g, ctx().num_sms, ctx().stream), "element kernel")) return 1;
+  ctx().kernel_launches++;
+  if (!cuda_ok(cudaStreamSynchronize(ctx().stream), "element kernel sync")) return 1;
+  if (res && !d_Re.download(res, (size_t)count * nv)) return 1;
+  if (mat) {
+    std::vector<double> stage((size_t)count * nv * nv);
+    if (!d_Ke.download(stage.data(), stage.size())) return 1;
+    const int b2 = bs * bs;
+    for (int e = 0; e < count; e++)
+      for (int i = 0; i < nn; i++)
+        for (int j = 0; j < nn; j++) {
+          const double *blk = &stage[((size_t)(e * nn + i) * nn + j) * b2];
+          for (int a = 0; a < bs; a++)
+            for (int b = 0; b < bs; b++)
+              mat[(size_t)e * nv * nv + (size_t)nv * (bs * i + a) + bs * j + b] = blk[bs * a + b];
+        }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// creator: partition, first-touch numbering, local meshes
+// ---------------------------------------------------------------------------------------------
+TACSCreator::TACSCreator(int vpn) { vars_per_node = vpn; }
+TACSCreator::~TACSCreator() {
+  for (auto e : elements)
+    if (e) e->decref();
+}
+
+void TACSCreator::setGlobalConnectivity(int nn, int ne, const int *ptr, const int *conn, const int *ids) {
+  num_nodes = nn;
+  num_elements = ne;
+  elem_node_ptr.assign(ptr, ptr + ne + 1);
+  elem_node_conn.assign(conn, conn + ptr[ne]);
+  elem_id_nums.assign(ids, ids + ne);
+}
+
+// TACSCreator.cpp:226-271
+void TACSCreator::setBoundaryConditions(int nb, const int *nodes, const int *ptr, const int *vars,
+                                        const double *vals) {
+  bc_nodes.assign(nodes, nodes + nb);
+  bc_ptr.resize(nb + 1);
+  if (ptr && vars) {
+    bc_ptr.assign(ptr, ptr + nb + 1);
+    bc_vars.assign(vars, vars + ptr[nb]);
+    if (vals) bc_vals.assign(vals, vals + ptr[nb]);
+    else bc_vals.assign(ptr[nb], 0.0);
+  } else {
+    bc_vars.resize((size_t)nb * vars_per_node);
+    bc_ptr[0] = 0;
+    for (int i = 0; i < nb; i++) {
+      bc_ptr[i + 1] = bc_ptr[i] + vars_per_node;
+      for (int j = 0; j < vars_per_node; j++) bc_vars[bc_ptr[i] + j] = j;
+    }
+    bc_vals.assign(bc_ptr[nb], 0.0);
+  }
+}
+
+void TACSCreator::setNodes(const double *X) { Xpts.assign(X, X + 3 * (size_t)num_nodes); }
+
+void TACSCreator::setElements(int n, TACSElement **elems) {
+  for (auto e : elements)
+    if (e) e->decref();
+  elements.assign(elems, elems + n);
+  for (auto e : elements)
+    if (e) e->incref();
+}
+
+// TacsUniqueSort (TacsUtilities.cpp:76-99)
+static int unique_sort(int len, int *a) {
+  std::sort(a, a + len);
+  int i = 0;
+  while (i < len && a[i] < 0) i++;
+  int n = 0;
+  for (; i < len; i++)
+    if (n == 0 || a[n - 1] != a[i]) a[n++] = a[i];
+  return n;
+}
+
+// TACSCreator::partitionMesh (TACSCreator.cpp:923-1209): element dual graph (elements adjacent when
+// they share a node, rows sorted ascending, diagonal removed) -> METIS recursive (< 8 parts) or
+// k-way; then first-touch node renumbering in global element order.
+int TACSCreator::partitionMesh(int split_size, const int *part) {
+  const int mpi_size = ctx().size;
+  if (split_size <= 0 || split_size > mpi_size) split_size = mpi_size;
+  partition.clear();
+  if (part) {
+    bool legit = true;
+    for (int i = 0; i < num_elements; i++)
+      if (part[i] < 0 || part[i] >= split_size) { legit = false; break; }
+    if (legit) partition.assign(part, part + num_elements);
+  }
+  if (partition.empty()) {
+    partition.assign(num_elements, 0);
+    if (split_size > 1) {
+      std::vector<int> node_elem_ptr(num_nodes + 1, 0);
+      for (int i = 0; i < num_elements; i++)
+        for (int j = elem_node_ptr[i]; j < elem_node_ptr[i + 1]; j++)
+          if (elem_node_conn[j] >= 0) node_elem_ptr[elem_node_conn[j] + 1]++;
+      for (int i = 0; i < num_nodes; i++) node_elem_ptr[i + 1] += node_elem_ptr[i];
+      std::vector<int> node_elem_conn(node_elem_ptr[num_nodes]);
+      {
+        std::vector<int> cursor(node_elem_ptr.begin(), node_elem_ptr.end() - 1);
+        for (int i = 0; i < num_elements; i++)
+          for (int j = elem_node_ptr[i]; j < elem_node_ptr[i + 1]; j++)
+            if (elem_node_conn[j] >= 0) node_elem_conn[cursor[elem_node_conn[j]]++] = i;
+      }
+      std::vector<int> elem_ptr(num_elements + 1, 0), elem_conn, row;
+      elem_conn.reserve((size_t)27 * num_elements);
+      for (int i = 0; i < num_elements; i++) {
+        row.clear();
+        for (int jp = elem_node_ptr[i]; jp < elem_node_ptr[i + 1]; jp++) {
+          int node = elem_node_conn[jp];
+          if (node >= 0)
+            for (int kp = node_elem_ptr[node]; kp < node_elem_ptr[node + 1]; kp++) row.push_back(node_elem_conn[kp]);
+        }
+        int len = unique_sort((int)row.size(), row.data());
+        for (int j = 0; j < len; j++)
+          if (row[j] != i) elem_conn.push_back(row[j]);
+        elem_ptr[i + 1] = (int)elem_conn.size();
+      }
+      int ncon = 1, options[METIS_NOPTIONS], objval = 0, nparts = split_size, ne = num_elements;
+      METIS_SetDefaultOptions(options);
+      options[METIS_OPTION_NUMBERING] = 0;
+      if (split_size < 8)
+        METIS_PartGraphRecursive(&ne, &ncon, elem_ptr.data(), elem_conn.data(), NULL, NULL, NULL, &nparts, NULL,
+                                 NULL, options, &objval, partition.data());
+      else
+        METIS_PartGraphKway(&ne, &ncon, elem_ptr.data(), elem_conn.data(), NULL, NULL, NULL, &nparts, NULL, NULL,
+                            options, &objval, partition.data());
+    }
+  }
+  // first-touch numbering (TACSCreator.cpp:1141-1205)
+  new_nodes.assign(num_nodes, 0);
+  owned_elements.assign(mpi_size, 0);
+  owned_nodes.assign(mpi_size, 0);
+  for (int j = 0; j < num_elements; j++) {
+    int owner = partition[j];
+    owned_elements[owner]++;
+    for (int i = elem_node_ptr[j]; i < elem_node_ptr[j + 1]; i++) {
+      int node = elem_node_conn[i];
+      if (node >= 0 && !new_nodes[node]) {
+        new_nodes[node] = 1;
+        owned_nodes[owner]++;
+      }
+    }
+  }
+  std::fill(new_nodes.begin(), new_nodes.end(), -1);
+  std::vector<int> split_offset(split_size, 0);
+  for (int k = 1; k < split_size; k++) split_offset[k] = split_offset[k - 1] + owned_nodes[k - 1];
+  for (int j = 0; j < num_elements; j++) {
+    int owner = partition[j];
+    for (int i = elem_node_ptr[j]; i < elem_node_ptr[j + 1]; i++) {
+      int node = elem_node_conn[i];
+      if (node >= 0 && new_nodes[node] < 0) new_nodes[node] = split_offset[owner]++;
+    }
+  }
+  return 0;
+}
+
+int TACSCreator::getNodeNums(const int **nn) {
+  if (nn) *nn = new_nodes.empty() ? nullptr : new_nodes.data();
+  return new_nodes.empty() ? 0 : num_nodes;
+}
+int TACSCreator::getElementPartition(const int **p) {
+  if (p) *p = partition.empty() ? nullptr : partition.data();
+  return partition.empty() ? 0 : num_elements;
+}
+
+// TACSCreator::createTACS (TACSCreator.cpp:436-909). Every rank holds the global mesh, so the
+// root->rank scatter of the reference becomes a local selection: the elements of this rank in
+// ascending global order (stable sort by partition, compare_arg_sort :37-47), connectivity in the
+// new global numbering, nodes of the owned range.
+TACSAssembler *TACSCreator::createTACS() {
+  if (ctx_init(-1)) return nullptr;
+  if (elements.empty()) {
+    fprintf(stderr, "[%d] TACSCreator: Elements and callback not defined\n", ctx().rank);
+    return nullptr;
+  }
+  if (partition.empty() || new_nodes.empty()) partitionMesh(ctx().size, nullptr);
+  const int rank = ctx().rank, size = ctx().size;
+  TACSAssembler *a = new TACSAssembler();
+  a->bs = vars_per_node;
+  a->rank = rank;
+  a->size = size;
+  a->owner_range.assign(size + 1, 0);
+  for (int k = 0; k < size; k++) a->owner_range[k + 1] = a->owner_range[k] + owned_nodes[k];
+  a->nowned = owned_nodes[rank];
+  a->nelems = owned_elements[rank];
+  a->elem_ptr.assign(1, 0);
+  for (int e = 0; e < num_elements; e++) {
+    if (partition[e] != rank) continue;
+    for (int i = elem_node_ptr[e]; i < elem_node_ptr[e + 1]; i++) {
+      int node = elem_node_conn[i];
+      if (node < 0) {
+        fprintf(stderr, "[%d] tacs_b200: dependent nodes are not supported on the device path\n", rank);
+        delete a;
+        return nullptr;
+      }
+      a->elem_conn_global.push_back(new_nodes[node]);
+    }
+    a->elem_ptr.push_back((int)a->elem_conn_global.size());
+    int id = elem_id_nums[e];
+    TACSElement *el = (id >= 0 && id < (int)elements.size()) ? elements[id] : nullptr;
+    if (!el) {
+      fprintf(stderr, "[%d] TACSCreator: Element undefined for element ID %d\n", rank, id);
+      delete a;
+      return nullptr;
+    }
+    a->elems.push_back(el);
+  }
+  // boundary conditions in the new numbering (TACSCreator.cpp:478-481, 836-851)
+  for (size_t k = 0; k < bc_nodes.size(); k++) {
+    int node = new_nodes[bc_nodes[k]];
+    if (node < 0) continue;
+    int mask = 0;
+    std::vector<double> vals(vars_per_node, 0.0);
+    int n = 0;
+    for (int j = bc_ptr[k]; j < bc_ptr[k + 1]; j++)
+      if (bc_vars[j] >= 0 && bc_vars[j] < vars_per_node) {
+        mask |= (1 << bc_vars[j]);
+        vals[bc_vars[j]] = bc_vals[j];
+        n++;
+      }
+    if (n > 0) {
+      a->bc_nodes.push_back(node);
+      a->bc_vars.push_back(mask);
+      a->bc_vals.insert(a->bc_vals.end(), vals.begin(), vals.end());
+    }
+  }
+  // external nodes, local order [ext < range | owned | ext >= range] (TACSAssembler.cpp:1013-1098)
+  const int lo = a->owner_range[rank], hi = a->owner_range[rank + 1];
+  {
+    std::vector<int> ext;
+    for (int g : a->elem_conn_global)
+      if (g < lo || g >= hi) ext.push_back(g);
+    int n = unique_sort((int)ext.size(), ext.data());
+    ext.resize(n);
+    a->ext_nodes = ext;
+    a->ext_before = (int)(std::lower_bound(ext.begin(), ext.end(), lo) - ext.begin());
+    a->ext_after = n - a->ext_before;
+    a->nlocal = a->nowned + n;
+  }
+  a->elem_conn_local.resize(a->elem_conn_global.size());
+  for (size_t k = 0; k < a->elem_conn_global.size(); k++) a->elem_conn_local[k] = a->localNode(a->elem_conn_global[k]);
+  for (auto e : a->elems) e->incref();
+  // node locations of every local node (the reference fills the ghosts with a halo exchange in
+  // setNodes, TACSAssembler.cpp:920-926; here every rank already holds the global coordinates)
+  std::vector<double> Xl((size_t)3 * a->nlocal, 0.0);
+  if (!Xpts.empty()) {
+    std::vector<int> inv(num_nodes, -1);
+    for (int i = 0; i < num_nodes; i++)
+      if (new_nodes[i] >= 0) inv[new_nodes[i]] = i;
+    for (int l = 0; l < a->nlocal; l++) {
+      int g;
+      if (l < a->ext_before) g = a->ext_nodes[l];
+      else if (l < a->ext_before + a->nowned) g = lo + (l - a->ext_before);
+      else g = a->ext_nodes[l - a->nowned];
+      int old = inv[g];
+      for (int c = 0; c < 3; c++) Xl[3 * (size_t)l + c] = Xpts[3 * (size_t)old + c];
+    }
+  }
+  if (a->finalize()) {
+    delete a;
+    return nullptr;
+  }
+  if (!a->xpts->data.upload(Xl)) {
+    delete a;
+    return nullptr;
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vectors
+// ---------------------------------------------------------------------------------------------
+TACSBVec::TACSBVec(int bs, int no, int eb, int ea) {
+  bsize = bs; nowned = no; ext_before = eb; ext_after = ea;
+  data.alloc((size_t)localSize());
+  zeroEntries();
+}
+
+static double *g_dot_partial = nullptr, *g_dot_out = nullptr, *g_dot_host = nullptr;
+static bool dot_buffers() {
+  if (g_dot_partial) return true;
+  const size_t np = (size_t)dot_num_partials(ctx().num_sms) * 8;
+  return cuda_ok(cudaMalloc(&g_dot_partial, np * sizeof(double)), "cudaMalloc") &&
+         cuda_ok(cudaMalloc(&g_dot_out, 8 * sizeof(double)), "cudaMalloc") &&
+         cuda_ok(cudaMallocHost(&g_dot_host, 8 * sizeof(double)), "cudaMallocHost");
+}
+
+int comm_allreduce_sum(double *dev_buf, int n);  // comm.cpp
+
+void TACSBVec::mdot(TACSBVec **ys, double *out, int n) {
+  dot_buffers();
+  for (int done = 0; done < n; done += 8) {
+    const int nv = std::min(8, n - done);
+    const double *ptrs[8];
+    for (int v = 0; v < nv; v++) ptrs[v] = ys[done + v]->owned();
+    cuda_ok(launch_mdot(ownedSize(), owned(), nv, ptrs, g_dot_partial, g_dot_out, ctx().num_sms, ctx().stream),
+            "mdot");
+    ctx().kernel_launches += 2;
+    if (ctx().size > 1) comm_allreduce_sum(g_dot_out, nv);
+    cuda_ok(cudaMemcpyAsync(g_dot_host, g_dot_out, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream),
+            "mdot D2H");
+    cuda_ok(cudaStreamSynchronize(ctx().stream), "mdot sync");
+    for (int v = 0; v < nv; v++) out[done + v] = g_dot_host[v];
+  }
+}
+double TACSBVec::dot(TACSBVec *y) {
+  double r = 0.0;
+  mdot(&y, &r, 1);
+  return r;
+}
+double TACSBVec::norm() {
+  TACSBVec *self = this;
+  double r = 0.0;
+  mdot(&self, &r, 1);
+  return sqrt(r);
+}
+void TACSBVec::axpy(double alpha, TACSBVec *x) {
+  cuda_ok(launch_axpy(ownedSize(), alpha, x->owned(), owned(), ctx().num_sms, ctx().stream), "axpy");
+  ctx().kernel_launches++;
+}
+void TACSBVec::axpby(double alpha, double beta, TACSBVec *x) {
+  cuda_ok(launch_axpby(ownedSize(), alpha, beta, x->owned(), owned(), ctx().num_sms, ctx().stream), "axpby");
+  ctx().kernel_launches++;
+}
+void TACSBVec::scale(double alpha) {
+  cuda_ok(launch_scale(ownedSize(), alpha, owned(), ctx().num_sms, ctx().stream), "scale");
+  ctx().kernel_launches++;
+}
+void TACSBVec::copyValues(TACSBVec *x) {
+  cuda_ok(cudaMemcpyAsync(owned(), x->owned(), ownedSize() * sizeof(double), cudaMemcpyDeviceToDevice,
+                          ctx().stream), "copyValues");
+}
+void TACSBVec::zeroEntries() {
+  if (data.count) cuda_ok(cudaMemsetAsync(data.ptr, 0, data.count * sizeof(double), ctx().stream), "zeroEntries");
+}
+int TACSBVec::getArray(double *out) {
+  if (ownedSize() == 0) return 0;
+  bool ok = cuda_ok(cudaMemcpyAsync(out, owned(), ownedSize() * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx().stream), "getArray") &&
+            cuda_ok(cudaStreamSynchronize(ctx().stream), "getArray sync");
+  return ok ? 0 : 1;
+}
+int TACSBVec::setArray(const double *in) {
+  if (ownedSize() == 0) return 0;
+  bool ok = cuda_ok(cudaMemcpyAsync(owned(), in, ownedSize() * sizeof(double), cudaMemcpyHostToDevice,
+                                    ctx().stream), "setArray") &&
+            cuda_ok(cudaStreamSynchronize(ctx().stream), "setArray sync");
+  return ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// assembler
+// ---------------------------------------------------------------------------------------------
+TACSAssembler::TACSAssembler() {}
+TACSAssembler::~TACSAssembler() {
+  for (auto e : elems) e->decref();
+  if (xpts) xpts->decref();
+  if (vars) vars->decref();
+  if (dvars) dvars->decref();
+  if (ddvars) ddvars->decref();
+}
+
+// TACSAssembler::getLocalNodeNum (TACSAssembler.cpp:1681-1731)
+int TACSAssembler::localNode(int g) const {
+  const int lo = owner_range[rank], hi = owner_range[rank + 1];
+  if (g >= lo && g < hi) return ext_before + (g - lo);
+  auto it = std::lower_bound(ext_nodes.begin(), ext_nodes.end(), g);
+  if (it == ext_nodes.end() || *it != g) return -1;
+  int k = (int)(it - ext_nodes.begin());
+  return k < ext_before ? k : nowned + k;
+}
+
+int TACSAssembler::finalize() {
+  // state vectors in local order
+  xpts = new TACSBVec(3, nowned, ext_before, ext_after);
+  vars = new TACSBVec(bs, nowned, ext_before, ext_after);
+  dvars = new TACSBVec(bs, nowned, ext_before, ext_after);
+  ddvars = new TACSBVec(bs, nowned, ext_before, ext_after);
+  xpts->incref(); vars->incref(); dvars->incref(); ddvars->incref();
+
+  // distinct descriptors -> device table; groups by kernel family, local order preserved
+  std::map<TACSElement *, int> index;
+  elem_desc.resize(nelems);
+  std::vector<double> table;
+  std::map<int, int> group_of_kind;
+  for (int e = 0; e < nelems; e++) {
+    TACSElement *el = elems[e];
+    if (el->getVarsPerNode() != bs || el->getNumNodes() != elem_ptr[e + 1] - elem_ptr[e]) {
+      fprintf(stderr, "[%d] TACSAssembler: Element %s does not match variables per node / connectivity\n", rank,
+              el->getObjectName());
+      return 1;
+    }
+    TACSElement3D *solid = dynamic_cast<TACSElement3D *>(el);
+    if (solid && !solid->model) {
+      fprintf(stderr, "[%d] tacs_b200: unsupported element model on the device path\n", rank);
+      return 1;
+    }
+    auto it = index.find(el);
+    if (it == index.end()) {
+      int row = (int)distinct.size();
+      index[el] = row;
+      distinct.push_back(el);
+      table.resize((size_t)32 * (row + 1));
+      el->fillDescriptor(&table[(size_t)32 * row]);
+      elem_desc[e] = row;
+    } else {
+      elem_desc[e] = it->second;
+    }
+    int kind = el->kernelKind();
+    if (!group_of_kind.count(kind)) {
+      group_of_kind[kind] = (int)groups.size();
+      groups.emplace_back();
+      groups.back().kind = kind;
+      groups.back().nn = elem_kind_nodes(kind);
+    }
+    groups[group_of_kind[kind]].local_elems.push_back(e);
+  }
+  if (!d_desc_table.upload(table)) return 1;
+  total_blocks = 0;
+  total_node_slots = 0;
+  for (auto &g : groups) {
+    g.nelem = (long)g.local_elems.size();
+    std::vector<int> conn((size_t)g.nelem * g.nn), desc(g.nelem);
+    for (long k = 0; k < g.nelem; k++) {
+      int e = g.local_elems[k];
+      for (int i = 0; i < g.nn; i++) conn[(size_t)k * g.nn + i] = elem_conn_local[elem_ptr[e] + i];
+      desc[k] = elem_desc[e];
+    }
+    std::vector<unsigned char> tab(elem_tables_bytes(g.kind));
+    elem_tables_build(g.kind, tab.data());
+    if (!g.d_conn.upload(conn) || !g.d_desc.upload(desc) || !g.d_tables.upload(tab.data(), tab.size())) return 1;
+    g.block_base = total_blocks;
+    g.node_base = total_node_slots;
+    total_blocks += g.nelem * g.nn * g.nn;
+    total_node_slots += g.nelem * g.nn;
+  }
+  if (total_blocks >= (1L << 31)) {
+    fprintf(stderr, "[%d] tacs_b200: %ld staging blocks exceed the 32-bit gather index\n", rank, total_blocks);
+    return 1;
+  }
+
+  // boundary conditions: merge duplicates in application order (sequential semantics of TACSBcMap)
+  {
+    std::map<int, int> pos;
+    std::vector<int> nodes, masks;
+    std::vector<double> vals;
+    for (size_t k = 0; k < bc_nodes.size(); k++) {
+      int g = bc_nodes[k];
+      auto it = pos.find(g);
+      int p;
+      if (it == pos.end()) {
+        p = (int)nodes.size();
+        pos[g] = p;
+        nodes.push_back(g);
+        masks.push_back(0);
+        vals.resize((size_t)bs * (p + 1), 0.0);
+      } else {
+        p = it->second;
+      }
+      masks[p] |= bc_vars[k];
+      for (int c = 0; c < bs; c++)
+        if (bc_vars[k] & (1 << c)) vals[(size_t)bs * p + c] = bc_vals[(size_t)bs * k + c];
+    }
+    const int lo = owner_range[rank], hi = owner_range[rank + 1];
+    std::vector<int> rows(nodes.size()), local(nodes.size());
+    for (size_t k = 0; k < nodes.size(); k++) {
+      rows[k] = (nodes[k] >= lo && nodes[k] < hi) ? nodes[k] - lo : -1;
+      local[k] = localNode(nodes[k]);
+    }
+    nbc_dev = (int)nodes.size();
+    if (!d_bc_rows.upload(rows) || !d_bc_vars.upload(masks) || !d_bc_vals.upload(vals) || !d_bc_local.upload(local))
+      return 1;
+  }
+
+  // residual gather plan: owned node -> staging slots (element, local node) in ascending element order
+  {
+    std::vector<int> ptr(nowned + 1, 0);
+    std::vector<long> slot_of_elem(nelems);
+    for (auto &g : groups)
+      for (long k = 0; k < g.nelem; k++) slot_of_elem[g.local_elems[k]] = g.node_base + k * g.nn;
+    for (int e = 0; e < nelems; e++)
+      for (int i = elem_ptr[e]; i < elem_ptr[e + 1]; i++) {
+        int l = elem_conn_local[i] - ext_before;
+        if (l >= 0 && l < nowned) ptr[l + 1]++;
+      }
+    for (int i = 0; i < nowned; i++) ptr[i + 1] += ptr[i];
+    std::vector<int> src(ptr[nowned]), cursor(ptr.begin(), ptr.end() - 1);
+    for (int e = 0; e < nelems; e++)
+      for (int i = elem_ptr[e]; i < elem_ptr[e + 1]; i++) {
+        int l = elem_conn_local[i] - ext_before;
+        if (l >= 0 && l < nowned) src[cursor[l]++] = (int)(slot_of_elem[e] + (i - elem_ptr[e]));
+      }
+    if (!r_ptr.upload(ptr) || !r_src.upload(src)) return 1;
+  }
+  if (!Re.alloc((size_t)total_node_slots * bs)) return 1;
+  return 0;
+}
+
+TACSBVec *TACSAssembler::createVec() { return new TACSBVec(bs, nowned, ext_before, ext_after); }
+TACSBVec *TACSAssembler::createNodeVec() { return new TACSBVec(3, nowned, ext_before, ext_after); }
+
+void halo_forward(TACSAssembler *a, TACSBVec *v);  // comm.cpp: fill the external blocks of v
+
+void TACSAssembler::setVariables(TACSBVec *q, TACSBVec *qdot, TACSBVec *qddot) {
+  if (q) {
+    vars->copyValues(q);
+    vars_zero = false;
+    if (size > 1) halo_forward(this, vars);
+  }
+  if (qdot) dvars->copyValues(qdot);
+  if (qddot) {
+    ddvars->copyValues(qddot);
+    ddvars_zero = false;
+    if (size > 1) halo_forward(this, ddvars);
+  }
+}
+void TACSAssembler::zeroVariables() {
+  vars->zeroEntries();
+  dvars->zeroEntries();
+  ddvars->zeroEntries();
+  vars_zero = ddvars_zero = true;
+}
+void TACSAssembler::getNodes(TACSBVec *X) { X->copyValues(xpts); }
+void TACSAssembler::setNodes(TACSBVec *X) {
+  xpts->copyValues(X);
+  if (size > 1) halo_forward(this, xpts);
+}
+
+void TACSAssembler::applyBCs(TACSBVec *v) {
+  cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, nullptr, 1.0, v->owned(),
+                               ctx().stream), "vec applyBCs");
+  ctx().kernel_launches++;
+}
+void TACSAssembler::setBCs(TACSBVec *v) {
+  cuda_ok(launch_vec_set_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, 1.0, v->owned(),
+                             ctx().stream), "vec setBCs");
+  ctx().kernel_launches++;
+}
+void TACSAssembler::applyBCs(TACSParallelMat *m) { m->applyBCs(); }
+
+int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat) {
+  if (want_mat && Ke.count < (size_t)total_blocks * bs * bs) {
+    if (!Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
+  }
+  for (auto &g : groups) {
+    ElemGroupArgs a;
+    a.kind = g.kind;
+    a.nelem = g.nelem;
+    a.conn = g.d_conn.ptr;
+    a.desc_index = g.d_desc.ptr;
+    a.desc_table = d_desc_table.ptr;
+    a.tables = g.d_tables.ptr;
+    a.Xpts = xpts->local();
+    a.vars = vars_zero ? nullptr : vars->local();
+    a.ddvars = ddvars_zero ? nullptr : ddvars->local();
+    a.alpha = alpha;
+    a.gamma = gamma;
+    a.Ke = want_mat ? Ke.ptr + (size_t)g.block_base * bs * bs : nullptr;
+    a.Re = Re.ptr + (size_t)g.node_base * bs;
+    if (!cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel")) return 1;
+    ctx().kernel_launches++;
+  }
+  return 0;
+}
+
+void residual_exchange(TACSAssembler *a, TACSBVec *res);  // comm.cpp (multi-rank reverse halo add)
+
+// TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
+int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
+  if (launchElements(1.0, 0.0, false)) return 1;
+  if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
+                                      ctx().stream), "gather residual")) return 1;
+  ctx().kernel_launches++;
+  if (size > 1) residual_exchange(this, res);
+  if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(), lambda,
+                                    res->owned(), ctx().stream), "residual BCs")) return 1;
+  ctx().kernel_launches++;
+  return 0;
+}
+
+void matrix_exchange(TACSAssembler *a, TACSParallelMat *A);  // comm.cpp (off-rank rows)
+
+// TACSAssembler::assembleJacobian (TACSAssembler.cpp:4291-4406)
+int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
+                                    double lambda) {
+  (void)beta;
+  if (launchElements(alpha, gamma, true)) return 1;
+  if (res) {
+    if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
+                                        ctx().stream), "gather residual")) return 1;
+    ctx().kernel_launches++;
+  }
+  if (size > 1) matrix_exchange(this, A);
+  if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
+                                    ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+  ctx().kernel_launches++;
+  if (A->Bext.nnzb() > 0) {
+    if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
+                                      ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+    ctx().kernel_launches++;
+  }
+  if (res) {
+    if (size > 1) residual_exchange(this, res);
+    if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
+                                      lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
+    ctx().kernel_launches++;
+  }
+  A->applyBCs();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// matrix: sparsity (TACSAssembler::createMat :3384, computeLocalNodeToNodeCSR :1899-2053,
+// TACSMatDistribute::computeLocalCSR :453-692) and the block gather plan
+// ---------------------------------------------------------------------------------------------
+TACSParallelMat *TACSAssembler::createMat() {
+  TACSParallelMat *m = new TACSParallelMat(this);
+  if (m->Aloc.bsize == 0) {
+    delete m;
+    return nullptr;
+  }
+  return m;
+}
+
+TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
+  assembler = a;
+  a->incref();
+  const int bs = a->bs, nowned = a->nowned, lo = a->owner_range[a->rank], hi = a->owner_range[a->rank + 1];
+  if (a->size > 1) {
+    fprintf(stderr, "[%d] tacs_b200: multi-rank matrices are created through the distributed plan\n", a->rank);
+  }
+  // node -> element adjacency over the local elements (owned rows only)
+  std::vector<int> ne_ptr(nowned + 1, 0);
+  for (int e = 0; e < a->nelems; e++)
+    for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) {
+      int g = a->elem_conn_global[i];
+      if (g >= lo && g < hi) ne_ptr[g - lo + 1]++;
+    }
+  for (int i = 0; i < nowned; i++) ne_ptr[i + 1] += ne_ptr[i];
+  std::vector<int> ne_elem(ne_ptr[nowned]), ne_slot(ne_ptr[nowned]);
+  {
+    std::vector<int> cursor(ne_ptr.begin(), ne_ptr.end() - 1);
+    for (int e = 0; e < a->nelems; e++)
+      for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) {
+        int g = a->elem_conn_global[i];
+        if (g >= lo && g < hi) {
+          int p = cursor[g - lo]++;
+          ne_elem[p] = e;
+          ne_slot[p] = i - a->elem_ptr[e];
+        }
+      }
+  }
+  // pass 1: row lengths; pass 2: sorted unique columns (global ids) per owned row
+  std::vector<int> rowlen(nowned, 0);
+  parallel_for(nowned, [&](long r0, long r1) {
+    std::vector<int> buf;
+    for (long r = r0; r < r1; r++) {
+      buf.clear();
+      for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
+        int e = ne_elem[p];
+        for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) buf.push_back(a->elem_conn_global[i]);
+      }
+      rowlen[r] = unique_sort((int)buf.size(), buf.data());
+    }
+  });
+  std::vector<long> gptr(nowned + 1, 0);
+  for (int r = 0; r < nowned; r++) gptr[r + 1] = gptr[r] + rowlen[r];
+  std::vector<int> gcols(gptr[nowned]);
+  parallel_for(nowned, [&](long r0, long r1) {
+    std::vector<int> buf;
+    for (long r = r0; r < r1; r++) {
+      buf.clear();
+      for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
+        int e = ne_elem[p];
+        for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) buf.push_back(a->elem_conn_global[i]);
+      }
+      int n = unique_sort((int)buf.size(), buf.data());
+      memcpy(&gcols[gptr[r]], buf.data(), n * sizeof(int));
+    }
+  });
+  if (gptr[nowned] >= (1L << 31)) {
+    fprintf(stderr, "[%d] tacs_b200: %ld blocks exceed the reference's 32-bit rowp (BCSRMat.cpp:234)\n", a->rank,
+            gptr[nowned]);
+    return;
+  }
+  // split into Aloc (owned columns, local index) and Bext (external columns -> index in the sorted
+  // unique list); np = first owned row with an external column
+  np = nowned;
+  for (int r = 0; r < nowned && np == nowned; r++)
+    for (long k = gptr[r]; k < gptr[r + 1]; k++)
+      if (gcols[k] < lo || gcols[k] >= hi) { np = r; break; }
+  {
+    std::vector<int> ext;
+    for (long k = 0; k < gptr[nowned]; k++)
+      if (gcols[k] < lo || gcols[k] >= hi) ext.push_back(gcols[k]);
+    int n = unique_sort((int)ext.size(), ext.data());
+    ext.resize(n);
+    ext_col_nodes = ext;
+  }
+  Aloc.bsize = bs; Aloc.nrows = nowned; Aloc.ncols = nowned;
+  Aloc.rowp.assign(nowned + 1, 0);
+  Bext.bsize = bs; Bext.nrows = nowned - np; Bext.ncols = (int)ext_col_nodes.size();
+  Bext.rowp.assign(Bext.nrows + 1, 0);
+  for (int r = 0; r < nowned; r++) {
+    for (long k = gptr[r]; k < gptr[r + 1]; k++) {
+      int g = gcols[k];
+      if (g >= lo && g < hi) Aloc.cols.push_back(g - lo);
+      else Bext.cols.push_back((int)(std::lower_bound(ext_col_nodes.begin(), ext_col_nodes.end(), g) -
+                                     ext_col_nodes.begin()));
+    }
+    Aloc.rowp[r + 1] = (int)Aloc.cols.size();
+    if (r >= np) Bext.rowp[r - np + 1] = (int)Bext.cols.size();
+  }
+  // gather plan: for every block of an owned row, the staging slots (element, i, j), ascending element
+  std::vector<long> blk_of_elem(a->nelems);
+  std::vector<int> nn_of_elem(a->nelems);
+  for (auto &g : a->groups)
+    for (long k = 0; k < g.nelem; k++) {
+      blk_of_elem[g.local_elems[k]] = g.block_base + k * g.nn * g.nn;
+      nn_of_elem[g.local_elems[k]] = g.nn;
+    }
+  const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
+  std::vector<int> acnt(nnzA + 1, 0), bcnt(nnzB + 1, 0);
+  auto locate = [&](int r, int gcol, bool &is_ext) -> long {
+    if (gcol >= lo && gcol < hi) {
+      is_ext = false;
+      const int *b = &Aloc.cols[Aloc.rowp[r]], *e = &Aloc.cols[0] + Aloc.rowp[r + 1];
+      return std::lower_bound(b, e, gcol - lo) - &Aloc.cols[0];
+    }
+    is_ext = true;
+    int c = (int)(std::lower_bound(ext_col_nodes.begin(), ext_col_nodes.end(), gcol) - ext_col_nodes.begin());
+    const int *b = &Bext.cols[Bext.rowp[r - np]], *e = &Bext.cols[0] + Bext.rowp[r - np + 1];
+    return std::lower_bound(b, e, c) - &Bext.cols[0];
+  };
+  parallel_for(nowned, [&](long r0, long r1) {
+    for (long r = r0; r < r1; r++)
+      for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
+        int e = ne_elem[p];
+        for (int j = a->elem_ptr[e]; j < a->elem_ptr[e + 1]; j++) {
+          bool is_ext;
+          long pos = locate((int)r, a->elem_conn_global[j], is_ext);
+          (is_ext ? bcnt : acnt)[pos + 1]++;
+        }
+      }
+  });
+  for (long k = 0; k < nnzA; k++) acnt[k + 1] += acnt[k];
+  for (long k = 0; k < nnzB; k++) bcnt[k + 1] += bcnt[k];
+  std::vector<int> asrc(acnt[nnzA]), bsrc(bcnt[nnzB]);
+  {
+    std::vector<int> acur(acnt.begin(), acnt.end() - 1), bcur(bcnt.begin(), bcnt.end() - 1);
+    parallel_for(nowned, [&](long r0, long r1) {
+      for (long r = r0; r < r1; r++)
+        for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
+          int e = ne_elem[p], i = ne_slot[p], nn = nn_of_elem[e];
+          for (int j = a->elem_ptr[e]; j < a->elem_ptr[e + 1]; j++) {
+            bool is_ext;
+            long pos = locate((int)r, a->elem_conn_global[j], is_ext);
+            int slot = (int)(blk_of_elem[e] + (long)i * nn + (j - a->elem_ptr[e]));
+            if (is_ext) bsrc[bcur[pos]++] = slot;
+            else asrc[acur[pos]++] = slot;
+          }
+        }
+    });
+  }
+  const size_t b2 = (size_t)bs * bs;
+  bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA) &&
+            a_ptr.upload(acnt) && a_src.upload(asrc);
+  if (ok && nnzB > 0)
+    ok = Bext.d_rowp.upload(Bext.rowp) && Bext.d_cols.upload(Bext.cols) && Bext.d_vals.alloc(b2 * nnzB) &&
+         b_ptr.upload(bcnt) && b_src.upload(bsrc) && x_ext.alloc((size_t)bs * Bext.ncols);
+  if (!ok) {
+    Aloc.bsize = 0;
+    return;
+  }
+  zeroEntries();
+}
+
+TACSParallelMat::~TACSParallelMat() { assembler->decref(); }
+
+void TACSParallelMat::zeroEntries() {
+  if (Aloc.d_vals.count)
+    cuda_ok(cudaMemsetAsync(Aloc.d_vals.ptr, 0, Aloc.d_vals.count * sizeof(double), ctx().stream), "zeroEntries");
+  if (Bext.d_vals.count)
+    cuda_ok(cudaMemsetAsync(Bext.d_vals.ptr, 0, Bext.d_vals.count * sizeof(double), ctx().stream), "zeroEntries");
+}
+
+TACSBVec *TACSParallelMat::createVec() { return new TACSBVec(Aloc.bsize, Aloc.nrows, 0, 0); }
+
+// TACSParallelMat::applyBCs (TACSParallelMat.cpp:343-374)
+void TACSParallelMat::applyBCs() {
+  TACSAssembler *a = assembler;
+  cuda_ok(launch_mat_apply_bcs(Aloc.bsize, a->nbc_dev, a->d_bc_rows.ptr, a->d_bc_vars.ptr, Aloc.d_rowp.ptr,
+                               Aloc.d_cols.ptr, Aloc.d_vals.ptr, 0, ctx().stream), "mat applyBCs");
+  ctx().kernel_launches++;
+  // Bext rows (row - np) are zeroed as well; handled by the distributed plan when Bext is not empty
+}
+
+void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x);  // comm.cpp
+void spmv_halo_end(TACSParallelMat *A);
+
+// TACSParallelMat::mult (TACSParallelMat.cpp:248-265): y = Aloc x + Bext x_ext, halo overlapped
+void TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
+  const bool dist = assembler->size > 1 && Bext.nnzb() > 0;
+  if (dist) spmv_halo_begin(this, x);
+  cuda_ok(launch_spmv(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr, x->owned(),
+                      y->owned(), 0, ctx().num_sms, ctx().stream), "spmv");
+  ctx().kernel_launches++;
+  if (dist) {
+    spmv_halo_end(this);
+    cuda_ok(launch_spmv(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr, x_ext.ptr,
+                        y->owned() + (size_t)Bext.bsize * np, 1, ctx().num_sms, ctx().stream), "spmv ext");
+    ctx().kernel_launches++;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GMRES (KSM.cpp:547-956), modified Gram-Schmidt (:526-532)
+// ---------------------------------------------------------------------------------------------
+GMRES::GMRES(TACSParallelMat *_mat, int _m, int _nrestart) {
+  mat = _mat;
+  mat->incref();
+  m = _m;
+  nrestart = _nrestart >= 0 ? _nrestart : 0;
+  for (int i = 0; i < m + 1; i++) {
+    W.push_back(mat->createVec());
+    W.back()->incref();
+  }
+  Hptr.assign(m + 1, 0);
+  for (int i = 0; i < m; i++) Hptr[i + 1] = Hptr[i] + i + 2;
+  H.assign(Hptr[m], 0.0);
+  res.assign(m + 1, 0.0);
+  Qsin.assign(m, 0.0);
+  Qcos.assign(m, 0.0);
+}
+GMRES::~GMRES() {
+  for (auto w : W) w->decref();
+  mat->decref();
+}
+
+int GMRES::solve(TACSBVec *b, TACSBVec *x, int zero_guess) {
+  double rhs_norm = 0.0;
+  int solve_flag = 0;
+  iters = 0;
+  for (int count = 0; count < nrestart + 1; count++) {
+    if (zero_guess && count == 0) {
+      x->zeroEntries();
+      W[0]->copyValues(b);
+      res[0] = W[0]->norm();
+      W[0]->scale(1.0 / res[0]);
+    } else {
+      mat->mult(x, W[0]);
+      W[0]->axpy(-1.0, b);
+      res[0] = W[0]->norm();
+      W[0]->scale(-1.0 / res[0]);
+    }
+    if (count == 0) {
+      rhs_norm = res[0];
+      resnorm = rhs_norm;
+    }
+    int niters = 0;
+    if (res[0] < atol) {
+      solve_flag = 1;
+      break;
+    }
+    for (int i = 0; i < m; i++) {
+      mat->mult(W[i], W[i + 1]);
+      double *h = &H[Hptr[i]];
+      for (int j = 0; j < i + 1; j++) {
+        h[j] = W[i + 1]->dot(W[j]);
+        W[i + 1]->axpy(-h[j], W[j]);
+      }
+      h[i + 1] = W[i + 1]->norm();
+      W[i + 1]->scale(1.0 / h[i + 1]);
+      double h1, h2;
+      for (int k = 0; k < i; k++) {
+        h1 = h[k];
+        h2 = h[k + 1];
+        h[k] = h1 * Qcos[k] + h2 * Qsin[k];
+        h[k + 1] = -h1 * Qsin[k] + h2 * Qcos[k];
+      }
+      h1 = h[i];
+      h2 = h[i + 1];
+      double sq = sqrt(h1 * h1 + h2 * h2);
+      Qcos[i] = h1 / sq;
+      Qsin[i] = h2 / sq;
+      h[i] = h1 * Qcos[i] + h2 * Qsin[i];
+      h[i + 1] = -h1 * Qsin[i] + h2 * Qcos[i];
+      h1 = res[i];
+      res[i] = h1 * Qcos[i];
+      res[i + 1] = -h1 * Qsin[i];
+      niters++;
+      resnorm = fabs(res[i + 1]);
+      if (resnorm < atol || resnorm < rtol * rhs_norm) {
+        solve_flag = 1;
+        break;
+      }
+    }
+    iters += niters;
+    for (int i = niters - 1; i >= 0; i--) {
+      for (int j = i + 1; j < niters; j++) res[i] = res[i] - H[i + Hptr[j]] * res[j];
+      res[i] = res[i] / H[i + Hptr[i]];
+    }
+    for (int i = 0; i < niters; i++) x->axpy(res[i], W[i]);
+    if (solve_flag) break;
+  }
+  cudaStreamSynchronize(ctx().stream);
+  return solve_flag;
+}
+
+}  // namespace tb2

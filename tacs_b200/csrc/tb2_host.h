@@ -1,0 +1,427 @@
+// Host-side object model of tacs_b200: a C++ mirror of the reference's plug-in interface for the
+// assembly + Krylov-operator path (same class names, argument meaning and error behaviour), with the
+// data living in B200 HBM and the work done by the kernels in kernels.cu.
+//
+//   TACSMaterialProperties / TACSOrthotropicPly      src/constitutive/TACSMaterialProperties.h:42-200
+//   TACSIsoShellConstitutive                         src/constitutive/TACSIsoShellConstitutive.h:31-36
+//   TACSCompositeShellConstitutive                   src/constitutive/TACSCompositeShellConstitutive.h:27-32
+//   TACSSolidConstitutive                            src/constitutive/TACSSolidConstitutive.h:34-36
+//   TACSShellNaturalTransform / RefAxisTransform     src/elements/shell/TACSShellElementTransform.h:21-215
+//   TACSQuad4Shell / TACSQuad9Shell                  src/elements/shell/TACSShellElementDefs.h:19-25
+//   TACSElement3D + TACSLinearElasticity3D + HexaBasis  src/elements/TACSElement3D.h:26
+//   TACSCreator                                      src/TACSCreator.h:46-120
+//   TACSAssembler                                    src/TACSAssembler.h:61-523
+//   TACSBVec / TACSParallelMat / BCSRMat / GMRES     src/bpmat/TACSBVec.h:67, TACSParallelMat.h:52, BCSRMat.h:34, KSM.h:392
+//
+// Elements are descriptors, not virtual device code: each recognised family has a hand-written
+// kernel, and per-object constants (tangent stiffness, mass moments, transform) are evaluated once
+// on the host and stored in a device table row. Unsupported combinations are rejected when the
+// assembler is created (non-zero return / stderr message, like TACSAssembler.cpp:513-581).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace tb2 {
+
+// ---------------------------------------------------------------------------------------------
+// runtime context: one process drives one GPU
+// ---------------------------------------------------------------------------------------------
+struct Context {
+  int device = -1;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t comm_stream = nullptr;  // halo / collective stream
+  int rank = 0, size = 1;
+  void *nccl_comm = nullptr;  // ncclComm_t when size > 1
+  long kernel_launches = 0;   // launches of tacs_b200 kernels since the last reset
+};
+Context &ctx();
+int ctx_init(int device);  // 0 ok; prints to stderr and returns non-zero when no usable GPU is present
+bool cuda_ok(cudaError_t err, const char *what);
+
+template <class T>
+struct DeviceArray {
+  T *ptr = nullptr;
+  size_t count = 0;
+  DeviceArray() {}
+  DeviceArray(const DeviceArray &) = delete;
+  DeviceArray &operator=(const DeviceArray &) = delete;
+  DeviceArray(DeviceArray &&o) noexcept : ptr(o.ptr), count(o.count) {
+    o.ptr = nullptr;
+    o.count = 0;
+  }
+  ~DeviceArray() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  bool alloc(size_t n) {
+    release();
+    count = n;
+    if (n == 0) return true;
+    return cuda_ok(cudaMalloc(&ptr, n * sizeof(T)), "cudaMalloc");
+  }
+  bool upload(const T *host, size_t n) {
+    if (n != count && !alloc(n)) return false;
+    if (n == 0) return true;
+    return cuda_ok(cudaMemcpyAsync(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream), "H2D") &&
+           cuda_ok(cudaStreamSynchronize(ctx().stream), "H2D sync");
+  }
+  bool upload(const std::vector<T> &v) { return upload(v.data(), v.size()); }
+  bool download(T *host, size_t n) const {
+    if (n == 0) return true;
+    return cuda_ok(cudaMemcpyAsync(host, ptr, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream), "D2H") &&
+           cuda_ok(cudaStreamSynchronize(ctx().stream), "D2H sync");
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// reference-counted base (TACSObject, src/TACSObject.h:106-135)
+// ---------------------------------------------------------------------------------------------
+class Object {
+ public:
+  Object() : refs(0) {}
+  virtual ~Object() {}
+  void incref() { refs++; }
+  void decref() {
+    if (--refs <= 0) delete this;
+  }
+  virtual const char *getObjectName() { return "TACSObject"; }
+
+ private:
+  std::atomic<int> refs;
+};
+
+// ---------------------------------------------------------------------------------------------
+// constitutive
+// ---------------------------------------------------------------------------------------------
+class TACSMaterialProperties : public Object {
+ public:
+  TACSMaterialProperties(double rho, double specific_heat, double E, double nu, double ys, double alpha,
+                         double kappa);
+  TACSMaterialProperties(double rho, double specific_heat, double E1, double E2, double E3, double nu12,
+                         double nu13, double nu23, double G12, double G13, double G23);
+  double getDensity() const { return rho; }
+  void evalTangentStiffness2D(double C[6]) const;
+  void evalTangentStiffness3D(double C[21]) const;
+  bool isotropic;
+  double rho, specific_heat, E, nu, G, ys, alpha, kappa;
+  double E1, E2, E3, nu12, nu13, nu23, G12, G13, G23;
+};
+
+class TACSOrthotropicPly : public Object {
+ public:
+  TACSOrthotropicPly(double ply_thickness, TACSMaterialProperties *props);
+  ~TACSOrthotropicPly();
+  void calculateQbar(double angle, double Qbar[6]) const;
+  void calculateAbar(double angle, double Abar[3]) const;
+  double getDensity() const { return rho; }
+  double plyThickness, rho;
+  double Q11, Q12, Q22, Q44, Q55, Q66, C12, C16, C26, C66;
+  TACSMaterialProperties *properties;
+};
+
+class TACSConstitutive : public Object {
+ public:
+  virtual int getNumStresses() = 0;
+  // 22 entries for shells (A,B,D,As,drill), 21 for solids; constant per object on this path
+  virtual void evalTangentStiffness(double C[]) = 0;
+  // fill one 32-double device descriptor row (layout in elem_phases.cuh)
+  virtual void fillDescriptor(double d[]) = 0;
+};
+
+class TACSShellConstitutive : public TACSConstitutive {
+ public:
+  int getNumStresses() { return 9; }
+  virtual void evalMassMoments(double moments[3]) = 0;
+  void fillDescriptor(double d[]);
+  static void setDrillingRegularization(double k) { DRILLING_REGULARIZATION = k; }
+  static double getDrillingRegularization() { return DRILLING_REGULARIZATION; }
+  static double DRILLING_REGULARIZATION;
+};
+
+class TACSIsoShellConstitutive : public TACSShellConstitutive {
+ public:
+  TACSIsoShellConstitutive(TACSMaterialProperties *props, double t, double tOffset, double kcorr);
+  ~TACSIsoShellConstitutive();
+  void evalTangentStiffness(double C[]);
+  void evalMassMoments(double moments[3]);
+  TACSMaterialProperties *properties;
+  double t, tOffset, kcorr;
+};
+
+class TACSCompositeShellConstitutive : public TACSShellConstitutive {
+ public:
+  TACSCompositeShellConstitutive(int num_plies, TACSOrthotropicPly **plies, const double *thickness,
+                                 const double *angles, double kcorr, double tOffset);
+  ~TACSCompositeShellConstitutive();
+  void evalTangentStiffness(double C[]);
+  void evalMassMoments(double moments[3]);
+  std::vector<TACSOrthotropicPly *> ply_props;
+  std::vector<double> ply_thickness, ply_angles;
+  double kcorr, tOffset;
+};
+
+class TACSSolidConstitutive : public TACSConstitutive {
+ public:
+  TACSSolidConstitutive(TACSMaterialProperties *props, double t);
+  ~TACSSolidConstitutive();
+  int getNumStresses() { return 6; }
+  void evalTangentStiffness(double C[]);
+  double evalDensity() { return t * properties->getDensity(); }
+  void fillDescriptor(double d[]);
+  TACSMaterialProperties *properties;
+  double t;
+};
+
+// ---------------------------------------------------------------------------------------------
+// transforms, models, bases, elements
+// ---------------------------------------------------------------------------------------------
+class TACSShellTransform : public Object {
+ public:
+  int kind;  // 0 natural, 1 reference axis
+  double axis[3];
+};
+class TACSShellNaturalTransform : public TACSShellTransform {
+ public:
+  TACSShellNaturalTransform();
+};
+class TACSShellRefAxisTransform : public TACSShellTransform {
+ public:
+  explicit TACSShellRefAxisTransform(const double axis[3]);
+  void getRefAxis(double a[3]) { a[0] = axis[0]; a[1] = axis[1]; a[2] = axis[2]; }
+};
+
+class TACSElementBasis : public Object {
+ public:
+  int order;  // 2: TACSLinearHexaBasis, 3: TACSQuadraticHexaBasis
+};
+class TACSLinearHexaBasis : public TACSElementBasis {
+ public:
+  TACSLinearHexaBasis() { order = 2; }
+};
+class TACSQuadraticHexaBasis : public TACSElementBasis {
+ public:
+  TACSQuadraticHexaBasis() { order = 3; }
+};
+
+class TACSElementModel : public Object {};
+class TACSLinearElasticity3D : public TACSElementModel {
+ public:
+  explicit TACSLinearElasticity3D(TACSSolidConstitutive *con);
+  ~TACSLinearElasticity3D();
+  TACSSolidConstitutive *stiff;
+};
+
+class TACSElement : public Object {
+ public:
+  virtual int getVarsPerNode() = 0;
+  virtual int getNumNodes() = 0;
+  int getNumVariables() { return getVarsPerNode() * getNumNodes(); }
+  virtual int kernelKind() = 0;  // ElemKind
+  virtual void fillDescriptor(double d[]) = 0;
+  // Evaluate `count` elements with this descriptor on the device (host arrays in/out), element-major:
+  // Xpts[count][3nn], vars/ddvars[count][nv] (ddvars may be null), res[count][nv], mat[count][nv*nv]
+  // (res or mat may be null). Mirrors TACSElement::addJacobian (TACSElement.h:450) for a batch.
+  int addJacobianBatch(int count, double alpha, double beta, double gamma, const double *Xpts,
+                       const double *vars, const double *dvars, const double *ddvars, double *res, double *mat);
+};
+
+class TACSShellElement : public TACSElement {
+ public:
+  TACSShellElement(int order, TACSShellTransform *t, TACSShellConstitutive *c);
+  ~TACSShellElement();
+  int getVarsPerNode() { return 6; }
+  int getNumNodes() { return order * order; }
+  int kernelKind() { return order == 2 ? ELEM_QUAD4_SHELL : ELEM_QUAD9_SHELL; }
+  void fillDescriptor(double d[]);
+  int order;
+  TACSShellTransform *transform;
+  TACSShellConstitutive *con;
+};
+
+class TACSElement3D : public TACSElement {
+ public:
+  TACSElement3D(TACSElementModel *model, TACSElementBasis *basis);
+  ~TACSElement3D();
+  int getVarsPerNode() { return 3; }
+  int getNumNodes() { return basis->order * basis->order * basis->order; }
+  int kernelKind() { return basis->order == 2 ? ELEM_HEX8 : ELEM_HEX27; }
+  void fillDescriptor(double d[]);
+  TACSLinearElasticity3D *model;
+  TACSElementBasis *basis;
+};
+
+// ---------------------------------------------------------------------------------------------
+// block-CSR storage (BCSRMatData, src/bpmat/BCSRMatImpl.h:27-46)
+// ---------------------------------------------------------------------------------------------
+struct BCSRPattern {
+  int bsize = 0, nrows = 0, ncols = 0;
+  std::vector<int> rowp, cols;  // host copies (bit-exact parity target)
+  DeviceArray<int> d_rowp, d_cols;
+  DeviceArray<double> d_vals;  // bsize^2 * nnzb, 64-bit offsets
+  long nnzb() const { return rowp.empty() ? 0 : rowp[nrows]; }
+};
+
+class TACSAssembler;
+
+// TACSBVec: owned block vector with room for the external (ghost) blocks in local order
+// [ext < range | owned | ext >= range] so that element kernels index it directly.
+class TACSBVec : public Object {
+ public:
+  TACSBVec(int bs, int nowned, int next_before, int next_after);
+  int bsize, nowned, ext_before, ext_after;
+  DeviceArray<double> data;  // (ext_before + nowned + ext_after) * bsize
+  double *owned() { return data.ptr + (size_t)ext_before * bsize; }
+  double *local() { return data.ptr; }
+  long ownedSize() const { return (long)nowned * bsize; }
+  long localSize() const { return (long)(ext_before + nowned + ext_after) * bsize; }
+  // TACSVec interface (KSM.h:91-115); reductions are over owned entries and all ranks
+  double norm();
+  double dot(TACSBVec *y);
+  void mdot(TACSBVec **ys, double *out, int n);
+  void axpy(double alpha, TACSBVec *x);
+  void axpby(double alpha, double beta, TACSBVec *x);
+  void scale(double alpha);
+  void copyValues(TACSBVec *x);
+  void zeroEntries();
+  int getArray(double *host_out);        // device -> host copy of the owned entries
+  int setArray(const double *host_in);   // host -> device
+};
+
+class TACSParallelMat : public Object {
+ public:
+  explicit TACSParallelMat(TACSAssembler *a);
+  ~TACSParallelMat();
+  TACSAssembler *assembler;
+  BCSRPattern Aloc, Bext;
+  int np = 0;                      // first owned row with an off-rank column (rows of Bext start here)
+  std::vector<int> ext_col_nodes;  // ascending global node ids of the external columns
+  // gather plan: staging slots of every block, ascending element order
+  DeviceArray<int> a_ptr, a_src, b_ptr, b_src;
+  DeviceArray<double> x_ext;  // external column values for the SpMV halo
+  void zeroEntries();
+  void mult(TACSBVec *x, TACSBVec *y);
+  void applyBCs();
+  TACSBVec *createVec();
+};
+
+// ---------------------------------------------------------------------------------------------
+// creator and assembler
+// ---------------------------------------------------------------------------------------------
+class TACSCreator : public Object {
+ public:
+  explicit TACSCreator(int vars_per_node);
+  ~TACSCreator();
+  void setGlobalConnectivity(int num_nodes, int num_elements, const int *ptr, const int *conn,
+                             const int *elem_id_nums);
+  void setBoundaryConditions(int num_bcs, const int *bc_nodes, const int *bc_ptr, const int *bc_vars,
+                             const double *bc_vals);
+  void setNodes(const double *Xpts);
+  void setElements(int num_elems, TACSElement **elems);
+  int partitionMesh(int split_size, const int *part);
+  int getNodeNums(const int **new_nodes);
+  int getElementPartition(const int **part);
+  TACSAssembler *createTACS();
+
+  int vars_per_node;
+  int num_nodes = 0, num_elements = 0;
+  std::vector<int> elem_node_ptr, elem_node_conn, elem_id_nums;
+  std::vector<int> bc_nodes, bc_ptr, bc_vars;
+  std::vector<double> bc_vals;
+  std::vector<double> Xpts;
+  std::vector<TACSElement *> elements;
+  std::vector<int> partition, new_nodes, owned_nodes, owned_elements;
+};
+
+struct ElemGroup {
+  int kind = 0, nn = 0;
+  long nelem = 0;
+  std::vector<int> local_elems;  // local element indices in this group (ascending)
+  DeviceArray<int> d_conn, d_desc;
+  DeviceArray<unsigned char> d_tables;
+  long block_base = 0;  // first staging slot (units of one bs x bs block) of this group
+  long node_base = 0;   // first residual staging slot (units of one node block)
+};
+
+class TACSAssembler : public Object {
+ public:
+  TACSAssembler();
+  ~TACSAssembler();
+  int getVarsPerNode() { return bs; }
+  int getNumNodes() { return nlocal; }
+  int getNumOwnedNodes() { return nowned; }
+  int getNumElements() { return nelems; }
+  TACSBVec *createVec();
+  TACSBVec *createNodeVec();
+  TACSParallelMat *createMat();
+  void setVariables(TACSBVec *q, TACSBVec *qdot, TACSBVec *qddot);
+  void zeroVariables();
+  void getNodes(TACSBVec *X);
+  void setNodes(TACSBVec *X);
+  void applyBCs(TACSBVec *v);
+  void applyBCs(TACSParallelMat *m);
+  void setBCs(TACSBVec *v);
+  int assembleRes(TACSBVec *res, double lambda);
+  int assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
+                       double lambda);
+
+  // --- data -------------------------------------------------------------------------------
+  int bs = 0, rank = 0, size = 1;
+  int nowned = 0, nlocal = 0, nelems = 0;
+  int ext_before = 0, ext_after = 0;
+  std::vector<int> owner_range;  // size+1
+  std::vector<int> ext_nodes;    // ascending global ids of external nodes
+  std::vector<int> elem_ptr, elem_conn_global, elem_conn_local;
+  std::vector<TACSElement *> elems;          // per local element
+  std::vector<TACSElement *> distinct;       // distinct descriptors (table rows)
+  std::vector<int> elem_desc;                // per local element: row of the descriptor table
+  // boundary conditions in the creator's order (global node, bit mask, values[bs]) + merged device form
+  std::vector<int> bc_nodes, bc_vars;
+  std::vector<double> bc_vals;
+  int nbc_dev = 0;
+  DeviceArray<int> d_bc_rows, d_bc_vars;  // owned-row index of each merged BC (or -1), mask
+  DeviceArray<double> d_bc_vals;
+  DeviceArray<int> d_bc_local;            // local node index (for state vectors in local order)
+  // state
+  TACSBVec *xpts = nullptr, *vars = nullptr, *dvars = nullptr, *ddvars = nullptr;
+  bool vars_zero = true, ddvars_zero = true;
+  // element groups, descriptor table, staging and residual gather plan
+  std::vector<ElemGroup> groups;
+  DeviceArray<double> d_desc_table;
+  DeviceArray<double> Ke, Re;
+  long total_blocks = 0, total_node_slots = 0;
+  DeviceArray<int> r_ptr, r_src;
+  int localNode(int global) const;
+  int finalize();  // build device data after the creator filled the host arrays
+  int launchElements(double alpha, double gamma, bool want_mat);
+};
+
+// GMRES (src/bpmat/KSM.cpp:547-956): right-preconditioned restarted GMRES with modified
+// Gram-Schmidt; host control flow, device vectors; optional block-Jacobi-free identity PC.
+class GMRES : public Object {
+ public:
+  GMRES(TACSParallelMat *mat, int m, int nrestart);
+  ~GMRES();
+  void setTolerances(double rtol, double atol) { this->rtol = rtol; this->atol = atol; }
+  int solve(TACSBVec *b, TACSBVec *x, int zero_guess);
+  int getIterCount() { return iters; }
+  double getResidualNorm() { return resnorm; }
+  TACSParallelMat *mat;
+  int m, nrestart, iters = 0;
+  double rtol = 1e-8, atol = 1e-30, resnorm = 0.0;
+  std::vector<TACSBVec *> W;
+  TACSBVec *work = nullptr;
+  std::vector<double> H, res, Qsin, Qcos;
+  std::vector<int> Hptr;
+};
+
+}  // namespace tb2

@@ -1,0 +1,97 @@
+// CPU replay of the device element phases (tacs_b200/csrc/elem_phases.cuh) for tests.
+//
+// The element mathematics of the CUDA kernels is written as host/device task functions; this
+// harness executes the same phases in the same order, one task after another, so the math and
+// the indexing of the kernels can be checked against the oracle on a machine without a GPU.
+// It is test scaffolding: it is compiled only by tests/ and is not part of the product library.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../tacs_b200/csrc/elem_phases.cuh"
+
+using namespace tb2;
+
+template <int O, int QC>
+static void run_shell(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                      double alpha, double gamma, double *res, double *mat) {
+  using WK = ShellWork<O, QC>;
+  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
+  static ShellTables<O> tab;
+  build_shell_tables<O>(tab);
+  WK *w = new WK;
+  for (int k = 0; k < 3 * n; k++) w->X[k] = Xpts[k];
+  for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
+  for (int k = 0; k < kDescStride; k++) w->desc[k] = desc[k];
+  for (int i = 0; i < n; i++) shell_p1_node<O, QC>(i, *w, tab);
+  for (int t = 0; t < nty; t++) shell_p2_tying<O, QC>(t, *w, tab);
+  for (int q = 0; q < nq; q++) shell_p2_qgeom<O, QC>(q, *w, tab);
+  std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
+  for (int q0 = 0; q0 < nq; q0 += QC) {
+    for (int t = 0; t < QC * n * 9; t++) shell_p3_brow<O, QC>(t, q0, *w, tab);
+    for (int t = 0; t < QC * n * 9; t++) shell_p4_cbrow<O, QC>(t, q0, *w);
+    for (int t = 0; t < WK::ntiles; t++)
+      tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+  }
+  for (int t = 0; t < WK::ntiles; t++) shell_p6_finish<O, QC>(t, *w, tab, alpha, gamma, &acc[36 * t]);
+  for (int t = 0; t < WK::ntiles; t++) {
+    int i = t / n, j = t % n;
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) mat[nd * (6 * i + a) + 6 * j + b] = acc[36 * t + 6 * a + b];
+  }
+  for (int k = 0; k < nd; k++) {
+    int i = k / 6, a = k % 6;
+    double s = 0.0;
+    for (int j = 0; j < n; j++) s += w->rpart[i * n + j][a];
+    res[k] = s;
+  }
+  delete w;
+}
+
+template <int O, int QC>
+static void run_solid(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                      double alpha, double gamma, double *res, double *mat) {
+  using WK = SolidWork<O, QC>;
+  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, TR = WK::TR, TC = WK::TC, ntc = nd / TC;
+  static SolidTables<O> tab;
+  build_solid_tables<O>(tab);
+  WK *w = new WK;
+  for (int k = 0; k < 3 * n; k++) w->X[k] = Xpts[k];
+  for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
+  for (int k = 0; k < kDescStride; k++) w->desc[k] = desc[k];
+  for (int q = 0; q < nq; q++) solid_p1_qgeom<O, QC>(q, *w, tab);
+  std::vector<double> acc((size_t)WK::ntiles * TR * TC, 0.0);
+  for (int q0 = 0; q0 < nq; q0 += QC) {
+    for (int t = 0; t < QC * n; t++) solid_p3_bcols<O, QC>(t, q0, *w, tab);
+    for (int t = 0; t < WK::ntiles; t++)
+      tile_accumulate<QC * 6, nd, TR, TC>(&w->B[0][0][0], &w->CB[0][0][0], TR * (t / ntc), TC * (t % ntc),
+                                          &acc[(size_t)TR * TC * t]);
+  }
+  for (int t = 0; t < WK::ntiles; t++) solid_p6_finish<O, QC>(t, *w, tab, alpha, gamma, &acc[(size_t)TR * TC * t]);
+  for (int t = 0; t < WK::ntiles; t++) {
+    int r0 = TR * (t / ntc), c0 = TC * (t % ntc);
+    for (int a = 0; a < TR; a++)
+      for (int b = 0; b < TC; b++) mat[nd * (r0 + a) + c0 + b] = acc[(size_t)TR * TC * t + a * TC + b];
+  }
+  for (int k = 0; k < nd; k++) {
+    int ti = k / TR, a = k % TR;
+    double s = 0.0;
+    for (int tj = 0; tj < ntc; tj++) s += w->rpart[ti * ntc + tj][a];
+    res[k] = s;
+  }
+  delete w;
+}
+
+extern "C" {
+// kind: 1 Quad4, 2 Quad9, 3 hex8, 4 hex27; desc = one 32-double descriptor row
+int emul_element(int kind, const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                 double alpha, double gamma, double *res, double *mat) {
+  switch (kind) {
+    case 1: run_shell<2, 2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
+    case 2: run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
+    case 3: run_solid<2, 4>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
+    case 4: run_solid<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
+  }
+  return 1;
+}
+}
