@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the TACS assembly + Krylov-operator hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # tacs_b200 (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path
+
+Workload (BASELINE.json configs[1]): synthetic 1000x1000 Quad4 MITC shell plate, 6 dof/node
+(~6M dof), isotropic, all edges clamped.  At N > 1 GPUs the plate grows to (1000*N) x 1000 elements
+(weak scaling: 1M elements per GPU), partitioned by the reference's METIS call.
+
+A step is one `assembleJacobian(1, 0, 0, res, A)`: element residuals + tangents, atomic-free
+gather into the BCSR matrix and the residual, boundary conditions.  `value` is elements/s with
+everything resident in HBM (CUDA events on the library's stream); `e2e` repeats the step through the
+C ABI with the state vector arriving from pinned host memory and the residual going back to it.
+The BCSR SpMV (the other half of the metric) is timed in its own loop and reported under `spmv`.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "elements/sec for Jacobian+residual assembly (BCSR SpMV GB/s vs HBM peak under 'spmv')"
+UNIT = "elements/s"
+# minimal-algorithm flops per element used for the FP64 roofline
+FLOPS_PER_ELEMENT = {"quad4": 57e3, "quad9": 551e3, "hex8": 69e3, "hex27": 2.28e6}
+
+
+def spmv_bytes(bs, nrows, nnzb):
+    """Algorithmic bytes of one SpMV: values + cols + rowp + x read once + y written once."""
+    return nnzb * (8 * bs * bs + 4) + 4 * (nrows + 1) + 16 * bs * nrows
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_threads():
+    return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
+
+def time_reference(nx, ny, steps, warmup):
+    """Reference CPU implementation (oracle/_ref, compiled from the unmodified sources) on an nx x ny plate.
+    The reference's intra-rank parallelism is its pthread work queue, capped at 16 threads
+    (src/TACSObject.h:150); MPI is not available in this image."""
+    from tacs_b200 import TACS as T
+    from tacs_b200 import binding, meshgen
+
+    so = os.path.join(ROOT, "oracle", "_ref", "libtacs_ref.so")
+    ref = binding.Lib(so, "ref_")
+    mesh = meshgen.plate(2, nx, ny)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)  # the reference prints a banner on stdout; keep ours one JSON line
+    try:
+        creator, asm = meshgen.build_model(T, ref, mesh, [meshgen.iso_shell_element(T, ref, 2)])
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    A, res, x, y = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+    x.setArray(meshgen.hash_vector(x.getSize()))
+    asm.applyBCs(x)
+    asm.setVariables(x)
+    threads = min(host_threads(), 16)
+    asm.setNumThreads(threads)
+    for _ in range(warmup):
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+    dt = (time.perf_counter() - t0) / steps
+    # bs=6 SpMV is threaded in the reference as well
+    A.mult(x, y)
+    t1 = time.perf_counter()
+    nsp = 10
+    for _ in range(nsp):
+        A.mult(x, y)
+    dts = (time.perf_counter() - t1) / nsp
+    bs, nrows, ncols, nnzb = A.getSizes()
+    return dict(elements=nx * ny, seconds_per_step=dt, threads=threads,
+                spmv_gbs=spmv_bytes(bs, nrows, nnzb) / dts * 1e-9, ynorm=y.norm())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx = ny = args.ref_n
+    r = time_reference(nx, ny, args.steps, args.warmup)
+    value = r["elements"] / r["seconds_per_step"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic 1000x1000 Quad4Shell plate (BASELINE configs[1])",
+                   "sample": f"{nx}x{ny} Quad4 plate of the same generator ({r['elements']} elements per step)",
+                   "timing": "host wall clock"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                         "sample": f"{nx}x{ny} Quad4 plate, assembleJacobian(1,0,0), reference pthreads "
+                                   f"(setNumThreads({r['threads']}))"},
+        "spmv": {"gbs": r["spmv_gbs"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import tacs_b200
+    from tacs_b200 import TACS as T
+    from tacs_b200 import meshgen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    lib = tacs_b200.load()  # raises when libtacs_b200.so is missing: there is no fallback
+    if lib.init(local_rank) != 0:
+        raise SystemExit("tacs_b200: no usable GPU")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (np.zeros(128, np.uint8))
+            assert lib.comm_unique_id(buf.ctypes.data_as(tacs_b200.binding.UP)) == 0
+            uid = torch.from_numpy(buf.copy())
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        buf = uid.cpu().numpy().copy()
+        assert lib.comm_init(rank, world, buf.ctypes.data_as(tacs_b200.binding.UP)) == 0
+
+    nx, ny = args.nx * world, args.ny
+    mesh = meshgen.plate(2, nx, ny)
+    creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.iso_shell_element(T, lib, 2)])
+    A, res, x, y = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+    n = x.getSize()
+    state = torch.empty(n, dtype=torch.float64).pin_memory()
+    out = torch.empty(n, dtype=torch.float64).pin_memory()
+    state_np, out_np = state.numpy(), out.numpy()
+    lo, hi = asm.getOwnerRange()
+    state_np[:] = meshgen.hash_vector(6 * creator.num_nodes)[6 * lo:6 * hi] if world > 1 else meshgen.hash_vector(n)
+    x.setArray(state_np)
+    asm.applyBCs(x)
+    asm.setVariables(x)
+    nelem_local = asm.getNumElements()
+    nelem_total = nx * ny
+    bs, nrows, ncols, nnzb = A.getSizes()
+
+    def barrier():
+        lib.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing --------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+    lib.profile_enable(1)
+    ms_k, cnt_k = np.zeros(8), np.zeros(8, np.int64)
+    lib.profile_collect(tacs_b200.binding.dptr(ms_k), cnt_k.ctypes.data_as(C.POINTER(C.c_long)))
+    barrier()
+    lib.kernel_launches(1)
+    with ClockSampler(local_rank) as clocks:
+        ms = lib.time_assemble_jacobian(asm.h, 1.0, 0.0, 0.0, res.h, A.h, args.steps)
+        launches = lib.kernel_launches(0)
+        lib.profile_collect(tacs_b200.binding.dptr(ms_k),
+                            cnt_k.ctypes.data_as(C.POINTER(C.c_long)))
+        # SpMV loop inside the same clock window
+        lib.time_mat_mult(A.h, x.h, y.h, 3)
+        nsp = 50
+        ms_spmv = lib.time_mat_mult(A.h, x.h, y.h, nsp) / nsp
+    lib.profile_enable(0)
+    barrier()
+    assert ms > 0, "device timing failed"
+    ms = max_over_ranks(ms)
+    ms_spmv = max_over_ranks(ms_spmv)
+    ms_per_step = ms / args.steps
+    value = nelem_total / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------
+    def e2e_step():
+        x.setArray(state_np)           # H2D from pinned memory
+        asm.setVariables(x)
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+        lib.vec_get_array(res.h, tacs_b200.binding.dptr(out_np))  # D2H into pinned memory
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e_value = nelem_total / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the kernels in the step ----------------------------------------------------------
+    hbm_peak, hbm_src = measured_peaks()
+    fp64_peak = lib.measure_fp64_tflops()
+    names = ["element", "gather_residual", "gather_blocks", "boundary_conditions", "spmv", "vector", "dot", "halo"]
+    per_launch = {names[k]: (ms_k[k] / cnt_k[k] if cnt_k[k] else None) for k in range(8)}
+    nn, b2 = 4, 36
+    # algorithmic HBM bytes per launch: element kernel reads X/u/conn and writes the staging
+    # blocks + residual slots; block gather reads the staging blocks and the plan, writes A once.
+    elem_bytes = nelem_local * (nn * (3 + 6) * 8 + nn * 4 + 4 + nn * nn * b2 * 8 + nn * 6 * 8)
+    gather_bytes = nelem_local * nn * nn * (b2 * 8 + 4) + nnzb * (b2 * 8 + 4)
+    kernels = []
+    if per_launch["element"]:
+        t = per_launch["element"] * 1e-3
+        kernels.append({"kernel": "shell_element_kernel<2>", "ms": per_launch["element"], "bound": "fp64",
+                        "achieved": FLOPS_PER_ELEMENT["quad4"] * nelem_local / t * 1e-12, "peak": fp64_peak,
+                        "unit": "TFLOP/s", "hbm_gbs": elem_bytes / t * 1e-9,
+                        "note": "flops = SURVEY 8d minimal-algorithm count (57 kFLOP/element); peak = live DFMA "
+                                "microbenchmark (tacsb200_measure_fp64_tflops)"})
+    if per_launch["gather_blocks"]:
+        t = per_launch["gather_blocks"] * 1e-3
+        kernels.append({"kernel": "gather_blocks_kernel<36>", "ms": per_launch["gather_blocks"], "bound": "hbm",
+                        "achieved": gather_bytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s"})
+    for k in kernels:
+        k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
+    dominant = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    roofline = None
+    if dominant:
+        roofline = {"kernel": dominant["kernel"], "bound": dominant["bound"], "achieved": dominant["achieved"],
+                    "peak": dominant["peak"], "unit": dominant["unit"], "frac": dominant["frac"], "traffic": None,
+                    "peak_source": hbm_src if dominant["bound"] == "hbm" else "live DFMA microbenchmark",
+                    "share_of_step": dominant["ms"] / ms_per_step}
+    sp_bytes = spmv_bytes(bs, nrows, nnzb)
+    spmv = {"kernel": "spmv6_kernel<0>", "ms": ms_spmv, "bound": "hbm", "achieved": sp_bytes / (ms_spmv * 1e-3) * 1e-9,
+            "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "bytes_per_launch": sp_bytes}
+    spmv["frac"] = spmv["achieved"] / spmv["peak"]
+
+    # ---- CPU baseline: the reference's own implementation on this box's host cores ---------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = time_reference(args.ref_n, args.ref_n, 2, 1)
+            cpu = {"value": r["elements"] / r["seconds_per_step"], "unit": UNIT, "cores": r["threads"],
+                   "kind": "reference",
+                   "sample": f"{args.ref_n}x{args.ref_n} Quad4 plate ({r['elements']} elements), "
+                             f"assembleJacobian(1,0,0), oracle/_ref with setNumThreads({r['threads']})",
+                   "spmv_gbs": r["spmv_gbs"]}
+        except Exception as exc:  # the reference build did not travel
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {exc}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {nx}x{ny} Quad4Shell plate (6 dof/node), isotropic, edges clamped: "
+                               f"assembleJacobian(1,0,0,res,A) per step; BASELINE configs[1] at 1 GPU, "
+                               f"{args.nx}x{args.ny} elements per GPU",
+                   "elements": nelem_total, "dof": 6 * creator.num_nodes, "nnzb": int(nnzb),
+                   "l2": "inputs larger than L2 (staging 4.6 GB + matrix 2.6 GB per step)",
+                   "partition": "METIS element partition (TACSCreator::partitionMesh)" if world > 1 else "single rank"},
+        "roofline": roofline, "kernels": kernels, "spmv": spmv, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8),
+                "note": "state vector from pinned host memory -> setVariables -> assembleJacobian -> residual to "
+                        "pinned host memory; the BCSR matrix stays in HBM for the device-side Krylov solver"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "fp64_peak_tflops": fp64_peak,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=1000, help="plate elements per GPU along x")
+    ap.add_argument("--ny", type=int, default=1000)
+    ap.add_argument("--ref-n", type=int, default=300, help="edge of the bounded CPU-baseline sample plate")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

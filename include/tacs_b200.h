@@ -185,6 +185,18 @@ double tacsb200_time_assemble_jacobian(tacsb200_handle a, double alpha, double b
 double tacsb200_time_assemble_res(tacsb200_handle a, tacsb200_handle res, int reps);
 double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y, int reps);
 
+
+/* Per-kernel device timing: when enabled every launch is bracketed by CUDA events on the launching
+   stream. collect() synchronises, sums the log into ms[8] / count[8] indexed by
+   {0 element, 1 residual gather, 2 block gather, 3 boundary conditions, 4 SpMV, 5 vector, 6 dot, 7 halo}
+   and clears it. */
+int tacsb200_profile_enable(int on);
+int tacsb200_profile_collect(double *ms, long *count);
+/* Roofline denominators measured on this device: FP64 FMA throughput (TFLOP/s, 2 flop per FMA) of a
+   register-resident DFMA stream, and device-to-device copy bandwidth (GB/s, read + write bytes). */
+double tacsb200_measure_fp64_tflops(void);
+double tacsb200_measure_copy_gbs(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,10 @@ PRODUCT_ONLY = {
     "time_assemble_jacobian": (D, [H, D, D, D, H, H, I]),
     "time_assemble_res": (D, [H, H, I]),
     "time_mat_mult": (D, [H, H, H, I]),
+    "profile_enable": (I, [I]),
+    "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
+    "measure_fp64_tflops": (D, []),
+    "measure_copy_gbs": (D, []),
 }
 
 # entry points that exist only in the reference interface (oracle/ref_capi.cpp)

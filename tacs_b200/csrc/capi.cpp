@@ -501,4 +501,43 @@ double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_ha
   });
 }
 
+int tacsb200_profile_enable(int on) {
+  profile_enable(on);
+  return 0;
+}
+int tacsb200_profile_collect(double *ms, long *count) { return profile_collect(ms, count); }
+
+double tacsb200_measure_fp64_tflops(void) {
+  if (ctx_init(-1)) return -1.0;
+  DeviceArray<double> out;
+  if (!out.alloc(8)) return -1.0;
+  const int iters = 20000, blocks = ctx().num_sms * 8;
+  launch_dfma_peak(out.ptr, 200, blocks, ctx().stream);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; rep++) {
+    double ms = timed(1, [&]() { return launch_dfma_peak(out.ptr, iters, blocks, ctx().stream) != cudaSuccess; });
+    if (ms <= 0.0) return -1.0;
+    double tf = 2.0 * 16.0 * iters * 256.0 * blocks / (ms * 1e-3) * 1e-12;
+    if (tf > best) best = tf;
+  }
+  return best;
+}
+
+double tacsb200_measure_copy_gbs(void) {
+  if (ctx_init(-1)) return -1.0;
+  const long n = 1L << 28;  // 2 GiB per buffer, far larger than L2
+  DeviceArray<double> a, b;
+  if (!a.alloc(n) || !b.alloc(n)) return -1.0;
+  cudaMemsetAsync(a.ptr, 0, n * sizeof(double), ctx().stream);
+  launch_copy(n, a.ptr, b.ptr, ctx().num_sms, ctx().stream);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    double ms = timed(1, [&]() { return launch_copy(n, a.ptr, b.ptr, ctx().num_sms, ctx().stream) != cudaSuccess; });
+    if (ms <= 0.0) return -1.0;
+    double gbs = 2.0 * n * sizeof(double) / (ms * 1e-3) * 1e-9;
+    if (gbs > best) best = gbs;
+  }
+  return best;
+}
+
 }  // extern "C"

@@ -680,4 +680,38 @@ cudaError_t launch_unpack_blocks(int bs, long count, const int *idx, const doubl
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// roofline denominators measured live: dependent-chain-free DFMA stream and a device copy
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed) {
+  double a[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = seed + k + threadIdx.x;
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = fma(a[k], m, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += a[k];
+  if (s == 12345.678) out[0] = s;  // keeps the chain live without a store in practice
+}
+
+cudaError_t launch_dfma_peak(double *out, int iters, int blocks, cudaStream_t s) {
+  dfma_peak_kernel<<<blocks, 256, 0, s>>>(out, iters, 1.0);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(long n2, const double2 *__restrict__ src, double2 *__restrict__ dst) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+cudaError_t launch_copy(long n, const double *src, double *dst, int num_sms, cudaStream_t s) {
+  copy_kernel<<<num_sms * 16, 256, 0, s>>>(n / 2, reinterpret_cast<const double2 *>(src),
+                                          reinterpret_cast<double2 *>(dst));
+  return cudaGetLastError();
+}
+
 }  // namespace tb2

@@ -68,4 +68,7 @@ cudaError_t launch_pack_blocks(int bs, long count, const int *idx, const double 
 cudaError_t launch_unpack_blocks(int bs, long count, const int *idx, const double *buf, double *x, int add,
                                  int num_sms, cudaStream_t s);
 
+cudaError_t launch_dfma_peak(double *out, int iters, int blocks, cudaStream_t s);
+cudaError_t launch_copy(long n, const double *src, double *dst, int num_sms, cudaStream_t s);
+
 }  // namespace tb2

@@ -53,6 +53,52 @@ int ctx_init(int device) {
   return 0;
 }
 
+// ---- event profiler ------------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfRec { KernelId id; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof_log;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void profile_enable(int on) { g_prof_on = on != 0; }
+KernelTimer::KernelTimer(KernelId id) : slot(-1) {
+  g_ctx.kernel_launches++;
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.id = id;
+  r.e0 = prof_event();
+  r.e1 = prof_event();
+  cudaEventRecord(r.e0, g_ctx.stream);
+  slot = (int)g_prof_log.size();
+  g_prof_log.push_back(r);
+}
+KernelTimer::~KernelTimer() {
+  if (slot >= 0) cudaEventRecord(g_prof_log[slot].e1, g_ctx.stream);
+}
+int profile_collect(double *ms, long *count) {
+  for (int k = 0; k < K_COUNT; k++) { ms[k] = 0.0; count[k] = 0; }
+  if (g_ctx.device < 0) return 1;
+  cudaStreamSynchronize(g_ctx.stream);
+  for (auto &r : g_prof_log) {
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms[r.id] += t;
+    count[r.id]++;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_log.clear();
+  return 0;
+}
+
 static void parallel_for(long n, const std::function<void(long, long)> &fn) {
   unsigned hw = std::thread::hardware_concurrency();
   long nt = hw ? hw : 4;
@@ -685,9 +731,12 @@ void TACSBVec::mdot(TACSBVec **ys, double *out, int n) {
     const int nv = std::min(8, n - done);
     const double *ptrs[8];
     for (int v = 0; v < nv; v++) ptrs[v] = ys[done + v]->owned();
-    cuda_ok(launch_mdot(ownedSize(), owned(), nv, ptrs, g_dot_partial, g_dot_out, ctx().num_sms, ctx().stream),
-            "mdot");
-    ctx().kernel_launches += 2;
+    {
+      KernelTimer kt(K_DOT);
+      cuda_ok(launch_mdot(ownedSize(), owned(), nv, ptrs, g_dot_partial, g_dot_out, ctx().num_sms, ctx().stream),
+              "mdot");
+      ctx().kernel_launches++;
+    }
     if (ctx().size > 1) comm_allreduce_sum(g_dot_out, nv);
     cuda_ok(cudaMemcpyAsync(g_dot_host, g_dot_out, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream),
             "mdot D2H");
@@ -707,16 +756,16 @@ double TACSBVec::norm() {
   return sqrt(r);
 }
 void TACSBVec::axpy(double alpha, TACSBVec *x) {
+  KernelTimer kt(K_VEC);
   cuda_ok(launch_axpy(ownedSize(), alpha, x->owned(), owned(), ctx().num_sms, ctx().stream), "axpy");
-  ctx().kernel_launches++;
 }
 void TACSBVec::axpby(double alpha, double beta, TACSBVec *x) {
+  KernelTimer kt(K_VEC);
   cuda_ok(launch_axpby(ownedSize(), alpha, beta, x->owned(), owned(), ctx().num_sms, ctx().stream), "axpby");
-  ctx().kernel_launches++;
 }
 void TACSBVec::scale(double alpha) {
+  KernelTimer kt(K_VEC);
   cuda_ok(launch_scale(ownedSize(), alpha, owned(), ctx().num_sms, ctx().stream), "scale");
-  ctx().kernel_launches++;
 }
 void TACSBVec::copyValues(TACSBVec *x) {
   cuda_ok(cudaMemcpyAsync(owned(), x->owned(), ownedSize() * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -919,14 +968,14 @@ void TACSAssembler::setNodes(TACSBVec *X) {
 }
 
 void TACSAssembler::applyBCs(TACSBVec *v) {
+  KernelTimer kt(K_BCS);
   cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, nullptr, 1.0, v->owned(),
                                ctx().stream), "vec applyBCs");
-  ctx().kernel_launches++;
 }
 void TACSAssembler::setBCs(TACSBVec *v) {
+  KernelTimer kt(K_BCS);
   cuda_ok(launch_vec_set_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, 1.0, v->owned(),
                              ctx().stream), "vec setBCs");
-  ctx().kernel_launches++;
 }
 void TACSAssembler::applyBCs(TACSParallelMat *m) { m->applyBCs(); }
 
@@ -949,8 +998,10 @@ int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat) {
     a.gamma = gamma;
     a.Ke = want_mat ? Ke.ptr + (size_t)g.block_base * bs * bs : nullptr;
     a.Re = Re.ptr + (size_t)g.node_base * bs;
-    if (!cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel")) return 1;
-    ctx().kernel_launches++;
+    {
+      KernelTimer kt(K_ELEMENT);
+      if (!cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel")) return 1;
+    }
   }
   return 0;
 }
@@ -960,13 +1011,17 @@ void residual_exchange(TACSAssembler *a, TACSBVec *res);  // comm.cpp (multi-ran
 // TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
   if (launchElements(1.0, 0.0, false)) return 1;
-  if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
-                                      ctx().stream), "gather residual")) return 1;
-  ctx().kernel_launches++;
+  {
+    KernelTimer kt(K_GATHER_RES);
+    if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
+                                        ctx().stream), "gather residual")) return 1;
+  }
   if (size > 1) residual_exchange(this, res);
-  if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(), lambda,
-                                    res->owned(), ctx().stream), "residual BCs")) return 1;
-  ctx().kernel_launches++;
+  {
+    KernelTimer kt(K_BCS);
+    if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
+                                      lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
+  }
   return 0;
 }
 
@@ -978,24 +1033,26 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
   (void)beta;
   if (launchElements(alpha, gamma, true)) return 1;
   if (res) {
+    KernelTimer kt(K_GATHER_RES);
     if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
                                         ctx().stream), "gather residual")) return 1;
-    ctx().kernel_launches++;
   }
   if (size > 1) matrix_exchange(this, A);
-  if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
-                                    ctx().num_sms, ctx().stream), "gather blocks")) return 1;
-  ctx().kernel_launches++;
+  {
+    KernelTimer kt(K_GATHER_MAT);
+    if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
+                                      ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+  }
   if (A->Bext.nnzb() > 0) {
+    KernelTimer kt(K_GATHER_MAT);
     if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
                                       ctx().num_sms, ctx().stream), "gather blocks")) return 1;
-    ctx().kernel_launches++;
   }
   if (res) {
     if (size > 1) residual_exchange(this, res);
+    KernelTimer kt(K_BCS);
     if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
                                       lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
-    ctx().kernel_launches++;
   }
   A->applyBCs();
   return 0;
@@ -1181,9 +1238,9 @@ TACSBVec *TACSParallelMat::createVec() { return new TACSBVec(Aloc.bsize, Aloc.nr
 // TACSParallelMat::applyBCs (TACSParallelMat.cpp:343-374)
 void TACSParallelMat::applyBCs() {
   TACSAssembler *a = assembler;
+  KernelTimer kt(K_BCS);
   cuda_ok(launch_mat_apply_bcs(Aloc.bsize, a->nbc_dev, a->d_bc_rows.ptr, a->d_bc_vars.ptr, Aloc.d_rowp.ptr,
                                Aloc.d_cols.ptr, Aloc.d_vals.ptr, 0, ctx().stream), "mat applyBCs");
-  ctx().kernel_launches++;
   // Bext rows (row - np) are zeroed as well; handled by the distributed plan when Bext is not empty
 }
 
@@ -1194,14 +1251,16 @@ void spmv_halo_end(TACSParallelMat *A);
 void TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
   const bool dist = assembler->size > 1 && Bext.nnzb() > 0;
   if (dist) spmv_halo_begin(this, x);
-  cuda_ok(launch_spmv(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr, x->owned(),
-                      y->owned(), 0, ctx().num_sms, ctx().stream), "spmv");
-  ctx().kernel_launches++;
+  {
+    KernelTimer kt(K_SPMV);
+    cuda_ok(launch_spmv(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr, x->owned(),
+                        y->owned(), 0, ctx().num_sms, ctx().stream), "spmv");
+  }
   if (dist) {
     spmv_halo_end(this);
+    KernelTimer kt(K_SPMV);
     cuda_ok(launch_spmv(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr, x_ext.ptr,
                         y->owned() + (size_t)Bext.bsize * np, 1, ctx().num_sms, ctx().stream), "spmv ext");
-    ctx().kernel_launches++;
   }
 }
 

@@ -43,6 +43,17 @@ struct Context {
   long kernel_launches = 0;   // launches of tacs_b200 kernels since the last reset
 };
 Context &ctx();
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+enum KernelId { K_ELEMENT = 0, K_GATHER_RES, K_GATHER_MAT, K_BCS, K_SPMV, K_VEC, K_DOT, K_HALO, K_COUNT };
+struct KernelTimer {
+  explicit KernelTimer(KernelId id);
+  ~KernelTimer();
+  int slot;
+};
+void profile_enable(int on);
+// sums the recorded launches: ms[K_COUNT], count[K_COUNT]; clears the log
+int profile_collect(double *ms, long *count);
 int ctx_init(int device);  // 0 ok; prints to stderr and returns non-zero when no usable GPU is present
 bool cuda_ok(cudaError_t err, const char *what);
 
