@@ -27,6 +27,8 @@
 // evaluated directly instead of through its first/second-derivative back-propagation chain.
 #pragma once
 
+#include <math.h>
+
 #include "elem_tables.h"
 
 namespace tb2 {
@@ -114,32 +116,35 @@ struct ShellWork {
   static constexpr int NS = 9;          // strain rows per quadrature point
   static constexpr int TR = 6, TC = 6;  // K tile of one thread = one node pair
   static constexpr int ntiles = n * n;
-  double X[3 * n];
+  static_assert(nq % QC == 0, "quadrature points must split evenly into chunks");
+  static_assert(ntiles * 6 <= QC * NS * nd, "residual partials are staged in the B rows");
   double u[nd];
   double acc[nd];  // second time derivative of the state
-  double desc[kDescStride];
   double fn[3 * n];
   double Bdr[n][nd];
   double Bty[nty][nd];
   double T[nq][9], A[nq][9], Az[nq][9];
   double wdet[nq];
-  double W[nq][5][nty];
-  double B[QC][NS][nd];
+  double W[QC][nty][6];   // tying-point -> strain-row weights of the current chunk (m padded to 6)
+  double Cw[QC][24];      // w det C of the current chunk (22 used)
+  double B[QC][NS][nd];   // strain rows of the current chunk; also holds X (start) and rpart (end)
   double CB[QC][NS][nd];
-  double rpart[ntiles][6];
+  TB2_HD double *X() { return &B[0][0][0]; }
+  TB2_HD double *rpart() { return &B[0][0][0]; }
 };
 
 // phase 1, task i in [0,n): node normal, nodal frame, nodal drill-strain row
 template <int O, int QC>
-TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
-  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
+TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc) {
+  constexpr int n = ShellDims<O>::n;
+  const double *X = w.X();
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
     const double d0 = tab.dNn[i][j][0], d1 = tab.dNn[i][j][1];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      Xxi[2 * c] += d0 * w.X[3 * j + c];
-      Xxi[2 * c + 1] += d1 * w.X[3 * j + c];
+      Xxi[2 * c] += d0 * X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * X[3 * j + c];
     }
   }
   double a[3] = {Xxi[0], Xxi[2], Xxi[4]}, b[3] = {Xxi[1], Xxi[3], Xxi[5]}, f[3];
@@ -161,7 +166,7 @@ TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab)
     Xd[3 * c + 1] = Xxi[2 * c + 1];
     Xd[3 * c + 2] = f[c];
   }
-  shell_frame((int)w.desc[25], &w.desc[26], Xxi, f, T);
+  shell_frame((int)desc[25], &desc[26], Xxi, f, T);
   inv3x3(Xd, Xdinv);
   mat3mul(Xdinv, T, XdinvT);
   for (int j = 0; j < n; j++) {
@@ -179,21 +184,21 @@ TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab)
   w.Bdr[i][6 * i + 3] = -t12[0];
   w.Bdr[i][6 * i + 4] = -t12[1];
   w.Bdr[i][6 * i + 5] = -t12[2];
-  (void)nd;
 }
 
-// phase 2, task ty in [0,nty): tying-strain row
+// phase 2, task ty in [0,nty): tying-strain row (reads fn of every node: runs after phase 1)
 template <int O, int QC>
 TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
   constexpr int n = ShellDims<O>::n;
+  const double *X = w.X();
   const int field = shell_ty_field<O>(ty);
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
     const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      Xxi[2 * c] += d0 * w.X[3 * j + c];
-      Xxi[2 * c + 1] += d1 * w.X[3 * j + c];
+      Xxi[2 * c] += d0 * X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * X[3 * j + c];
       n0[c] += N * w.fn[3 * j + c];
     }
   }
@@ -226,26 +231,26 @@ TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &ta
   }
 }
 
-// phase 2 (same barrier interval), task q in [0,nq): geometry at a quadrature point and the weights
-// that turn tying-point strains into the membrane / transverse-shear strain rows
+// phase 2 (same barrier interval), task q in [0,nq): frame, inverse Jacobian products, weighted determinant
 template <int O, int QC>
-TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
-  constexpr int n = ShellDims<O>::n, nty = ShellDims<O>::nty;
+TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc) {
+  constexpr int n = ShellDims<O>::n;
+  const double *X = w.X();
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
   double nxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
     const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      Xxi[2 * c] += d0 * w.X[3 * j + c];
-      Xxi[2 * c + 1] += d1 * w.X[3 * j + c];
+      Xxi[2 * c] += d0 * X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * X[3 * j + c];
       n0[c] += N * w.fn[3 * j + c];
       nxi[2 * c] += d0 * w.fn[3 * j + c];
       nxi[2 * c + 1] += d1 * w.fn[3 * j + c];
     }
   }
   double T[9], Xd[9], Xdz[9], Xdinv[9], A[9], Az[9], tmp[9];
-  shell_frame((int)w.desc[25], &w.desc[26], Xxi, n0, T);
+  shell_frame((int)desc[25], &desc[26], Xxi, n0, T);
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     Xd[3 * c] = Xxi[2 * c];
@@ -268,113 +273,115 @@ TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab
     w.A[q][k] = A[k];
     w.Az[q][k] = Az[k];
   }
-  // e0ty(a,b) = sum_cd A(c,a) G(c,d) A(d,b); rows of the strain vector fed by e0ty:
-  //   m=0: e0 = e0ty(0,0)  m=1: e1 = e0ty(1,1)  m=2: e2 = 2 e0ty(0,1)  m=3: e6 = 2 e0ty(1,2)  m=4: e7 = 2 e0ty(0,2)
-  for (int ty = 0; ty < nty; ty++) {
+}
+
+// phase 3a, tasks [0, QC*nty): weights that turn the tying-point strains into the membrane /
+// transverse-shear strain rows at quadrature point q0+ql; tasks [QC*nty, QC*(nty+22)): w det C
+//   e0ty(a,b) = sum_cd A(c,a) G(c,d) A(d,b); strain rows fed by e0ty:
+//   m=0: e0 = e0ty(0,0)  m=1: e1 = e0ty(1,1)  m=2: e2 = 2 e0ty(0,1)  m=3: e6 = 2 e0ty(1,2)  m=4: e7 = 2 e0ty(0,2)
+template <int O, int QC>
+TB2_HD void shell_p3_weights(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc) {
+  constexpr int nty = ShellDims<O>::nty;
+  if (task < QC * nty) {
+    const int ql = task / nty, ty = task % nty, q = q0 + ql;
+    const double *A = w.A[q];
     const int f = shell_ty_field<O>(ty);
-    const int c = (f == 1 || f == 3) ? 1 : 0;            // g11,g12,g13 -> 0 ; g22,g23 -> 1
+    const int c = (f == 1 || f == 3) ? 1 : 0;  // g11,g12,g13 -> 0 ; g22,g23 -> 1
     const int d = (f == 0) ? 0 : ((f == 1 || f == 2) ? 1 : 2);
     const double Nt = tab.Ntq[q][ty];
 #pragma unroll
     for (int m = 0; m < 5; m++) {
       const int a = (m == 1 || m == 3) ? 1 : 0;
       const int b = (m == 0) ? 0 : ((m == 1 || m == 2) ? 1 : 2);
-      double coef = (c == d) ? A[3 * c + a] * A[3 * c + b]
-                             : A[3 * c + a] * A[3 * d + b] + A[3 * d + a] * A[3 * c + b];
-      w.W[q][m][ty] = ((m >= 2) ? 2.0 : 1.0) * Nt * coef;
+      double coef = (c == d) ? A[3 * c + a] * A[3 * c + b] : A[3 * c + a] * A[3 * d + b] + A[3 * d + a] * A[3 * c + b];
+      w.W[ql][ty][m] = ((m >= 2) ? 2.0 : 1.0) * Nt * coef;
     }
+    w.W[ql][ty][5] = 0.0;
+  } else {
+    const int t = task - QC * nty;
+    const int ql = t / 22, k = t % 22;
+    w.Cw[ql][k] = w.wdet[q0 + ql] * desc[k];
   }
 }
 
-// phase 3, task (ql, j, r): six entries of strain row r for node j at quadrature point q0+ql
+// phase 3b, task (ql, j, c) with c in {0,1,2}: the two columns 6j+c (displacement) and 6j+3+c (rotation)
+// of the nine strain rows B and of CB = w det C B at quadrature point q0+ql
 template <int O, int QC>
-TB2_HD void shell_p3_brow(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
   constexpr int n = ShellDims<O>::n, nty = ShellDims<O>::nty;
-  const int r = task % 9, j = (task / 9) % n, ql = task / (9 * n);
+  const int c = task % 3, j = (task / 3) % n, ql = task / (3 * n);
   const int q = q0 + ql;
-  double out[6];
-  if (r == 8) {
-    // drill strain: nodal values interpolated with the nodal shape functions
+  const int cu = 6 * j + c, cq = cu + 3;
+  double bu[9], bq[9];
+  // rows 0,1,2,6,7: tying-strain rows combined with the weights of this quadrature point
+  {
+    double su[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, sq[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int ty = 0; ty < nty; ty++) {
+      const double tu = w.Bty[ty][cu], tq = w.Bty[ty][cq];
 #pragma unroll
-    for (int c = 0; c < 6; c++) out[c] = 0.0;
-    for (int i = 0; i < n; i++) {
-      const double N = tab.Nq[q][i];
-#pragma unroll
-      for (int c = 0; c < 6; c++) out[c] += N * w.Bdr[i][6 * j + c];
-    }
-  } else if (r >= 3 && r < 6) {
-    // bending strains from u1x = T^T (u1d XdinvT + u0d XdinvzT)
-    const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
-    const double *T = w.T[q], *A = w.A[q], *Az = w.Az[q];
-    double hz0 = d0 * Az[0] + d1 * Az[3], hz1 = d0 * Az[1] + d1 * Az[4];
-    double h0 = d0 * A[0] + d1 * A[3] + N * Az[6], h1 = d0 * A[1] + d1 * A[4] + N * Az[7];
-    double rd[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      if (r == 3) {
-        out[c] = T[3 * c] * hz0;
-        rd[c] = T[3 * c] * h0;
-      } else if (r == 4) {
-        out[c] = T[3 * c + 1] * hz1;
-        rd[c] = T[3 * c + 1] * h1;
-      } else {
-        out[c] = T[3 * c] * hz1 + T[3 * c + 1] * hz0;
-        rd[c] = T[3 * c] * h1 + T[3 * c + 1] * h0;
+      for (int m = 0; m < 5; m++) {
+        const double wt = w.W[ql][ty][m];
+        su[m] += wt * tu;
+        sq[m] += wt * tq;
       }
     }
-    cross3(&w.fn[3 * j], rd, &out[3]);
-  } else {
-    const int m = (r < 3) ? r : r - 3;  // rows 0,1,2,6,7 -> m = 0..4
-#pragma unroll
-    for (int c = 0; c < 6; c++) out[c] = 0.0;
-    for (int ty = 0; ty < nty; ty++) {
-      const double wt = w.W[q][m][ty];
-#pragma unroll
-      for (int c = 0; c < 6; c++) out[c] += wt * w.Bty[ty][6 * j + c];
-    }
+    bu[0] = su[0]; bu[1] = su[1]; bu[2] = su[2]; bu[6] = su[3]; bu[7] = su[4];
+    bq[0] = sq[0]; bq[1] = sq[1]; bq[2] = sq[2]; bq[6] = sq[3]; bq[7] = sq[4];
   }
+  // rows 3,4,5: bending strains from u1x = T^T (u1d XdinvT + u0d XdinvzT); rotation part through d = q x n
+  {
+    const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
+    const double *T = w.T[q], *A = w.A[q], *Az = w.Az[q];
+    const double hz0 = d0 * Az[0] + d1 * Az[3], hz1 = d0 * Az[1] + d1 * Az[4];
+    const double h0 = d0 * A[0] + d1 * A[3] + N * Az[6], h1 = d0 * A[1] + d1 * A[4] + N * Az[7];
+    bu[3] = T[3 * c] * hz0;
+    bu[4] = T[3 * c + 1] * hz1;
+    bu[5] = T[3 * c] * hz1 + T[3 * c + 1] * hz0;
+    const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    const double f1 = w.fn[3 * j + c1], f2 = w.fn[3 * j + c2];
+    // (fn x rd)_c = fn[c1] rd[c2] - fn[c2] rd[c1]
+    bq[3] = f1 * (T[3 * c2] * h0) - f2 * (T[3 * c1] * h0);
+    bq[4] = f1 * (T[3 * c2 + 1] * h1) - f2 * (T[3 * c1 + 1] * h1);
+    bq[5] = f1 * (T[3 * c2] * h1 + T[3 * c2 + 1] * h0) - f2 * (T[3 * c1] * h1 + T[3 * c1 + 1] * h0);
+  }
+  // row 8: drill strain, nodal values interpolated with the nodal shape functions
+  {
+    double su = 0.0, sq = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double N = tab.Nq[q][i];
+      su += N * w.Bdr[i][cu];
+      sq += N * w.Bdr[i][cq];
+    }
+    bu[8] = su;
+    bq[8] = sq;
+  }
+  // CB = (w det C) B, C = [A B 0; B D 0; 0 0 As | drill], symmetric 3x3 blocks packed [0 1 2; 1 3 4; 2 4 5]
+  const double *C = w.Cw[ql];
+  double cbu[9], cbq[9];
 #pragma unroll
-  for (int c = 0; c < 6; c++) w.B[ql][r][6 * j + c] = out[c];
-}
-
-// phase 4, task (ql, j, r): CB = w det C B for six entries
-template <int O, int QC>
-TB2_HD void shell_p4_cbrow(int task, int q0, ShellWork<O, QC> &w) {
-  constexpr int n = ShellDims<O>::n;
-  const int r = task % 9, j = (task / 9) % n, ql = task / (9 * n);
-  const double wd = w.wdet[q0 + ql];
-  const double *Cs = w.desc;
-  double coef[6];
-  int first = 0, cnt = 0;
-  if (r < 3) {
-    // [A | B] row r of the symmetric packing [0 1 2; 1 3 4; 2 4 5]
+  for (int r = 0; r < 3; r++) {
     const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
               i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
-    coef[0] = Cs[i0]; coef[1] = Cs[i1]; coef[2] = Cs[i2];
-    coef[3] = Cs[6 + i0]; coef[4] = Cs[6 + i1]; coef[5] = Cs[6 + i2];
-    first = 0; cnt = 6;
-  } else if (r < 6) {
-    const int rr = r - 3;
-    const int i0 = (rr == 0) ? 0 : ((rr == 1) ? 1 : 2), i1 = (rr == 0) ? 1 : ((rr == 1) ? 3 : 4),
-              i2 = (rr == 0) ? 2 : ((rr == 1) ? 4 : 5);
-    coef[0] = Cs[6 + i0]; coef[1] = Cs[6 + i1]; coef[2] = Cs[6 + i2];
-    coef[3] = Cs[12 + i0]; coef[4] = Cs[12 + i1]; coef[5] = Cs[12 + i2];
-    first = 0; cnt = 6;
-  } else if (r == 6) {
-    coef[0] = Cs[18]; coef[1] = Cs[19]; first = 6; cnt = 2;
-  } else if (r == 7) {
-    coef[0] = Cs[19]; coef[1] = Cs[20]; first = 6; cnt = 2;
-  } else {
-    coef[0] = Cs[21]; first = 8; cnt = 1;
+    cbu[r] = C[i0] * bu[0] + C[i1] * bu[1] + C[i2] * bu[2] + C[6 + i0] * bu[3] + C[6 + i1] * bu[4] + C[6 + i2] * bu[5];
+    cbq[r] = C[i0] * bq[0] + C[i1] * bq[1] + C[i2] * bq[2] + C[6 + i0] * bq[3] + C[6 + i1] * bq[4] + C[6 + i2] * bq[5];
+    cbu[3 + r] = C[6 + i0] * bu[0] + C[6 + i1] * bu[1] + C[6 + i2] * bu[2] + C[12 + i0] * bu[3] + C[12 + i1] * bu[4] +
+                 C[12 + i2] * bu[5];
+    cbq[3 + r] = C[6 + i0] * bq[0] + C[6 + i1] * bq[1] + C[6 + i2] * bq[2] + C[12 + i0] * bq[3] + C[12 + i1] * bq[4] +
+                 C[12 + i2] * bq[5];
   }
-  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int k = 0; k < cnt; k++) {
-    const double ck = coef[k];
+  cbu[6] = C[18] * bu[6] + C[19] * bu[7];
+  cbq[6] = C[18] * bq[6] + C[19] * bq[7];
+  cbu[7] = C[19] * bu[6] + C[20] * bu[7];
+  cbq[7] = C[19] * bq[6] + C[20] * bq[7];
+  cbu[8] = C[21] * bu[8];
+  cbq[8] = C[21] * bq[8];
 #pragma unroll
-    for (int c = 0; c < 6; c++) out[c] += ck * w.B[ql][first + k][6 * j + c];
+  for (int r = 0; r < 9; r++) {
+    w.B[ql][r][cu] = bu[r];
+    w.B[ql][r][cq] = bq[r];
+    w.CB[ql][r][cu] = cbu[r];
+    w.CB[ql][r][cq] = cbq[r];
   }
-#pragma unroll
-  for (int c = 0; c < 6; c++) w.CB[ql][r][6 * j + c] = wd * out[c];
 }
 
 // phase 5 (all families): one TRxTC tile of K accumulates B^T (CB) over the rows of this chunk
@@ -394,49 +401,61 @@ TB2_HD void tile_accumulate(const double *B, const double *CB, int row0, int col
   }
 }
 
-// phase 6, task tile (i,j): inertial block, residual partials; Kt = alpha*acc + gamma*M is left in acc
+// phase 6, task tile (i,j): inertial block (only when `inertia`), residual partials; on return acc holds
+// alpha*K_tile + gamma*M_tile. Runs after the last chunk barrier: the partials reuse the B rows.
 template <int O, int QC>
-TB2_HD void shell_p6_finish(int tile, ShellWork<O, QC> &w, const ShellTables<O> &tab, double alpha,
-                            double gamma, double *acc) {
+TB2_HD void shell_p6_finish(int tile, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc,
+                            double alpha, double gamma, bool inertia, double *acc, double *rp) {
   constexpr int n = ShellDims<O>::n, nq = ShellDims<O>::nq;
   const int i = tile / n, j = tile % n;
-  double S = 0.0;
-  for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][i] * tab.Nq[q][j];
-  const double m0 = w.desc[22], m1 = w.desc[23], m2 = w.desc[24];
-  // d = D q with D(c,e) = eps_{cef} t_f  (director d = q x t)
-  const double *ti = &w.fn[3 * i], *tj = &w.fn[3 * j];
-  const double Di[9] = {0.0, ti[2], -ti[1], -ti[2], 0.0, ti[0], ti[1], -ti[0], 0.0};
-  const double Dj[9] = {0.0, tj[2], -tj[1], -tj[2], 0.0, tj[0], tj[1], -tj[0], 0.0};
-  double M[36];
-#pragma unroll
-  for (int k = 0; k < 36; k++) M[k] = 0.0;
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    M[6 * c + c] = S * m0;
-#pragma unroll
-    for (int e = 0; e < 3; e++) {
-      M[6 * c + 3 + e] = S * m1 * Dj[3 * c + e];
-      M[6 * (3 + e) + c] = S * m1 * Di[3 * c + e];
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 3; e++)
-#pragma unroll
-    for (int f = 0; f < 3; f++) {
-      double v = 0.0;
-#pragma unroll
-      for (int c = 0; c < 3; c++) v += Di[3 * c + e] * Dj[3 * c + f];
-      M[6 * (3 + e) + 3 + f] = S * m2 * v;
-    }
 #pragma unroll
   for (int a = 0; a < 6; a++) {
-    double rp = 0.0;
+    double s = 0.0;
 #pragma unroll
-    for (int b = 0; b < 6; b++) rp += acc[6 * a + b] * w.u[6 * j + b] + M[6 * a + b] * w.acc[6 * j + b];
-    w.rpart[tile][a] = rp;
+    for (int b = 0; b < 6; b++) s += acc[6 * a + b] * w.u[6 * j + b];
+    rp[a] = s;
   }
 #pragma unroll
-  for (int k = 0; k < 36; k++) acc[k] = alpha * acc[k] + gamma * M[k];
+  for (int k = 0; k < 36; k++) acc[k] *= alpha;
+  if (inertia) {
+    double S = 0.0;
+    for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][i] * tab.Nq[q][j];
+    const double m0 = desc[22], m1 = desc[23], m2 = desc[24];
+    // d = D q with D(c,e) = eps_{cef} t_f  (director d = q x t)
+    const double *ti = &w.fn[3 * i], *tj = &w.fn[3 * j];
+    const double Di[9] = {0.0, ti[2], -ti[1], -ti[2], 0.0, ti[0], ti[1], -ti[0], 0.0};
+    const double Dj[9] = {0.0, tj[2], -tj[1], -tj[2], 0.0, tj[0], tj[1], -tj[0], 0.0};
+    double M[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) M[k] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      M[6 * c + c] = S * m0;
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        M[6 * c + 3 + e] = S * m1 * Dj[3 * c + e];
+        M[6 * (3 + e) + c] = S * m1 * Di[3 * c + e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 3; e++)
+#pragma unroll
+      for (int f = 0; f < 3; f++) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) v += Di[3 * c + e] * Dj[3 * c + f];
+        M[6 * (3 + e) + 3 + f] = S * m2 * v;
+      }
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < 6; b++) s += M[6 * a + b] * w.acc[6 * j + b];
+      rp[a] += s;
+    }
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] += gamma * M[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -508,36 +527,40 @@ TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTab
     }
 }
 
-// phase 6, task tile: consistent mass block, residual partials; acc <- alpha*acc + gamma*M
+// phase 6, task tile: residual partials, consistent mass block (only when `inertia`);
+// acc <- alpha*acc + gamma*M
 template <int O, int QC>
 TB2_HD void solid_p6_finish(int tile, SolidWork<O, QC> &w, const SolidTables<O> &tab, double alpha,
-                            double gamma, double *acc) {
+                            double gamma, bool inertia, double *acc) {
   using WK = SolidWork<O, QC>;
   constexpr int TR = WK::TR, TC = WK::TC, nq = WK::nq, ntc = WK::nd / TC;
   const int row0 = (tile / ntc) * TR, col0 = (tile % ntc) * TC;
-  const double rho = w.desc[21];
-  double M[TR * TC];
-#pragma unroll
-  for (int k = 0; k < TR * TC; k++) M[k] = 0.0;
-#pragma unroll
-  for (int an = 0; an < TR / 3; an++)
-#pragma unroll
-    for (int bn = 0; bn < TC / 3; bn++) {
-      const int na = row0 / 3 + an, nb = col0 / 3 + bn;
-      double S = 0.0;
-      for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][na] * tab.Nq[q][nb];
-#pragma unroll
-      for (int c = 0; c < 3; c++) M[(3 * an + c) * TC + 3 * bn + c] = rho * S;
-    }
 #pragma unroll
   for (int a = 0; a < TR; a++) {
     double rp = 0.0;
 #pragma unroll
-    for (int b = 0; b < TC; b++) rp += acc[a * TC + b] * w.u[col0 + b] + M[a * TC + b] * w.acc[col0 + b];
+    for (int b = 0; b < TC; b++) rp += acc[a * TC + b] * w.u[col0 + b];
     w.rpart[tile][a] = rp;
   }
 #pragma unroll
-  for (int k = 0; k < TR * TC; k++) acc[k] = alpha * acc[k] + gamma * M[k];
+  for (int k = 0; k < TR * TC; k++) acc[k] *= alpha;
+  if (inertia) {
+    const double rho = w.desc[21];
+#pragma unroll
+    for (int an = 0; an < TR / 3; an++)
+#pragma unroll
+      for (int bn = 0; bn < TC / 3; bn++) {
+        const int na = row0 / 3 + an, nb = col0 / 3 + bn;
+        double S = 0.0;
+        for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][na] * tab.Nq[q][nb];
+        const double m = rho * S;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          w.rpart[tile][3 * an + c] += m * w.acc[col0 + 3 * bn + c];
+          acc[(3 * an + c) * TC + 3 * bn + c] += gamma * m;
+        }
+      }
+  }
 }
 
 }  // namespace tb2

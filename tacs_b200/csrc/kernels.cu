@@ -69,14 +69,19 @@ __device__ __forceinline__ void team_sync() {
 // ------------------------------------------------------------------------------------------
 // element kernels
 // ------------------------------------------------------------------------------------------
+// WORK_STRIDE: distance between the work areas of consecutive teams. sizeof(Work) rounded up to 16 bytes
+// plus a skew chosen so that the two teams of a warp hit disjoint shared-memory banks when they read the
+// same field (the tile loop reads 4 distinct 48-byte chunks per team: banks {0,12,24,4}+2a).
 template <int O>
 struct ShellFamily {
-  static constexpr int QC = (O == 2) ? 2 : 3;
+  static constexpr int QC = (O == 2) ? 1 : 3;
   using Work = ShellWork<O, QC>;
   using Tables = ShellTables<O>;
   static constexpr int TEAM = (O == 2) ? 16 : 96;
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
+  static constexpr int MIN_CTAS = (O == 2) ? 3 : 2;
   static constexpr int BS = 6;
+  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 8;
 };
 
 template <int O>
@@ -87,24 +92,23 @@ struct SolidFamily {
   static constexpr int TEAM = (O == 2) ? 16 : 96;
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
   static constexpr int BS = 3;
+  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 8;
 };
 
 template <class Work, int BS>
-__device__ __forceinline__ void team_load(Work &w, const ElemGroupArgs &g, long e, int tid, int team) {
+__device__ __forceinline__ void team_load(Work &w, double *Xdst, const ElemGroupArgs &g, long e, int tid, int team) {
   constexpr int n = Work::n, nd = Work::nd;
   const int *conn = g.conn + e * n;
-  for (int k = tid; k < 3 * n; k += team) w.X[k] = g.Xpts[3 * (long)conn[k / 3] + k % 3];
+  for (int k = tid; k < 3 * n; k += team) Xdst[k] = g.Xpts[3 * (long)conn[k / 3] + k % 3];
   for (int k = tid; k < nd; k += team) {
     const long src = (long)BS * conn[k / BS] + k % BS;
     w.u[k] = g.vars ? g.vars[src] : 0.0;
     w.acc[k] = g.ddvars ? g.ddvars[src] : 0.0;
   }
-  const double *d = g.desc_table + (long)kDescStride * g.desc_index[e];
-  for (int k = tid; k < kDescStride; k += team) w.desc[k] = d[k];
 }
 
 template <int O>
-__global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS)
+__global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, ShellFamily<O>::MIN_CTAS)
     shell_element_kernel(ElemGroupArgs g) {
   using F = ShellFamily<O>;
   using Work = typename F::Work;
@@ -113,24 +117,26 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typename F::Tables &tab = *reinterpret_cast<typename F::Tables *>(smem_raw);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(typename F::Tables));
-  Work *works = reinterpret_cast<Work *>(smem_raw + sizeof(typename F::Tables) + 16);
+  unsigned char *work_base = smem_raw + sizeof(typename F::Tables) + 16;
   stage_tables(&tab, g.tables, (uint32_t)sizeof(typename F::Tables), mbar);
 
   const int team_in_cta = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
-  Work &w = works[team_in_cta];
+  Work &w = *reinterpret_cast<Work *>(work_base + (size_t)team_in_cta * F::WORK_STRIDE);
   const long nteams = (long)gridDim.x * TEAMS;
   const long nelem = g.nelem;
+  const bool inertia = (g.gamma != 0.0) || (g.ddvars != nullptr);
   // uniform trip count inside a CTA so that barriers are reached by every thread
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
-    team_load<Work, 6>(w, g, e, tid, TEAM);
+    const double *desc = g.desc_table + (long)kDescStride * __ldg(g.desc_index + e);
+    team_load<Work, 6>(w, w.X(), g, e, tid, TEAM);
     team_sync<TEAM>();
-    for (int t = tid; t < n; t += TEAM) shell_p1_node<O, QC>(t, w, tab);
+    for (int t = tid; t < n; t += TEAM) shell_p1_node<O, QC>(t, w, tab, desc);
     team_sync<TEAM>();
     for (int t = tid; t < nty + nq; t += TEAM) {
       if (t < nty) shell_p2_tying<O, QC>(t, w, tab);
-      else shell_p2_qgeom<O, QC>(t - nty, w, tab);
+      else shell_p2_qgeom<O, QC>(t - nty, w, tab, desc);
     }
     team_sync<TEAM>();
     double acc[36];
@@ -139,15 +145,15 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS)
     const bool has_tile = tid < n * n;
     const int ti = tid / n, tj = tid % n;
     for (int q0 = 0; q0 < nq; q0 += QC) {
-      for (int t = tid; t < QC * n * 9; t += TEAM) shell_p3_brow<O, QC>(t, q0, w, tab);
+      for (int t = tid; t < QC * (nty + 22); t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab, desc);
       team_sync<TEAM>();
-      for (int t = tid; t < QC * n * 9; t += TEAM) shell_p4_cbrow<O, QC>(t, q0, w);
+      for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
       team_sync<TEAM>();
       if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
       team_sync<TEAM>();
     }
     if (has_tile) {
-      shell_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, acc);
+      shell_p6_finish<O, QC>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, w.rpart() + 6 * tid);
       if (live && g.Ke) {
         double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
 #pragma unroll
@@ -156,10 +162,11 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS)
     }
     team_sync<TEAM>();
     if (live && g.Re) {
+      const double *rp = w.rpart();
       for (int k = tid; k < nd; k += TEAM) {
         const int i = k / 6, a = k % 6;
         double s = 0.0;
-        for (int j = 0; j < n; j++) s += w.rpart[i * n + j][a];
+        for (int j = 0; j < n; j++) s += rp[(i * n + j) * 6 + a];
         g.Re[e * nd + k] = s;
       }
     }
@@ -178,17 +185,22 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typename F::Tables &tab = *reinterpret_cast<typename F::Tables *>(smem_raw);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(typename F::Tables));
-  Work *works = reinterpret_cast<Work *>(smem_raw + sizeof(typename F::Tables) + 16);
+  unsigned char *work_base = smem_raw + sizeof(typename F::Tables) + 16;
   stage_tables(&tab, g.tables, (uint32_t)sizeof(typename F::Tables), mbar);
 
   const int team_in_cta = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
-  Work &w = works[team_in_cta];
+  Work &w = *reinterpret_cast<Work *>(work_base + (size_t)team_in_cta * F::WORK_STRIDE);
+  const bool inertia = (g.gamma != 0.0) || (g.ddvars != nullptr);
   const long nteams = (long)gridDim.x * TEAMS;
   const long nelem = g.nelem;
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
-    team_load<Work, 3>(w, g, e, tid, TEAM);
+    team_load<Work, 3>(w, w.X, g, e, tid, TEAM);
+    {
+      const double *d = g.desc_table + (long)kDescStride * g.desc_index[e];
+      for (int k = tid; k < kDescStride; k += TEAM) w.desc[k] = d[k];
+    }
     team_sync<TEAM>();
     for (int t = tid; t < nq; t += TEAM) solid_p1_qgeom<O, QC>(t, w, tab);
     team_sync<TEAM>();
@@ -205,7 +217,7 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
       team_sync<TEAM>();
     }
     if (has_tile) {
-      solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, acc);
+      solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, inertia, acc);
       if (live && g.Ke) {
         // the tile covers (TR/3)x(TC/3) node pairs; staging is node-pair-major, 3x3 row-major inside
 #pragma unroll
@@ -236,7 +248,7 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
 
 template <class F>
 static size_t family_smem() {
-  return sizeof(typename F::Tables) + 16 + sizeof(typename F::Work) * F::TEAMS;
+  return sizeof(typename F::Tables) + 16 + F::WORK_STRIDE * F::TEAMS;
 }
 
 size_t elem_tables_bytes(int kind) {

@@ -20,20 +20,21 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
   static ShellTables<O> tab;
   build_shell_tables<O>(tab);
   WK *w = new WK;
-  for (int k = 0; k < 3 * n; k++) w->X[k] = Xpts[k];
+  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
   for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
-  for (int k = 0; k < kDescStride; k++) w->desc[k] = desc[k];
-  for (int i = 0; i < n; i++) shell_p1_node<O, QC>(i, *w, tab);
+  const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
+  for (int i = 0; i < n; i++) shell_p1_node<O, QC>(i, *w, tab, desc);
   for (int t = 0; t < nty; t++) shell_p2_tying<O, QC>(t, *w, tab);
-  for (int q = 0; q < nq; q++) shell_p2_qgeom<O, QC>(q, *w, tab);
+  for (int q = 0; q < nq; q++) shell_p2_qgeom<O, QC>(q, *w, tab, desc);
   std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
   for (int q0 = 0; q0 < nq; q0 += QC) {
-    for (int t = 0; t < QC * n * 9; t++) shell_p3_brow<O, QC>(t, q0, *w, tab);
-    for (int t = 0; t < QC * n * 9; t++) shell_p4_cbrow<O, QC>(t, q0, *w);
+    for (int t = 0; t < QC * (nty + 22); t++) shell_p3_weights<O, QC>(t, q0, *w, tab, desc);
+    for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
     for (int t = 0; t < WK::ntiles; t++)
       tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
   }
-  for (int t = 0; t < WK::ntiles; t++) shell_p6_finish<O, QC>(t, *w, tab, alpha, gamma, &acc[36 * t]);
+  for (int t = 0; t < WK::ntiles; t++)
+    shell_p6_finish<O, QC>(t, *w, tab, desc, alpha, gamma, inertia, &acc[36 * t], w->rpart() + 6 * t);
   for (int t = 0; t < WK::ntiles; t++) {
     int i = t / n, j = t % n;
     for (int a = 0; a < 6; a++)
@@ -42,7 +43,7 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
   for (int k = 0; k < nd; k++) {
     int i = k / 6, a = k % 6;
     double s = 0.0;
-    for (int j = 0; j < n; j++) s += w->rpart[i * n + j][a];
+    for (int j = 0; j < n; j++) s += w->rpart()[(i * n + j) * 6 + a];
     res[k] = s;
   }
   delete w;
@@ -67,7 +68,7 @@ static void run_solid(const double *Xpts, const double *vars, const double *ddva
       tile_accumulate<QC * 6, nd, TR, TC>(&w->B[0][0][0], &w->CB[0][0][0], TR * (t / ntc), TC * (t % ntc),
                                           &acc[(size_t)TR * TC * t]);
   }
-  for (int t = 0; t < WK::ntiles; t++) solid_p6_finish<O, QC>(t, *w, tab, alpha, gamma, &acc[(size_t)TR * TC * t]);
+  for (int t = 0; t < WK::ntiles; t++) solid_p6_finish<O, QC>(t, *w, tab, alpha, gamma, (gamma != 0.0) || (ddvars != nullptr), &acc[(size_t)TR * TC * t]);
   for (int t = 0; t < WK::ntiles; t++) {
     int r0 = TR * (t / ntc), c0 = TC * (t % ntc);
     for (int a = 0; a < TR; a++)
@@ -87,7 +88,7 @@ extern "C" {
 int emul_element(int kind, const double *Xpts, const double *vars, const double *ddvars, const double *desc,
                  double alpha, double gamma, double *res, double *mat) {
   switch (kind) {
-    case 1: run_shell<2, 2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
+    case 1: run_shell<2, 1>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
     case 2: run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
     case 3: run_solid<2, 4>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
     case 4: run_solid<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
