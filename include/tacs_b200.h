@@ -115,6 +115,20 @@ int tacsb200_creator_get_node_nums(tacsb200_handle c, int *new_nodes);
 int tacsb200_creator_get_element_partition(tacsb200_handle c, int *partition);
 tacsb200_handle tacsb200_creator_create_tacs(tacsb200_handle c);
 
+/* Host-only planning (no GPU is touched): the integer pipeline of rank `rank` out of `size` for the
+   creator's mesh -- local element order, node maps, Aloc/Bext sparsity, gather plans and the neighbour
+   exchange lists (src/TACSCreator.cpp:436-909, src/TACSAssembler.cpp:1013-1098, 3384-3440,
+   src/bpmat/TACSMatDistribute.cpp:65-415, src/bpmat/TACSBVecDistribute.cpp:299-467). Used by the
+   CPU test-suite (including 2-rank gloo runs) and by tools that inspect a decomposition. */
+tacsb200_handle tacsb200_creator_create_plan(tacsb200_handle c, int rank, int size);
+/* copies the named integer array (out may be NULL to query the length); returns the length or -1.
+   names: elem_global elem_ptr elem_conn_global elem_conn_local ext_nodes owner_range scalars
+          Aloc_rowp Aloc_cols Bext_rowp Bext_cols ext_col_nodes a_ptr a_src b_ptr b_src r_ptr r_src
+          {state,cols,rows,blocks}_{send_peers,send_ptr,send_idx,recv_peers,recv_ptr}
+   scalars = [nelems, nowned, nlocal, ext_before, ext_after, np, local_blocks, recv_blocks,
+              local_node_slots, recv_node_slots] */
+int tacsb200_plan_get_array(tacsb200_handle plan, const char *name, int *out);
+
 /* ---- TACSAssembler: src/TACSAssembler.h:61-523 ------------------------------------------------ */
 int tacsb200_assembler_get_vars_per_node(tacsb200_handle a);
 int tacsb200_assembler_get_num_nodes(tacsb200_handle a);

@@ -398,3 +398,25 @@ class Creator(_Obj):
 
     def createTACS(self):
         return Assembler(self.lib, self.lib.creator_create_tacs(self.h))
+
+    def createPlan(self, rank, size):
+        """Host-only plan of `rank` out of `size` ranks (product library only; needs no GPU)."""
+        return Plan(self.lib, self.lib.creator_create_plan(self.h, rank, size))
+
+
+class Plan(_Obj):
+    def __init__(self, lib, handle):
+        super().__init__(lib, handle, "creator_create_plan")
+
+    def array(self, name):
+        n = self.lib.plan_get_array(self.h, name.encode(), None)
+        if n < 0:
+            raise KeyError(name)
+        out = np.zeros(max(n, 1), np.int32)
+        self.lib.plan_get_array(self.h, name.encode(), B.iptr(out))
+        return out[:n]
+
+    def scalars(self):
+        names = ["nelems", "nowned", "nlocal", "ext_before", "ext_after", "np", "local_blocks", "recv_blocks",
+                 "local_node_slots", "recv_node_slots"]
+        return dict(zip(names, (int(v) for v in self.array("scalars"))))

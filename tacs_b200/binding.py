@@ -114,6 +114,8 @@ PRODUCT_ONLY = {
     "time_assemble_jacobian": (D, [H, D, D, D, H, H, I]),
     "time_assemble_res": (D, [H, H, I]),
     "time_mat_mult": (D, [H, H, H, I]),
+    "creator_create_plan": (H, [H, I, I]),
+    "plan_get_array": (I, [H, C.c_char_p, IP]),
     "profile_enable": (I, [I]),
     "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
     "measure_fp64_tflops": (D, []),

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "../../include/tacs_b200.h"
@@ -247,6 +248,58 @@ tacsb200_handle tacsb200_creator_create_tacs(tacsb200_handle c) {
   return keep(cr->createTACS());
 }
 
+/* ---- host-only plan -------------------------------------------------------------------------- */
+tacsb200_handle tacsb200_creator_create_plan(tacsb200_handle c, int rank, int size) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE_H(cr, "creator");
+  return keep(cr->createPlan(rank, size));
+}
+int tacsb200_plan_get_array(tacsb200_handle plan, const char *name, int *out) {
+  PlanObject *po = as<PlanObject>(plan);
+  if (!po) return -1;
+  HostPlan &P = po->plan;
+  std::vector<int> tmp;
+  const std::vector<int> *v = nullptr;
+  std::string n(name);
+  auto ex = [&](const char *prefix, ExchangePlan &x) -> const std::vector<int> * {
+    std::string p(prefix);
+    if (n == p + "_send_peers") return &x.send_peers;
+    if (n == p + "_send_ptr") return &x.send_ptr;
+    if (n == p + "_send_idx") return &x.send_idx;
+    if (n == p + "_recv_peers") return &x.recv_peers;
+    if (n == p + "_recv_ptr") return &x.recv_ptr;
+    return nullptr;
+  };
+  if (n == "elem_global") v = &P.elem_global;
+  else if (n == "elem_ptr") v = &P.elem_ptr;
+  else if (n == "elem_conn_global") v = &P.elem_conn_global;
+  else if (n == "elem_conn_local") v = &P.elem_conn_local;
+  else if (n == "ext_nodes") v = &P.ext_nodes;
+  else if (n == "owner_range") v = &P.owner_range;
+  else if (n == "Aloc_rowp") v = &P.Aloc.rowp;
+  else if (n == "Aloc_cols") v = &P.Aloc.cols;
+  else if (n == "Bext_rowp") v = &P.Bext.rowp;
+  else if (n == "Bext_cols") v = &P.Bext.cols;
+  else if (n == "ext_col_nodes") v = &P.ext_col_nodes;
+  else if (n == "a_ptr") v = &P.a_ptr;
+  else if (n == "a_src") v = &P.a_src;
+  else if (n == "b_ptr") v = &P.b_ptr;
+  else if (n == "b_src") v = &P.b_src;
+  else if (n == "r_ptr") v = &P.r_ptr;
+  else if (n == "r_src") v = &P.r_src;
+  else if (n == "scalars") {
+    tmp = {P.nelems, P.nowned, P.nlocal, P.ext_before, P.ext_after, P.np, (int)P.local_blocks, (int)P.recv_blocks,
+           (int)P.local_node_slots, (int)P.recv_node_slots};
+    v = &tmp;
+  } else if (!(v = ex("state", P.state)) && !(v = ex("cols", P.cols)) && !(v = ex("rows", P.rows)) &&
+             !(v = ex("blocks", P.blocks))) {
+    fprintf(stderr, "tacs_b200: unknown plan array '%s'\n", name);
+    return -1;
+  }
+  if (out && !v->empty()) memcpy(out, v->data(), v->size() * sizeof(int));
+  return (int)v->size();
+}
+
 /* ---- assembler ------------------------------------------------------------------------------ */
 #define ASM(a)                           \
   TACSAssembler *t = as<TACSAssembler>(a); \
@@ -264,19 +317,14 @@ int tacsb200_assembler_get_owner_range(tacsb200_handle a, int *lo, int *hi) {
 int tacsb200_assembler_get_element_connectivity(tacsb200_handle a, int *ptr, int *conn) {
   TACSAssembler *t = as<TACSAssembler>(a);
   if (!t) return -1;
-  if (ptr) memcpy(ptr, t->elem_ptr.data(), t->elem_ptr.size() * sizeof(int));
-  if (conn) memcpy(conn, t->elem_conn_global.data(), t->elem_conn_global.size() * sizeof(int));
-  return (int)t->elem_conn_global.size();
+  if (ptr) memcpy(ptr, t->plan->elem_ptr.data(), t->plan->elem_ptr.size() * sizeof(int));
+  if (conn) memcpy(conn, t->plan->elem_conn_global.data(), t->plan->elem_conn_global.size() * sizeof(int));
+  return (int)t->plan->elem_conn_global.size();
 }
 int tacsb200_assembler_get_local_to_global(tacsb200_handle a, int *global) {
   TACSAssembler *t = as<TACSAssembler>(a);
   if (!t) return -1;
-  const int lo = t->owner_range[t->rank];
-  for (int l = 0; l < t->nlocal; l++) {
-    if (l < t->ext_before) global[l] = t->ext_nodes[l];
-    else if (l < t->ext_before + t->nowned) global[l] = lo + (l - t->ext_before);
-    else global[l] = t->ext_nodes[l - t->nowned];
-  }
+  for (int l = 0; l < t->nlocal; l++) global[l] = t->plan->globalNode(l);
   return t->nlocal;
 }
 tacsb200_handle tacsb200_assembler_create_vec(tacsb200_handle a) {

@@ -100,12 +100,95 @@ int comm_allreduce_sum(double *dev_buf, int n) {
                  "ncclAllReduce") ? 0 : 1;
 }
 
-// The distributed halo / off-rank-row exchanges are installed by the distributed plan (next
-// milestone); on one rank they are never reached.
-void halo_forward(TACSAssembler *a, TACSBVec *v) { (void)a; (void)v; }
-void residual_exchange(TACSAssembler *a, TACSBVec *res) { (void)a; (void)res; }
-void matrix_exchange(TACSAssembler *a, TACSParallelMat *A) { (void)a; (void)A; }
-void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x) { (void)A; (void)x; }
-void spmv_halo_end(TACSParallelMat *A) { (void)A; }
+// ---------------------------------------------------------------------------------------------
+// neighbour exchanges
+// ---------------------------------------------------------------------------------------------
+int comm_setup_exchange(DeviceExchange &dx, const ExchangePlan &x) {
+  dx.send_peers = x.send_peers;
+  dx.send_ptr = x.send_ptr;
+  dx.recv_peers = x.recv_peers;
+  dx.recv_ptr = x.recv_ptr;
+  if (!x.send_idx.empty() && !dx.d_send_idx.upload(x.send_idx)) return 1;
+  return 0;
+}
+
+// pack src[send_idx] (chunks of `chunk` doubles) and exchange with the neighbours; peer p's chunks
+// land at recv_base(k) for the k-th receive peer. All on stream `s`.
+template <class RecvBase>
+static int exchange(DeviceExchange &dx, int chunk, const double *src, RecvBase recv_base, cudaStream_t s) {
+  Context &c = ctx();
+  const long ns = dx.sendTotal();
+  if (ns > 0) {
+    if (dx.sendbuf.count < (size_t)ns * chunk && !dx.sendbuf.alloc((size_t)ns * chunk)) return 1;
+    KernelTimer kt(K_HALO);
+    if (!cuda_ok(launch_pack_blocks(chunk, ns, dx.d_send_idx.ptr, src, dx.sendbuf.ptr, c.num_sms, s), "halo pack"))
+      return 1;
+  }
+  if (!nccl_ok(nccl.group_start(), "ncclGroupStart")) return 1;
+  for (size_t k = 0; k < dx.send_peers.size(); k++) {
+    const size_t off = (size_t)dx.send_ptr[k] * chunk, cnt = (size_t)(dx.send_ptr[k + 1] - dx.send_ptr[k]) * chunk;
+    if (!nccl_ok(nccl.send(dx.sendbuf.ptr + off, cnt, kNcclFloat64, dx.send_peers[k], c.nccl_comm, s), "ncclSend"))
+      return 1;
+  }
+  for (size_t k = 0; k < dx.recv_peers.size(); k++) {
+    const size_t cnt = (size_t)(dx.recv_ptr[k + 1] - dx.recv_ptr[k]) * chunk;
+    if (!nccl_ok(nccl.recv(recv_base((int)k), cnt, kNcclFloat64, dx.recv_peers[k], c.nccl_comm, s), "ncclRecv"))
+      return 1;
+  }
+  return nccl_ok(nccl.group_end(), "ncclGroupEnd") ? 0 : 1;
+}
+
+// TACSBVecDistribute::beginForward/endForward for the assembler's external nodes: the ext blocks of a
+// local-order vector are [ext < range | owned | ext >= range]; each owner's nodes are contiguous.
+void halo_forward(TACSAssembler *a, TACSBVec *v) {
+  if (a->size <= 1) return;
+  DeviceExchange &dx = a->x_state;
+  const int chunk = v->bsize, eb = a->ext_before, no = a->nowned;
+  exchange(dx, chunk, v->owned(),
+           [&](int k) {
+             const int first = dx.recv_ptr[k];  // position in the sorted external list
+             const long local = first < eb ? first : (long)no + first;
+             return v->local() + local * chunk;
+           },
+           ctx().stream);
+}
+
+// Off-rank rows (TACSMatDistribute::beginAssembly/endAssembly, TACSBVecDistribute reverse): rows of the
+// residual staging (and the matching block rows of the matrix staging) that belong to nodes owned by a
+// neighbour are sent to it and land in the tail of its staging arrays, where its gather plans find them.
+void staging_exchange(TACSAssembler *a, bool with_blocks) {
+  if (a->size <= 1) return;
+  HostPlan &P = *a->plan;
+  const int bs = a->bs;
+  exchange(a->x_rows, bs, a->Re.ptr,
+           [&](int k) { return a->Re.ptr + ((size_t)P.local_node_slots + a->x_rows.recv_ptr[k]) * bs; },
+           ctx().stream);
+  if (with_blocks)
+    exchange(a->x_blocks, bs * bs, a->Ke.ptr,
+             [&](int k) { return a->Ke.ptr + ((size_t)P.local_blocks + a->x_blocks.recv_ptr[k]) * bs * bs; },
+             ctx().stream);
+}
+
+// SpMV halo (TACSParallelMat::mult, TACSParallelMat.cpp:248-265): gather the external columns on the
+// communication stream while the compute stream runs the local product.
+static cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
+void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x) {
+  Context &c = ctx();
+  if (!ev_x_ready) {
+    cudaEventCreateWithFlags(&ev_x_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_halo_done, cudaEventDisableTiming);
+  }
+  cudaEventRecord(ev_x_ready, c.stream);
+  cudaStreamWaitEvent(c.comm_stream, ev_x_ready, 0);
+  DeviceExchange &dx = A->x_cols;
+  const int chunk = A->Aloc.bsize;
+  exchange(dx, chunk, x->owned(), [&](int k) { return A->x_ext.ptr + (size_t)dx.recv_ptr[k] * chunk; },
+           c.comm_stream);
+  cudaEventRecord(ev_halo_done, c.comm_stream);
+}
+void spmv_halo_end(TACSParallelMat *A) {
+  (void)A;
+  cudaStreamWaitEvent(ctx().stream, ev_halo_done, 0);
+}
 
 }  // namespace tb2

@@ -1,0 +1,100 @@
+// Host-side (CPU only, no CUDA) planning of one rank's share of the mesh: the integer pipeline that
+// fixes the local element order, node maps, matrix sparsity and the atomic-free gather plans, and
+// the neighbour exchange lists that replace the reference's MPI traffic.
+//
+// What it reproduces (bit-exact integer results are the parity target):
+//   TACSCreator::createTACS local selection          src/TACSCreator.cpp:493-747 (stable sort by partition)
+//   TACSAssembler::computeExtNodes / local order     src/TACSAssembler.cpp:1013-1098, 1681-1770
+//   TACSAssembler::createMat + TACSMatDistribute     src/TACSAssembler.cpp:3384-3440,
+//       (Aloc / Bext patterns incl. rows contributed   src/bpmat/TACSMatDistribute.cpp:65-415, 453-692
+//        by elements of other ranks, np, ext columns)
+//   TACSBVecDistribute plans (state halo, column halo)  src/bpmat/TACSBVecDistribute.cpp:299-467
+//   TACSMatDistribute off-rank rows                   src/bpmat/TACSMatDistribute.cpp:1154-1267
+//
+// Every rank holds the whole mesh (synthetic meshes are generated on every rank; the Python layer
+// broadcasts a root-only mesh), so each plan is computed locally and deterministically: both ends
+// of an exchange derive the same ordered lists and no set-up communication is needed.
+#pragma once
+
+#include <memory>
+#include <vector>
+
+namespace tb2 {
+
+// the whole mesh in the creator's NEW node numbering (after first-touch renumbering)
+struct GlobalMesh {
+  int num_nodes = 0, num_elements = 0, size = 1;
+  std::vector<int> ptr, conn;    // element -> nodes
+  std::vector<int> part;         // element -> owning rank
+  std::vector<int> owner_range;  // size+1, contiguous node ranges
+  int ownerOf(int node) const;
+};
+
+// One neighbour exchange at a fixed granularity (a "chunk" of doubles): the sender packs
+// source[send_idx[k]] chunks for each peer, the receiver gets each peer's chunks contiguously.
+struct ExchangePlan {
+  std::vector<int> send_peers, send_ptr, send_idx;  // send_ptr has send_peers.size()+1 entries
+  std::vector<int> recv_peers, recv_ptr;            // offsets (chunks) inside the receive region
+  int sendTotal() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
+  int recvTotal() const { return recv_ptr.empty() ? 0 : recv_ptr.back(); }
+};
+
+struct HostBCSR {
+  int bsize = 0, nrows = 0, ncols = 0;
+  std::vector<int> rowp, cols;
+  long nnzb() const { return rowp.empty() ? 0 : rowp[nrows]; }
+};
+
+// one (element, local node) pair that contributes to an owned matrix/residual row
+struct RowContribution {
+  int gelem;        // global element id (summation order key)
+  int nn;           // nodes of the element
+  const int *conn;  // its connectivity in global (new) numbering
+  int res_slot;     // residual staging slot (units of one node block)
+  int blk_base;     // staging slot of block (i, 0) (units of one bs x bs block); +j for column node j
+};
+
+struct HostPlan {
+  int bs = 0, rank = 0, size = 1;
+  std::vector<int> owner_range;
+  // local mesh (TACSAssembler's element order and numbering)
+  int nelems = 0, nowned = 0, nlocal = 0, ext_before = 0, ext_after = 0;
+  std::vector<int> elem_global, elem_ptr, elem_conn_global, elem_conn_local;
+  std::vector<int> ext_nodes;
+  // staging layout: elements grouped by kernel family keep their local order inside a group
+  std::vector<int> elem_kind;                // per local element (ElemKind)
+  std::vector<int> group_kinds;              // distinct kinds in first-appearance order
+  std::vector<std::vector<int>> group_elems; // local element ids of each group
+  std::vector<long> group_block_base, group_node_base;
+  std::vector<long> elem_block_base, elem_node_base;  // per local element
+  long local_blocks = 0, local_node_slots = 0;        // staging produced by this rank's element kernels
+  long recv_blocks = 0, recv_node_slots = 0;          // staging received from other ranks (tail region)
+  // contributions to owned rows, ascending (owned row, global element)
+  std::vector<int> adj_ptr;
+  std::vector<RowContribution> adj;
+  std::vector<int> adj_i;  // local node index i of each contribution
+  // residual gather plan
+  std::vector<int> r_ptr, r_src;
+  // matrix (filled by buildMatrix)
+  bool has_matrix = false;
+  HostBCSR Aloc, Bext;
+  int np = 0;
+  std::vector<int> ext_col_nodes;
+  std::vector<int> a_ptr, a_src, b_ptr, b_src;
+  // neighbour exchanges (empty on one rank)
+  ExchangePlan state;   // chunk = one node block of a state vector: owned node -> ext slots of peers
+  ExchangePlan cols;    // chunk = one node block of x: owned node -> x_ext of peers (SpMV)
+  ExchangePlan blocks;  // chunk = one bs x bs staging block: rows owned by a peer
+  ExchangePlan rows;    // chunk = one node block of the residual staging
+  std::shared_ptr<const GlobalMesh> gm;
+
+  int localNode(int global) const;
+  int globalNode(int local) const;
+  // `elem_kinds[e]` is the kernel family of global element e (same on every rank)
+  int build(std::shared_ptr<const GlobalMesh> mesh, int bs, int rank, const std::vector<int> &elem_kinds);
+  int buildMatrix();
+};
+
+int kind_nodes(int kind);
+
+}  // namespace tb2

@@ -13,6 +13,7 @@
 #include <thread>
 
 #include "metis_shim/metis.h"
+#include "plan.h"
 
 namespace tb2 {
 
@@ -514,8 +515,10 @@ static int unique_sort(int len, int *a) {
 // TACSCreator::partitionMesh (TACSCreator.cpp:923-1209): element dual graph (elements adjacent when
 // they share a node, rows sorted ascending, diagonal removed) -> METIS recursive (< 8 parts) or
 // k-way; then first-touch node renumbering in global element order.
+int TACSCreator::comm_size() const { return plan_size > 0 ? plan_size : ctx().size; }
+
 int TACSCreator::partitionMesh(int split_size, const int *part) {
-  const int mpi_size = ctx().size;
+  const int mpi_size = comm_size();
   if (split_size <= 0 || split_size > mpi_size) split_size = mpi_size;
   partition.clear();
   if (part) {
@@ -602,47 +605,91 @@ int TACSCreator::getElementPartition(const int **p) {
 }
 
 // TACSCreator::createTACS (TACSCreator.cpp:436-909). Every rank holds the global mesh, so the
-// root->rank scatter of the reference becomes a local selection: the elements of this rank in
-// ascending global order (stable sort by partition, compare_arg_sort :37-47), connectivity in the
-// new global numbering, nodes of the owned range.
-TACSAssembler *TACSCreator::createTACS() {
-  if (ctx_init(-1)) return nullptr;
+// root->rank scatter of the reference becomes a local selection (plan.cpp): the elements of this rank
+// in ascending global order, connectivity in the new global numbering, nodes of the owned range.
+int TACSCreator::prepareMesh(int rank, int size, std::shared_ptr<GlobalMesh> &gm, std::vector<int> &kinds) {
   if (elements.empty()) {
-    fprintf(stderr, "[%d] TACSCreator: Elements and callback not defined\n", ctx().rank);
-    return nullptr;
+    fprintf(stderr, "[%d] TACSCreator: Elements and callback not defined\n", rank);
+    return 1;
   }
-  if (partition.empty() || new_nodes.empty()) partitionMesh(ctx().size, nullptr);
-  const int rank = ctx().rank, size = ctx().size;
-  TACSAssembler *a = new TACSAssembler();
-  a->bs = vars_per_node;
-  a->rank = rank;
-  a->size = size;
-  a->owner_range.assign(size + 1, 0);
-  for (int k = 0; k < size; k++) a->owner_range[k + 1] = a->owner_range[k] + owned_nodes[k];
-  a->nowned = owned_nodes[rank];
-  a->nelems = owned_elements[rank];
-  a->elem_ptr.assign(1, 0);
-  for (int e = 0; e < num_elements; e++) {
-    if (partition[e] != rank) continue;
-    for (int i = elem_node_ptr[e]; i < elem_node_ptr[e + 1]; i++) {
-      int node = elem_node_conn[i];
-      if (node < 0) {
-        fprintf(stderr, "[%d] tacs_b200: dependent nodes are not supported on the device path\n", rank);
-        delete a;
-        return nullptr;
-      }
-      a->elem_conn_global.push_back(new_nodes[node]);
+  if (partition.empty() || new_nodes.empty() || (int)owned_nodes.size() != size) partitionMesh(size, nullptr);
+  gm = std::make_shared<GlobalMesh>();
+  gm->num_nodes = num_nodes;
+  gm->num_elements = num_elements;
+  gm->size = size;
+  gm->ptr = elem_node_ptr;
+  gm->conn.resize(elem_node_conn.size());
+  for (size_t k = 0; k < elem_node_conn.size(); k++) {
+    if (elem_node_conn[k] < 0) {
+      fprintf(stderr, "[%d] tacs_b200: dependent nodes are not supported on the device path\n", rank);
+      return 1;
     }
-    a->elem_ptr.push_back((int)a->elem_conn_global.size());
+    gm->conn[k] = new_nodes[elem_node_conn[k]];
+  }
+  gm->part = partition;
+  gm->owner_range.assign(size + 1, 0);
+  for (int k = 0; k < size; k++) gm->owner_range[k + 1] = gm->owner_range[k] + owned_nodes[k];
+  kinds.assign(num_elements, 0);
+  for (int e = 0; e < num_elements; e++) {
     int id = elem_id_nums[e];
     TACSElement *el = (id >= 0 && id < (int)elements.size()) ? elements[id] : nullptr;
     if (!el) {
       fprintf(stderr, "[%d] TACSCreator: Element undefined for element ID %d\n", rank, id);
-      delete a;
-      return nullptr;
+      return 1;
     }
-    a->elems.push_back(el);
+    kinds[e] = el->kernelKind();
+    if (el->getVarsPerNode() != vars_per_node || el->getNumNodes() != elem_node_ptr[e + 1] - elem_node_ptr[e]) {
+      fprintf(stderr, "[%d] TACSAssembler: Element %s does not match variables per node / connectivity\n", rank,
+              el->getObjectName());
+      return 1;
+    }
+    TACSElement3D *solid = dynamic_cast<TACSElement3D *>(el);
+    if (solid && !solid->model) {
+      fprintf(stderr, "[%d] tacs_b200: unsupported element model on the device path\n", rank);
+      return 1;
+    }
   }
+  return 0;
+}
+
+PlanObject *TACSCreator::createPlan(int rank, int size) {
+  plan_size = size;
+  std::shared_ptr<GlobalMesh> gm;
+  std::vector<int> kinds;
+  if (prepareMesh(rank, size, gm, kinds)) return nullptr;
+  PlanObject *po = new PlanObject();
+  if (po->plan.build(gm, vars_per_node, rank, kinds) || po->plan.buildMatrix()) {
+    delete po;
+    return nullptr;
+  }
+  return po;
+}
+
+TACSAssembler *TACSCreator::createTACS() {
+  if (ctx_init(-1)) return nullptr;
+  const int rank = ctx().rank, size = ctx().size;
+  plan_size = 0;
+  std::shared_ptr<GlobalMesh> gm;
+  std::vector<int> kinds;
+  if (prepareMesh(rank, size, gm, kinds)) return nullptr;
+  TACSAssembler *a = new TACSAssembler();
+  a->plan.reset(new HostPlan());
+  if (a->plan->build(gm, vars_per_node, rank, kinds)) {
+    delete a;
+    return nullptr;
+  }
+  HostPlan &P = *a->plan;
+  a->bs = vars_per_node;
+  a->rank = rank;
+  a->size = size;
+  a->owner_range = P.owner_range;
+  a->nowned = P.nowned;
+  a->nlocal = P.nlocal;
+  a->nelems = P.nelems;
+  a->ext_before = P.ext_before;
+  a->ext_after = P.ext_after;
+  for (int e = 0; e < P.nelems; e++) a->elems.push_back(elements[elem_id_nums[P.elem_global[e]]]);
+  for (auto e : a->elems) e->incref();
   // boundary conditions in the new numbering (TACSCreator.cpp:478-481, 836-851)
   for (size_t k = 0; k < bc_nodes.size(); k++) {
     int node = new_nodes[bc_nodes[k]];
@@ -662,22 +709,6 @@ TACSAssembler *TACSCreator::createTACS() {
       a->bc_vals.insert(a->bc_vals.end(), vals.begin(), vals.end());
     }
   }
-  // external nodes, local order [ext < range | owned | ext >= range] (TACSAssembler.cpp:1013-1098)
-  const int lo = a->owner_range[rank], hi = a->owner_range[rank + 1];
-  {
-    std::vector<int> ext;
-    for (int g : a->elem_conn_global)
-      if (g < lo || g >= hi) ext.push_back(g);
-    int n = unique_sort((int)ext.size(), ext.data());
-    ext.resize(n);
-    a->ext_nodes = ext;
-    a->ext_before = (int)(std::lower_bound(ext.begin(), ext.end(), lo) - ext.begin());
-    a->ext_after = n - a->ext_before;
-    a->nlocal = a->nowned + n;
-  }
-  a->elem_conn_local.resize(a->elem_conn_global.size());
-  for (size_t k = 0; k < a->elem_conn_global.size(); k++) a->elem_conn_local[k] = a->localNode(a->elem_conn_global[k]);
-  for (auto e : a->elems) e->incref();
   // node locations of every local node (the reference fills the ghosts with a halo exchange in
   // setNodes, TACSAssembler.cpp:920-926; here every rank already holds the global coordinates)
   std::vector<double> Xl((size_t)3 * a->nlocal, 0.0);
@@ -686,11 +717,7 @@ TACSAssembler *TACSCreator::createTACS() {
     for (int i = 0; i < num_nodes; i++)
       if (new_nodes[i] >= 0) inv[new_nodes[i]] = i;
     for (int l = 0; l < a->nlocal; l++) {
-      int g;
-      if (l < a->ext_before) g = a->ext_nodes[l];
-      else if (l < a->ext_before + a->nowned) g = lo + (l - a->ext_before);
-      else g = a->ext_nodes[l - a->nowned];
-      int old = inv[g];
+      int old = inv[P.globalNode(l)];
       for (int c = 0; c < 3; c++) Xl[3 * (size_t)l + c] = Xpts[3 * (size_t)old + c];
     }
   }
@@ -801,17 +828,12 @@ TACSAssembler::~TACSAssembler() {
   if (ddvars) ddvars->decref();
 }
 
-// TACSAssembler::getLocalNodeNum (TACSAssembler.cpp:1681-1731)
-int TACSAssembler::localNode(int g) const {
-  const int lo = owner_range[rank], hi = owner_range[rank + 1];
-  if (g >= lo && g < hi) return ext_before + (g - lo);
-  auto it = std::lower_bound(ext_nodes.begin(), ext_nodes.end(), g);
-  if (it == ext_nodes.end() || *it != g) return -1;
-  int k = (int)(it - ext_nodes.begin());
-  return k < ext_before ? k : nowned + k;
-}
+int TACSAssembler::localNode(int g) const { return plan->localNode(g); }
+
+int comm_setup_exchange(DeviceExchange &dx, const ExchangePlan &x);  // comm.cpp
 
 int TACSAssembler::finalize() {
+  HostPlan &P = *plan;
   // state vectors in local order
   xpts = new TACSBVec(3, nowned, ext_before, ext_after);
   vars = new TACSBVec(bs, nowned, ext_before, ext_after);
@@ -819,23 +841,12 @@ int TACSAssembler::finalize() {
   ddvars = new TACSBVec(bs, nowned, ext_before, ext_after);
   xpts->incref(); vars->incref(); dvars->incref(); ddvars->incref();
 
-  // distinct descriptors -> device table; groups by kernel family, local order preserved
+  // distinct descriptors -> device table
   std::map<TACSElement *, int> index;
   elem_desc.resize(nelems);
   std::vector<double> table;
-  std::map<int, int> group_of_kind;
   for (int e = 0; e < nelems; e++) {
     TACSElement *el = elems[e];
-    if (el->getVarsPerNode() != bs || el->getNumNodes() != elem_ptr[e + 1] - elem_ptr[e]) {
-      fprintf(stderr, "[%d] TACSAssembler: Element %s does not match variables per node / connectivity\n", rank,
-              el->getObjectName());
-      return 1;
-    }
-    TACSElement3D *solid = dynamic_cast<TACSElement3D *>(el);
-    if (solid && !solid->model) {
-      fprintf(stderr, "[%d] tacs_b200: unsupported element model on the device path\n", rank);
-      return 1;
-    }
     auto it = index.find(el);
     if (it == index.end()) {
       int row = (int)distinct.size();
@@ -847,38 +858,31 @@ int TACSAssembler::finalize() {
     } else {
       elem_desc[e] = it->second;
     }
-    int kind = el->kernelKind();
-    if (!group_of_kind.count(kind)) {
-      group_of_kind[kind] = (int)groups.size();
-      groups.emplace_back();
-      groups.back().kind = kind;
-      groups.back().nn = elem_kind_nodes(kind);
-    }
-    groups[group_of_kind[kind]].local_elems.push_back(e);
   }
   if (!d_desc_table.upload(table)) return 1;
-  total_blocks = 0;
-  total_node_slots = 0;
-  for (auto &g : groups) {
+  // element groups by kernel family (local order preserved inside a group)
+  groups.clear();
+  for (size_t gi = 0; gi < P.group_kinds.size(); gi++) {
+    groups.emplace_back();
+    ElemGroup &g = groups.back();
+    g.kind = P.group_kinds[gi];
+    g.nn = elem_kind_nodes(g.kind);
+    g.local_elems = P.group_elems[gi];
     g.nelem = (long)g.local_elems.size();
+    g.block_base = P.group_block_base[gi];
+    g.node_base = P.group_node_base[gi];
     std::vector<int> conn((size_t)g.nelem * g.nn), desc(g.nelem);
     for (long k = 0; k < g.nelem; k++) {
       int e = g.local_elems[k];
-      for (int i = 0; i < g.nn; i++) conn[(size_t)k * g.nn + i] = elem_conn_local[elem_ptr[e] + i];
+      for (int i = 0; i < g.nn; i++) conn[(size_t)k * g.nn + i] = P.elem_conn_local[P.elem_ptr[e] + i];
       desc[k] = elem_desc[e];
     }
     std::vector<unsigned char> tab(elem_tables_bytes(g.kind));
     elem_tables_build(g.kind, tab.data());
     if (!g.d_conn.upload(conn) || !g.d_desc.upload(desc) || !g.d_tables.upload(tab.data(), tab.size())) return 1;
-    g.block_base = total_blocks;
-    g.node_base = total_node_slots;
-    total_blocks += g.nelem * g.nn * g.nn;
-    total_node_slots += g.nelem * g.nn;
   }
-  if (total_blocks >= (1L << 31)) {
-    fprintf(stderr, "[%d] tacs_b200: %ld staging blocks exceed the 32-bit gather index\n", rank, total_blocks);
-    return 1;
-  }
+  total_blocks = P.local_blocks + P.recv_blocks;
+  total_node_slots = P.local_node_slots + P.recv_node_slots;
 
   // boundary conditions: merge duplicates in application order (sequential semantics of TACSBcMap)
   {
@@ -909,31 +913,17 @@ int TACSAssembler::finalize() {
       local[k] = localNode(nodes[k]);
     }
     nbc_dev = (int)nodes.size();
+    h_bc_rows = rows;
     if (!d_bc_rows.upload(rows) || !d_bc_vars.upload(masks) || !d_bc_vals.upload(vals) || !d_bc_local.upload(local))
       return 1;
   }
-
-  // residual gather plan: owned node -> staging slots (element, local node) in ascending element order
-  {
-    std::vector<int> ptr(nowned + 1, 0);
-    std::vector<long> slot_of_elem(nelems);
-    for (auto &g : groups)
-      for (long k = 0; k < g.nelem; k++) slot_of_elem[g.local_elems[k]] = g.node_base + k * g.nn;
-    for (int e = 0; e < nelems; e++)
-      for (int i = elem_ptr[e]; i < elem_ptr[e + 1]; i++) {
-        int l = elem_conn_local[i] - ext_before;
-        if (l >= 0 && l < nowned) ptr[l + 1]++;
-      }
-    for (int i = 0; i < nowned; i++) ptr[i + 1] += ptr[i];
-    std::vector<int> src(ptr[nowned]), cursor(ptr.begin(), ptr.end() - 1);
-    for (int e = 0; e < nelems; e++)
-      for (int i = elem_ptr[e]; i < elem_ptr[e + 1]; i++) {
-        int l = elem_conn_local[i] - ext_before;
-        if (l >= 0 && l < nowned) src[cursor[l]++] = (int)(slot_of_elem[e] + (i - elem_ptr[e]));
-      }
-    if (!r_ptr.upload(ptr) || !r_src.upload(src)) return 1;
-  }
+  if (!r_ptr.upload(P.r_ptr) || !r_src.upload(P.r_src)) return 1;
   if (!Re.alloc((size_t)total_node_slots * bs)) return 1;
+  if (size > 1) {
+    if (comm_setup_exchange(x_state, P.state) || comm_setup_exchange(x_rows, P.rows) ||
+        comm_setup_exchange(x_blocks, P.blocks))
+      return 1;
+  }
   return 0;
 }
 
@@ -1006,17 +996,17 @@ int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat) {
   return 0;
 }
 
-void residual_exchange(TACSAssembler *a, TACSBVec *res);  // comm.cpp (multi-rank reverse halo add)
+void staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank rows of Re (and Ke)
 
 // TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
   if (launchElements(1.0, 0.0, false)) return 1;
+  if (size > 1) staging_exchange(this, false);
   {
     KernelTimer kt(K_GATHER_RES);
     if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
                                         ctx().stream), "gather residual")) return 1;
   }
-  if (size > 1) residual_exchange(this, res);
   {
     KernelTimer kt(K_BCS);
     if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
@@ -1025,19 +1015,18 @@ int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
   return 0;
 }
 
-void matrix_exchange(TACSAssembler *a, TACSParallelMat *A);  // comm.cpp (off-rank rows)
 
 // TACSAssembler::assembleJacobian (TACSAssembler.cpp:4291-4406)
 int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
                                     double lambda) {
   (void)beta;
   if (launchElements(alpha, gamma, true)) return 1;
+  if (size > 1) staging_exchange(this, true);
   if (res) {
     KernelTimer kt(K_GATHER_RES);
     if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
                                         ctx().stream), "gather residual")) return 1;
   }
-  if (size > 1) matrix_exchange(this, A);
   {
     KernelTimer kt(K_GATHER_MAT);
     if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
@@ -1049,7 +1038,6 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
                                       ctx().num_sms, ctx().stream), "gather blocks")) return 1;
   }
   if (res) {
-    if (size > 1) residual_exchange(this, res);
     KernelTimer kt(K_BCS);
     if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
                                       lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
@@ -1074,152 +1062,36 @@ TACSParallelMat *TACSAssembler::createMat() {
 TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
   assembler = a;
   a->incref();
-  const int bs = a->bs, nowned = a->nowned, lo = a->owner_range[a->rank], hi = a->owner_range[a->rank + 1];
-  if (a->size > 1) {
-    fprintf(stderr, "[%d] tacs_b200: multi-rank matrices are created through the distributed plan\n", a->rank);
-  }
-  // node -> element adjacency over the local elements (owned rows only)
-  std::vector<int> ne_ptr(nowned + 1, 0);
-  for (int e = 0; e < a->nelems; e++)
-    for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) {
-      int g = a->elem_conn_global[i];
-      if (g >= lo && g < hi) ne_ptr[g - lo + 1]++;
-    }
-  for (int i = 0; i < nowned; i++) ne_ptr[i + 1] += ne_ptr[i];
-  std::vector<int> ne_elem(ne_ptr[nowned]), ne_slot(ne_ptr[nowned]);
-  {
-    std::vector<int> cursor(ne_ptr.begin(), ne_ptr.end() - 1);
-    for (int e = 0; e < a->nelems; e++)
-      for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) {
-        int g = a->elem_conn_global[i];
-        if (g >= lo && g < hi) {
-          int p = cursor[g - lo]++;
-          ne_elem[p] = e;
-          ne_slot[p] = i - a->elem_ptr[e];
-        }
-      }
-  }
-  // pass 1: row lengths; pass 2: sorted unique columns (global ids) per owned row
-  std::vector<int> rowlen(nowned, 0);
-  parallel_for(nowned, [&](long r0, long r1) {
-    std::vector<int> buf;
-    for (long r = r0; r < r1; r++) {
-      buf.clear();
-      for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
-        int e = ne_elem[p];
-        for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) buf.push_back(a->elem_conn_global[i]);
-      }
-      rowlen[r] = unique_sort((int)buf.size(), buf.data());
-    }
-  });
-  std::vector<long> gptr(nowned + 1, 0);
-  for (int r = 0; r < nowned; r++) gptr[r + 1] = gptr[r] + rowlen[r];
-  std::vector<int> gcols(gptr[nowned]);
-  parallel_for(nowned, [&](long r0, long r1) {
-    std::vector<int> buf;
-    for (long r = r0; r < r1; r++) {
-      buf.clear();
-      for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
-        int e = ne_elem[p];
-        for (int i = a->elem_ptr[e]; i < a->elem_ptr[e + 1]; i++) buf.push_back(a->elem_conn_global[i]);
-      }
-      int n = unique_sort((int)buf.size(), buf.data());
-      memcpy(&gcols[gptr[r]], buf.data(), n * sizeof(int));
-    }
-  });
-  if (gptr[nowned] >= (1L << 31)) {
-    fprintf(stderr, "[%d] tacs_b200: %ld blocks exceed the reference's 32-bit rowp (BCSRMat.cpp:234)\n", a->rank,
-            gptr[nowned]);
-    return;
-  }
-  // split into Aloc (owned columns, local index) and Bext (external columns -> index in the sorted
-  // unique list); np = first owned row with an external column
-  np = nowned;
-  for (int r = 0; r < nowned && np == nowned; r++)
-    for (long k = gptr[r]; k < gptr[r + 1]; k++)
-      if (gcols[k] < lo || gcols[k] >= hi) { np = r; break; }
-  {
-    std::vector<int> ext;
-    for (long k = 0; k < gptr[nowned]; k++)
-      if (gcols[k] < lo || gcols[k] >= hi) ext.push_back(gcols[k]);
-    int n = unique_sort((int)ext.size(), ext.data());
-    ext.resize(n);
-    ext_col_nodes = ext;
-  }
-  Aloc.bsize = bs; Aloc.nrows = nowned; Aloc.ncols = nowned;
-  Aloc.rowp.assign(nowned + 1, 0);
-  Bext.bsize = bs; Bext.nrows = nowned - np; Bext.ncols = (int)ext_col_nodes.size();
-  Bext.rowp.assign(Bext.nrows + 1, 0);
-  for (int r = 0; r < nowned; r++) {
-    for (long k = gptr[r]; k < gptr[r + 1]; k++) {
-      int g = gcols[k];
-      if (g >= lo && g < hi) Aloc.cols.push_back(g - lo);
-      else Bext.cols.push_back((int)(std::lower_bound(ext_col_nodes.begin(), ext_col_nodes.end(), g) -
-                                     ext_col_nodes.begin()));
-    }
-    Aloc.rowp[r + 1] = (int)Aloc.cols.size();
-    if (r >= np) Bext.rowp[r - np + 1] = (int)Bext.cols.size();
-  }
-  // gather plan: for every block of an owned row, the staging slots (element, i, j), ascending element
-  std::vector<long> blk_of_elem(a->nelems);
-  std::vector<int> nn_of_elem(a->nelems);
-  for (auto &g : a->groups)
-    for (long k = 0; k < g.nelem; k++) {
-      blk_of_elem[g.local_elems[k]] = g.block_base + k * g.nn * g.nn;
-      nn_of_elem[g.local_elems[k]] = g.nn;
-    }
-  const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
-  std::vector<int> acnt(nnzA + 1, 0), bcnt(nnzB + 1, 0);
-  auto locate = [&](int r, int gcol, bool &is_ext) -> long {
-    if (gcol >= lo && gcol < hi) {
-      is_ext = false;
-      const int *b = &Aloc.cols[Aloc.rowp[r]], *e = &Aloc.cols[0] + Aloc.rowp[r + 1];
-      return std::lower_bound(b, e, gcol - lo) - &Aloc.cols[0];
-    }
-    is_ext = true;
-    int c = (int)(std::lower_bound(ext_col_nodes.begin(), ext_col_nodes.end(), gcol) - ext_col_nodes.begin());
-    const int *b = &Bext.cols[Bext.rowp[r - np]], *e = &Bext.cols[0] + Bext.rowp[r - np + 1];
-    return std::lower_bound(b, e, c) - &Bext.cols[0];
+  HostPlan &P = *a->plan;
+  if (P.buildMatrix()) return;
+  np = P.np;
+  ext_col_nodes = P.ext_col_nodes;
+  auto copy = [](BCSRPattern &d, const HostBCSR &h) {
+    d.bsize = h.bsize; d.nrows = h.nrows; d.ncols = h.ncols;
+    d.rowp = h.rowp; d.cols = h.cols;
   };
-  parallel_for(nowned, [&](long r0, long r1) {
-    for (long r = r0; r < r1; r++)
-      for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
-        int e = ne_elem[p];
-        for (int j = a->elem_ptr[e]; j < a->elem_ptr[e + 1]; j++) {
-          bool is_ext;
-          long pos = locate((int)r, a->elem_conn_global[j], is_ext);
-          (is_ext ? bcnt : acnt)[pos + 1]++;
-        }
-      }
-  });
-  for (long k = 0; k < nnzA; k++) acnt[k + 1] += acnt[k];
-  for (long k = 0; k < nnzB; k++) bcnt[k + 1] += bcnt[k];
-  std::vector<int> asrc(acnt[nnzA]), bsrc(bcnt[nnzB]);
-  {
-    std::vector<int> acur(acnt.begin(), acnt.end() - 1), bcur(bcnt.begin(), bcnt.end() - 1);
-    parallel_for(nowned, [&](long r0, long r1) {
-      for (long r = r0; r < r1; r++)
-        for (int p = ne_ptr[r]; p < ne_ptr[r + 1]; p++) {
-          int e = ne_elem[p], i = ne_slot[p], nn = nn_of_elem[e];
-          for (int j = a->elem_ptr[e]; j < a->elem_ptr[e + 1]; j++) {
-            bool is_ext;
-            long pos = locate((int)r, a->elem_conn_global[j], is_ext);
-            int slot = (int)(blk_of_elem[e] + (long)i * nn + (j - a->elem_ptr[e]));
-            if (is_ext) bsrc[bcur[pos]++] = slot;
-            else asrc[acur[pos]++] = slot;
-          }
-        }
-    });
-  }
-  const size_t b2 = (size_t)bs * bs;
+  copy(Aloc, P.Aloc);
+  copy(Bext, P.Bext);
+  const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
+  const size_t b2 = (size_t)Aloc.bsize * Aloc.bsize;
   bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA) &&
-            a_ptr.upload(acnt) && a_src.upload(asrc);
+            a_ptr.upload(P.a_ptr) && a_src.upload(P.a_src);
   if (ok && nnzB > 0)
     ok = Bext.d_rowp.upload(Bext.rowp) && Bext.d_cols.upload(Bext.cols) && Bext.d_vals.alloc(b2 * nnzB) &&
-         b_ptr.upload(bcnt) && b_src.upload(bsrc) && x_ext.alloc((size_t)bs * Bext.ncols);
+         b_ptr.upload(P.b_ptr) && b_src.upload(P.b_src) && x_ext.alloc((size_t)Aloc.bsize * Bext.ncols);
+  if (ok && a->size > 1) ok = comm_setup_exchange(x_cols, P.cols) == 0;
   if (!ok) {
     Aloc.bsize = 0;
     return;
+  }
+  // Bext rows of constrained nodes: row index relative to np
+  {
+    std::vector<int> rows;
+    for (int r : a->h_bc_rows) rows.push_back((r >= np) ? r - np : -1);
+    if (!d_bc_rows_ext.upload(rows)) {
+      Aloc.bsize = 0;
+      return;
+    }
   }
   zeroEntries();
 }
@@ -1241,7 +1113,11 @@ void TACSParallelMat::applyBCs() {
   KernelTimer kt(K_BCS);
   cuda_ok(launch_mat_apply_bcs(Aloc.bsize, a->nbc_dev, a->d_bc_rows.ptr, a->d_bc_vars.ptr, Aloc.d_rowp.ptr,
                                Aloc.d_cols.ptr, Aloc.d_vals.ptr, 0, ctx().stream), "mat applyBCs");
-  // Bext rows (row - np) are zeroed as well; handled by the distributed plan when Bext is not empty
+  if (Bext.nnzb() > 0) {
+    KernelTimer kt2(K_BCS);
+    cuda_ok(launch_mat_apply_bcs(Bext.bsize, a->nbc_dev, d_bc_rows_ext.ptr, a->d_bc_vars.ptr, Bext.d_rowp.ptr,
+                                 Bext.d_cols.ptr, Bext.d_vals.ptr, -1, ctx().stream), "mat applyBCs ext");
+  }
 }
 
 void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x);  // comm.cpp

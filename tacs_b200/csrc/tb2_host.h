@@ -26,7 +26,10 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
 #include "kernels.h"
+#include "plan.h"
 
 namespace tb2 {
 
@@ -92,6 +95,15 @@ struct DeviceArray {
     return cuda_ok(cudaMemcpyAsync(host, ptr, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream), "D2H") &&
            cuda_ok(cudaStreamSynchronize(ctx().stream), "D2H sync");
   }
+};
+
+// device side of an ExchangePlan (comm.cpp): packed send indices and buffers
+struct DeviceExchange {
+  std::vector<int> send_peers, send_ptr, recv_peers, recv_ptr;
+  DeviceArray<int> d_send_idx;
+  DeviceArray<double> sendbuf;  // sized on first use for the largest chunk
+  int sendTotal() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
+  int recvTotal() const { return recv_ptr.empty() ? 0 : recv_ptr.back(); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -319,6 +331,8 @@ class TACSParallelMat : public Object {
   // gather plan: staging slots of every block, ascending element order
   DeviceArray<int> a_ptr, a_src, b_ptr, b_src;
   DeviceArray<double> x_ext;  // external column values for the SpMV halo
+  DeviceArray<int> d_bc_rows_ext;  // Bext row (owned row - np) of each merged BC, or -1
+  DeviceExchange x_cols;
   void zeroEntries();
   void mult(TACSBVec *x, TACSBVec *y);
   void applyBCs();
@@ -342,6 +356,11 @@ class TACSCreator : public Object {
   int getNodeNums(const int **new_nodes);
   int getElementPartition(const int **part);
   TACSAssembler *createTACS();
+  // host-only plan of `rank` of `size` (no GPU): shares the mesh preparation with createTACS
+  class PlanObject *createPlan(int rank, int size);
+  int prepareMesh(int rank, int size, std::shared_ptr<GlobalMesh> &gm, std::vector<int> &kinds);
+  int comm_size() const;
+  int plan_size = 0;  // > 0: partition for this many ranks without a communicator (host-only planning)
 
   int vars_per_node;
   int num_nodes = 0, num_elements = 0;
@@ -351,6 +370,11 @@ class TACSCreator : public Object {
   std::vector<double> Xpts;
   std::vector<TACSElement *> elements;
   std::vector<int> partition, new_nodes, owned_nodes, owned_elements;
+};
+
+class PlanObject : public Object {
+ public:
+  HostPlan plan;
 };
 
 struct ElemGroup {
@@ -390,8 +414,6 @@ class TACSAssembler : public Object {
   int nowned = 0, nlocal = 0, nelems = 0;
   int ext_before = 0, ext_after = 0;
   std::vector<int> owner_range;  // size+1
-  std::vector<int> ext_nodes;    // ascending global ids of external nodes
-  std::vector<int> elem_ptr, elem_conn_global, elem_conn_local;
   std::vector<TACSElement *> elems;          // per local element
   std::vector<TACSElement *> distinct;       // distinct descriptors (table rows)
   std::vector<int> elem_desc;                // per local element: row of the descriptor table
@@ -399,6 +421,7 @@ class TACSAssembler : public Object {
   std::vector<int> bc_nodes, bc_vars;
   std::vector<double> bc_vals;
   int nbc_dev = 0;
+  std::vector<int> h_bc_rows;  // owned-row index of each merged BC (or -1)
   DeviceArray<int> d_bc_rows, d_bc_vars;  // owned-row index of each merged BC (or -1), mask
   DeviceArray<double> d_bc_vals;
   DeviceArray<int> d_bc_local;            // local node index (for state vectors in local order)
@@ -411,6 +434,8 @@ class TACSAssembler : public Object {
   DeviceArray<double> Ke, Re;
   long total_blocks = 0, total_node_slots = 0;
   DeviceArray<int> r_ptr, r_src;
+  std::unique_ptr<HostPlan> plan;
+  DeviceExchange x_state, x_rows, x_blocks;
   int localNode(int global) const;
   int finalize();  // build device data after the creator filled the host arrays
   int launchElements(double alpha, double gamma, bool want_mat);
