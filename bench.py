@@ -280,7 +280,9 @@ def run_b200(args):
     hbm_peak, hbm_src = measured_peaks()
     fp64_peak = lib.measure_fp64_tflops()
     names = ["element", "gather_residual", "gather_blocks", "boundary_conditions", "spmv", "vector", "dot", "halo"]
-    per_launch = {names[k]: (ms_k[k] / cnt_k[k] if cnt_k[k] else None) for k in range(8)}
+    # per-step device time of each kernel family (a family may launch more than once per step, e.g. the
+    # Aloc and Bext gathers on several ranks)
+    per_launch = {names[k]: (ms_k[k] / args.steps if cnt_k[k] else None) for k in range(8)}
     nn, b2 = 4, 36
     # algorithmic HBM bytes per launch: element kernel reads X/u/conn and writes the staging
     # blocks + residual slots; block gather reads the staging blocks and the plan, writes A once.
