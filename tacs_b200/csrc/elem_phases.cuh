@@ -66,6 +66,17 @@ TB2_HD void mat3mul(const double *A, const double *B, double *C) {
       C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 
+// six consecutive doubles from a 16-byte aligned shared-memory address: three 128-bit loads on the device
+TB2_HD void load6(const double *p, double *o) {
+#if defined(__CUDA_ARCH__)
+  const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1],
+                c = reinterpret_cast<const double2 *>(p)[2];
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y;
+#else
+  for (int k = 0; k < 6; k++) o[k] = p[k];
+#endif
+}
+
 // Local shell frame T = [t1 t2 n] (columns). kind 0: natural transform, which removes the normal
 // component from t1[0] only (the reference repeats one line three times, Transform.h:42-44);
 // kind 1: reference-axis transform with a pre-normalised axis.
@@ -110,7 +121,7 @@ static constexpr int kDescStride = 32;
 // shell work area and phases
 // ------------------------------------------------------------------------------------------
 template <int O, int QC>
-struct ShellWork {
+struct alignas(16) ShellWork {
   using D = ShellDims<O>;
   static constexpr int n = D::n, nd = D::nd, nq = D::nq, nty = D::nty;
   static constexpr int NS = 9;          // strain rows per quadrature point
@@ -125,10 +136,10 @@ struct ShellWork {
   double Bty[nty][nd];
   double T[nq][9], A[nq][9], Az[nq][9];
   double wdet[nq];
-  double W[QC][nty][6];   // tying-point -> strain-row weights of the current chunk (m padded to 6)
+  alignas(16) double W[QC][nty][6];  // tying-point -> strain-row weights of the current chunk (m padded to 6)
   double Cw[QC][24];      // w det C of the current chunk (22 used)
-  double B[QC][NS][nd];   // strain rows of the current chunk; also holds X (start) and rpart (end)
-  double CB[QC][NS][nd];
+  alignas(16) double B[QC][NS][nd];  // strain rows of the current chunk; also holds X (start), rpart (end)
+  alignas(16) double CB[QC][NS][nd];
   TB2_HD double *X() { return &B[0][0][0]; }
   TB2_HD double *rpart() { return &B[0][0][0]; }
 };
@@ -186,12 +197,20 @@ TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab,
   w.Bdr[i][6 * i + 5] = -t12[2];
 }
 
-// phase 2, task ty in [0,nty): tying-strain row (reads fn of every node: runs after phase 1)
+// phase 2, task ty in [0,nty): tying-strain row (reads fn of every node: runs after phase 1).
+// The five strain definitions (Model.h:46-70) are evaluated by one branch-free expression with
+// per-field 0 / 1 / 0.5 coefficients so that the tasks of a team do not diverge:
+//   row_u[c] = p00 d0 X,1[c] + p01 d0 X,2[c] + p10 d1 X,1[c] + p11 d1 X,2[c] + n0[c] (s0 d0 + s1 d1)
+//   row_d[c] = N (t0 X,1[c] + t1 X,2[c])          (d0 = dN/dxi1, d1 = dN/dxi2, X,k = dX/dxi_k)
+// Multiplying by an exact 0 or 1 does not change the rounded value of the surviving term.
 template <int O, int QC>
 TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
   constexpr int n = ShellDims<O>::n;
   const double *X = w.X();
   const int field = shell_ty_field<O>(ty);
+  const double p00 = (field == 0) ? 1.0 : 0.0, p11 = (field == 1) ? 1.0 : 0.0;
+  const double p01 = (field == 2) ? 0.5 : 0.0, p10 = p01;
+  const double s0 = (field == 4) ? 0.5 : 0.0, s1 = (field == 3) ? 0.5 : 0.0;
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
     const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
@@ -204,24 +223,14 @@ TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &ta
   }
   for (int j = 0; j < n; j++) {
     const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
-    double du[3], dd[3] = {0.0, 0.0, 0.0};
+    const double a1 = p00 * d0 + p10 * d1, a2 = p01 * d0 + p11 * d1, an = s0 * d0 + s1 * d1;
+    const double b1 = s0 * N, b2 = s1 * N;  // t0 == s0, t1 == s1
+    double du[3], dd[3], dq[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      if (field == 0) {
-        du[c] = d0 * Xxi[2 * c];
-      } else if (field == 1) {
-        du[c] = d1 * Xxi[2 * c + 1];
-      } else if (field == 2) {
-        du[c] = 0.5 * (d0 * Xxi[2 * c + 1] + d1 * Xxi[2 * c]);
-      } else if (field == 3) {
-        du[c] = 0.5 * n0[c] * d1;
-        dd[c] = 0.5 * N * Xxi[2 * c + 1];
-      } else {
-        du[c] = 0.5 * n0[c] * d0;
-        dd[c] = 0.5 * N * Xxi[2 * c];
-      }
+      du[c] = a1 * Xxi[2 * c] + a2 * Xxi[2 * c + 1] + an * n0[c];
+      dd[c] = b1 * Xxi[2 * c] + b2 * Xxi[2 * c + 1];
     }
-    double dq[3];
     cross3(&w.fn[3 * j], dd, dq);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -275,33 +284,35 @@ TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab
   }
 }
 
-// phase 3a, tasks [0, QC*nty): weights that turn the tying-point strains into the membrane /
-// transverse-shear strain rows at quadrature point q0+ql; tasks [QC*nty, QC*(nty+22)): w det C
+// phase 3a, task (ql, ty): weights that turn the tying-point strains into the membrane /
+// transverse-shear strain rows at quadrature point q0+ql
 //   e0ty(a,b) = sum_cd A(c,a) G(c,d) A(d,b); strain rows fed by e0ty:
 //   m=0: e0 = e0ty(0,0)  m=1: e1 = e0ty(1,1)  m=2: e2 = 2 e0ty(0,1)  m=3: e6 = 2 e0ty(1,2)  m=4: e7 = 2 e0ty(0,2)
 template <int O, int QC>
-TB2_HD void shell_p3_weights(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc) {
+TB2_HD void shell_p3_weights(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
   constexpr int nty = ShellDims<O>::nty;
-  if (task < QC * nty) {
-    const int ql = task / nty, ty = task % nty, q = q0 + ql;
-    const double *A = w.A[q];
-    const int f = shell_ty_field<O>(ty);
-    const int c = (f == 1 || f == 3) ? 1 : 0;  // g11,g12,g13 -> 0 ; g22,g23 -> 1
-    const int d = (f == 0) ? 0 : ((f == 1 || f == 2) ? 1 : 2);
-    const double Nt = tab.Ntq[q][ty];
-#pragma unroll
-    for (int m = 0; m < 5; m++) {
-      const int a = (m == 1 || m == 3) ? 1 : 0;
-      const int b = (m == 0) ? 0 : ((m == 1 || m == 2) ? 1 : 2);
-      double coef = (c == d) ? A[3 * c + a] * A[3 * c + b] : A[3 * c + a] * A[3 * d + b] + A[3 * d + a] * A[3 * c + b];
-      w.W[ql][ty][m] = ((m >= 2) ? 2.0 : 1.0) * Nt * coef;
-    }
-    w.W[ql][ty][5] = 0.0;
-  } else {
-    const int t = task - QC * nty;
-    const int ql = t / 22, k = t % 22;
-    w.Cw[ql][k] = w.wdet[q0 + ql] * desc[k];
-  }
+  const int ql = task / nty, ty = task % nty, q = q0 + ql;
+  const double *A = w.A[q];
+  const int f = shell_ty_field<O>(ty);
+  const int c = (f == 1 || f == 3) ? 1 : 0;  // g11,g12,g13 -> 0 ; g22,g23 -> 1
+  const int d = (f == 0) ? 0 : ((f == 1 || f == 2) ? 1 : 2);
+  const double off = (c == d) ? 0.0 : 1.0;   // off-diagonal tensor components appear twice
+  const double Nt = tab.Ntq[q][ty];
+  const double Ac0 = A[3 * c], Ac1 = A[3 * c + 1], Ac2 = A[3 * c + 2];
+  const double Ad0 = A[3 * d], Ad1 = A[3 * d + 1], Ad2 = A[3 * d + 2];
+  w.W[ql][ty][0] = Nt * (Ac0 * Ad0 + off * (Ad0 * Ac0));
+  w.W[ql][ty][1] = Nt * (Ac1 * Ad1 + off * (Ad1 * Ac1));
+  w.W[ql][ty][2] = 2.0 * Nt * (Ac0 * Ad1 + off * (Ad0 * Ac1));
+  w.W[ql][ty][3] = 2.0 * Nt * (Ac1 * Ad2 + off * (Ad1 * Ac2));
+  w.W[ql][ty][4] = 2.0 * Nt * (Ac0 * Ad2 + off * (Ad0 * Ac2));
+  w.W[ql][ty][5] = 0.0;
+}
+
+// phase 3a (same barrier interval), task (ql, k < 22): w det C
+template <int O, int QC>
+TB2_HD void shell_p3_cw(int task, int q0, ShellWork<O, QC> &w, const double *desc) {
+  const int ql = task / 22, k = task % 22;
+  w.Cw[ql][k] = w.wdet[q0 + ql] * desc[k];
 }
 
 // phase 3b, task (ql, j, c) with c in {0,1,2}: the two columns 6j+c (displacement) and 6j+3+c (rotation)
@@ -318,11 +329,12 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
     double su[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, sq[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int ty = 0; ty < nty; ty++) {
       const double tu = w.Bty[ty][cu], tq = w.Bty[ty][cq];
+      double wt[6];
+      load6(&w.W[ql][ty][0], wt);
 #pragma unroll
       for (int m = 0; m < 5; m++) {
-        const double wt = w.W[ql][ty][m];
-        su[m] += wt * tu;
-        sq[m] += wt * tq;
+        su[m] += wt[m] * tu;
+        sq[m] += wt[m] * tq;
       }
     }
     bu[0] = su[0]; bu[1] = su[1]; bu[2] = su[2]; bu[6] = su[3]; bu[7] = su[4];
@@ -390,10 +402,16 @@ TB2_HD void tile_accumulate(const double *B, const double *CB, int row0, int col
 #pragma unroll 3
   for (int r = 0; r < NROWS; r++) {
     double bi[TR], cj[TC];
+    if (TR == 6 && TC == 6 && LD % 2 == 0) {
+      // rows are 16-byte aligned and the tile starts at a multiple of 6 doubles: 128-bit loads
+      load6(&B[r * LD + row0], bi);
+      load6(&CB[r * LD + col0], cj);
+    } else {
 #pragma unroll
-    for (int a = 0; a < TR; a++) bi[a] = B[r * LD + row0 + a];
+      for (int a = 0; a < TR; a++) bi[a] = B[r * LD + row0 + a];
 #pragma unroll
-    for (int b = 0; b < TC; b++) cj[b] = CB[r * LD + col0 + b];
+      for (int b = 0; b < TC; b++) cj[b] = CB[r * LD + col0 + b];
+    }
 #pragma unroll
     for (int a = 0; a < TR; a++)
 #pragma unroll

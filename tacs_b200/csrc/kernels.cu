@@ -69,9 +69,10 @@ __device__ __forceinline__ void team_sync() {
 // ------------------------------------------------------------------------------------------
 // element kernels
 // ------------------------------------------------------------------------------------------
-// WORK_STRIDE: distance between the work areas of consecutive teams. sizeof(Work) rounded up to 16 bytes
-// plus a skew chosen so that the two teams of a warp hit disjoint shared-memory banks when they read the
-// same field (the tile loop reads 4 distinct 48-byte chunks per team: banks {0,12,24,4}+2a).
+// WORK_STRIDE: distance between the work areas of consecutive teams: sizeof(Work) rounded up to 128 bytes
+// plus a 64-byte skew, so that the two teams of a warp hit disjoint shared-memory banks when they read the
+// same field with 128-bit loads (the tile loop reads 4 distinct 48-byte chunks per team: 16-byte bank
+// groups {0,3,6,1}+k for team 0 and {4,7,2,5}+k for team 1).
 template <int O>
 struct ShellFamily {
   static constexpr int QC = (O == 2) ? 1 : 3;
@@ -81,7 +82,7 @@ struct ShellFamily {
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
   static constexpr int MIN_CTAS = (O == 2) ? 3 : 2;
   static constexpr int BS = 6;
-  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 8;
+  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
 template <int O>
@@ -92,7 +93,7 @@ struct SolidFamily {
   static constexpr int TEAM = (O == 2) ? 16 : 96;
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
   static constexpr int BS = 3;
-  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 8;
+  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
 template <class Work, int BS>
@@ -125,13 +126,51 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
   const long nteams = (long)gridDim.x * TEAMS;
   const long nelem = g.nelem;
   const bool inertia = (g.gamma != 0.0) || (g.ddvars != nullptr);
+  // Software pipeline over elements: the inputs of the next element (node ids -> coordinates, state) are
+  // loaded into registers while the current element is being evaluated, so the dependent global loads
+  // never sit on the critical path of a team.
+  constexpr int NU = (nd + TEAM - 1) / TEAM;
+  double pX = 0.0, pu[NU], pa[NU];
+  int pdesc = 0;
+  auto prefetch = [&](long e) {
+    const int *conn = g.conn + e * n;
+    if (tid < 3 * n) pX = g.Xpts[3 * (long)__ldg(conn + tid / 3) + tid % 3];
+#pragma unroll
+    for (int m = 0; m < NU; m++) {
+      const int kk = tid + m * TEAM;
+      pu[m] = 0.0;
+      pa[m] = 0.0;
+      if (kk < nd) {
+        const long src = 6 * (long)__ldg(conn + kk / 6) + kk % 6;
+        if (g.vars) pu[m] = g.vars[src];
+        if (g.ddvars) pa[m] = g.ddvars[src];
+      }
+    }
+    pdesc = __ldg(g.desc_index + e);
+  };
+  {
+    const long e0 = (long)blockIdx.x * TEAMS + team_in_cta;
+    prefetch(e0 < nelem ? e0 : nelem - 1);
+  }
   // uniform trip count inside a CTA so that barriers are reached by every thread
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
-    const double *desc = g.desc_table + (long)kDescStride * __ldg(g.desc_index + e);
-    team_load<Work, 6>(w, w.X(), g, e, tid, TEAM);
+    const double *desc = g.desc_table + (long)kDescStride * pdesc;
+    if (tid < 3 * n) w.X()[tid] = pX;
+#pragma unroll
+    for (int m = 0; m < NU; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < nd) {
+        w.u[kk] = pu[m];
+        w.acc[kk] = pa[m];
+      }
+    }
     team_sync<TEAM>();
+    {
+      const long en = base + nteams + team_in_cta;
+      prefetch(en < nelem ? en : nelem - 1);
+    }
     for (int t = tid; t < n; t += TEAM) shell_p1_node<O, QC>(t, w, tab, desc);
     team_sync<TEAM>();
     for (int t = tid; t < nty + nq; t += TEAM) {
@@ -145,7 +184,8 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     const bool has_tile = tid < n * n;
     const int ti = tid / n, tj = tid % n;
     for (int q0 = 0; q0 < nq; q0 += QC) {
-      for (int t = tid; t < QC * (nty + 22); t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab, desc);
+      for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
+      for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
       team_sync<TEAM>();
       for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
       team_sync<TEAM>();

@@ -28,7 +28,8 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
   for (int q = 0; q < nq; q++) shell_p2_qgeom<O, QC>(q, *w, tab, desc);
   std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
   for (int q0 = 0; q0 < nq; q0 += QC) {
-    for (int t = 0; t < QC * (nty + 22); t++) shell_p3_weights<O, QC>(t, q0, *w, tab, desc);
+    for (int t = 0; t < QC * nty; t++) shell_p3_weights<O, QC>(t, q0, *w, tab);
+    for (int t = 0; t < QC * 22; t++) shell_p3_cw<O, QC>(t, q0, *w, desc);
     for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
     for (int t = 0; t < WK::ntiles; t++)
       tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
