@@ -132,8 +132,9 @@ struct alignas(16) ShellWork {
   double u[nd];
   double acc[nd];  // second time derivative of the state
   double fn[3 * n];
-  double Bdr[n][nd];
-  double Bty[nty][nd];
+  static constexpr int LDT = nd + 1;  // odd row stride: one-row-per-lane writes hit distinct banks
+  double Bdr[n][LDT];
+  double Bty[nty][LDT];
   double T[nq][9], A[nq][9], Az[nq][9];
   double wdet[nq];
   alignas(16) double W[QC][nty][6];  // tying-point -> strain-row weights of the current chunk (m padded to 6)
@@ -151,7 +152,7 @@ TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab,
   const double *X = w.X();
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
-    const double d0 = tab.dNn[i][j][0], d1 = tab.dNn[i][j][1];
+    const double d0 = tab.dNn_T[j][0][i], d1 = tab.dNn_T[j][1][i];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       Xxi[2 * c] += d0 * X[3 * j + c];
@@ -181,7 +182,7 @@ TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab,
   inv3x3(Xd, Xdinv);
   mat3mul(Xdinv, T, XdinvT);
   for (int j = 0; j < n; j++) {
-    const double d0 = tab.dNn[i][j][0], d1 = tab.dNn[i][j][1];
+    const double d0 = tab.dNn_T[j][0][i], d1 = tab.dNn_T[j][1][i];
     const double g0 = d0 * XdinvT[0] + d1 * XdinvT[3];
     const double g1 = d0 * XdinvT[1] + d1 * XdinvT[4];
 #pragma unroll
@@ -213,7 +214,7 @@ TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &ta
   const double s0 = (field == 4) ? 0.5 : 0.0, s1 = (field == 3) ? 0.5 : 0.0;
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
-    const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
+    const double d0 = tab.dNt_T[j][0][ty], d1 = tab.dNt_T[j][1][ty], N = tab.Nt_T[j][ty];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       Xxi[2 * c] += d0 * X[3 * j + c];
@@ -222,7 +223,7 @@ TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &ta
     }
   }
   for (int j = 0; j < n; j++) {
-    const double d0 = tab.dNt[ty][j][0], d1 = tab.dNt[ty][j][1], N = tab.Nt[ty][j];
+    const double d0 = tab.dNt_T[j][0][ty], d1 = tab.dNt_T[j][1][ty], N = tab.Nt_T[j][ty];
     const double a1 = p00 * d0 + p10 * d1, a2 = p01 * d0 + p11 * d1, an = s0 * d0 + s1 * d1;
     const double b1 = s0 * N, b2 = s1 * N;  // t0 == s0, t1 == s1
     double du[3], dd[3], dq[3];
@@ -248,7 +249,7 @@ TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
   double nxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int j = 0; j < n; j++) {
-    const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
+    const double d0 = tab.dNq_T[j][0][q], d1 = tab.dNq_T[j][1][q], N = tab.Nq_T[j][q];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       Xxi[2 * c] += d0 * X[3 * j + c];

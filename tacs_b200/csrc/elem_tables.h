@@ -51,6 +51,11 @@ struct alignas(16) ShellTables {
   double Nt[D::nty][D::n];       // shape functions at tying points
   double dNt[D::nty][D::n][2];   // derivatives at tying points
   double Ntq[D::nq][D::nty];     // tying-strain interpolation evaluated at quadrature points
+  // transposed copies for the phases whose tasks are "one lane per tying point / node / quadrature point":
+  // the lane index is the fastest dimension, so a team's loads hit consecutive shared-memory banks
+  double Nt_T[D::n][D::nty], dNt_T[D::n][2][D::nty];
+  double dNn_T[D::n][2][D::n];   // [j][k][i] = dNn[i][j][k]
+  double Nq_T[D::n][D::nq], dNq_T[D::n][2][D::nq];
 };
 
 template <int O>
@@ -157,6 +162,22 @@ inline void build_shell_tables(ShellTables<O> &t) {
     else if (f == 1 || f == 3) { pt[0] = full[ty % O]; pt[1] = red[ty / O]; }
     else { pt[0] = red[ty % (O - 1)]; pt[1] = red[ty / (O - 1)]; }
     shape2d<O>(pt, t.Nt[index], t.dNt[index]);
+  }
+  for (int j = 0; j < D::n; j++) {
+    for (int ty = 0; ty < D::nty; ty++) {
+      t.Nt_T[j][ty] = t.Nt[ty][j];
+      t.dNt_T[j][0][ty] = t.dNt[ty][j][0];
+      t.dNt_T[j][1][ty] = t.dNt[ty][j][1];
+    }
+    for (int i = 0; i < D::n; i++) {
+      t.dNn_T[j][0][i] = t.dNn[i][j][0];
+      t.dNn_T[j][1][i] = t.dNn[i][j][1];
+    }
+    for (int q = 0; q < D::nq; q++) {
+      t.Nq_T[j][q] = t.Nq[q][j];
+      t.dNq_T[j][0][q] = t.dNq[q][j][0];
+      t.dNq_T[j][1][q] = t.dNq[q][j][1];
+    }
   }
 }
 
