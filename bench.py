@@ -148,24 +148,61 @@ def time_reference(nx, ny, steps, warmup):
                 spmv_gbs=spmv_bytes(bs, nrows, nnzb) / dts * 1e-9, ynorm=y.norm())
 
 
+def time_reference_mpi(nx, ny, nranks, reps):
+    """The reference's MPI path: N ranks (one per host core) through TACSCreator + METIS, run by
+    oracle/_ref/ref_driver over the forked-rank MPI stand-in (no mpirun in this image)."""
+    from oracle import ref_mpi
+    from tacs_b200 import meshgen
+
+    mesh = meshgen.plate(2, nx, ny)
+    summary, _, _ = ref_mpi.run(mesh, 1, 0, nranks, reps=reps, timeout=1500, load=False)
+    return summary
+
+
+def best_cpu_baseline(n, steps, warmup):
+    """Fastest of the reference's two CPU parallel modes on this box: pthreads (<= 16) and MPI ranks."""
+    cores = host_threads()
+    r = time_reference(n, n, steps, warmup)
+    best = {"value": r["elements"] / r["seconds_per_step"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+            "sample": f"{n}x{n} Quad4 plate ({r['elements']} elements per step), assembleJacobian(1,0,0), "
+                      f"oracle/_ref, 1 rank x {r['threads']} pthreads (setNumThreads)",
+            "spmv_gbs": r["spmv_gbs"], "seconds_per_step": r["seconds_per_step"]}
+    try:
+        from oracle import ref_mpi
+
+        if ref_mpi.available() and cores > 1:
+            nranks = min(cores, 64)
+            m = time_reference_mpi(n, n, nranks, max(steps, 2))
+            if m and m["elements_per_s"] > best["value"]:
+                best = {"value": m["elements_per_s"], "unit": UNIT, "cores": nranks, "kind": "reference",
+                        "sample": f"{n}x{n} Quad4 plate ({m['elements']} elements per step), assembleJacobian(1,0,0), "
+                                  f"oracle/_ref ref_driver, {nranks} MPI ranks (forked-rank stand-in, METIS partition)",
+                        "spmv_gbs": None, "seconds_per_step": m["jac_s"],
+                        "pthreads_value": best["value"], "pthreads_cores": best["cores"]}
+            else:
+                best["mpi_value"] = m["elements_per_s"] if m else None
+                best["mpi_ranks"] = nranks
+    except Exception as exc:
+        best["mpi_error"] = str(exc)[:200]
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     nx = ny = args.ref_n
-    r = time_reference(nx, ny, args.steps, args.warmup)
-    value = r["elements"] / r["seconds_per_step"]
+    cpu = best_cpu_baseline(nx, args.steps, args.warmup)
+    value = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": cpu["seconds_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic 1000x1000 Quad4Shell plate (BASELINE configs[1])",
-                   "sample": f"{nx}x{ny} Quad4 plate of the same generator ({r['elements']} elements per step)",
+                   "sample": f"{nx}x{ny} Quad4 plate of the same generator ({nx * ny} elements per step)",
                    "timing": "host wall clock"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference",
-                         "sample": f"{nx}x{ny} Quad4 plate, assembleJacobian(1,0,0), reference pthreads "
-                                   f"(setNumThreads({r['threads']}))"},
-        "spmv": {"gbs": r["spmv_gbs"]},
+        "cpu_baseline": cpu,
+        "spmv": {"gbs": cpu.get("spmv_gbs")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -318,12 +355,7 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = time_reference(args.ref_n, args.ref_n, 2, 1)
-            cpu = {"value": r["elements"] / r["seconds_per_step"], "unit": UNIT, "cores": r["threads"],
-                   "kind": "reference",
-                   "sample": f"{args.ref_n}x{args.ref_n} Quad4 plate ({r['elements']} elements), "
-                             f"assembleJacobian(1,0,0), oracle/_ref with setNumThreads({r['threads']})",
-                   "spmv_gbs": r["spmv_gbs"]}
+            cpu = best_cpu_baseline(args.ref_n, 2, 1)
         except Exception as exc:  # the reference build did not travel
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {exc}"}
 

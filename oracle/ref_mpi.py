@@ -1,5 +1,5 @@
 """Run the unmodified reference on N ranks (oracle/_ref/ref_driver over oracle/mpistub/mpi_procs.c) and
-load what every rank dumped -- test infrastructure."""
+load what every rank dumped -- test infrastructure (used by tests/ and by bench.py's CPU-baseline legs)."""
 import json
 import os
 import subprocess
@@ -19,7 +19,7 @@ def available():
     return os.path.exists(DRIVER)
 
 
-def run(mesh, kind, con_kind, nranks, reps=0, timeout=900):
+def run(mesh, kind, con_kind, nranks, reps=0, timeout=900, load=True):
     """Returns (summary dict, per-rank dict of arrays, root arrays new_nodes/partition)."""
     with tempfile.TemporaryDirectory() as tmp:
         ind, outd = os.path.join(tmp, "in"), os.path.join(tmp, "out")
@@ -43,13 +43,13 @@ def run(mesh, kind, con_kind, nranks, reps=0, timeout=900):
             if line.startswith("{"):
                 summary = json.loads(line)
         ranks = []
-        for r in range(nranks):
+        for r in range(nranks if load else 0):
             d = {}
             for name in INT_ARRAYS:
                 d[name] = np.fromfile(os.path.join(outd, f"r{r}_{name}.bin"), dtype=np.int32)
             for name in F64_ARRAYS:
                 d[name] = np.fromfile(os.path.join(outd, f"r{r}_{name}.bin"), dtype=np.float64)
             ranks.append(d)
-        root = dict(new_nodes=np.fromfile(os.path.join(outd, "r0_new_nodes.bin"), dtype=np.int32),
+        root = None if not load else dict(new_nodes=np.fromfile(os.path.join(outd, "r0_new_nodes.bin"), dtype=np.int32),
                     partition=np.fromfile(os.path.join(outd, "r0_partition.bin"), dtype=np.int32))
     return summary, ranks, root

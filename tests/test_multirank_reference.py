@@ -7,7 +7,8 @@ A, residual and A*x are compared with the serial oracle in the same numbering (1
 import numpy as np
 import pytest
 
-from tests import oracle_port, ref_mpi
+from oracle import ref_mpi
+from tests import oracle_port
 from tests.test_distributed_plan import CASES, build_plans
 
 CON_KIND = {"quad4_plate": 0, "hex8_cube": 2, "quad9_cylinder": 1}
