@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Strong-scaling run of the n^3 hex8 solid (BASELINE configs[3]: 200^3, 24M dof) on WORLD_SIZE GPUs.
 
-    python -m torch.distributed.run --nproc-per-node N scripts/scale_hex.py --n 200 [--part metis|blocks]
+    python -m torch.distributed.run --nproc-per-node N scripts/scale_hex.py --edge 200 [--part metis|blocks]
 
 Prints one JSON line (rank 0): aggregate elements/s of assembleJacobian(1,0,0,res,A), SpMV time and
 aggregate GB/s, and the set-up times. Device timing with CUDA events, max over ranks.
@@ -29,7 +29,7 @@ def block_partition(n, parts):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=200)
+    ap.add_argument("--edge", type=int, default=200)
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--part", default="metis")
@@ -57,9 +57,9 @@ def main():
         buf = t.cpu().numpy().copy()
         assert lib.comm_init(rank, world, buf.ctypes.data_as(binding.UP)) == 0
     t0 = time.time()
-    mesh = meshgen.cube(args.order, args.n)
+    mesh = meshgen.cube(args.order, args.edge)
     t1 = time.time()
-    part = block_partition(args.n, world) if (args.part == "blocks" and world > 1) else None
+    part = block_partition(args.edge, world) if (args.part == "blocks" and world > 1) else None
     creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.solid_element(T, lib, args.order)], part=part,
                                        split_size=world if part is not None else 0)
     t2 = time.time()
@@ -100,10 +100,10 @@ def main():
     bsB = A.getSizes(1)
     bytes_local = (bsA[3] + bsB[3]) * (8 * 9 + 4) + 4 * (bsA[1] + 1) + 16 * 3 * bsA[1]
     bytes_total = sumr(float(bytes_local))
-    ne_total = args.n ** 3
+    ne_total = args.edge ** 3
     ynorm = y.norm()
     s = asm.getNumElements()
-    out = dict(workload=f"{args.n}^3 hex{8 if args.order == 2 else 27} solid", n_gpus=world, partition=args.part if world > 1 else "single",
+    out = dict(workload=f"{args.edge}^3 hex{8 if args.order == 2 else 27} solid", n_gpus=world, partition=args.part if world > 1 else "single",
                elements=ne_total, local_elements_rank0=s, jac_ms=ms, elements_per_s=ne_total / ms * 1e3,
                spmv_ms=ms_sp, spmv_gbs_aggregate=bytes_total / ms_sp * 1e-6, ynorm=ynorm,
                setup_s=dict(mesh=t1 - t0, create_tacs=t2 - t1, create_mat=t3 - t2),

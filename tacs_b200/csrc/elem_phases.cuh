@@ -318,7 +318,7 @@ TB2_HD void shell_p3_cw(int task, int q0, ShellWork<O, QC> &w, const double *des
 
 // phase 3b, task (ql, j, c) with c in {0,1,2}: the two columns 6j+c (displacement) and 6j+3+c (rotation)
 // of the nine strain rows B and of CB = w det C B at quadrature point q0+ql
-template <int O, int QC>
+template <int O, int QC, bool WITH_CB = true>
 TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
   constexpr int n = ShellDims<O>::n, nty = ShellDims<O>::nty;
   const int c = task % 3, j = (task / 3) % n, ql = task / (3 * n);
@@ -368,6 +368,14 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
     bu[8] = su;
     bq[8] = sq;
   }
+  if (!WITH_CB) {
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      w.B[ql][r][cu] = bu[r];
+      w.B[ql][r][cq] = bq[r];
+    }
+    return;
+  }
   // CB = (w det C) B, C = [A B 0; B D 0; 0 0 As | drill], symmetric 3x3 blocks packed [0 1 2; 1 3 4; 2 4 5]
   const double *C = w.Cw[ql];
   double cbu[9], cbq[9];
@@ -395,6 +403,40 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
     w.CB[ql][r][cu] = cbu[r];
     w.CB[ql][r][cq] = cbq[r];
   }
+}
+
+// residual-only path (assembleRes): strains of the chunk, task (ql, r): e = B u, kept in the unused CB rows
+template <int O, int QC>
+TB2_HD void shell_res_strain(int task, ShellWork<O, QC> &w) {
+  constexpr int nd = ShellDims<O>::nd;
+  const int ql = task / 9, r = task % 9;
+  double e = 0.0;
+  for (int k = 0; k < nd; k++) e += w.B[ql][r][k] * w.u[k];
+  w.CB[ql][0][r] = e;
+}
+
+// residual-only path, task dof k: returns sum_ql sum_r B[ql][r][k] * (w det C e)[r]
+template <int O, int QC>
+TB2_HD double shell_res_accumulate(int k, ShellWork<O, QC> &w) {
+  double out = 0.0;
+  for (int ql = 0; ql < QC; ql++) {
+    const double *C = w.Cw[ql], *e = &w.CB[ql][0][0];
+    double s[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
+                i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
+      s[r] = C[i0] * e[0] + C[i1] * e[1] + C[i2] * e[2] + C[6 + i0] * e[3] + C[6 + i1] * e[4] + C[6 + i2] * e[5];
+      s[3 + r] = C[6 + i0] * e[0] + C[6 + i1] * e[1] + C[6 + i2] * e[2] + C[12 + i0] * e[3] + C[12 + i1] * e[4] +
+                 C[12 + i2] * e[5];
+    }
+    s[6] = C[18] * e[6] + C[19] * e[7];
+    s[7] = C[19] * e[6] + C[20] * e[7];
+    s[8] = C[21] * e[8];
+#pragma unroll
+    for (int r = 0; r < 9; r++) out += w.B[ql][r][k] * s[r];
+  }
+  return out;
 }
 
 // phase 5 (all families): one TRxTC tile of K accumulates B^T (CB) over the rows of this chunk
@@ -544,6 +586,27 @@ TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTab
       for (int k = 0; k < 6; k++) s += C[idx[r][k]] * Ba[k][c];
       w.CB[ql][r][3 * a + c] = wd * s;
     }
+}
+
+// residual-only path (assembleRes), task (ql, r): e = B u, staged in rpart (free until phase 6)
+template <int O, int QC>
+TB2_HD void solid_res_strain(int task, SolidWork<O, QC> &w) {
+  constexpr int nd = SolidDims<O>::nd;
+  const int ql = task / 6, r = task % 6;
+  double e = 0.0;
+  for (int k = 0; k < nd; k++) e += w.B[ql][r][k] * w.u[k];
+  (&w.rpart[0][0])[6 * ql + r] = e;
+}
+
+// residual-only path, task dof k: sum_ql sum_r (w det C B)[ql][r][k] e[ql][r]   (C symmetric)
+template <int O, int QC>
+TB2_HD double solid_res_accumulate(int k, SolidWork<O, QC> &w) {
+  const double *e = &w.rpart[0][0];
+  double out = 0.0;
+  for (int ql = 0; ql < QC; ql++)
+#pragma unroll
+    for (int r = 0; r < 6; r++) out += w.CB[ql][r][k] * e[6 * ql + r];
+  return out;
 }
 
 // phase 6, task tile: residual partials, consistent mass block (only when `inertia`);

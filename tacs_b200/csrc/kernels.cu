@@ -183,31 +183,72 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     for (int k = 0; k < 36; k++) acc[k] = 0.0;
     const bool has_tile = tid < n * n;
     const int ti = tid / n, tj = tid % n;
-    for (int q0 = 0; q0 < nq; q0 += QC) {
-      for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
-      for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
-      team_sync<TEAM>();
-      for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
-      team_sync<TEAM>();
-      if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
-      team_sync<TEAM>();
-    }
-    if (has_tile) {
-      shell_p6_finish<O, QC>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, w.rpart() + 6 * tid);
-      if (live && g.Ke) {
-        double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
-#pragma unroll
-        for (int k = 0; k < 18; k++) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+    if (g.Ke) {
+      for (int q0 = 0; q0 < nq; q0 += QC) {
+        for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
+        for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
+        team_sync<TEAM>();
+        for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
+        team_sync<TEAM>();
+        if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
+        team_sync<TEAM>();
       }
-    }
-    team_sync<TEAM>();
-    if (live && g.Re) {
-      const double *rp = w.rpart();
-      for (int k = tid; k < nd; k += TEAM) {
-        const int i = k / 6, a = k % 6;
-        double s = 0.0;
-        for (int j = 0; j < n; j++) s += rp[(i * n + j) * 6 + a];
-        g.Re[e * nd + k] = s;
+      if (has_tile) {
+        shell_p6_finish<O, QC>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, w.rpart() + 6 * tid);
+        if (live) {
+          double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
+#pragma unroll
+          for (int k = 0; k < 18; k++) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+        }
+      }
+      team_sync<TEAM>();
+      if (live && g.Re) {
+        const double *rp = w.rpart();
+        for (int k = tid; k < nd; k += TEAM) {
+          const int i = k / 6, a = k % 6;
+          double s = 0.0;
+          for (int j = 0; j < n; j++) s += rp[(i * n + j) * 6 + a];
+          g.Re[e * nd + k] = s;
+        }
+      }
+    } else {
+      // residual only (assembleRes): res = sum_q B^T (w det C) B u, no tangent tiles
+      double racc[NU];
+#pragma unroll
+      for (int m = 0; m < NU; m++) racc[m] = 0.0;
+      for (int q0 = 0; q0 < nq; q0 += QC) {
+        for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
+        for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
+        team_sync<TEAM>();
+        for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC, false>(t, q0, w, tab);
+        team_sync<TEAM>();
+        for (int t = tid; t < QC * 9; t += TEAM) shell_res_strain<O, QC>(t, w);
+        team_sync<TEAM>();
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) racc[m] += shell_res_accumulate<O, QC>(kk, w);
+        }
+        team_sync<TEAM>();
+      }
+      if (inertia) {
+        if (has_tile) shell_p6_finish<O, QC>(tid, w, tab, desc, 0.0, 0.0, true, acc, w.rpart() + 6 * tid);
+        team_sync<TEAM>();
+      }
+      if (live && g.Re) {
+        const double *rp = w.rpart();
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) {
+            double s = racc[m];
+            if (inertia) {
+              const int i = kk / 6, a = kk % 6;
+              for (int j = 0; j < n; j++) s += rp[(i * n + j) * 6 + a];
+            }
+            g.Re[e * nd + kk] = s;
+          }
+        }
       }
     }
     team_sync<TEAM>();
@@ -249,37 +290,74 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
     for (int k = 0; k < TR * TC; k++) acc[k] = 0.0;
     const bool has_tile = tid < ntiles;
     const int ti = tid / ntc, tj = tid % ntc;
-    for (int q0 = 0; q0 < nq; q0 += QC) {
-      for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
-      team_sync<TEAM>();
-      if (has_tile)
-        tile_accumulate<QC * 6, nd, TR, TC>(&w.B[0][0][0], &w.CB[0][0][0], TR * ti, TC * tj, acc);
-      team_sync<TEAM>();
-    }
-    if (has_tile) {
-      solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, inertia, acc);
-      if (live && g.Ke) {
-        // the tile covers (TR/3)x(TC/3) node pairs; staging is node-pair-major, 3x3 row-major inside
-#pragma unroll
-        for (int an = 0; an < TR / 3; an++)
-#pragma unroll
-          for (int bn = 0; bn < TC / 3; bn++) {
-            const long na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
-            double *dst = g.Ke + ((e * n + na) * n + nb) * 9;
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-              for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
-          }
+    if (g.Ke) {
+      for (int q0 = 0; q0 < nq; q0 += QC) {
+        for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
+        team_sync<TEAM>();
+        if (has_tile)
+          tile_accumulate<QC * 6, nd, TR, TC>(&w.B[0][0][0], &w.CB[0][0][0], TR * ti, TC * tj, acc);
+        team_sync<TEAM>();
       }
-    }
-    team_sync<TEAM>();
-    if (live && g.Re) {
-      for (int k = tid; k < nd; k += TEAM) {
-        const int ri = k / TR, a = k % TR;
-        double s = 0.0;
-        for (int j = 0; j < ntc; j++) s += w.rpart[ri * ntc + j][a];
-        g.Re[e * nd + k] = s;
+      if (has_tile) {
+        solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, inertia, acc);
+        if (live) {
+          // the tile covers (TR/3)x(TC/3) node pairs; staging is node-pair-major, 3x3 row-major inside
+#pragma unroll
+          for (int an = 0; an < TR / 3; an++)
+#pragma unroll
+            for (int bn = 0; bn < TC / 3; bn++) {
+              const long na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
+              double *dst = g.Ke + ((e * n + na) * n + nb) * 9;
+#pragma unroll
+              for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+            }
+        }
+      }
+      team_sync<TEAM>();
+      if (live && g.Re) {
+        for (int k = tid; k < nd; k += TEAM) {
+          const int ri = k / TR, a = k % TR;
+          double s = 0.0;
+          for (int j = 0; j < ntc; j++) s += w.rpart[ri * ntc + j][a];
+          g.Re[e * nd + k] = s;
+        }
+      }
+    } else {
+      constexpr int NU = (nd + TEAM - 1) / TEAM;
+      double racc[NU];
+#pragma unroll
+      for (int m = 0; m < NU; m++) racc[m] = 0.0;
+      for (int q0 = 0; q0 < nq; q0 += QC) {
+        for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
+        team_sync<TEAM>();
+        for (int t = tid; t < QC * 6; t += TEAM) solid_res_strain<O, QC>(t, w);
+        team_sync<TEAM>();
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) racc[m] += solid_res_accumulate<O, QC>(kk, w);
+        }
+        team_sync<TEAM>();
+      }
+      if (inertia) {
+        if (has_tile) solid_p6_finish<O, QC>(tid, w, tab, 0.0, 0.0, true, acc);
+        team_sync<TEAM>();
+      }
+      if (live && g.Re) {
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) {
+            double s = racc[m];
+            if (inertia) {
+              const int ri = kk / TR, a = kk % TR;
+              for (int j = 0; j < ntc; j++) s += w.rpart[ri * ntc + j][a];
+            }
+            g.Re[e * nd + kk] = s;
+          }
+        }
       }
     }
     team_sync<TEAM>();
