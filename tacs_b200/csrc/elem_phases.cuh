@@ -131,6 +131,7 @@ struct alignas(16) ShellWork {
   static_assert(ntiles * 6 <= QC * NS * nd, "residual partials are staged in the B rows");
   double u[nd];
   double acc[nd];  // second time derivative of the state
+  double desc[kDescStride];  // descriptor row of this element (constitutive constants, transform)
   double fn[3 * n];
   static constexpr int LDT = nd + 1;  // odd row stride: one-row-per-lane writes hit distinct banks
   double Bdr[n][LDT];
@@ -328,7 +329,16 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
   // rows 0,1,2,6,7: tying-strain rows combined with the weights of this quadrature point
   {
     double su[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, sq[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int ty = 0; ty < nty; ty++) {
+    // the g11, g22, g12 tying strains do not involve the director: their rotation columns are exactly zero
+    constexpr int nmem = ShellDims<O>::c11 + ShellDims<O>::c22 + ShellDims<O>::c12;
+    for (int ty = 0; ty < nmem; ty++) {
+      const double tu = w.Bty[ty][cu];
+      double wt[6];
+      load6(&w.W[ql][ty][0], wt);
+#pragma unroll
+      for (int m = 0; m < 5; m++) su[m] += wt[m] * tu;
+    }
+    for (int ty = nmem; ty < nty; ty++) {
       const double tu = w.Bty[ty][cu], tq = w.Bty[ty][cq];
       double wt[6];
       load6(&w.W[ql][ty][0], wt);
@@ -568,24 +578,27 @@ TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTab
   const double gx = x0 * J[0] + x1 * J[3] + x2 * J[6];
   const double gy = x0 * J[1] + x1 * J[4] + x2 * J[7];
   const double gz = x0 * J[2] + x1 * J[5] + x2 * J[8];
-  // strain order xx,yy,zz,yz,xz,xy with engineering shears (TACSLinearElasticity.cpp:1186-1192)
-  const double Ba[6][3] = {{gx, 0.0, 0.0}, {0.0, gy, 0.0}, {0.0, 0.0, gz},
-                           {0.0, gz, gy},  {gz, 0.0, gx},  {gy, gx, 0.0}};
+  // strain order xx,yy,zz,yz,xz,xy with engineering shears (TACSLinearElasticity.cpp:1186-1192):
+  //   column x: (gx,0,0,0,gz,gy)   column y: (0,gy,0,gz,0,gx)   column z: (0,0,gz,gy,gx,0)
   const double *C = w.desc;
   // symmetric 6x6 from the upper triangle stored by rows
   const int idx[6][6] = {{0, 1, 2, 3, 4, 5},     {1, 6, 7, 8, 9, 10},    {2, 7, 11, 12, 13, 14},
                          {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
   const double wd = w.wdet[q];
+  const int c0 = 3 * a;
+  w.B[ql][0][c0] = gx;  w.B[ql][0][c0 + 1] = 0.0; w.B[ql][0][c0 + 2] = 0.0;
+  w.B[ql][1][c0] = 0.0; w.B[ql][1][c0 + 1] = gy;  w.B[ql][1][c0 + 2] = 0.0;
+  w.B[ql][2][c0] = 0.0; w.B[ql][2][c0 + 1] = 0.0; w.B[ql][2][c0 + 2] = gz;
+  w.B[ql][3][c0] = 0.0; w.B[ql][3][c0 + 1] = gz;  w.B[ql][3][c0 + 2] = gy;
+  w.B[ql][4][c0] = gz;  w.B[ql][4][c0 + 1] = 0.0; w.B[ql][4][c0 + 2] = gx;
+  w.B[ql][5][c0] = gy;  w.B[ql][5][c0 + 1] = gx;  w.B[ql][5][c0 + 2] = 0.0;
 #pragma unroll
-  for (int r = 0; r < 6; r++)
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      w.B[ql][r][3 * a + c] = Ba[r][c];
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 6; k++) s += C[idx[r][k]] * Ba[k][c];
-      w.CB[ql][r][3 * a + c] = wd * s;
-    }
+  for (int r = 0; r < 6; r++) {
+    // only the three structurally non-zero strain entries of each displacement column contribute
+    w.CB[ql][r][c0] = wd * (C[idx[r][0]] * gx + C[idx[r][4]] * gz + C[idx[r][5]] * gy);
+    w.CB[ql][r][c0 + 1] = wd * (C[idx[r][1]] * gy + C[idx[r][3]] * gz + C[idx[r][5]] * gx);
+    w.CB[ql][r][c0 + 2] = wd * (C[idx[r][2]] * gz + C[idx[r][3]] * gy + C[idx[r][4]] * gx);
+  }
 }
 
 // residual-only path (assembleRes), task (ql, r): e = B u, staged in rpart (free until phase 6)

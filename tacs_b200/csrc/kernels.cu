@@ -130,34 +130,60 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
   // loaded into registers while the current element is being evaluated, so the dependent global loads
   // never sit on the critical path of a team.
   constexpr int NU = (nd + TEAM - 1) / TEAM;
-  double pX = 0.0, pu[NU], pa[NU];
-  int pdesc = 0;
-  auto prefetch = [&](long e) {
+  constexpr int ND = (kDescStride + TEAM - 1) / TEAM;
+  double pX = 0.0, pu[NU], pa[NU], pd[ND];
+  // two-deep pipeline: node ids / descriptor index of the element after next, data of the next element.
+  // The data loads of iteration i use ids that were requested in iteration i-1, so no load ever waits for
+  // the address it depends on.
+  int cX = 0, cU[NU], cD = 0;
+  auto prefetch_ids = [&](long e) {
     const int *conn = g.conn + e * n;
-    if (tid < 3 * n) pX = g.Xpts[3 * (long)__ldg(conn + tid / 3) + tid % 3];
+    if (tid < 3 * n) cX = __ldg(conn + tid / 3);
+#pragma unroll
+    for (int m = 0; m < NU; m++) {
+      const int kk = tid + m * TEAM;
+      cU[m] = kk < nd ? __ldg(conn + kk / 6) : 0;
+    }
+    cD = __ldg(g.desc_index + e);
+  };
+  auto prefetch_data = [&]() {
+    if (tid < 3 * n) pX = g.Xpts[3 * (long)cX + tid % 3];
 #pragma unroll
     for (int m = 0; m < NU; m++) {
       const int kk = tid + m * TEAM;
       pu[m] = 0.0;
       pa[m] = 0.0;
       if (kk < nd) {
-        const long src = 6 * (long)__ldg(conn + kk / 6) + kk % 6;
+        const long src = 6 * (long)cU[m] + kk % 6;
         if (g.vars) pu[m] = g.vars[src];
         if (g.ddvars) pa[m] = g.ddvars[src];
       }
     }
-    pdesc = __ldg(g.desc_index + e);
+    const double *drow = g.desc_table + (long)kDescStride * cD;
+#pragma unroll
+    for (int m = 0; m < ND; m++) {
+      const int kk = tid + m * TEAM;
+      pd[m] = kk < kDescStride ? __ldg(drow + kk) : 0.0;
+    }
   };
+  auto clamp_elem = [&](long e) { return e < nelem ? e : nelem - 1; };
   {
     const long e0 = (long)blockIdx.x * TEAMS + team_in_cta;
-    prefetch(e0 < nelem ? e0 : nelem - 1);
+    prefetch_ids(clamp_elem(e0));
+    prefetch_data();
+    prefetch_ids(clamp_elem(e0 + nteams));
   }
   // uniform trip count inside a CTA so that barriers are reached by every thread
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
-    const double *desc = g.desc_table + (long)kDescStride * pdesc;
+    const double *desc = w.desc;
     if (tid < 3 * n) w.X()[tid] = pX;
+#pragma unroll
+    for (int m = 0; m < ND; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < kDescStride) w.desc[kk] = pd[m];
+    }
 #pragma unroll
     for (int m = 0; m < NU; m++) {
       const int kk = tid + m * TEAM;
@@ -167,10 +193,8 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
       }
     }
     team_sync<TEAM>();
-    {
-      const long en = base + nteams + team_in_cta;
-      prefetch(en < nelem ? en : nelem - 1);
-    }
+    prefetch_data();                                               // next element (ids already here)
+    prefetch_ids(clamp_elem(base + 2 * nteams + team_in_cta));     // element after next
     for (int t = tid; t < n; t += TEAM) shell_p1_node<O, QC>(t, w, tab, desc);
     team_sync<TEAM>();
     for (int t = tid; t < nty + nq; t += TEAM) {
@@ -274,15 +298,81 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
   const bool inertia = (g.gamma != 0.0) || (g.ddvars != nullptr);
   const long nteams = (long)gridDim.x * TEAMS;
   const long nelem = g.nelem;
+  // two-deep input pipeline (see shell_element_kernel)
+  constexpr int NX = (3 * n + TEAM - 1) / TEAM;
+  constexpr int NUI = (nd + TEAM - 1) / TEAM;
+  constexpr int NDI = (kDescStride + TEAM - 1) / TEAM;
+  double pX[NX], pu[NUI], pa[NUI], pd[NDI];
+  int cX[NX], cU[NUI], cD = 0;
+  auto prefetch_ids = [&](long e) {
+    const int *conn = g.conn + e * n;
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+      const int kk = tid + m * TEAM;
+      cX[m] = kk < 3 * n ? __ldg(conn + kk / 3) : 0;
+    }
+#pragma unroll
+    for (int m = 0; m < NUI; m++) {
+      const int kk = tid + m * TEAM;
+      cU[m] = kk < nd ? __ldg(conn + kk / 3) : 0;
+    }
+    cD = __ldg(g.desc_index + e);
+  };
+  auto prefetch_data = [&]() {
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+      const int kk = tid + m * TEAM;
+      pX[m] = kk < 3 * n ? g.Xpts[3 * (long)cX[m] + kk % 3] : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < NUI; m++) {
+      const int kk = tid + m * TEAM;
+      pu[m] = 0.0;
+      pa[m] = 0.0;
+      if (kk < nd) {
+        const long src = 3 * (long)cU[m] + kk % 3;
+        if (g.vars) pu[m] = g.vars[src];
+        if (g.ddvars) pa[m] = g.ddvars[src];
+      }
+    }
+    const double *drow = g.desc_table + (long)kDescStride * cD;
+#pragma unroll
+    for (int m = 0; m < NDI; m++) {
+      const int kk = tid + m * TEAM;
+      pd[m] = kk < kDescStride ? __ldg(drow + kk) : 0.0;
+    }
+  };
+  auto clamp_elem = [&](long e) { return e < nelem ? e : nelem - 1; };
+  {
+    const long e0 = (long)blockIdx.x * TEAMS + team_in_cta;
+    prefetch_ids(clamp_elem(e0));
+    prefetch_data();
+    prefetch_ids(clamp_elem(e0 + nteams));
+  }
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
-    team_load<Work, 3>(w, w.X, g, e, tid, TEAM);
-    {
-      const double *d = g.desc_table + (long)kDescStride * g.desc_index[e];
-      for (int k = tid; k < kDescStride; k += TEAM) w.desc[k] = d[k];
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < 3 * n) w.X[kk] = pX[m];
+    }
+#pragma unroll
+    for (int m = 0; m < NUI; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < nd) {
+        w.u[kk] = pu[m];
+        w.acc[kk] = pa[m];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < NDI; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < kDescStride) w.desc[kk] = pd[m];
     }
     team_sync<TEAM>();
+    prefetch_data();
+    prefetch_ids(clamp_elem(base + 2 * nteams + team_in_cta));
     for (int t = tid; t < nq; t += TEAM) solid_p1_qgeom<O, QC>(t, w, tab);
     team_sync<TEAM>();
     double acc[TR * TC];
