@@ -335,7 +335,7 @@ def run_b200(args):
                                 "microbenchmark (tacsb200_measure_fp64_tflops)"})
     if per_launch["gather_blocks"]:
         t = per_launch["gather_blocks"] * 1e-3
-        kernels.append({"kernel": "gather_blocks_kernel<36>", "ms": per_launch["gather_blocks"], "bound": "hbm",
+        kernels.append({"kernel": "gather_blocks36_kernel", "ms": per_launch["gather_blocks"], "bound": "hbm",
                         "achieved": gather_bytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s"})
     for k in kernels:
         k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None

@@ -516,8 +516,9 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
 // One thread per scalar entry of a block; the threads of a block read consecutive staging
 // addresses (coalesced) and every block is written exactly once.
 template <int B2>
-__global__ void gather_blocks_kernel(long nblocks, const int *__restrict__ ptr, const int *__restrict__ src,
-                                     const double *__restrict__ Ke, double *__restrict__ A) {
+__global__ void __launch_bounds__(256) gather_blocks_kernel(long nblocks, const int *__restrict__ ptr,
+                                                           const int *__restrict__ src, const double *__restrict__ Ke,
+                                                           double *__restrict__ A) {
   const long total = nblocks * B2;
   for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
     const long b = g / B2;
@@ -525,6 +526,43 @@ __global__ void gather_blocks_kernel(long nblocks, const int *__restrict__ ptr, 
     const int beg = ptr[b], end = ptr[b + 1];
     double s = 0.0;
     for (int k = beg; k < end; k++) s += Ke[(long)src[k] * B2 + entry];
+    A[g] = s;
+  }
+}
+
+// 6x6 blocks: one thread per pair of entries (128-bit accesses); the slot indices and then the values of up
+// to four contributions are requested before any of them is consumed (memory-level parallelism), and the
+// sum is still formed in ascending element order.
+__global__ void __launch_bounds__(256) gather_blocks36_kernel(long nblocks, const int *__restrict__ ptr,
+                                                             const int *__restrict__ src,
+                                                             const double2 *__restrict__ Ke, double2 *__restrict__ A) {
+  const long total = nblocks * 18;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long b = g / 18;
+    const int entry = (int)(g - b * 18);
+    const int beg = __ldg(ptr + b), end = __ldg(ptr + b + 1);
+    double2 s = make_double2(0.0, 0.0);
+    int k = beg;
+    for (; k + 4 <= end; k += 4) {
+      const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1), s2 = __ldg(src + k + 2), s3 = __ldg(src + k + 3);
+      const double2 v0 = __ldg(Ke + (long)s0 * 18 + entry), v1 = __ldg(Ke + (long)s1 * 18 + entry);
+      const double2 v2 = __ldg(Ke + (long)s2 * 18 + entry), v3 = __ldg(Ke + (long)s3 * 18 + entry);
+      s.x += v0.x; s.y += v0.y;
+      s.x += v1.x; s.y += v1.y;
+      s.x += v2.x; s.y += v2.y;
+      s.x += v3.x; s.y += v3.y;
+    }
+    if (k + 2 <= end) {
+      const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1);
+      const double2 v0 = __ldg(Ke + (long)s0 * 18 + entry), v1 = __ldg(Ke + (long)s1 * 18 + entry);
+      s.x += v0.x; s.y += v0.y;
+      s.x += v1.x; s.y += v1.y;
+      k += 2;
+    }
+    if (k < end) {
+      const double2 v0 = __ldg(Ke + (long)__ldg(src + k) * 18 + entry);
+      s.x += v0.x; s.y += v0.y;
+    }
     A[g] = s;
   }
 }
@@ -545,7 +583,7 @@ __global__ void gather_residual_kernel(long nnodes, const int *__restrict__ ptr,
 
 static inline unsigned grid_for(long total, int block, int num_sms) {
   long want = (total + block - 1) / block;
-  long cap = (long)num_sms * 16;  // a whole number of CTAs per SM, grid-stride beyond that
+  long cap = (long)num_sms * 64;  // a whole number of CTAs per SM, grid-stride beyond that
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (unsigned)want;
@@ -556,7 +594,8 @@ cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int
   if (nblocks <= 0) return cudaSuccess;
   const int block = 256;
   if (bs == 6)
-    gather_blocks_kernel<36><<<grid_for(nblocks * 36, block, num_sms), block, 0, s>>>(nblocks, ptr, src, Ke, A);
+    gather_blocks36_kernel<<<grid_for(nblocks * 18, block, num_sms), block, 0, s>>>(
+        nblocks, ptr, src, reinterpret_cast<const double2 *>(Ke), reinterpret_cast<double2 *>(A));
   else if (bs == 3)
     gather_blocks_kernel<9><<<grid_for(nblocks * 9, block, num_sms), block, 0, s>>>(nblocks, ptr, src, Ke, A);
   else

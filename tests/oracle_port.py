@@ -131,20 +131,24 @@ def assemble(mesh, kind, new_nodes=None, desc=None, vars=None, ddvars=None, x=No
     cols = np.zeros(nnz, np.int32)
     L.oracle_node_to_node_csr(nnodes, ne, _p(mesh["ptr"]), _p(conn), _p(rowp), _p(cols))
     bc_nodes = np.ascontiguousarray(new_nodes[mesh["bc_nodes"]], np.int32)
+    bc_vals = None
     if mesh.get("bc_ptr") is None:
         bc_vars = np.full(bc_nodes.size, (1 << bs) - 1, np.int32)
     else:
         bc_vars = np.zeros(bc_nodes.size, np.int32)
+        bc_vals = np.zeros((bc_nodes.size, bs))
         for k in range(bc_nodes.size):
             for j in range(mesh["bc_ptr"][k], mesh["bc_ptr"][k + 1]):
                 bc_vars[k] |= 1 << int(mesh["bc_vars"][j])
+                if mesh.get("bc_vals") is not None:
+                    bc_vals[k, int(mesh["bc_vars"][j])] = mesh["bc_vals"][j]
     res, A = np.zeros(bs * nnodes), np.zeros(bs * bs * nnz)
     u = None if vars is None else np.ascontiguousarray(vars, float)
     a = None if ddvars is None else np.ascontiguousarray(ddvars, float)
     edesc = np.ascontiguousarray(mesh["elem_ids"], np.int32)
     rc = L.oracle_assemble_jacobian(kind, nnodes, ne, _p(conn), _p(edesc), _p(desc.ravel()), _p(X.ravel()), _p(u),
                                     _p(a), alpha, 0.0, gamma, _p(rowp), _p(cols), bc_nodes.size, _p(bc_nodes),
-                                    _p(bc_vars), None, lam, _p(res), _p(A))
+                                    _p(bc_vars), _p(bc_vals), lam, _p(res), _p(A))
     assert rc == 0
     out = dict(rowp=rowp, cols=cols, A=A.reshape(nnz, bs, bs), res=res, new_nodes=new_nodes)
     if x is not None:
