@@ -133,9 +133,9 @@ struct alignas(16) ShellWork {
   double acc[nd];  // second time derivative of the state
   double desc[kDescStride];  // descriptor row of this element (constitutive constants, transform)
   double fn[3 * n];
-  static constexpr int LDT = nd + 1;  // odd row stride: one-row-per-lane writes hit distinct banks
-  double Bdr[n][LDT];
-  double Bty[nty][LDT];
+  static constexpr int LDT = nd + 2;  // padded row stride (16-byte aligned rows, lanes spread over banks)
+  alignas(16) double Bdr[n][LDT];
+  alignas(16) double Bty[nty][LDT];
   double T[nq][9], A[nq][9], Az[nq][9];
   double wdet[nq];
   alignas(16) double W[QC][nty][6];  // tying-point -> strain-row weights of the current chunk (m padded to 6)
@@ -415,6 +415,119 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// membrane/bending-uncoupled shells (B block of the constitutive matrix == 0, e.g. isotropic plates without
+// offset and symmetric laminates): the tying-strain part and the drill part of K do not need per-point rows,
+//   K = Bty^T S Bty + Bdr^T Sd Bdr + sum_q Bb_q^T (w det D) Bb_q,
+//   S  = sum_q w det W_q^T [A 0; 0 As] W_q   (nty x nty),   Sd = drill * sum_q w det N_q N_q^T   (n x n),
+// so the tile loop runs over nty + n + 3 nq rows instead of 9 nq and the per-point column work shrinks to
+// the three bending rows. The scratch below overlays W .. CB of ShellWork (QC == 1 for the q loop).
+// ------------------------------------------------------------------------------------------
+template <int O, int QC>
+struct ShellUncoupledView {
+  using WK = ShellWork<O, QC>;
+  static constexpr int n = WK::n, nd = WK::nd, nty = WK::nty;
+  // during the quadrature loop
+  static constexpr int oBb = 0, oDBb = 3 * nd;                       // inside B rows: [3][nd] each
+  // after the loop (overlaying W, Cw, B, CB)
+  static constexpr int oS = 0, oSd = oS + nty * nty + (nty * nty) % 2, oSB = oSd + n * n + (n * n) % 2;
+  static constexpr int oSdB = oSB + nty * nd, oRp = oSdB + n * nd, total = oRp + n * n * 6;
+  static_assert(total <= (int)((sizeof(WK::W) + sizeof(WK::Cw) + sizeof(WK::B) + sizeof(WK::CB)) / sizeof(double)),
+                "uncoupled scratch does not fit in the chunk buffers");
+  TB2_HD static double *base(WK &w) { return &w.W[0][0][0]; }
+  TB2_HD static double *Bb(WK &w) { return &w.B[0][0][0] + oBb; }
+  TB2_HD static double *DBb(WK &w) { return &w.B[0][0][0] + oDBb; }
+};
+
+// S accumulation, entry k = (t1, t2) of the nty x nty matrix at quadrature point q:
+//   S[t1][t2] += sum_m W[m][t1] * (w det C_TT W)[m][t2],  C_TT = [A 0; 0 As] on rows (e0,e1,e2 | e6,e7)
+template <int O, int QC>
+TB2_HD double shell_unc_S_entry(int k, ShellWork<O, QC> &w) {
+  constexpr int nty = ShellDims<O>::nty;
+  const int t1 = k / nty, t2 = k % nty;
+  const double *C = w.Cw[0];
+  double a[6], b[6];
+  load6(&w.W[0][t1][0], a);
+  load6(&w.W[0][t2][0], b);
+  const double v0 = C[0] * b[0] + C[1] * b[1] + C[2] * b[2];
+  const double v1 = C[1] * b[0] + C[3] * b[1] + C[4] * b[2];
+  const double v2 = C[2] * b[0] + C[4] * b[1] + C[5] * b[2];
+  const double v3 = C[18] * b[3] + C[19] * b[4];
+  const double v4 = C[19] * b[3] + C[20] * b[4];
+  return a[0] * v0 + a[1] * v1 + a[2] * v2 + a[3] * v3 + a[4] * v4;
+}
+
+// bending columns at quadrature point q, task (j, c): rows 3,4,5 of B and of (w det D) B for the columns
+// 6j+c and 6j+3+c (same expressions as shell_p3_columns)
+template <int O, int QC>
+TB2_HD void shell_unc_bending(int task, int q, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+  using V = ShellUncoupledView<O, QC>;
+  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
+  const int c = task % 3, j = (task / 3) % n;
+  const int cu = 6 * j + c, cq = cu + 3;
+  const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
+  const double *T = w.T[q], *A = w.A[q], *Az = w.Az[q];
+  const double hz0 = d0 * Az[0] + d1 * Az[3], hz1 = d0 * Az[1] + d1 * Az[4];
+  const double h0 = d0 * A[0] + d1 * A[3] + N * Az[6], h1 = d0 * A[1] + d1 * A[4] + N * Az[7];
+  double bu[3], bq[3];
+  bu[0] = T[3 * c] * hz0;
+  bu[1] = T[3 * c + 1] * hz1;
+  bu[2] = T[3 * c] * hz1 + T[3 * c + 1] * hz0;
+  const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+  const double f1 = w.fn[3 * j + c1], f2 = w.fn[3 * j + c2];
+  bq[0] = f1 * (T[3 * c2] * h0) - f2 * (T[3 * c1] * h0);
+  bq[1] = f1 * (T[3 * c2 + 1] * h1) - f2 * (T[3 * c1 + 1] * h1);
+  bq[2] = f1 * (T[3 * c2] * h1 + T[3 * c2 + 1] * h0) - f2 * (T[3 * c1] * h1 + T[3 * c1 + 1] * h0);
+  const double *C = w.Cw[0];  // w det C; D block at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
+  double *Bb = V::Bb(w), *DBb = V::DBb(w);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
+              i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
+    Bb[r * nd + cu] = bu[r];
+    Bb[r * nd + cq] = bq[r];
+    DBb[r * nd + cu] = C[12 + i0] * bu[0] + C[12 + i1] * bu[1] + C[12 + i2] * bu[2];
+    DBb[r * nd + cq] = C[12 + i0] * bq[0] + C[12 + i1] * bq[1] + C[12 + i2] * bq[2];
+  }
+}
+
+// after the loop, task (ty, j): six entries of SB = S Bty ; task nty*n + (i, j): six entries of SdB = Sd Bdr
+template <int O, int QC>
+TB2_HD void shell_unc_products(int task, ShellWork<O, QC> &w) {
+  using V = ShellUncoupledView<O, QC>;
+  using WK = ShellWork<O, QC>;
+  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd, nty = ShellDims<O>::nty;
+  double *base = V::base(w);
+  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (task < nty * n) {
+    const int ty = task / n, j = task % n;
+    const double *S = base + V::oS + ty * nty;
+    for (int t = 0; t < nty; t++) {
+      const double s = S[t];
+      double b[6];
+      load6(&w.Bty[t][6 * j], b);
+#pragma unroll
+      for (int c = 0; c < 6; c++) out[c] += s * b[c];
+    }
+    double *dst = base + V::oSB + ty * nd + 6 * j;
+#pragma unroll
+    for (int c = 0; c < 6; c++) dst[c] = out[c];
+  } else {
+    const int t2 = task - nty * n, i = t2 / n, j = t2 % n;
+    const double *Sd = base + V::oSd + i * n;
+    for (int t = 0; t < n; t++) {
+      const double s = Sd[t];
+      double b[6];
+      load6(&w.Bdr[t][6 * j], b);
+#pragma unroll
+      for (int c = 0; c < 6; c++) out[c] += s * b[c];
+    }
+    double *dst = base + V::oSdB + i * nd + 6 * j;
+#pragma unroll
+    for (int c = 0; c < 6; c++) dst[c] = out[c];
+  }
+}
+
 // residual-only path (assembleRes): strains of the chunk, task (ql, r): e = B u, kept in the unused CB rows
 template <int O, int QC>
 TB2_HD void shell_res_strain(int task, ShellWork<O, QC> &w) {
@@ -450,20 +563,20 @@ TB2_HD double shell_res_accumulate(int k, ShellWork<O, QC> &w) {
 }
 
 // phase 5 (all families): one TRxTC tile of K accumulates B^T (CB) over the rows of this chunk
-template <int NROWS, int LD, int TR, int TC>
+template <int NROWS, int LD, int TR, int TC, int LDC = LD>
 TB2_HD void tile_accumulate(const double *B, const double *CB, int row0, int col0, double *acc) {
 #pragma unroll 3
   for (int r = 0; r < NROWS; r++) {
     double bi[TR], cj[TC];
-    if (TR == 6 && TC == 6 && LD % 2 == 0) {
+    if (TR == 6 && TC == 6 && LD % 2 == 0 && LDC % 2 == 0) {
       // rows are 16-byte aligned and the tile starts at a multiple of 6 doubles: 128-bit loads
       load6(&B[r * LD + row0], bi);
-      load6(&CB[r * LD + col0], cj);
+      load6(&CB[r * LDC + col0], cj);
     } else {
 #pragma unroll
       for (int a = 0; a < TR; a++) bi[a] = B[r * LD + row0 + a];
 #pragma unroll
-      for (int b = 0; b < TC; b++) cj[b] = CB[r * LD + col0 + b];
+      for (int b = 0; b < TC; b++) cj[b] = CB[r * LDC + col0 + b];
     }
 #pragma unroll
     for (int a = 0; a < TR; a++)

@@ -208,17 +208,57 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     const bool has_tile = tid < n * n;
     const int ti = tid / n, tj = tid % n;
     if (g.Ke) {
-      for (int q0 = 0; q0 < nq; q0 += QC) {
-        for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
-        for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
+      double *rpart = w.rpart();
+      if (QC == 1 && g.uncoupled) {
+        // membrane/bending-uncoupled constitutive matrix: tying and drill parts in "tying space"
+        using UV = ShellUncoupledView<O, QC>;
+        constexpr int NSA = (nty * nty + TEAM - 1) / TEAM;
+        double sacc[NSA], sdacc = 0.0;
+#pragma unroll
+        for (int m = 0; m < NSA; m++) sacc[m] = 0.0;
+        for (int q = 0; q < nq; q++) {
+          for (int t = tid; t < nty; t += TEAM) shell_p3_weights<O, QC>(t, q, w, tab);
+          for (int t = tid; t < 22; t += TEAM) shell_p3_cw<O, QC>(t, q, w, desc);
+          team_sync<TEAM>();
+          for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O, QC>(t, q, w, tab);
+#pragma unroll
+          for (int m = 0; m < NSA; m++) {
+            const int kk = tid + m * TEAM;
+            if (kk < nty * nty) sacc[m] += shell_unc_S_entry<O, QC>(kk, w);
+          }
+          if (has_tile) sdacc += w.Cw[0][21] * tab.Nq[q][ti] * tab.Nq[q][tj];
+          team_sync<TEAM>();
+          if (has_tile) tile_accumulate<3, nd, 6, 6>(UV::Bb(w), UV::DBb(w), 6 * ti, 6 * tj, acc);
+          team_sync<TEAM>();
+        }
+        double *ub = UV::base(w);
+#pragma unroll
+        for (int m = 0; m < NSA; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nty * nty) ub[UV::oS + kk] = sacc[m];
+        }
+        if (has_tile) ub[UV::oSd + tid] = sdacc;
         team_sync<TEAM>();
-        for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
+        for (int t = tid; t < nty * n + n * n; t += TEAM) shell_unc_products<O, QC>(t, w);
         team_sync<TEAM>();
-        if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
-        team_sync<TEAM>();
+        if (has_tile) {
+          tile_accumulate<nty, Work::LDT, 6, 6, nd>(&w.Bty[0][0], ub + UV::oSB, 6 * ti, 6 * tj, acc);
+          tile_accumulate<n, Work::LDT, 6, 6, nd>(&w.Bdr[0][0], ub + UV::oSdB, 6 * ti, 6 * tj, acc);
+        }
+        rpart = ub + UV::oRp;
+      } else {
+        for (int q0 = 0; q0 < nq; q0 += QC) {
+          for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
+          for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
+          team_sync<TEAM>();
+          for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
+          team_sync<TEAM>();
+          if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
+          team_sync<TEAM>();
+        }
       }
       if (has_tile) {
-        shell_p6_finish<O, QC>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, w.rpart() + 6 * tid);
+        shell_p6_finish<O, QC>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, rpart + 6 * tid);
         if (live) {
           double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
 #pragma unroll
@@ -227,7 +267,7 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
       }
       team_sync<TEAM>();
       if (live && g.Re) {
-        const double *rp = w.rpart();
+        const double *rp = rpart;
         for (int k = tid; k < nd; k += TEAM) {
           const int i = k / 6, a = k % 6;
           double s = 0.0;

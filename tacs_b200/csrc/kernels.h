@@ -30,6 +30,7 @@ struct ElemGroupArgs {
   const double *vars;        // [nlocal][bs] or null (zero state)
   const double *ddvars;      // [nlocal][bs] or null
   double alpha, gamma;
+  int uncoupled;             // 1: every shell descriptor of the group has a zero membrane-bending block
   double *Ke;                // staging [nelem][nn][nn][bs*bs] or null (residual only)
   double *Re;                // staging [nelem][nn*bs] or null
 };

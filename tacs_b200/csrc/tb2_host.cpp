@@ -100,24 +100,6 @@ int profile_collect(double *ms, long *count) {
   return 0;
 }
 
-static void parallel_for(long n, const std::function<void(long, long)> &fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  long nt = hw ? hw : 4;
-  if (nt > 64) nt = 64;
-  if (n < 4096 || nt <= 1) {
-    fn(0, n);
-    return;
-  }
-  std::vector<std::thread> th;
-  long chunk = (n + nt - 1) / nt;
-  for (long t = 0; t < nt; t++) {
-    long lo = t * chunk, hi = std::min(n, lo + chunk);
-    if (lo >= hi) break;
-    th.emplace_back(fn, lo, hi);
-  }
-  for (auto &t : th) t.join();
-}
-
 // ---------------------------------------------------------------------------------------------
 // constitutive objects
 // ---------------------------------------------------------------------------------------------
@@ -433,6 +415,9 @@ int TACSElement::addJacobianBatch(int count, double alpha, double beta, double g
   g.kind = kind; g.nelem = count; g.conn = d_conn.ptr; g.desc_index = d_desc.ptr; g.desc_table = d_table.ptr;
   g.tables = d_tab.ptr; g.Xpts = d_X.ptr; g.vars = d_u.ptr; g.ddvars = ddvars ? d_a.ptr : nullptr;
   g.alpha = alpha; g.gamma = gamma; g.Ke = mat ? d_Ke.ptr : nullptr; g.Re = d_Re.ptr;
+  g.uncoupled = 1;
+  for (int i = 6; i < 12; i++)
+    if (drow[i] != 0.0) g.uncoupled = 0;
   if (!cuda_ok(launch_element_group(g, ctx().num_sms, ctx().stream), "element kernel")) return 1;
   ctx().kernel_launches++;
   if (!cuda_ok(cudaStreamSynchronize(ctx().stream), "element kernel sync")) return 1;
@@ -860,6 +845,11 @@ int TACSAssembler::finalize() {
     }
   }
   if (!d_desc_table.upload(table)) return 1;
+  // shells whose constitutive B block (entries 6..11) vanishes take the cheaper uncoupled kernel path
+  shells_uncoupled = true;
+  for (size_t row = 0; row < distinct.size(); row++)
+    for (int i = 6; i < 12; i++)
+      if (table[32 * row + i] != 0.0) shells_uncoupled = false;
   // element groups by kernel family (local order preserved inside a group)
   groups.clear();
   for (size_t gi = 0; gi < P.group_kinds.size(); gi++) {
@@ -986,6 +976,7 @@ int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat) {
     a.ddvars = ddvars_zero ? nullptr : ddvars->local();
     a.alpha = alpha;
     a.gamma = gamma;
+    a.uncoupled = shells_uncoupled ? 1 : 0;
     a.Ke = want_mat ? Ke.ptr + (size_t)g.block_base * bs * bs : nullptr;
     a.Re = Re.ptr + (size_t)g.node_base * bs;
     {

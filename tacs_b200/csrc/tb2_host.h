@@ -428,6 +428,7 @@ class TACSAssembler : public Object {
   // state
   TACSBVec *xpts = nullptr, *vars = nullptr, *dvars = nullptr, *ddvars = nullptr;
   bool vars_zero = true, ddvars_zero = true;
+  bool shells_uncoupled = false;  // all shell descriptors have a zero membrane-bending block
   // element groups, descriptor table, staging and residual gather plan
   std::vector<ElemGroup> groups;
   DeviceArray<double> d_desc_table;

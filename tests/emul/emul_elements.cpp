@@ -27,15 +27,42 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
   for (int t = 0; t < nty; t++) shell_p2_tying<O, QC>(t, *w, tab);
   for (int q = 0; q < nq; q++) shell_p2_qgeom<O, QC>(q, *w, tab, desc);
   std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
-  for (int q0 = 0; q0 < nq; q0 += QC) {
-    for (int t = 0; t < QC * nty; t++) shell_p3_weights<O, QC>(t, q0, *w, tab);
-    for (int t = 0; t < QC * 22; t++) shell_p3_cw<O, QC>(t, q0, *w, desc);
-    for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
-    for (int t = 0; t < WK::ntiles; t++)
-      tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+  bool uncoupled = (QC == 1);
+  for (int i = 6; i < 12; i++)
+    if (desc[i] != 0.0) uncoupled = false;
+  double *rpart = w->rpart();
+  if (uncoupled) {
+    using UV = ShellUncoupledView<O, QC>;
+    std::vector<double> S((size_t)nty * nty, 0.0), Sd((size_t)n * n, 0.0);
+    for (int q = 0; q < nq; q++) {
+      for (int t = 0; t < nty; t++) shell_p3_weights<O, QC>(t, q, *w, tab);
+      for (int t = 0; t < 22; t++) shell_p3_cw<O, QC>(t, q, *w, desc);
+      for (int t = 0; t < n * 3; t++) shell_unc_bending<O, QC>(t, q, *w, tab);
+      for (int k = 0; k < nty * nty; k++) S[k] += shell_unc_S_entry<O, QC>(k, *w);
+      for (int t = 0; t < n * n; t++) Sd[t] += w->Cw[0][21] * tab.Nq[q][t / n] * tab.Nq[q][t % n];
+      for (int t = 0; t < WK::ntiles; t++)
+        tile_accumulate<3, nd, 6, 6>(UV::Bb(*w), UV::DBb(*w), 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+    }
+    double *ub = UV::base(*w);
+    for (int k = 0; k < nty * nty; k++) ub[UV::oS + k] = S[k];
+    for (int t = 0; t < n * n; t++) ub[UV::oSd + t] = Sd[t];
+    for (int t = 0; t < nty * n + n * n; t++) shell_unc_products<O, QC>(t, *w);
+    for (int t = 0; t < WK::ntiles; t++) {
+      tile_accumulate<nty, WK::LDT, 6, 6, nd>(&w->Bty[0][0], ub + UV::oSB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+      tile_accumulate<n, WK::LDT, 6, 6, nd>(&w->Bdr[0][0], ub + UV::oSdB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+    }
+    rpart = ub + UV::oRp;
+  } else {
+    for (int q0 = 0; q0 < nq; q0 += QC) {
+      for (int t = 0; t < QC * nty; t++) shell_p3_weights<O, QC>(t, q0, *w, tab);
+      for (int t = 0; t < QC * 22; t++) shell_p3_cw<O, QC>(t, q0, *w, desc);
+      for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
+      for (int t = 0; t < WK::ntiles; t++)
+        tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+    }
   }
   for (int t = 0; t < WK::ntiles; t++)
-    shell_p6_finish<O, QC>(t, *w, tab, desc, alpha, gamma, inertia, &acc[36 * t], w->rpart() + 6 * t);
+    shell_p6_finish<O, QC>(t, *w, tab, desc, alpha, gamma, inertia, &acc[36 * t], rpart + 6 * t);
   for (int t = 0; t < WK::ntiles; t++) {
     int i = t / n, j = t % n;
     for (int a = 0; a < 6; a++)
@@ -44,7 +71,7 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
   for (int k = 0; k < nd; k++) {
     int i = k / 6, a = k % 6;
     double s = 0.0;
-    for (int j = 0; j < n; j++) s += w->rpart()[(i * n + j) * 6 + a];
+    for (int j = 0; j < n; j++) s += rpart[(i * n + j) * 6 + a];
     res[k] = s;
   }
   delete w;

@@ -58,7 +58,9 @@ def test_device_phases_replayed_on_host_match_oracle(emul, kind):
     order = 2 if kind in (1, 3) else 3
     X, u, a = (common.shell_batch if kind <= 2 else common.solid_batch)(order, 4, seed=10 + kind)
     descs = [oracle_port.solid_desc()] if kind > 2 else [
-        oracle_port.iso_shell_desc(t=0.02, tOffset=0.3, transform=0), oracle_port.composite_shell_desc(axis=(1, .3, .2))]
+        oracle_port.iso_shell_desc(t=0.02, tOffset=0.3, transform=0), oracle_port.composite_shell_desc(axis=(1, .3, .2)),
+        oracle_port.iso_shell_desc(t=0.01, tOffset=0.0, transform=1, axis=(1, .3, .2)),
+        oracle_port.iso_shell_desc(t=0.03, tOffset=0.0, transform=0)]
     DP = C.POINTER(C.c_double)
     for desc in descs:
         for e in range(X.shape[0]):

@@ -259,3 +259,25 @@ def test_single_element_and_error_paths(lib):
     c3.setElements([meshgen.solid_element(T, lib, 2)])
     with pytest.raises(RuntimeError):
         c3.createTACS()
+
+
+def test_gmres_linear_static_matches_reference(lib, ref):
+    """Linear static solve K u = f with unpreconditioned GMRES on both sides: same iteration count,
+    displacements within 1e-10 relative (north_star)."""
+    mesh = meshgen.cube(2, 4)
+    sol = {}
+    for name, L in (("b200", lib), ("ref", ref)):
+        creator, asm = meshgen.build_model(T, L, mesh, [meshgen.solid_element(T, L, 2)])
+        A, res, b, x = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+        f = np.zeros(b.getSize())
+        f[2::3] = 1.0
+        b.setArray(f)
+        asm.applyBCs(b)
+        ksm = T.KSM(L, A, m=120, nrestart=3)
+        ksm.setTolerances(1e-13, 1e-30)
+        flag = ksm.solve(b, x)
+        sol[name] = (flag, ksm.getIterCount(), x.getArray(), (creator, asm, A, ksm))
+    assert sol["b200"][0] == 1 and sol["ref"][0] == 1
+    assert abs(sol["b200"][1] - sol["ref"][1]) <= 1
+    assert relerr(sol["b200"][2], sol["ref"][2]) < 1e-10
