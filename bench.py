@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "elements/sec for Jacobian+residual assembly (BCSR SpMV GB/s vs HBM peak under 'spmv')"
 UNIT = "elements/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this command at the
+# default workload (profiles/r1_d_kernels_ncu.txt); reported only when the run uses that workload on one GPU
+NCU_TRAFFIC_BYTES = {"shell_element_kernel<2>": 0.139460e9 + 4.795389e9, "gather_blocks36_kernel": 4.744171e9 + 2.586922e9,
+                     "spmv6_kernel<0>": 2.690065e9 + 0.049695e9}
 # minimal-algorithm flops per element used for the FP64 roofline
 FLOPS_PER_ELEMENT = {"quad4": 57e3, "quad9": 551e3, "hex8": 69e3, "hex27": 2.28e6}
 
@@ -337,19 +341,23 @@ def run_b200(args):
         t = per_launch["gather_blocks"] * 1e-3
         kernels.append({"kernel": "gather_blocks36_kernel", "ms": per_launch["gather_blocks"], "bound": "hbm",
                         "achieved": gather_bytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s"})
+    default_workload = world == 1 and args.nx == 1000 and args.ny == 1000
     for k in kernels:
         k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
+        k["traffic"] = NCU_TRAFFIC_BYTES.get(k["kernel"]) if default_workload else None
     dominant = max(kernels, key=lambda k: k["ms"]) if kernels else None
     roofline = None
     if dominant:
         roofline = {"kernel": dominant["kernel"], "bound": dominant["bound"], "achieved": dominant["achieved"],
-                    "peak": dominant["peak"], "unit": dominant["unit"], "frac": dominant["frac"], "traffic": None,
+                    "peak": dominant["peak"], "unit": dominant["unit"], "frac": dominant["frac"],
+                    "traffic": dominant["traffic"], "algorithmic_bytes": elem_bytes if dominant["bound"] == "fp64" else gather_bytes,
                     "peak_source": hbm_src if dominant["bound"] == "hbm" else "live DFMA microbenchmark",
                     "share_of_step": dominant["ms"] / ms_per_step}
     sp_bytes = spmv_bytes(bs, nrows, nnzb)
     spmv = {"kernel": "spmv6_kernel<0>", "ms": ms_spmv, "bound": "hbm", "achieved": sp_bytes / (ms_spmv * 1e-3) * 1e-9,
             "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "bytes_per_launch": sp_bytes}
     spmv["frac"] = spmv["achieved"] / spmv["peak"]
+    spmv["traffic"] = NCU_TRAFFIC_BYTES["spmv6_kernel<0>"] if default_workload else None
 
     # ---- CPU baseline: the reference's own implementation on this box's host cores ---------------------
     cpu = None
