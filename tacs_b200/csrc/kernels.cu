@@ -96,18 +96,6 @@ struct SolidFamily {
   static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
-template <class Work, int BS>
-__device__ __forceinline__ void team_load(Work &w, double *Xdst, const ElemGroupArgs &g, long e, int tid, int team) {
-  constexpr int n = Work::n, nd = Work::nd;
-  const int *conn = g.conn + e * n;
-  for (int k = tid; k < 3 * n; k += team) Xdst[k] = g.Xpts[3 * (long)conn[k / 3] + k % 3];
-  for (int k = tid; k < nd; k += team) {
-    const long src = (long)BS * conn[k / BS] + k % BS;
-    w.u[k] = g.vars ? g.vars[src] : 0.0;
-    w.acc[k] = g.ddvars ? g.ddvars[src] : 0.0;
-  }
-}
-
 template <int O>
 __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, ShellFamily<O>::MIN_CTAS)
     shell_element_kernel(ElemGroupArgs g) {
