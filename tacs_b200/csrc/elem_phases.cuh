@@ -659,8 +659,8 @@ struct SolidWork {
   double desc[kDescStride];
   double J[nq][9];
   double wdet[nq];
-  double B[QC][NS][nd];
-  double CB[QC][NS][nd];
+  double G[QC][nd];        // physical shape-function gradients: G[ql][3a+dir] = dN_a/dx_dir
+  double CB[QC][NS][nd];   // w det C B; the strain rows B themselves are implied by G (3 non-zeros per column)
   double rpart[ntiles][TR];
 };
 
@@ -699,12 +699,9 @@ TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTab
                          {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
   const double wd = w.wdet[q];
   const int c0 = 3 * a;
-  w.B[ql][0][c0] = gx;  w.B[ql][0][c0 + 1] = 0.0; w.B[ql][0][c0 + 2] = 0.0;
-  w.B[ql][1][c0] = 0.0; w.B[ql][1][c0 + 1] = gy;  w.B[ql][1][c0 + 2] = 0.0;
-  w.B[ql][2][c0] = 0.0; w.B[ql][2][c0 + 1] = 0.0; w.B[ql][2][c0 + 2] = gz;
-  w.B[ql][3][c0] = 0.0; w.B[ql][3][c0 + 1] = gz;  w.B[ql][3][c0 + 2] = gy;
-  w.B[ql][4][c0] = gz;  w.B[ql][4][c0 + 1] = 0.0; w.B[ql][4][c0 + 2] = gx;
-  w.B[ql][5][c0] = gy;  w.B[ql][5][c0 + 1] = gx;  w.B[ql][5][c0 + 2] = 0.0;
+  w.G[ql][c0] = gx;
+  w.G[ql][c0 + 1] = gy;
+  w.G[ql][c0 + 2] = gz;
 #pragma unroll
   for (int r = 0; r < 6; r++) {
     // only the three structurally non-zero strain entries of each displacement column contribute
@@ -714,13 +711,21 @@ TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTab
   }
 }
 
-// residual-only path (assembleRes), task (ql, r): e = B u, staged in rpart (free until phase 6)
+// residual-only path (assembleRes), task (ql, r): strain e_r = (B u)_r from the gradients, staged in rpart
+// (free until phase 6). Strain order xx,yy,zz,yz,xz,xy with engineering shears.
 template <int O, int QC>
 TB2_HD void solid_res_strain(int task, SolidWork<O, QC> &w) {
-  constexpr int nd = SolidDims<O>::nd;
+  constexpr int n = SolidDims<O>::n;
   const int ql = task / 6, r = task % 6;
+  // e_r = sum_a G[a][d1] u[a][c1] + G[a][d2] u[a][c2]   (normal strains use one term)
+  const int c1 = (r < 3) ? r : ((r == 3) ? 1 : 0);
+  const int d1 = (r < 3) ? r : ((r == 5) ? 1 : 2);
+  const int c2 = (r == 5) ? 1 : 2;
+  const int d2 = (r == 3) ? 1 : 0;
+  const double two = (r < 3) ? 0.0 : 1.0;
   double e = 0.0;
-  for (int k = 0; k < nd; k++) e += w.B[ql][r][k] * w.u[k];
+  for (int a = 0; a < n; a++)
+    e += w.G[ql][3 * a + d1] * w.u[3 * a + c1] + two * (w.G[ql][3 * a + d2] * w.u[3 * a + c2]);
   (&w.rpart[0][0])[6 * ql + r] = e;
 }
 
@@ -733,6 +738,36 @@ TB2_HD double solid_res_accumulate(int k, SolidWork<O, QC> &w) {
 #pragma unroll
     for (int r = 0; r < 6; r++) out += w.CB[ql][r][k] * e[6 * ql + r];
   return out;
+}
+
+// phase 5 for solids: a TRxTC tile of K accumulates B^T (CB) using the three structurally non-zero strain
+// entries of every displacement column (x: rows 0,4,5 = gx,gz,gy; y: rows 1,3,5 = gy,gz,gx; z: rows 2,3,4 =
+// gz,gy,gx) -- half the multiply-adds of the dense row product.
+template <int QC, int ND, int TR, int TC>
+TB2_HD void solid_tile_accumulate(const double *G, const double *CB, int row0, int col0, double *acc) {
+  for (int ql = 0; ql < QC; ql++) {
+    const double *g = G + ql * ND + row0;
+    const double *cbq = CB + ql * 6 * ND + col0;
+#pragma unroll
+    for (int bn = 0; bn < TC / 3; bn++) {
+      double cb[6][3];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) cb[r][b] = cbq[r * ND + 3 * bn + b];
+#pragma unroll
+      for (int an = 0; an < TR / 3; an++) {
+        const double gx = g[3 * an], gy = g[3 * an + 1], gz = g[3 * an + 2];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          double *ax = &acc[(3 * an) * TC + 3 * bn + b];
+          ax[0] += gx * cb[0][b] + gz * cb[4][b] + gy * cb[5][b];
+          ax[TC] += gy * cb[1][b] + gz * cb[3][b] + gx * cb[5][b];
+          ax[2 * TC] += gz * cb[2][b] + gy * cb[3][b] + gx * cb[4][b];
+        }
+      }
+    }
+  }
 }
 
 // phase 6, task tile: residual partials, consistent mass block (only when `inertia`);

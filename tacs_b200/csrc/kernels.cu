@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
         for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
         team_sync<TEAM>();
         if (has_tile)
-          tile_accumulate<QC * 6, nd, TR, TC>(&w.B[0][0][0], &w.CB[0][0][0], TR * ti, TC * tj, acc);
+          solid_tile_accumulate<QC, nd, TR, TC>(&w.G[0][0], &w.CB[0][0][0], TR * ti, TC * tj, acc);
         team_sync<TEAM>();
       }
       if (has_tile) {
