@@ -551,9 +551,21 @@ __global__ void __launch_bounds__(256) gather_blocks_kernel(long nblocks, const 
   for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
     const long b = g / B2;
     const int entry = (int)(g - b * B2);
-    const int beg = ptr[b], end = ptr[b + 1];
+    const int beg = __ldg(ptr + b), end = __ldg(ptr + b + 1);
     double s = 0.0;
-    for (int k = beg; k < end; k++) s += Ke[(long)src[k] * B2 + entry];
+    int k = beg;
+    // request the slots and then the values of four contributions before consuming any (memory-level
+    // parallelism); the sum is still formed in ascending element order
+    for (; k + 4 <= end; k += 4) {
+      const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1), s2 = __ldg(src + k + 2), s3 = __ldg(src + k + 3);
+      const double v0 = __ldg(Ke + (long)s0 * B2 + entry), v1 = __ldg(Ke + (long)s1 * B2 + entry);
+      const double v2 = __ldg(Ke + (long)s2 * B2 + entry), v3 = __ldg(Ke + (long)s3 * B2 + entry);
+      s += v0;
+      s += v1;
+      s += v2;
+      s += v3;
+    }
+    for (; k < end; k++) s += __ldg(Ke + (long)__ldg(src + k) * B2 + entry);
     A[g] = s;
   }
 }
