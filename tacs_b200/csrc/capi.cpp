@@ -327,15 +327,23 @@ int tacsb200_assembler_get_local_to_global(tacsb200_handle a, int *global) {
   for (int l = 0; l < t->nlocal; l++) global[l] = t->plan->globalNode(l);
   return t->nlocal;
 }
+// a vector whose device allocation failed is not handed out (the message was printed by cudaMalloc's check)
+static tacsb200_handle keep_vec(TACSBVec *v) {
+  if (v && v->localSize() > 0 && !v->data.ptr) {
+    delete v;
+    return nullptr;
+  }
+  return keep(v);
+}
 tacsb200_handle tacsb200_assembler_create_vec(tacsb200_handle a) {
   TACSAssembler *t = as<TACSAssembler>(a);
   REQUIRE_H(t, "assembler");
-  return keep(t->createVec());
+  return keep_vec(t->createVec());
 }
 tacsb200_handle tacsb200_assembler_create_node_vec(tacsb200_handle a) {
   TACSAssembler *t = as<TACSAssembler>(a);
   REQUIRE_H(t, "assembler");
-  return keep(t->createNodeVec());
+  return keep_vec(t->createNodeVec());
 }
 tacsb200_handle tacsb200_assembler_create_mat(tacsb200_handle a) {
   TACSAssembler *t = as<TACSAssembler>(a);
@@ -494,7 +502,7 @@ int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv)
 tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m) {
   TACSParallelMat *A = as<TACSParallelMat>(m);
   REQUIRE_H(A, "matrix");
-  return keep(A->createVec());
+  return keep_vec(A->createVec());
 }
 
 /* ---- GMRES --------------------------------------------------------------------------------------- */
