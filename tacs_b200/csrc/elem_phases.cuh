@@ -439,22 +439,42 @@ struct ShellUncoupledView {
   TB2_HD static double *DBb(WK &w) { return &w.B[0][0][0] + oDBb; }
 };
 
-// S accumulation, entry k = (t1, t2) of the nty x nty matrix at quadrature point q:
-//   S[t1][t2] += sum_m W[m][t1] * (w det C_TT W)[m][t2],  C_TT = [A 0; 0 As] on rows (e0,e1,e2 | e6,e7)
+// V = (w det C_TT) W for one tying point, task ty (runs in the weights phase right after W[ty] is known; reads
+// the constitutive constants from the descriptor row, not from Cw, which other lanes are still writing):
+//   C_TT = [A 0; 0 As] on the strain rows (e0,e1,e2 | e6,e7); V lives in the CB rows, unused on this path
+template <int O, int QC>
+TB2_HD void shell_unc_V(int ty, int q, ShellWork<O, QC> &w, const double *desc) {
+  const double wd = w.wdet[q];
+  const double *b = &w.W[0][ty][0];
+  double *V = &w.CB[0][0][0] + 6 * ty;
+  V[0] = wd * (desc[0] * b[0] + desc[1] * b[1] + desc[2] * b[2]);
+  V[1] = wd * (desc[1] * b[0] + desc[3] * b[1] + desc[4] * b[2]);
+  V[2] = wd * (desc[2] * b[0] + desc[4] * b[1] + desc[5] * b[2]);
+  V[3] = wd * (desc[18] * b[3] + desc[19] * b[4]);
+  V[4] = wd * (desc[19] * b[3] + desc[20] * b[4]);
+  V[5] = 0.0;
+}
+
+// S accumulation: entry k of the upper triangle (t1 <= t2) of the symmetric nty x nty matrix,
+//   S[t1][t2] += sum_m W[t1][m] V[t2][m]
+template <int O, int QC>
+TB2_HD void shell_unc_tri(int k, int &t1, int &t2) {
+  constexpr int nty = ShellDims<O>::nty;
+  t1 = 0;
+  while (k >= nty - t1) {
+    k -= nty - t1;
+    t1++;
+  }
+  t2 = t1 + k;
+}
 template <int O, int QC>
 TB2_HD double shell_unc_S_entry(int k, ShellWork<O, QC> &w) {
-  constexpr int nty = ShellDims<O>::nty;
-  const int t1 = k / nty, t2 = k % nty;
-  const double *C = w.Cw[0];
-  double a[6], b[6];
+  int t1, t2;
+  shell_unc_tri<O, QC>(k, t1, t2);
+  double a[6], v[6];
   load6(&w.W[0][t1][0], a);
-  load6(&w.W[0][t2][0], b);
-  const double v0 = C[0] * b[0] + C[1] * b[1] + C[2] * b[2];
-  const double v1 = C[1] * b[0] + C[3] * b[1] + C[4] * b[2];
-  const double v2 = C[2] * b[0] + C[4] * b[1] + C[5] * b[2];
-  const double v3 = C[18] * b[3] + C[19] * b[4];
-  const double v4 = C[19] * b[3] + C[20] * b[4];
-  return a[0] * v0 + a[1] * v1 + a[2] * v2 + a[3] * v3 + a[4] * v4;
+  load6(&w.CB[0][0][0] + 6 * t2, v);
+  return a[0] * v[0] + a[1] * v[1] + a[2] * v[2] + a[3] * v[3] + a[4] * v[4];
 }
 
 // bending columns at quadrature point q, task (j, c): rows 3,4,5 of B and of (w det D) B for the columns

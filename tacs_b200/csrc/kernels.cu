@@ -200,19 +200,23 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
       if (QC == 1 && g.uncoupled) {
         // membrane/bending-uncoupled constitutive matrix: tying and drill parts in "tying space"
         using UV = ShellUncoupledView<O, QC>;
-        constexpr int NSA = (nty * nty + TEAM - 1) / TEAM;
+        constexpr int NTRI = nty * (nty + 1) / 2;  // S is symmetric: upper triangle only
+        constexpr int NSA = (NTRI + TEAM - 1) / TEAM;
         double sacc[NSA], sdacc = 0.0;
 #pragma unroll
         for (int m = 0; m < NSA; m++) sacc[m] = 0.0;
         for (int q = 0; q < nq; q++) {
-          for (int t = tid; t < nty; t += TEAM) shell_p3_weights<O, QC>(t, q, w, tab);
+          for (int t = tid; t < nty; t += TEAM) {
+            shell_p3_weights<O, QC>(t, q, w, tab);
+            shell_unc_V<O, QC>(t, q, w, desc);
+          }
           for (int t = tid; t < 22; t += TEAM) shell_p3_cw<O, QC>(t, q, w, desc);
           team_sync<TEAM>();
           for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O, QC>(t, q, w, tab);
 #pragma unroll
           for (int m = 0; m < NSA; m++) {
             const int kk = tid + m * TEAM;
-            if (kk < nty * nty) sacc[m] += shell_unc_S_entry<O, QC>(kk, w);
+            if (kk < NTRI) sacc[m] += shell_unc_S_entry<O, QC>(kk, w);
           }
           if (has_tile) sdacc += w.Cw[0][21] * tab.Nq[q][ti] * tab.Nq[q][tj];
           team_sync<TEAM>();
@@ -223,7 +227,12 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
 #pragma unroll
         for (int m = 0; m < NSA; m++) {
           const int kk = tid + m * TEAM;
-          if (kk < nty * nty) ub[UV::oS + kk] = sacc[m];
+          if (kk < NTRI) {
+            int t1, t2;
+            shell_unc_tri<O, QC>(kk, t1, t2);
+            ub[UV::oS + t1 * nty + t2] = sacc[m];
+            ub[UV::oS + t2 * nty + t1] = sacc[m];
+          }
         }
         if (has_tile) ub[UV::oSd + tid] = sdacc;
         team_sync<TEAM>();

@@ -35,10 +35,19 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
     using UV = ShellUncoupledView<O, QC>;
     std::vector<double> S((size_t)nty * nty, 0.0), Sd((size_t)n * n, 0.0);
     for (int q = 0; q < nq; q++) {
-      for (int t = 0; t < nty; t++) shell_p3_weights<O, QC>(t, q, *w, tab);
+      for (int t = 0; t < nty; t++) {
+        shell_p3_weights<O, QC>(t, q, *w, tab);
+        shell_unc_V<O, QC>(t, q, *w, desc);
+      }
       for (int t = 0; t < 22; t++) shell_p3_cw<O, QC>(t, q, *w, desc);
       for (int t = 0; t < n * 3; t++) shell_unc_bending<O, QC>(t, q, *w, tab);
-      for (int k = 0; k < nty * nty; k++) S[k] += shell_unc_S_entry<O, QC>(k, *w);
+      for (int k = 0; k < nty * (nty + 1) / 2; k++) {
+        int t1, t2;
+        shell_unc_tri<O, QC>(k, t1, t2);
+        double v = shell_unc_S_entry<O, QC>(k, *w);
+        S[t1 * nty + t2] += v;
+        if (t1 != t2) S[t2 * nty + t1] += v;
+      }
       for (int t = 0; t < n * n; t++) Sd[t] += w->Cw[0][21] * tab.Nq[q][t / n] * tab.Nq[q][t % n];
       for (int t = 0; t < WK::ntiles; t++)
         tile_accumulate<3, nd, 6, 6>(UV::Bb(*w), UV::DBb(*w), 6 * (t / n), 6 * (t % n), &acc[36 * t]);
