@@ -147,8 +147,8 @@ struct alignas(16) ShellWork {
 };
 
 // phase 1, task i in [0,n): node normal, nodal frame, nodal drill-strain row
-template <int O, int QC>
-TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc) {
+template <int O, class WK>
+TB2_HD void shell_p1_node(int i, WK &w, const ShellTables<O> &tab, const double *desc) {
   constexpr int n = ShellDims<O>::n;
   const double *X = w.X();
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -205,8 +205,8 @@ TB2_HD void shell_p1_node(int i, ShellWork<O, QC> &w, const ShellTables<O> &tab,
 //   row_u[c] = p00 d0 X,1[c] + p01 d0 X,2[c] + p10 d1 X,1[c] + p11 d1 X,2[c] + n0[c] (s0 d0 + s1 d1)
 //   row_d[c] = N (t0 X,1[c] + t1 X,2[c])          (d0 = dN/dxi1, d1 = dN/dxi2, X,k = dX/dxi_k)
 // Multiplying by an exact 0 or 1 does not change the rounded value of the surviving term.
-template <int O, int QC>
-TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
+template <int O, class WK>
+TB2_HD void shell_p2_tying(int ty, WK &w, const ShellTables<O> &tab) {
   constexpr int n = ShellDims<O>::n;
   const double *X = w.X();
   const int field = shell_ty_field<O>(ty);
@@ -243,8 +243,8 @@ TB2_HD void shell_p2_tying(int ty, ShellWork<O, QC> &w, const ShellTables<O> &ta
 }
 
 // phase 2 (same barrier interval), task q in [0,nq): frame, inverse Jacobian products, weighted determinant
-template <int O, int QC>
-TB2_HD void shell_p2_qgeom(int q, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc) {
+template <int O, class WK>
+TB2_HD void shell_p2_qgeom(int q, WK &w, const ShellTables<O> &tab, const double *desc) {
   constexpr int n = ShellDims<O>::n;
   const double *X = w.X();
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
@@ -421,67 +421,135 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
 //   K = Bty^T S Bty + Bdr^T Sd Bdr + sum_q Bb_q^T (w det D) Bb_q,
 //   S  = sum_q w det W_q^T [A 0; 0 As] W_q   (nty x nty),   Sd = drill * sum_q w det N_q N_q^T   (n x n),
 // so the tile loop runs over nty + n + 3 nq rows instead of 9 nq and the per-point column work shrinks to
-// the three bending rows. The scratch below overlays W .. CB of ShellWork (QC == 1 for the q loop).
+// the three bending rows. The tying weights factor as W_q[ty][m] = Ntq[q][ty] * P_q[field(ty)][m] (the five
+// tying fields share the frame products P_q), hence
+//   S[t1][t2] = sum_q Ntq[q][t1] Ntq[q][t2] G_q[f1][f2],   G_q = w det P_q [A 0; 0 As] P_q^T   (5 x 5 per point),
+// which moves all the S arithmetic out of the quadrature loop.
 // ------------------------------------------------------------------------------------------
-template <int O, int QC>
-struct ShellUncoupledView {
-  using WK = ShellWork<O, QC>;
-  static constexpr int n = WK::n, nd = WK::nd, nty = WK::nty;
-  // during the quadrature loop
-  static constexpr int oBb = 0, oDBb = 3 * nd;                       // inside B rows: [3][nd] each
-  // after the loop (overlaying W, Cw, B, CB)
-  static constexpr int oS = 0, oSd = oS + nty * nty + (nty * nty) % 2, oSB = oSd + n * n + (n * n) % 2;
-  static constexpr int oSdB = oSB + nty * nd, oRp = oSdB + n * nd, total = oRp + n * n * 6;
-  static_assert(total <= (int)((sizeof(WK::W) + sizeof(WK::Cw) + sizeof(WK::B) + sizeof(WK::CB)) / sizeof(double)),
-                "uncoupled scratch does not fit in the chunk buffers");
-  TB2_HD static double *base(WK &w) { return &w.W[0][0][0]; }
-  TB2_HD static double *Bb(WK &w) { return &w.B[0][0][0] + oBb; }
-  TB2_HD static double *DBb(WK &w) { return &w.B[0][0][0] + oDBb; }
+template <int O>
+struct alignas(16) ShellUncWork {
+  using D = ShellDims<O>;
+  static constexpr int n = D::n, nd = D::nd, nq = D::nq, nty = D::nty;
+  static constexpr int ntiles = n * n;
+  static constexpr int LDT = nd + 2;  // padded row stride (16-byte aligned rows, lanes spread over banks)
+  static constexpr int even(int x) { return x + (x & 1); }
+  static constexpr int imax(int a, int b) { return a > b ? a : b; }
+  // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S, Sd [.. products];
+  // SB, SdB [products .. first tile pass]; bending buffers 0/1 [first tile pass .. loop end]; Rp [finish].
+  static constexpr int oS = 0, oSd = even(nty * nty);
+  static constexpr int oP = oSd + even(n * n);       // P[nq][5][6]
+  static constexpr int oG = oP + 30 * nq;            // G[nq][26]
+  static constexpr int oX = oG + 26 * nq;            // X[3n]
+  static constexpr int LBUF = 6 * nd;                // one bending buffer: Bb[3][nd] then DBb[3][nd]
+  static constexpr int oSB = imax(LBUF, oP);         // SB[nty][nd]: clear of buffer 0, S and Sd
+  static constexpr int oSdB = oSB + nty * nd;        // SdB[n][nd]
+  static constexpr int oRp = 0;                      // residual partials [ntiles][6]
+  static constexpr int SCR = imax(imax(oSdB + n * nd, oX + even(3 * n)), imax(2 * LBUF, 6 * ntiles));
+  double u[nd];
+  double acc[nd];            // second time derivative of the state
+  double desc[kDescStride];  // descriptor row of this element
+  double fn[3 * n];
+  alignas(16) double Bdr[n][LDT];
+  alignas(16) double Bty[nty][LDT];
+  double T[nq][9], A[nq][9], Az[nq][9];
+  double wdet[nq];
+  alignas(16) double scr[SCR];
+  TB2_HD double *X() { return scr + oX; }
+  TB2_HD double *rpart() { return scr + oRp; }
+  TB2_HD double *buf(int k) { return scr + k * LBUF; }
 };
 
-// V = (w det C_TT) W for one tying point, task ty (runs in the weights phase right after W[ty] is known; reads
-// the constitutive constants from the descriptor row, not from Cw, which other lanes are still writing):
-//   C_TT = [A 0; 0 As] on the strain rows (e0,e1,e2 | e6,e7); V lives in the CB rows, unused on this path
-template <int O, int QC>
-TB2_HD void shell_unc_V(int ty, int q, ShellWork<O, QC> &w, const double *desc) {
-  const double wd = w.wdet[q];
-  const double *b = &w.W[0][ty][0];
-  double *V = &w.CB[0][0][0] + 6 * ty;
-  V[0] = wd * (desc[0] * b[0] + desc[1] * b[1] + desc[2] * b[2]);
-  V[1] = wd * (desc[1] * b[0] + desc[3] * b[1] + desc[4] * b[2]);
-  V[2] = wd * (desc[2] * b[0] + desc[4] * b[1] + desc[5] * b[2]);
-  V[3] = wd * (desc[18] * b[3] + desc[19] * b[4]);
-  V[4] = wd * (desc[19] * b[3] + desc[20] * b[4]);
-  V[5] = 0.0;
+// same barrier interval as shell_p2_qgeom (same lane, after it), task q: the frame products of the five tying
+// fields, P[f][m] with (c,d) = (0,0) (1,1) (0,1) (1,2) (0,2) -- the expressions of shell_p3_weights without Ntq
+template <int O>
+TB2_HD void shell_unc_P(int q, ShellUncWork<O> &w) {
+  using WK = ShellUncWork<O>;
+  const double *A = w.A[q];
+  double *P = w.scr + WK::oP + 30 * q;
+#pragma unroll
+  for (int f = 0; f < 5; f++) {
+    const int c = (f == 1 || f == 3) ? 1 : 0;
+    const int d = (f == 0) ? 0 : ((f == 1 || f == 2) ? 1 : 2);
+    const double off = (c == d) ? 0.0 : 1.0;
+    const double Ac0 = A[3 * c], Ac1 = A[3 * c + 1], Ac2 = A[3 * c + 2];
+    const double Ad0 = A[3 * d], Ad1 = A[3 * d + 1], Ad2 = A[3 * d + 2];
+    P[6 * f + 0] = Ac0 * Ad0 + off * (Ad0 * Ac0);
+    P[6 * f + 1] = Ac1 * Ad1 + off * (Ad1 * Ac1);
+    P[6 * f + 2] = 2.0 * (Ac0 * Ad1 + off * (Ad0 * Ac1));
+    P[6 * f + 3] = 2.0 * (Ac1 * Ad2 + off * (Ad1 * Ac2));
+    P[6 * f + 4] = 2.0 * (Ac0 * Ad2 + off * (Ad0 * Ac2));
+    P[6 * f + 5] = 0.0;
+  }
 }
 
-// S accumulation: entry k of the upper triangle (t1 <= t2) of the symmetric nty x nty matrix,
-//   S[t1][t2] += sum_m W[t1][m] V[t2][m]
-template <int O, int QC>
-TB2_HD void shell_unc_tri(int k, int &t1, int &t2) {
+// G phase, task (q, f2): column f2 of G_q = P_q (w det C_TT) P_q^T, C_TT = [A 0; 0 As] on (e0,e1,e2 | e6,e7)
+template <int O>
+TB2_HD void shell_unc_G(int task, ShellUncWork<O> &w) {
+  using WK = ShellUncWork<O>;
+  const int q = task / 5, f2 = task % 5;
+  const double *P = w.scr + WK::oP + 30 * q;
+  const double *desc = w.desc;
+  const double wd = w.wdet[q];
+  double b[6], v[5];
+  load6(P + 6 * f2, b);
+  v[0] = wd * (desc[0] * b[0] + desc[1] * b[1] + desc[2] * b[2]);
+  v[1] = wd * (desc[1] * b[0] + desc[3] * b[1] + desc[4] * b[2]);
+  v[2] = wd * (desc[2] * b[0] + desc[4] * b[1] + desc[5] * b[2]);
+  v[3] = wd * (desc[18] * b[3] + desc[19] * b[4]);
+  v[4] = wd * (desc[19] * b[3] + desc[20] * b[4]);
+  double *G = w.scr + WK::oG + 26 * q;
+#pragma unroll
+  for (int f1 = 0; f1 < 5; f1++) {
+    double a[6];
+    load6(P + 6 * f1, a);
+    G[5 * f1 + f2] = a[0] * v[0] + a[1] * v[1] + a[2] * v[2] + a[3] * v[3] + a[4] * v[4];
+  }
+}
+
+// G phase, task (i, j): Sd[i][j] = sum_q (w det drill) N_q[i] N_q[j]
+template <int O>
+TB2_HD void shell_unc_Sd(int task, ShellUncWork<O> &w, const ShellTables<O> &tab) {
+  using WK = ShellUncWork<O>;
+  constexpr int n = WK::n, nq = WK::nq;
+  const int i = task / n, j = task % n;
+  const double drill = w.desc[21];
+  double s = 0.0;
+  for (int q = 0; q < nq; q++) s += (w.wdet[q] * drill) * tab.Nq[q][i] * tab.Nq[q][j];
+  w.scr[WK::oSd + task] = s;
+}
+
+// entry k of the upper triangle (t1 <= t2) of the symmetric nty x nty matrix S, packed for the kernel as
+// t1 | t2 << 8 | (5 f1 + f2) << 16 (decoded once per thread, outside the element loop)
+template <int O>
+TB2_HD int shell_unc_tri(int k) {
   constexpr int nty = ShellDims<O>::nty;
-  t1 = 0;
+  int t1 = 0;
   while (k >= nty - t1) {
     k -= nty - t1;
     t1++;
   }
-  t2 = t1 + k;
+  const int t2 = t1 + k;
+  return t1 | (t2 << 8) | ((5 * shell_ty_field<O>(t1) + shell_ty_field<O>(t2)) << 16);
 }
-template <int O, int QC>
-TB2_HD double shell_unc_S_entry(int k, ShellWork<O, QC> &w) {
-  int t1, t2;
-  shell_unc_tri<O, QC>(k, t1, t2);
-  double a[6], v[6];
-  load6(&w.W[0][t1][0], a);
-  load6(&w.CB[0][0][0] + 6 * t2, v);
-  return a[0] * v[0] + a[1] * v[1] + a[2] * v[2] + a[3] * v[3] + a[4] * v[4];
+
+// S phase, one packed entry: S[t1][t2] = S[t2][t1] = sum_q Ntq[q][t1] Ntq[q][t2] G_q[f1][f2]
+template <int O>
+TB2_HD void shell_unc_S_entry(int packed, ShellUncWork<O> &w, const ShellTables<O> &tab) {
+  using WK = ShellUncWork<O>;
+  constexpr int nty = WK::nty, nq = WK::nq;
+  const int t1 = packed & 0xff, t2 = (packed >> 8) & 0xff, g = packed >> 16;
+  const double *G = w.scr + WK::oG + g;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < nq; q++) s += (tab.Ntq[q][t1] * tab.Ntq[q][t2]) * G[26 * q];
+  w.scr[WK::oS + t1 * nty + t2] = s;
+  w.scr[WK::oS + t2 * nty + t1] = s;
 }
 
 // bending columns at quadrature point q, task (j, c): rows 3,4,5 of B and of (w det D) B for the columns
-// 6j+c and 6j+3+c (same expressions as shell_p3_columns)
-template <int O, int QC>
-TB2_HD void shell_unc_bending(int task, int q, ShellWork<O, QC> &w, const ShellTables<O> &tab) {
-  using V = ShellUncoupledView<O, QC>;
+// 6j+c and 6j+3+c (same expressions as shell_p3_columns), written to the bending buffer `buf`
+template <int O>
+TB2_HD void shell_unc_bending(int task, int q, ShellUncWork<O> &w, const ShellTables<O> &tab, double *buf) {
   constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
   const int c = task % 3, j = (task / 3) % n;
   const int cu = 6 * j + c, cq = cu + 3;
@@ -498,30 +566,30 @@ TB2_HD void shell_unc_bending(int task, int q, ShellWork<O, QC> &w, const ShellT
   bq[0] = f1 * (T[3 * c2] * h0) - f2 * (T[3 * c1] * h0);
   bq[1] = f1 * (T[3 * c2 + 1] * h1) - f2 * (T[3 * c1 + 1] * h1);
   bq[2] = f1 * (T[3 * c2] * h1 + T[3 * c2 + 1] * h0) - f2 * (T[3 * c1] * h1 + T[3 * c1 + 1] * h0);
-  const double *C = w.Cw[0];  // w det C; D block at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
-  double *Bb = V::Bb(w), *DBb = V::DBb(w);
+  // D block of the descriptor at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
+  const double *Dm = w.desc + 12;
+  const double wd = w.wdet[q];
+  double *Bb = buf, *DBb = buf + 3 * nd;
 #pragma unroll
   for (int r = 0; r < 3; r++) {
     const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
               i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
     Bb[r * nd + cu] = bu[r];
     Bb[r * nd + cq] = bq[r];
-    DBb[r * nd + cu] = C[12 + i0] * bu[0] + C[12 + i1] * bu[1] + C[12 + i2] * bu[2];
-    DBb[r * nd + cq] = C[12 + i0] * bq[0] + C[12 + i1] * bq[1] + C[12 + i2] * bq[2];
+    DBb[r * nd + cu] = wd * (Dm[i0] * bu[0] + Dm[i1] * bu[1] + Dm[i2] * bu[2]);
+    DBb[r * nd + cq] = wd * (Dm[i0] * bq[0] + Dm[i1] * bq[1] + Dm[i2] * bq[2]);
   }
 }
 
-// after the loop, task (ty, j): six entries of SB = S Bty ; task nty*n + (i, j): six entries of SdB = Sd Bdr
-template <int O, int QC>
-TB2_HD void shell_unc_products(int task, ShellWork<O, QC> &w) {
-  using V = ShellUncoupledView<O, QC>;
-  using WK = ShellWork<O, QC>;
-  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd, nty = ShellDims<O>::nty;
-  double *base = V::base(w);
+// products phase, task (ty, j): six entries of SB = S Bty ; task nty*n + (i, j): six entries of SdB = Sd Bdr
+template <int O>
+TB2_HD void shell_unc_products(int task, ShellUncWork<O> &w) {
+  using WK = ShellUncWork<O>;
+  constexpr int n = WK::n, nd = WK::nd, nty = WK::nty;
   double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (task < nty * n) {
     const int ty = task / n, j = task % n;
-    const double *S = base + V::oS + ty * nty;
+    const double *S = w.scr + WK::oS + ty * nty;
     for (int t = 0; t < nty; t++) {
       const double s = S[t];
       double b[6];
@@ -529,12 +597,12 @@ TB2_HD void shell_unc_products(int task, ShellWork<O, QC> &w) {
 #pragma unroll
       for (int c = 0; c < 6; c++) out[c] += s * b[c];
     }
-    double *dst = base + V::oSB + ty * nd + 6 * j;
+    double *dst = w.scr + WK::oSB + ty * nd + 6 * j;
 #pragma unroll
     for (int c = 0; c < 6; c++) dst[c] = out[c];
   } else {
     const int t2 = task - nty * n, i = t2 / n, j = t2 % n;
-    const double *Sd = base + V::oSd + i * n;
+    const double *Sd = w.scr + WK::oSd + i * n;
     for (int t = 0; t < n; t++) {
       const double s = Sd[t];
       double b[6];
@@ -542,7 +610,7 @@ TB2_HD void shell_unc_products(int task, ShellWork<O, QC> &w) {
 #pragma unroll
       for (int c = 0; c < 6; c++) out[c] += s * b[c];
     }
-    double *dst = base + V::oSdB + i * nd + 6 * j;
+    double *dst = w.scr + WK::oSdB + i * nd + 6 * j;
 #pragma unroll
     for (int c = 0; c < 6; c++) dst[c] = out[c];
   }
@@ -607,8 +675,8 @@ TB2_HD void tile_accumulate(const double *B, const double *CB, int row0, int col
 
 // phase 6, task tile (i,j): inertial block (only when `inertia`), residual partials; on return acc holds
 // alpha*K_tile + gamma*M_tile. Runs after the last chunk barrier: the partials reuse the B rows.
-template <int O, int QC>
-TB2_HD void shell_p6_finish(int tile, ShellWork<O, QC> &w, const ShellTables<O> &tab, const double *desc,
+template <int O, class WK>
+TB2_HD void shell_p6_finish(int tile, WK &w, const ShellTables<O> &tab, const double *desc,
                             double alpha, double gamma, bool inertia, double *acc, double *rp) {
   constexpr int n = ShellDims<O>::n, nq = ShellDims<O>::nq;
   const int i = tile / n, j = tile % n;

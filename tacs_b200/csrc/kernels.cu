@@ -18,6 +18,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "elem_phases.cuh"
 #include "kernels.h"
 
@@ -73,10 +75,10 @@ __device__ __forceinline__ void team_sync() {
 // plus a 64-byte skew, so that the two teams of a warp hit disjoint shared-memory banks when they read the
 // same field with 128-bit loads (the tile loop reads 4 distinct 48-byte chunks per team: 16-byte bank
 // groups {0,3,6,1}+k for team 0 and {4,7,2,5}+k for team 1).
-template <int O>
+template <int O, bool UNC = false>
 struct ShellFamily {
   static constexpr int QC = (O == 2) ? 1 : 3;
-  using Work = ShellWork<O, QC>;
+  using Work = typename std::conditional<UNC, ShellUncWork<O>, ShellWork<O, QC>>::type;
   using Tables = ShellTables<O>;
   static constexpr int TEAM = (O == 2) ? 16 : 96;
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
@@ -96,10 +98,12 @@ struct SolidFamily {
   static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
-template <int O>
-__global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, ShellFamily<O>::MIN_CTAS)
+// UNC: every descriptor of the group has a zero membrane-bending block and a tangent is requested
+// (the residual-only request always runs the general instantiation)
+template <int O, bool UNC>
+__global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>::TEAMS, ShellFamily<O, UNC>::MIN_CTAS)
     shell_element_kernel(ElemGroupArgs g) {
-  using F = ShellFamily<O>;
+  using F = ShellFamily<O, UNC>;
   using Work = typename F::Work;
   constexpr int TEAM = F::TEAM, TEAMS = F::TEAMS, QC = F::QC;
   constexpr int n = Work::n, nd = Work::nd, nq = Work::nq, nty = Work::nty;
@@ -161,6 +165,14 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     prefetch_data();
     prefetch_ids(clamp_elem(e0 + nteams));
   }
+  // uncoupled path: the entries of the symmetric tying-space matrix S this thread owns (decoded once)
+  constexpr int NTRI = nty * (nty + 1) / 2;
+  constexpr int NSA = UNC ? (NTRI + TEAM - 1) / TEAM : 1;
+  int stri[NSA];
+  if constexpr (UNC) {
+#pragma unroll
+    for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
+  }
   // uniform trip count inside a CTA so that barriers are reached by every thread
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
@@ -183,11 +195,15 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     team_sync<TEAM>();
     prefetch_data();                                               // next element (ids already here)
     prefetch_ids(clamp_elem(base + 2 * nteams + team_in_cta));     // element after next
-    for (int t = tid; t < n; t += TEAM) shell_p1_node<O, QC>(t, w, tab, desc);
+    for (int t = tid; t < n; t += TEAM) shell_p1_node<O>(t, w, tab, desc);
     team_sync<TEAM>();
     for (int t = tid; t < nty + nq; t += TEAM) {
-      if (t < nty) shell_p2_tying<O, QC>(t, w, tab);
-      else shell_p2_qgeom<O, QC>(t - nty, w, tab, desc);
+      if (t < nty) {
+        shell_p2_tying<O>(t, w, tab);
+      } else {
+        shell_p2_qgeom<O>(t - nty, w, tab, desc);
+        if constexpr (UNC) shell_unc_P<O>(t - nty, w);
+      }
     }
     team_sync<TEAM>();
     double acc[36];
@@ -197,52 +213,34 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     const int ti = tid / n, tj = tid % n;
     if (g.Ke) {
       double *rpart = w.rpart();
-      if (QC == 1 && g.uncoupled) {
-        // membrane/bending-uncoupled constitutive matrix: tying and drill parts in "tying space"
-        using UV = ShellUncoupledView<O, QC>;
-        constexpr int NTRI = nty * (nty + 1) / 2;  // S is symmetric: upper triangle only
-        constexpr int NSA = (NTRI + TEAM - 1) / TEAM;
-        double sacc[NSA], sdacc = 0.0;
-#pragma unroll
-        for (int m = 0; m < NSA; m++) sacc[m] = 0.0;
-        for (int q = 0; q < nq; q++) {
-          for (int t = tid; t < nty; t += TEAM) {
-            shell_p3_weights<O, QC>(t, q, w, tab);
-            shell_unc_V<O, QC>(t, q, w, desc);
-          }
-          for (int t = tid; t < 22; t += TEAM) shell_p3_cw<O, QC>(t, q, w, desc);
-          team_sync<TEAM>();
-          for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O, QC>(t, q, w, tab);
-#pragma unroll
-          for (int m = 0; m < NSA; m++) {
-            const int kk = tid + m * TEAM;
-            if (kk < NTRI) sacc[m] += shell_unc_S_entry<O, QC>(kk, w);
-          }
-          if (has_tile) sdacc += w.Cw[0][21] * tab.Nq[q][ti] * tab.Nq[q][tj];
-          team_sync<TEAM>();
-          if (has_tile) tile_accumulate<3, nd, 6, 6>(UV::Bb(w), UV::DBb(w), 6 * ti, 6 * tj, acc);
-          team_sync<TEAM>();
+      if constexpr (UNC) {
+        // tying and drill parts in "tying space" (elem_phases.cuh), all of it outside the quadrature loop
+        for (int t = tid; t < n * n + 5 * nq; t += TEAM) {
+          if (t < n * n) shell_unc_Sd<O>(t, w, tab);
+          else shell_unc_G<O>(t - n * n, w);
         }
-        double *ub = UV::base(w);
+        team_sync<TEAM>();
 #pragma unroll
-        for (int m = 0; m < NSA; m++) {
-          const int kk = tid + m * TEAM;
-          if (kk < NTRI) {
-            int t1, t2;
-            shell_unc_tri<O, QC>(kk, t1, t2);
-            ub[UV::oS + t1 * nty + t2] = sacc[m];
-            ub[UV::oS + t2 * nty + t1] = sacc[m];
-          }
-        }
-        if (has_tile) ub[UV::oSd + tid] = sdacc;
+        for (int m = 0; m < NSA; m++)
+          if (tid + m * TEAM < NTRI) shell_unc_S_entry<O>(stri[m], w, tab);
         team_sync<TEAM>();
-        for (int t = tid; t < nty * n + n * n; t += TEAM) shell_unc_products<O, QC>(t, w);
+        for (int t = tid; t < nty * n + n * n; t += TEAM) shell_unc_products<O>(t, w);
         team_sync<TEAM>();
+        // bending rows of point 0 go to buffer 0 while the tying / drill rows are contracted; inside the loop the
+        // rows of point q+1 are produced in the barrier interval that contracts those of point q
+        for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O>(t, 0, w, tab, w.buf(0));
         if (has_tile) {
-          tile_accumulate<nty, Work::LDT, 6, 6, nd>(&w.Bty[0][0], ub + UV::oSB, 6 * ti, 6 * tj, acc);
-          tile_accumulate<n, Work::LDT, 6, 6, nd>(&w.Bdr[0][0], ub + UV::oSdB, 6 * ti, 6 * tj, acc);
+          tile_accumulate<nty, Work::LDT, 6, 6, nd>(&w.Bty[0][0], w.scr + Work::oSB, 6 * ti, 6 * tj, acc);
+          tile_accumulate<n, Work::LDT, 6, 6, nd>(&w.Bdr[0][0], w.scr + Work::oSdB, 6 * ti, 6 * tj, acc);
         }
-        rpart = ub + UV::oRp;
+        team_sync<TEAM>();
+        for (int q = 0; q < nq; q++) {
+          if (q + 1 < nq)
+            for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O>(t, q + 1, w, tab, w.buf((q + 1) & 1));
+          const double *Bb = w.buf(q & 1);
+          if (has_tile) tile_accumulate<3, nd, 6, 6>(Bb, Bb + 3 * nd, 6 * ti, 6 * tj, acc);
+          team_sync<TEAM>();
+        }
       } else {
         for (int q0 = 0; q0 < nq; q0 += QC) {
           for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
@@ -255,7 +253,7 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
         }
       }
       if (has_tile) {
-        shell_p6_finish<O, QC>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, rpart + 6 * tid);
+        shell_p6_finish<O>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, rpart + 6 * tid);
         if (live) {
           double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
 #pragma unroll
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
           g.Re[e * nd + k] = s;
         }
       }
-    } else {
+    } else if constexpr (!UNC) {
       // residual only (assembleRes): res = sum_q B^T (w det C) B u, no tangent tiles
       double racc[NU];
 #pragma unroll
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
         team_sync<TEAM>();
       }
       if (inertia) {
-        if (has_tile) shell_p6_finish<O, QC>(tid, w, tab, desc, 0.0, 0.0, true, acc, w.rpart() + 6 * tid);
+        if (has_tile) shell_p6_finish<O>(tid, w, tab, desc, 0.0, 0.0, true, acc, w.rpart() + 6 * tid);
         team_sync<TEAM>();
       }
       if (live && g.Re) {
@@ -539,8 +537,12 @@ static cudaError_t launch_family(K kernel, const ElemGroupArgs &g, int num_sms, 
 cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream_t s) {
   if (g.nelem <= 0) return cudaSuccess;
   switch (g.kind) {
-    case ELEM_QUAD4_SHELL: return launch_family<ShellFamily<2>>(shell_element_kernel<2>, g, num_sms, s);
-    case ELEM_QUAD9_SHELL: return launch_family<ShellFamily<3>>(shell_element_kernel<3>, g, num_sms, s);
+    case ELEM_QUAD4_SHELL:
+      if (g.uncoupled && g.Ke) return launch_family<ShellFamily<2, true>>(shell_element_kernel<2, true>, g, num_sms, s);
+      return launch_family<ShellFamily<2, false>>(shell_element_kernel<2, false>, g, num_sms, s);
+    case ELEM_QUAD9_SHELL:
+      if (g.uncoupled && g.Ke) return launch_family<ShellFamily<3, true>>(shell_element_kernel<3, true>, g, num_sms, s);
+      return launch_family<ShellFamily<3, false>>(shell_element_kernel<3, false>, g, num_sms, s);
     case ELEM_HEX8: return launch_family<SolidFamily<2>>(solid_element_kernel<2>, g, num_sms, s);
     case ELEM_HEX27: return launch_family<SolidFamily<3>>(solid_element_kernel<3>, g, num_sms, s);
   }

@@ -12,66 +12,19 @@
 
 using namespace tb2;
 
-template <int O, int QC>
-static void run_shell(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
-                      double alpha, double gamma, double *res, double *mat) {
-  using WK = ShellWork<O, QC>;
-  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
-  static ShellTables<O> tab;
-  build_shell_tables<O>(tab);
-  WK *w = new WK;
-  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
-  for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
-  const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
-  for (int i = 0; i < n; i++) shell_p1_node<O, QC>(i, *w, tab, desc);
-  for (int t = 0; t < nty; t++) shell_p2_tying<O, QC>(t, *w, tab);
-  for (int q = 0; q < nq; q++) shell_p2_qgeom<O, QC>(q, *w, tab, desc);
-  std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
-  bool uncoupled = (QC == 1);
+static bool desc_uncoupled(const double *desc) {
   for (int i = 6; i < 12; i++)
-    if (desc[i] != 0.0) uncoupled = false;
+    if (desc[i] != 0.0) return false;
+  return true;
+}
+
+template <int O, class WK>
+static void shell_outputs(WK *w, const ShellTables<O> &tab, const double *desc, double alpha, double gamma,
+                          bool inertia, std::vector<double> &acc, double *res, double *mat) {
+  constexpr int n = WK::n, nd = WK::nd;
   double *rpart = w->rpart();
-  if (uncoupled) {
-    using UV = ShellUncoupledView<O, QC>;
-    std::vector<double> S((size_t)nty * nty, 0.0), Sd((size_t)n * n, 0.0);
-    for (int q = 0; q < nq; q++) {
-      for (int t = 0; t < nty; t++) {
-        shell_p3_weights<O, QC>(t, q, *w, tab);
-        shell_unc_V<O, QC>(t, q, *w, desc);
-      }
-      for (int t = 0; t < 22; t++) shell_p3_cw<O, QC>(t, q, *w, desc);
-      for (int t = 0; t < n * 3; t++) shell_unc_bending<O, QC>(t, q, *w, tab);
-      for (int k = 0; k < nty * (nty + 1) / 2; k++) {
-        int t1, t2;
-        shell_unc_tri<O, QC>(k, t1, t2);
-        double v = shell_unc_S_entry<O, QC>(k, *w);
-        S[t1 * nty + t2] += v;
-        if (t1 != t2) S[t2 * nty + t1] += v;
-      }
-      for (int t = 0; t < n * n; t++) Sd[t] += w->Cw[0][21] * tab.Nq[q][t / n] * tab.Nq[q][t % n];
-      for (int t = 0; t < WK::ntiles; t++)
-        tile_accumulate<3, nd, 6, 6>(UV::Bb(*w), UV::DBb(*w), 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-    }
-    double *ub = UV::base(*w);
-    for (int k = 0; k < nty * nty; k++) ub[UV::oS + k] = S[k];
-    for (int t = 0; t < n * n; t++) ub[UV::oSd + t] = Sd[t];
-    for (int t = 0; t < nty * n + n * n; t++) shell_unc_products<O, QC>(t, *w);
-    for (int t = 0; t < WK::ntiles; t++) {
-      tile_accumulate<nty, WK::LDT, 6, 6, nd>(&w->Bty[0][0], ub + UV::oSB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-      tile_accumulate<n, WK::LDT, 6, 6, nd>(&w->Bdr[0][0], ub + UV::oSdB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-    }
-    rpart = ub + UV::oRp;
-  } else {
-    for (int q0 = 0; q0 < nq; q0 += QC) {
-      for (int t = 0; t < QC * nty; t++) shell_p3_weights<O, QC>(t, q0, *w, tab);
-      for (int t = 0; t < QC * 22; t++) shell_p3_cw<O, QC>(t, q0, *w, desc);
-      for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
-      for (int t = 0; t < WK::ntiles; t++)
-        tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-    }
-  }
   for (int t = 0; t < WK::ntiles; t++)
-    shell_p6_finish<O, QC>(t, *w, tab, desc, alpha, gamma, inertia, &acc[36 * t], rpart + 6 * t);
+    shell_p6_finish<O>(t, *w, tab, desc, alpha, gamma, inertia, &acc[36 * t], rpart + 6 * t);
   for (int t = 0; t < WK::ntiles; t++) {
     int i = t / n, j = t % n;
     for (int a = 0; a < 6; a++)
@@ -83,6 +36,73 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
     for (int j = 0; j < n; j++) s += rpart[(i * n + j) * 6 + a];
     res[k] = s;
   }
+}
+
+// coupled path: the general kernel flow (shell_element_kernel<O, false>)
+template <int O, int QC>
+static void run_shell(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                      double alpha, double gamma, double *res, double *mat) {
+  using WK = ShellWork<O, QC>;
+  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
+  static ShellTables<O> tab;
+  build_shell_tables<O>(tab);
+  WK *w = new WK;
+  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
+  for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
+  const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
+  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, desc);
+  for (int t = 0; t < nty; t++) shell_p2_tying<O>(t, *w, tab);
+  for (int q = 0; q < nq; q++) shell_p2_qgeom<O>(q, *w, tab, desc);
+  std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
+  for (int q0 = 0; q0 < nq; q0 += QC) {
+    for (int t = 0; t < QC * nty; t++) shell_p3_weights<O, QC>(t, q0, *w, tab);
+    for (int t = 0; t < QC * 22; t++) shell_p3_cw<O, QC>(t, q0, *w, desc);
+    for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
+    for (int t = 0; t < WK::ntiles; t++)
+      tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+  }
+  shell_outputs<O>(w, tab, desc, alpha, gamma, inertia, acc, res, mat);
+  delete w;
+}
+
+// membrane/bending-uncoupled path (shell_element_kernel<O, true>), same order of phases and buffers
+template <int O>
+static void run_shell_unc(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                          double alpha, double gamma, double *res, double *mat) {
+  using WK = ShellUncWork<O>;
+  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
+  static ShellTables<O> tab;
+  build_shell_tables<O>(tab);
+  WK *w = new WK;
+  for (int k = 0; k < WK::SCR; k++) w->scr[k] = std::nan("");  // stale scratch must never be consumed
+  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
+  for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
+  for (int k = 0; k < kDescStride; k++) w->desc[k] = desc[k];
+  const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
+  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, w->desc);
+  for (int t = 0; t < nty; t++) shell_p2_tying<O>(t, *w, tab);
+  for (int q = 0; q < nq; q++) {
+    shell_p2_qgeom<O>(q, *w, tab, w->desc);
+    shell_unc_P<O>(q, *w);
+  }
+  for (int t = 0; t < n * n; t++) shell_unc_Sd<O>(t, *w, tab);
+  for (int t = 0; t < 5 * nq; t++) shell_unc_G<O>(t, *w);
+  for (int k = 0; k < nty * (nty + 1) / 2; k++) shell_unc_S_entry<O>(shell_unc_tri<O>(k), *w, tab);
+  for (int t = 0; t < nty * n + n * n; t++) shell_unc_products<O>(t, *w);
+  std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
+  for (int t = 0; t < n * 3; t++) shell_unc_bending<O>(t, 0, *w, tab, w->buf(0));
+  for (int t = 0; t < WK::ntiles; t++) {
+    tile_accumulate<nty, WK::LDT, 6, 6, nd>(&w->Bty[0][0], w->scr + WK::oSB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+    tile_accumulate<n, WK::LDT, 6, 6, nd>(&w->Bdr[0][0], w->scr + WK::oSdB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+  }
+  for (int q = 0; q < nq; q++) {
+    if (q + 1 < nq)
+      for (int t = 0; t < n * 3; t++) shell_unc_bending<O>(t, q + 1, *w, tab, w->buf((q + 1) & 1));
+    const double *Bb = w->buf(q & 1);
+    for (int t = 0; t < WK::ntiles; t++)
+      tile_accumulate<3, nd, 6, 6>(Bb, Bb + 3 * nd, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+  }
+  shell_outputs<O>(w, tab, w->desc, alpha, gamma, inertia, acc, res, mat);
   delete w;
 }
 
@@ -125,8 +145,14 @@ extern "C" {
 int emul_element(int kind, const double *Xpts, const double *vars, const double *ddvars, const double *desc,
                  double alpha, double gamma, double *res, double *mat) {
   switch (kind) {
-    case 1: run_shell<2, 1>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
-    case 2: run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
+    case 1:
+      if (desc_uncoupled(desc)) run_shell_unc<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      else run_shell<2, 1>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      return 0;
+    case 2:
+      if (desc_uncoupled(desc)) run_shell_unc<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      else run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      return 0;
     case 3: run_solid<2, 4>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
     case 4: run_solid<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
   }
