@@ -144,6 +144,8 @@ struct alignas(16) ShellWork {
   alignas(16) double CB[QC][NS][nd];
   TB2_HD double *X() { return &B[0][0][0]; }
   TB2_HD double *rpart() { return &B[0][0][0]; }
+  TB2_HD double *uvec() { return u; }
+  TB2_HD double *avec() { return acc; }
 };
 
 // phase 1, task i in [0,n): node normal, nodal frame, nodal drill-strain row
@@ -434,37 +436,74 @@ struct alignas(16) ShellUncWork {
   static constexpr int LDT = nd + 2;  // padded row stride (16-byte aligned rows, lanes spread over banks)
   static constexpr int even(int x) { return x + (x & 1); }
   static constexpr int imax(int a, int b) { return a > b ? a : b; }
-  // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S, Sd [.. products];
-  // SB, SdB [products .. first tile pass]; bending buffers 0/1 [first tile pass .. loop end]; Rp [finish].
-  static constexpr int oS = 0, oSd = even(nty * nty);
-  static constexpr int oP = oSd + even(n * n);       // P[nq][5][6]
+  // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S [S .. products];
+  // SB [products .. tying tile pass]; row buffers 0/1 [tying tile pass .. loop end]; u, acc, Rp [last loop
+  // iteration .. finish] in the row buffer that the last iteration does not read.
+  static constexpr int oS = 0;
+  static constexpr int oP = even(nty * nty);         // P[nq][5][6]
   static constexpr int oG = oP + 30 * nq;            // G[nq][26]
   static constexpr int oX = oG + 26 * nq;            // X[3n]
-  static constexpr int LBUF = 6 * nd;                // one bending buffer: Bb[3][nd] then DBb[3][nd]
-  static constexpr int oSB = imax(LBUF, oP);         // SB[nty][nd]: clear of buffer 0, S and Sd
-  static constexpr int oSdB = oSB + nty * nd;        // SdB[n][nd]
-  static constexpr int oRp = 0;                      // residual partials [ntiles][6]
-  static constexpr int SCR = imax(imax(oSdB + n * nd, oX + even(3 * n)), imax(2 * LBUF, 6 * ntiles));
-  double u[nd];
-  double acc[nd];            // second time derivative of the state
-  double desc[kDescStride];  // descriptor row of this element
+  static constexpr int LBUF = 8 * nd;                // one row buffer: L[4][nd] (3 bending + drill) then R[4][nd]
+  static constexpr int oSB = imax(LBUF, oP);         // SB[nty][nd]: clear of buffer 0 and of S
+  static constexpr int oU = (nq & 1) * LBUF, oAcc = oU + nd, oRp = oAcc + nd;
+  static constexpr int SCR = imax(imax(oSB + nty * nd, oX + even(3 * n)), imax(2 * LBUF, oRp + 6 * ntiles));
   double fn[3 * n];
   alignas(16) double Bdr[n][LDT];
   alignas(16) double Bty[nty][LDT];
-  double T[nq][9], A[nq][9], Az[nq][9];
+  // per quadrature point: T(0,1,3,4,6,7) A(0,1,3,4) Az(0,1,3,4,6,7) -- the frame entries the bending rows use
+  alignas(16) double geo[nq][16];
   double wdet[nq];
   alignas(16) double scr[SCR];
   TB2_HD double *X() { return scr + oX; }
   TB2_HD double *rpart() { return scr + oRp; }
+  TB2_HD double *uvec() { return scr + oU; }
+  TB2_HD double *avec() { return scr + oAcc; }
   TB2_HD double *buf(int k) { return scr + k * LBUF; }
 };
 
-// same barrier interval as shell_p2_qgeom (same lane, after it), task q: the frame products of the five tying
-// fields, P[f][m] with (c,d) = (0,0) (1,1) (0,1) (1,2) (0,2) -- the expressions of shell_p3_weights without Ntq
+// phase 2 (same barrier interval as shell_p2_tying), task q: frame, inverse Jacobian products, weighted
+// determinant (as shell_p2_qgeom) and the frame products of the five tying fields,
+// P[f][m] with (c,d) = (0,0) (1,1) (0,1) (1,2) (0,2) -- the expressions of shell_p3_weights without Ntq
 template <int O>
-TB2_HD void shell_unc_P(int q, ShellUncWork<O> &w) {
+TB2_HD void shell_unc_qgeom(int q, ShellUncWork<O> &w, const ShellTables<O> &tab, const double *desc) {
   using WK = ShellUncWork<O>;
-  const double *A = w.A[q];
+  constexpr int n = WK::n;
+  const double *X = w.X();
+  double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
+  double nxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = 0; j < n; j++) {
+    const double d0 = tab.dNq_T[j][0][q], d1 = tab.dNq_T[j][1][q], N = tab.Nq_T[j][q];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      Xxi[2 * c] += d0 * X[3 * j + c];
+      Xxi[2 * c + 1] += d1 * X[3 * j + c];
+      n0[c] += N * w.fn[3 * j + c];
+      nxi[2 * c] += d0 * w.fn[3 * j + c];
+      nxi[2 * c + 1] += d1 * w.fn[3 * j + c];
+    }
+  }
+  double T[9], Xd[9], Xdz[9], Xdinv[9], A[9], Az[9], tmp[9];
+  shell_frame((int)desc[25], &desc[26], Xxi, n0, T);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    Xd[3 * c] = Xxi[2 * c];
+    Xd[3 * c + 1] = Xxi[2 * c + 1];
+    Xd[3 * c + 2] = n0[c];
+    Xdz[3 * c] = nxi[2 * c];
+    Xdz[3 * c + 1] = nxi[2 * c + 1];
+    Xdz[3 * c + 2] = 0.0;
+  }
+  const double det = inv3x3(Xd, Xdinv);
+  mat3mul(Xdinv, Xdz, tmp);
+#pragma unroll
+  for (int k = 0; k < 9; k++) tmp[k] = -tmp[k];
+  mat3mul(Xdinv, T, A);
+  mat3mul(tmp, A, Az);
+  w.wdet[q] = det * tab.wq[q];
+  double *geo = w.geo[q];
+  geo[0] = T[0]; geo[1] = T[1]; geo[2] = T[3]; geo[3] = T[4]; geo[4] = T[6]; geo[5] = T[7];
+  geo[6] = A[0]; geo[7] = A[1]; geo[8] = A[3]; geo[9] = A[4];
+  geo[10] = Az[0]; geo[11] = Az[1]; geo[12] = Az[3]; geo[13] = Az[4]; geo[14] = Az[6]; geo[15] = Az[7];
   double *P = w.scr + WK::oP + 30 * q;
 #pragma unroll
   for (int f = 0; f < 5; f++) {
@@ -484,11 +523,10 @@ TB2_HD void shell_unc_P(int q, ShellUncWork<O> &w) {
 
 // G phase, task (q, f2): column f2 of G_q = P_q (w det C_TT) P_q^T, C_TT = [A 0; 0 As] on (e0,e1,e2 | e6,e7)
 template <int O>
-TB2_HD void shell_unc_G(int task, ShellUncWork<O> &w) {
+TB2_HD void shell_unc_G(int task, ShellUncWork<O> &w, const double *desc) {
   using WK = ShellUncWork<O>;
   const int q = task / 5, f2 = task % 5;
   const double *P = w.scr + WK::oP + 30 * q;
-  const double *desc = w.desc;
   const double wd = w.wdet[q];
   double b[6], v[5];
   load6(P + 6 * f2, b);
@@ -504,18 +542,6 @@ TB2_HD void shell_unc_G(int task, ShellUncWork<O> &w) {
     load6(P + 6 * f1, a);
     G[5 * f1 + f2] = a[0] * v[0] + a[1] * v[1] + a[2] * v[2] + a[3] * v[3] + a[4] * v[4];
   }
-}
-
-// G phase, task (i, j): Sd[i][j] = sum_q (w det drill) N_q[i] N_q[j]
-template <int O>
-TB2_HD void shell_unc_Sd(int task, ShellUncWork<O> &w, const ShellTables<O> &tab) {
-  using WK = ShellUncWork<O>;
-  constexpr int n = WK::n, nq = WK::nq;
-  const int i = task / n, j = task % n;
-  const double drill = w.desc[21];
-  double s = 0.0;
-  for (int q = 0; q < nq; q++) s += (w.wdet[q] * drill) * tab.Nq[q][i] * tab.Nq[q][j];
-  w.scr[WK::oSd + task] = s;
 }
 
 // entry k of the upper triangle (t1 <= t2) of the symmetric nty x nty matrix S, packed for the kernel as
@@ -546,74 +572,75 @@ TB2_HD void shell_unc_S_entry(int packed, ShellUncWork<O> &w, const ShellTables<
   w.scr[WK::oS + t2 * nty + t1] = s;
 }
 
-// bending columns at quadrature point q, task (j, c): rows 3,4,5 of B and of (w det D) B for the columns
-// 6j+c and 6j+3+c (same expressions as shell_p3_columns), written to the bending buffer `buf`
-template <int O>
-TB2_HD void shell_unc_bending(int task, int q, ShellUncWork<O> &w, const ShellTables<O> &tab, double *buf) {
-  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
-  const int c = task % 3, j = (task / 3) % n;
-  const int cu = 6 * j + c, cq = cu + 3;
-  const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
-  const double *T = w.T[q], *A = w.A[q], *Az = w.Az[q];
-  const double hz0 = d0 * Az[0] + d1 * Az[3], hz1 = d0 * Az[1] + d1 * Az[4];
-  const double h0 = d0 * A[0] + d1 * A[3] + N * Az[6], h1 = d0 * A[1] + d1 * A[4] + N * Az[7];
-  double bu[3], bq[3];
-  bu[0] = T[3 * c] * hz0;
-  bu[1] = T[3 * c + 1] * hz1;
-  bu[2] = T[3 * c] * hz1 + T[3 * c + 1] * hz0;
-  const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
-  const double f1 = w.fn[3 * j + c1], f2 = w.fn[3 * j + c2];
-  bq[0] = f1 * (T[3 * c2] * h0) - f2 * (T[3 * c1] * h0);
-  bq[1] = f1 * (T[3 * c2 + 1] * h1) - f2 * (T[3 * c1 + 1] * h1);
-  bq[2] = f1 * (T[3 * c2] * h1 + T[3 * c2 + 1] * h0) - f2 * (T[3 * c1] * h1 + T[3 * c1 + 1] * h0);
-  // D block of the descriptor at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
-  const double *Dm = w.desc + 12;
-  const double wd = w.wdet[q];
-  double *Bb = buf, *DBb = buf + 3 * nd;
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-    const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
-              i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
-    Bb[r * nd + cu] = bu[r];
-    Bb[r * nd + cq] = bq[r];
-    DBb[r * nd + cu] = wd * (Dm[i0] * bu[0] + Dm[i1] * bu[1] + Dm[i2] * bu[2]);
-    DBb[r * nd + cq] = wd * (Dm[i0] * bq[0] + Dm[i1] * bq[1] + Dm[i2] * bq[2]);
-  }
-}
-
-// products phase, task (ty, j): six entries of SB = S Bty ; task nty*n + (i, j): six entries of SdB = Sd Bdr
+// products phase, task (ty, j): six entries of SB = S Bty
 template <int O>
 TB2_HD void shell_unc_products(int task, ShellUncWork<O> &w) {
   using WK = ShellUncWork<O>;
   constexpr int n = WK::n, nd = WK::nd, nty = WK::nty;
   double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (task < nty * n) {
-    const int ty = task / n, j = task % n;
-    const double *S = w.scr + WK::oS + ty * nty;
-    for (int t = 0; t < nty; t++) {
-      const double s = S[t];
-      double b[6];
-      load6(&w.Bty[t][6 * j], b);
+  const int ty = task / n, j = task % n;
+  const double *S = w.scr + WK::oS + ty * nty;
+  for (int t = 0; t < nty; t++) {
+    const double s = S[t];
+    double b[6];
+    load6(&w.Bty[t][6 * j], b);
 #pragma unroll
-      for (int c = 0; c < 6; c++) out[c] += s * b[c];
-    }
-    double *dst = w.scr + WK::oSB + ty * nd + 6 * j;
-#pragma unroll
-    for (int c = 0; c < 6; c++) dst[c] = out[c];
-  } else {
-    const int t2 = task - nty * n, i = t2 / n, j = t2 % n;
-    const double *Sd = w.scr + WK::oSd + i * n;
-    for (int t = 0; t < n; t++) {
-      const double s = Sd[t];
-      double b[6];
-      load6(&w.Bdr[t][6 * j], b);
-#pragma unroll
-      for (int c = 0; c < 6; c++) out[c] += s * b[c];
-    }
-    double *dst = w.scr + WK::oSdB + i * nd + 6 * j;
-#pragma unroll
-    for (int c = 0; c < 6; c++) dst[c] = out[c];
+    for (int c = 0; c < 6; c++) out[c] += s * b[c];
   }
+  double *dst = w.scr + WK::oSB + ty * nd + 6 * j;
+#pragma unroll
+  for (int c = 0; c < 6; c++) dst[c] = out[c];
+}
+
+// row buffer of quadrature point q, task (j, c): the columns 6j+c and 6j+3+c of
+//   L rows 0..2: bending rows 3,4,5 of B (same expressions as shell_p3_columns);  L row 3: drill row
+//   R rows 0..2: (w det D) L;                                                     R row 3: (w det drill) L3
+template <int O>
+TB2_HD void shell_unc_rows(int task, int q, ShellUncWork<O> &w, const ShellTables<O> &tab, const double *desc,
+                           double *buf) {
+  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
+  const int c = task % 3, j = (task / 3) % n;
+  const int cu = 6 * j + c, cq = cu + 3;
+  const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
+  const double *geo = w.geo[q];
+  const double *T = geo, *A = geo + 6, *Az = geo + 10;  // T(r,0..1) at T[2r..], A(0..1,0..1) at A[2r..], Az rows 0..2
+  const double hz0 = d0 * Az[0] + d1 * Az[2], hz1 = d0 * Az[1] + d1 * Az[3];
+  const double h0 = d0 * A[0] + d1 * A[2] + N * Az[4], h1 = d0 * A[1] + d1 * A[3] + N * Az[5];
+  double bu[4], bq[4];
+  bu[0] = T[2 * c] * hz0;
+  bu[1] = T[2 * c + 1] * hz1;
+  bu[2] = T[2 * c] * hz1 + T[2 * c + 1] * hz0;
+  const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+  const double f1 = w.fn[3 * j + c1], f2 = w.fn[3 * j + c2];
+  bq[0] = f1 * (T[2 * c2] * h0) - f2 * (T[2 * c1] * h0);
+  bq[1] = f1 * (T[2 * c2 + 1] * h1) - f2 * (T[2 * c1 + 1] * h1);
+  bq[2] = f1 * (T[2 * c2] * h1 + T[2 * c2 + 1] * h0) - f2 * (T[2 * c1] * h1 + T[2 * c1 + 1] * h0);
+  // drill strain: nodal rows interpolated with the nodal shape functions; the rotation columns of node i's
+  // row are non-zero at node i only
+  {
+    double su = 0.0;
+    for (int i = 0; i < n; i++) su += tab.Nq[q][i] * w.Bdr[i][cu];
+    bu[3] = su;
+    bq[3] = N * w.Bdr[j][cq];
+  }
+  // D block of the descriptor at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
+  const double *Dm = desc + 12;
+  const double wd = w.wdet[q];
+  double *L = buf, *R = buf + 4 * nd;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
+              i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
+    L[r * nd + cu] = bu[r];
+    L[r * nd + cq] = bq[r];
+    R[r * nd + cu] = wd * (Dm[i0] * bu[0] + Dm[i1] * bu[1] + Dm[i2] * bu[2]);
+    R[r * nd + cq] = wd * (Dm[i0] * bq[0] + Dm[i1] * bq[1] + Dm[i2] * bq[2]);
+  }
+  const double wdr = wd * desc[21];
+  L[3 * nd + cu] = bu[3];
+  L[3 * nd + cq] = bq[3];
+  R[3 * nd + cu] = wdr * bu[3];
+  R[3 * nd + cq] = wdr * bq[3];
 }
 
 // residual-only path (assembleRes): strains of the chunk, task (ql, r): e = B u, kept in the unused CB rows
@@ -684,7 +711,7 @@ TB2_HD void shell_p6_finish(int tile, WK &w, const ShellTables<O> &tab, const do
   for (int a = 0; a < 6; a++) {
     double s = 0.0;
 #pragma unroll
-    for (int b = 0; b < 6; b++) s += acc[6 * a + b] * w.u[6 * j + b];
+    for (int b = 0; b < 6; b++) s += acc[6 * a + b] * w.uvec()[6 * j + b];
     rp[a] = s;
   }
 #pragma unroll
@@ -722,7 +749,7 @@ TB2_HD void shell_p6_finish(int tile, WK &w, const ShellTables<O> &tab, const do
     for (int a = 0; a < 6; a++) {
       double s = 0.0;
 #pragma unroll
-      for (int b = 0; b < 6; b++) s += M[6 * a + b] * w.acc[6 * j + b];
+      for (int b = 0; b < 6; b++) s += M[6 * a + b] * w.avec()[6 * j + b];
       rp[a] += s;
     }
 #pragma unroll

@@ -122,12 +122,12 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
   // loaded into registers while the current element is being evaluated, so the dependent global loads
   // never sit on the critical path of a team.
   constexpr int NU = (nd + TEAM - 1) / TEAM;
-  constexpr int ND = (kDescStride + TEAM - 1) / TEAM;
+  constexpr int ND = UNC ? 1 : (kDescStride + TEAM - 1) / TEAM;
   double pX = 0.0, pu[NU], pa[NU], pd[ND];
   // two-deep pipeline: node ids / descriptor index of the element after next, data of the next element.
   // The data loads of iteration i use ids that were requested in iteration i-1, so no load ever waits for
   // the address it depends on.
-  int cX = 0, cU[NU], cD = 0;
+  int cX = 0, cU[NU], cD = 0, dnext = 0;
   auto prefetch_ids = [&](long e) {
     const int *conn = g.conn + e * n;
     if (tid < 3 * n) cX = __ldg(conn + tid / 3);
@@ -152,10 +152,16 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
       }
     }
     const double *drow = g.desc_table + (long)kDescStride * cD;
+    dnext = cD;
+    if constexpr (UNC) {
+      // the uncoupled kernel reads the descriptor row in place (L1): pull its two lines in ahead of time
+      if (tid < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(drow + 16 * tid));
+    } else {
 #pragma unroll
-    for (int m = 0; m < ND; m++) {
-      const int kk = tid + m * TEAM;
-      pd[m] = kk < kDescStride ? __ldg(drow + kk) : 0.0;
+      for (int m = 0; m < ND; m++) {
+        const int kk = tid + m * TEAM;
+        pd[m] = kk < kDescStride ? __ldg(drow + kk) : 0.0;
+      }
     }
   };
   auto clamp_elem = [&](long e) { return e < nelem ? e : nelem - 1; };
@@ -177,19 +183,30 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
-    const double *desc = w.desc;
     if (tid < 3 * n) w.X()[tid] = pX;
+    const double *desc;
+    double cu[NU], ca[NU];  // uncoupled kernel: the state stays in registers until the last quadrature interval
+    if constexpr (UNC) {
+      desc = g.desc_table + (long)kDescStride * dnext;
 #pragma unroll
-    for (int m = 0; m < ND; m++) {
-      const int kk = tid + m * TEAM;
-      if (kk < kDescStride) w.desc[kk] = pd[m];
-    }
+      for (int m = 0; m < NU; m++) {
+        cu[m] = pu[m];
+        ca[m] = pa[m];
+      }
+    } else {
+      desc = w.desc;
 #pragma unroll
-    for (int m = 0; m < NU; m++) {
-      const int kk = tid + m * TEAM;
-      if (kk < nd) {
-        w.u[kk] = pu[m];
-        w.acc[kk] = pa[m];
+      for (int m = 0; m < ND; m++) {
+        const int kk = tid + m * TEAM;
+        if (kk < kDescStride) w.desc[kk] = pd[m];
+      }
+#pragma unroll
+      for (int m = 0; m < NU; m++) {
+        const int kk = tid + m * TEAM;
+        if (kk < nd) {
+          w.u[kk] = pu[m];
+          w.acc[kk] = pa[m];
+        }
       }
     }
     team_sync<TEAM>();
@@ -201,8 +218,8 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
       if (t < nty) {
         shell_p2_tying<O>(t, w, tab);
       } else {
-        shell_p2_qgeom<O>(t - nty, w, tab, desc);
-        if constexpr (UNC) shell_unc_P<O>(t - nty, w);
+        if constexpr (UNC) shell_unc_qgeom<O>(t - nty, w, tab, desc);
+        else shell_p2_qgeom<O>(t - nty, w, tab, desc);
       }
     }
     team_sync<TEAM>();
@@ -214,31 +231,37 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
     if (g.Ke) {
       double *rpart = w.rpart();
       if constexpr (UNC) {
-        // tying and drill parts in "tying space" (elem_phases.cuh), all of it outside the quadrature loop
-        for (int t = tid; t < n * n + 5 * nq; t += TEAM) {
-          if (t < n * n) shell_unc_Sd<O>(t, w, tab);
-          else shell_unc_G<O>(t - n * n, w);
-        }
+        // tying part in "tying space" (elem_phases.cuh), all of it outside the quadrature loop
+        for (int t = tid; t < 5 * nq; t += TEAM) shell_unc_G<O>(t, w, desc);
         team_sync<TEAM>();
 #pragma unroll
         for (int m = 0; m < NSA; m++)
           if (tid + m * TEAM < NTRI) shell_unc_S_entry<O>(stri[m], w, tab);
         team_sync<TEAM>();
-        for (int t = tid; t < nty * n + n * n; t += TEAM) shell_unc_products<O>(t, w);
+        for (int t = tid; t < nty * n; t += TEAM) shell_unc_products<O>(t, w);
         team_sync<TEAM>();
-        // bending rows of point 0 go to buffer 0 while the tying / drill rows are contracted; inside the loop the
-        // rows of point q+1 are produced in the barrier interval that contracts those of point q
-        for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O>(t, 0, w, tab, w.buf(0));
-        if (has_tile) {
-          tile_accumulate<nty, Work::LDT, 6, 6, nd>(&w.Bty[0][0], w.scr + Work::oSB, 6 * ti, 6 * tj, acc);
-          tile_accumulate<n, Work::LDT, 6, 6, nd>(&w.Bdr[0][0], w.scr + Work::oSdB, 6 * ti, 6 * tj, acc);
-        }
+        // the rows of point 0 (bending + drill) go to buffer 0 while the tying rows are contracted; inside the
+        // loop the rows of point q+1 are produced in the barrier interval that contracts those of point q
+        for (int t = tid; t < n * 3; t += TEAM) shell_unc_rows<O>(t, 0, w, tab, desc, w.buf(0));
+        if (has_tile) tile_accumulate<nty, Work::LDT, 6, 6, nd>(&w.Bty[0][0], w.scr + Work::oSB, 6 * ti, 6 * tj, acc);
         team_sync<TEAM>();
+#pragma unroll 1
         for (int q = 0; q < nq; q++) {
-          if (q + 1 < nq)
-            for (int t = tid; t < n * 3; t += TEAM) shell_unc_bending<O>(t, q + 1, w, tab, w.buf((q + 1) & 1));
-          const double *Bb = w.buf(q & 1);
-          if (has_tile) tile_accumulate<3, nd, 6, 6>(Bb, Bb + 3 * nd, 6 * ti, 6 * tj, acc);
+          if (q + 1 < nq) {
+            for (int t = tid; t < n * 3; t += TEAM) shell_unc_rows<O>(t, q + 1, w, tab, desc, w.buf((q + 1) & 1));
+          } else {
+            // last interval: the state enters shared memory in the row buffer that is no longer read
+#pragma unroll
+            for (int m = 0; m < NU; m++) {
+              const int kk = tid + m * TEAM;
+              if (kk < nd) {
+                w.uvec()[kk] = cu[m];
+                w.avec()[kk] = ca[m];
+              }
+            }
+          }
+          const double *L = w.buf(q & 1);
+          if (has_tile) tile_accumulate<4, nd, 6, 6>(L, L + 4 * nd, 6 * ti, 6 * tj, acc);
           team_sync<TEAM>();
         }
       } else {

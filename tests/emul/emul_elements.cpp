@@ -76,33 +76,29 @@ static void run_shell_unc(const double *Xpts, const double *vars, const double *
   WK *w = new WK;
   for (int k = 0; k < WK::SCR; k++) w->scr[k] = std::nan("");  // stale scratch must never be consumed
   for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
-  for (int k = 0; k < nd; k++) { w->u[k] = vars[k]; w->acc[k] = ddvars ? ddvars[k] : 0.0; }
-  for (int k = 0; k < kDescStride; k++) w->desc[k] = desc[k];
   const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
-  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, w->desc);
+  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, desc);
   for (int t = 0; t < nty; t++) shell_p2_tying<O>(t, *w, tab);
-  for (int q = 0; q < nq; q++) {
-    shell_p2_qgeom<O>(q, *w, tab, w->desc);
-    shell_unc_P<O>(q, *w);
-  }
-  for (int t = 0; t < n * n; t++) shell_unc_Sd<O>(t, *w, tab);
-  for (int t = 0; t < 5 * nq; t++) shell_unc_G<O>(t, *w);
+  for (int q = 0; q < nq; q++) shell_unc_qgeom<O>(q, *w, tab, desc);
+  for (int t = 0; t < 5 * nq; t++) shell_unc_G<O>(t, *w, desc);
   for (int k = 0; k < nty * (nty + 1) / 2; k++) shell_unc_S_entry<O>(shell_unc_tri<O>(k), *w, tab);
-  for (int t = 0; t < nty * n + n * n; t++) shell_unc_products<O>(t, *w);
+  for (int t = 0; t < nty * n; t++) shell_unc_products<O>(t, *w);
   std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
-  for (int t = 0; t < n * 3; t++) shell_unc_bending<O>(t, 0, *w, tab, w->buf(0));
-  for (int t = 0; t < WK::ntiles; t++) {
+  for (int t = 0; t < n * 3; t++) shell_unc_rows<O>(t, 0, *w, tab, desc, w->buf(0));
+  for (int t = 0; t < WK::ntiles; t++)
     tile_accumulate<nty, WK::LDT, 6, 6, nd>(&w->Bty[0][0], w->scr + WK::oSB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-    tile_accumulate<n, WK::LDT, 6, 6, nd>(&w->Bdr[0][0], w->scr + WK::oSdB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-  }
   for (int q = 0; q < nq; q++) {
-    if (q + 1 < nq)
-      for (int t = 0; t < n * 3; t++) shell_unc_bending<O>(t, q + 1, *w, tab, w->buf((q + 1) & 1));
-    const double *Bb = w->buf(q & 1);
+    if (q + 1 < nq) {
+      for (int t = 0; t < n * 3; t++) shell_unc_rows<O>(t, q + 1, *w, tab, desc, w->buf((q + 1) & 1));
+    } else {
+      // the state enters shared memory in the last interval, in the row buffer that is no longer read
+      for (int k = 0; k < nd; k++) { w->uvec()[k] = vars[k]; w->avec()[k] = ddvars ? ddvars[k] : 0.0; }
+    }
+    const double *L = w->buf(q & 1);
     for (int t = 0; t < WK::ntiles; t++)
-      tile_accumulate<3, nd, 6, 6>(Bb, Bb + 3 * nd, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
+      tile_accumulate<4, nd, 6, 6>(L, L + 4 * nd, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
   }
-  shell_outputs<O>(w, tab, w->desc, alpha, gamma, inertia, acc, res, mat);
+  shell_outputs<O>(w, tab, desc, alpha, gamma, inertia, acc, res, mat);
   delete w;
 }
 
