@@ -146,6 +146,7 @@ struct alignas(16) ShellWork {
   TB2_HD double *rpart() { return &B[0][0][0]; }
   TB2_HD double *uvec() { return u; }
   TB2_HD double *avec() { return acc; }
+  TB2_HD double &bty(int ty, int col) { return Bty[ty][col]; }
 };
 
 // phase 1, task i in [0,n): node normal, nodal frame, nodal drill-strain row
@@ -238,8 +239,8 @@ TB2_HD void shell_p2_tying(int ty, WK &w, const ShellTables<O> &tab) {
     cross3(&w.fn[3 * j], dd, dq);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      w.Bty[ty][6 * j + c] = du[c];
-      w.Bty[ty][6 * j + 3 + c] = dq[c];
+      w.bty(ty, 6 * j + c) = du[c];
+      w.bty(ty, 6 * j + 3 + c) = dq[c];
     }
   }
 }
@@ -459,14 +460,55 @@ struct alignas(16) ShellUncWork {
   TB2_HD double *uvec() { return scr + oU; }
   TB2_HD double *avec() { return scr + oAcc; }
   TB2_HD double *buf(int k) { return scr + k * LBUF; }
+  TB2_HD double &bty(int ty, int col) { return Bty[ty][col]; }
+  static constexpr int LDS_ = nty;               // row stride of S
+  static constexpr bool kColMajorRows = false;   // row buffers are [row][col]
 };
+
+// Quad4 work area of the tensor-core (DMMA m8n8k4) kernel. Every operand of a matrix product is kept as
+// "k-step panels" X[kstep][col][4]: the four rows of one k-step are contiguous per column, so that the A / B
+// fragment of lane l for tile t of a panel is the single double at panel[32 t + l] (a warp reads 256 contiguous
+// bytes, conflict free) and the producers of the rows store 128-bit pieces.
+struct alignas(16) ShellQ4MmaWork {
+  static constexpr int n = 4, nd = 24, nq = 4, nty = 9;
+  static constexpr int ntiles = n * n;
+  static constexpr int LDT = nd + 2;
+  static constexpr int KS = 3;       // k-steps of the tying rows (9 rows padded to 12; pad rows stay zero)
+  static constexpr int LDP = 100;    // panel stride (96 + 4: the C-fragment stores of two panels hit distinct banks)
+  static constexpr int LDS_ = 12;    // row stride of S (A operand of S * Bty, k padded to 12 with zeros)
+  static constexpr bool kColMajorRows = true;
+  // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S [S .. SB product];
+  // Rty = S Bty [SB product .. tying contraction]; row buffer 0 [after SB product ..], row buffer 1 overlays Rty
+  // [after the tying contraction ..]; u, acc, residual, Rp [last loop interval .. finish] in buffer 0.
+  static constexpr int oS = 0;               // S[16][12] (rows 9..15 are never written: their products are dropped)
+  static constexpr int oG = 192;             // G[nq][26]
+  static constexpr int oP = 296;             // P[nq][5][6]
+  static constexpr int oX = 416;             // X[3n]
+  static constexpr int LBUF = 8 * nd;        // row buffer: L[col][4] then R[col][4]
+  static constexpr int oRty = LBUF;          // Rty[KS][LDP]
+  static constexpr int oU = 0, oAcc = 24, oRes = 48, oRp = 72;
+  static constexpr int SCR = oRty + KS * LDP;
+  double fn[3 * n];
+  alignas(16) double Bdr[n][LDT];
+  alignas(16) double Lty[KS][LDP];
+  alignas(16) double geo[nq][16];
+  double wdet[nq];
+  alignas(16) double scr[SCR];
+  TB2_HD double *X() { return scr + oX; }
+  TB2_HD double *rpart() { return scr + oRp; }
+  TB2_HD double *uvec() { return scr + oU; }
+  TB2_HD double *avec() { return scr + oAcc; }
+  TB2_HD double *buf(int k) { return scr + k * LBUF; }
+  TB2_HD double &bty(int ty, int col) { return Lty[ty >> 2][col * 4 + (ty & 3)]; }
+};
+static_assert(ShellQ4MmaWork::oX + 12 <= ShellQ4MmaWork::SCR && ShellQ4MmaWork::oRp + 96 <= ShellQ4MmaWork::LBUF,
+              "scratch overlays");
 
 // phase 2 (same barrier interval as shell_p2_tying), task q: frame, inverse Jacobian products, weighted
 // determinant (as shell_p2_qgeom) and the frame products of the five tying fields,
 // P[f][m] with (c,d) = (0,0) (1,1) (0,1) (1,2) (0,2) -- the expressions of shell_p3_weights without Ntq
-template <int O>
-TB2_HD void shell_unc_qgeom(int q, ShellUncWork<O> &w, const ShellTables<O> &tab, const double *desc) {
-  using WK = ShellUncWork<O>;
+template <int O, class WK>
+TB2_HD void shell_unc_qgeom(int q, WK &w, const ShellTables<O> &tab, const double *desc) {
   constexpr int n = WK::n;
   const double *X = w.X();
   double Xxi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, n0[3] = {0.0, 0.0, 0.0};
@@ -522,9 +564,8 @@ TB2_HD void shell_unc_qgeom(int q, ShellUncWork<O> &w, const ShellTables<O> &tab
 }
 
 // G phase, task (q, f2): column f2 of G_q = P_q (w det C_TT) P_q^T, C_TT = [A 0; 0 As] on (e0,e1,e2 | e6,e7)
-template <int O>
-TB2_HD void shell_unc_G(int task, ShellUncWork<O> &w, const double *desc) {
-  using WK = ShellUncWork<O>;
+template <int O, class WK>
+TB2_HD void shell_unc_G(int task, WK &w, const double *desc) {
   const int q = task / 5, f2 = task % 5;
   const double *P = w.scr + WK::oP + 30 * q;
   const double wd = w.wdet[q];
@@ -559,17 +600,16 @@ TB2_HD int shell_unc_tri(int k) {
 }
 
 // S phase, one packed entry: S[t1][t2] = S[t2][t1] = sum_q Ntq[q][t1] Ntq[q][t2] G_q[f1][f2]
-template <int O>
-TB2_HD void shell_unc_S_entry(int packed, ShellUncWork<O> &w, const ShellTables<O> &tab) {
-  using WK = ShellUncWork<O>;
-  constexpr int nty = WK::nty, nq = WK::nq;
+template <int O, class WK>
+TB2_HD void shell_unc_S_entry(int packed, WK &w, const ShellTables<O> &tab) {
+  constexpr int nq = WK::nq;
   const int t1 = packed & 0xff, t2 = (packed >> 8) & 0xff, g = packed >> 16;
   const double *G = w.scr + WK::oG + g;
   double s = 0.0;
 #pragma unroll
   for (int q = 0; q < nq; q++) s += (tab.Ntq[q][t1] * tab.Ntq[q][t2]) * G[26 * q];
-  w.scr[WK::oS + t1 * nty + t2] = s;
-  w.scr[WK::oS + t2 * nty + t1] = s;
+  w.scr[WK::oS + t1 * WK::LDS_ + t2] = s;
+  w.scr[WK::oS + t2 * WK::LDS_ + t1] = s;
 }
 
 // products phase, task (ty, j): six entries of SB = S Bty
@@ -595,9 +635,8 @@ TB2_HD void shell_unc_products(int task, ShellUncWork<O> &w) {
 // row buffer of quadrature point q, task (j, c): the columns 6j+c and 6j+3+c of
 //   L rows 0..2: bending rows 3,4,5 of B (same expressions as shell_p3_columns);  L row 3: drill row
 //   R rows 0..2: (w det D) L;                                                     R row 3: (w det drill) L3
-template <int O>
-TB2_HD void shell_unc_rows(int task, int q, ShellUncWork<O> &w, const ShellTables<O> &tab, const double *desc,
-                           double *buf) {
+template <int O, class WK>
+TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, const double *desc, double *buf) {
   constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
   const int c = task % 3, j = (task / 3) % n;
   const int cu = 6 * j + c, cq = cu + 3;
@@ -626,21 +665,42 @@ TB2_HD void shell_unc_rows(int task, int q, ShellUncWork<O> &w, const ShellTable
   // D block of the descriptor at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
   const double *Dm = desc + 12;
   const double wd = w.wdet[q];
-  double *L = buf, *R = buf + 4 * nd;
+  double ru[4], rq[4];
 #pragma unroll
   for (int r = 0; r < 3; r++) {
     const int i0 = (r == 0) ? 0 : ((r == 1) ? 1 : 2), i1 = (r == 0) ? 1 : ((r == 1) ? 3 : 4),
               i2 = (r == 0) ? 2 : ((r == 1) ? 4 : 5);
-    L[r * nd + cu] = bu[r];
-    L[r * nd + cq] = bq[r];
-    R[r * nd + cu] = wd * (Dm[i0] * bu[0] + Dm[i1] * bu[1] + Dm[i2] * bu[2]);
-    R[r * nd + cq] = wd * (Dm[i0] * bq[0] + Dm[i1] * bq[1] + Dm[i2] * bq[2]);
+    ru[r] = wd * (Dm[i0] * bu[0] + Dm[i1] * bu[1] + Dm[i2] * bu[2]);
+    rq[r] = wd * (Dm[i0] * bq[0] + Dm[i1] * bq[1] + Dm[i2] * bq[2]);
   }
   const double wdr = wd * desc[21];
-  L[3 * nd + cu] = bu[3];
-  L[3 * nd + cq] = bq[3];
-  R[3 * nd + cu] = wdr * bu[3];
-  R[3 * nd + cq] = wdr * bq[3];
+  ru[3] = wdr * bu[3];
+  rq[3] = wdr * bq[3];
+  double *L = buf, *R = buf + 4 * nd;
+  if (WK::kColMajorRows) {
+    // panels L[col][4], R[col][4]: the four rows of a column are contiguous (two 128-bit stores each)
+#if defined(__CUDA_ARCH__)
+    double2 *Lu = reinterpret_cast<double2 *>(L + 4 * cu), *Lq = reinterpret_cast<double2 *>(L + 4 * cq);
+    double2 *Ru = reinterpret_cast<double2 *>(R + 4 * cu), *Rq = reinterpret_cast<double2 *>(R + 4 * cq);
+    Lu[0] = make_double2(bu[0], bu[1]); Lu[1] = make_double2(bu[2], bu[3]);
+    Lq[0] = make_double2(bq[0], bq[1]); Lq[1] = make_double2(bq[2], bq[3]);
+    Ru[0] = make_double2(ru[0], ru[1]); Ru[1] = make_double2(ru[2], ru[3]);
+    Rq[0] = make_double2(rq[0], rq[1]); Rq[1] = make_double2(rq[2], rq[3]);
+#else
+    for (int r = 0; r < 4; r++) {
+      L[4 * cu + r] = bu[r]; L[4 * cq + r] = bq[r];
+      R[4 * cu + r] = ru[r]; R[4 * cq + r] = rq[r];
+    }
+#endif
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      L[r * nd + cu] = bu[r];
+      L[r * nd + cq] = bq[r];
+      R[r * nd + cu] = ru[r];
+      R[r * nd + cq] = rq[r];
+    }
+  }
 }
 
 // residual-only path (assembleRes): strains of the chunk, task (ql, r): e = B u, kept in the unused CB rows
@@ -700,13 +760,47 @@ TB2_HD void tile_accumulate(const double *B, const double *CB, int row0, int col
   }
 }
 
+// inertial block of node pair (i,j): M = int rho-moments N_i N_j [I, D_j; D_i^T, D_i^T D_j] (director d = q x t)
+template <int O, class WK>
+TB2_HD void shell_mass_tile(int tile, WK &w, const ShellTables<O> &tab, const double *desc, double *M) {
+  constexpr int n = ShellDims<O>::n, nq = ShellDims<O>::nq;
+  const int i = tile / n, j = tile % n;
+  double S = 0.0;
+  for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][i] * tab.Nq[q][j];
+  const double m0 = desc[22], m1 = desc[23], m2 = desc[24];
+  // d = D q with D(c,e) = eps_{cef} t_f
+  const double *ti = &w.fn[3 * i], *tj = &w.fn[3 * j];
+  const double Di[9] = {0.0, ti[2], -ti[1], -ti[2], 0.0, ti[0], ti[1], -ti[0], 0.0};
+  const double Dj[9] = {0.0, tj[2], -tj[1], -tj[2], 0.0, tj[0], tj[1], -tj[0], 0.0};
+#pragma unroll
+  for (int k = 0; k < 36; k++) M[k] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    M[6 * c + c] = S * m0;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      M[6 * c + 3 + e] = S * m1 * Dj[3 * c + e];
+      M[6 * (3 + e) + c] = S * m1 * Di[3 * c + e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) v += Di[3 * c + e] * Dj[3 * c + f];
+      M[6 * (3 + e) + 3 + f] = S * m2 * v;
+    }
+}
+
 // phase 6, task tile (i,j): inertial block (only when `inertia`), residual partials; on return acc holds
 // alpha*K_tile + gamma*M_tile. Runs after the last chunk barrier: the partials reuse the B rows.
 template <int O, class WK>
 TB2_HD void shell_p6_finish(int tile, WK &w, const ShellTables<O> &tab, const double *desc,
                             double alpha, double gamma, bool inertia, double *acc, double *rp) {
-  constexpr int n = ShellDims<O>::n, nq = ShellDims<O>::nq;
-  const int i = tile / n, j = tile % n;
+  constexpr int n = ShellDims<O>::n;
+  const int j = tile % n;
 #pragma unroll
   for (int a = 0; a < 6; a++) {
     double s = 0.0;
@@ -717,34 +811,8 @@ TB2_HD void shell_p6_finish(int tile, WK &w, const ShellTables<O> &tab, const do
 #pragma unroll
   for (int k = 0; k < 36; k++) acc[k] *= alpha;
   if (inertia) {
-    double S = 0.0;
-    for (int q = 0; q < nq; q++) S += w.wdet[q] * tab.Nq[q][i] * tab.Nq[q][j];
-    const double m0 = desc[22], m1 = desc[23], m2 = desc[24];
-    // d = D q with D(c,e) = eps_{cef} t_f  (director d = q x t)
-    const double *ti = &w.fn[3 * i], *tj = &w.fn[3 * j];
-    const double Di[9] = {0.0, ti[2], -ti[1], -ti[2], 0.0, ti[0], ti[1], -ti[0], 0.0};
-    const double Dj[9] = {0.0, tj[2], -tj[1], -tj[2], 0.0, tj[0], tj[1], -tj[0], 0.0};
     double M[36];
-#pragma unroll
-    for (int k = 0; k < 36; k++) M[k] = 0.0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      M[6 * c + c] = S * m0;
-#pragma unroll
-      for (int e = 0; e < 3; e++) {
-        M[6 * c + 3 + e] = S * m1 * Dj[3 * c + e];
-        M[6 * (3 + e) + c] = S * m1 * Di[3 * c + e];
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 3; e++)
-#pragma unroll
-      for (int f = 0; f < 3; f++) {
-        double v = 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) v += Di[3 * c + e] * Dj[3 * c + f];
-        M[6 * (3 + e) + 3 + f] = S * m2 * v;
-      }
+    shell_mass_tile<O>(tile, w, tab, desc, M);
 #pragma unroll
     for (int a = 0; a < 6; a++) {
       double s = 0.0;

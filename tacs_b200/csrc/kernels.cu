@@ -337,6 +337,284 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Quad4 shells with an uncoupled constitutive matrix: tensor-core kernel
+// ------------------------------------------------------------------------------------------
+// Same mathematics as shell_element_kernel<2, true> (elem_phases.cuh: K = Bty^T S Bty + sum_q L_q^T R_q), but the
+// two matrix products S*Bty and L^T R run on the FP64 tensor cores (mma.sync m8n8k4). ncu shows the FMA version
+// bound by the L1/shared-memory data pipe (88 % busy feeding 6x6 register tiles); the fragment loads of the MMA
+// version move a third of those bytes. A warp holds two elements (one per half-warp for the scalar phases); the
+// MMA phases are executed by the whole warp, first for one element and then for the other.
+struct ShellQ4MmaFamily {
+  using Work = ShellQ4MmaWork;
+  using Tables = ShellTables<2>;
+  static constexpr int TEAM = 16, TEAMS = 8, MIN_CTAS = 3, BS = 6;
+  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAMS, ShellQ4MmaFamily::MIN_CTAS)
+    shell4_mma_kernel(ElemGroupArgs g) {
+  using F = ShellQ4MmaFamily;
+  using Work = ShellQ4MmaWork;
+  constexpr int O = 2, TEAM = F::TEAM, TEAMS = F::TEAMS;
+  constexpr int n = Work::n, nd = Work::nd, nq = Work::nq, nty = Work::nty, KS = Work::KS, LDP = Work::LDP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  F::Tables &tab = *reinterpret_cast<F::Tables *>(smem_raw);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(F::Tables));
+  unsigned char *work_base = smem_raw + sizeof(F::Tables) + 16;
+  stage_tables(&tab, g.tables, (uint32_t)sizeof(F::Tables), mbar);
+
+  const int team_in_cta = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+  const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;  // MMA fragment coordinates of this lane
+  Work &w = *reinterpret_cast<Work *>(work_base + (size_t)team_in_cta * F::WORK_STRIDE);
+  Work *const we[2] = {reinterpret_cast<Work *>(work_base + (size_t)(team_in_cta & ~1) * F::WORK_STRIDE),
+                       reinterpret_cast<Work *>(work_base + (size_t)(team_in_cta | 1) * F::WORK_STRIDE)};
+  // the pad rows of the tying panels must be exact zeros and every other word finite before the first product
+  for (int k = tid; k < (int)(sizeof(Work) / sizeof(double)); k += TEAM) reinterpret_cast<double *>(&w)[k] = 0.0;
+  const long nteams = (long)gridDim.x * TEAMS;
+  const long nelem = g.nelem;
+  const bool inertia = (g.gamma != 0.0) || (g.ddvars != nullptr);
+  // two-deep input pipeline (see shell_element_kernel)
+  constexpr int NU = (nd + TEAM - 1) / TEAM;
+  double pX = 0.0, pu[NU], pa[NU];
+  int cX = 0, cU[NU], cD = 0, dnext = 0;
+  auto prefetch_ids = [&](long e) {
+    const int *conn = g.conn + e * n;
+    if (tid < 3 * n) cX = __ldg(conn + tid / 3);
+#pragma unroll
+    for (int m = 0; m < NU; m++) {
+      const int kk = tid + m * TEAM;
+      cU[m] = kk < nd ? __ldg(conn + kk / 6) : 0;
+    }
+    cD = __ldg(g.desc_index + e);
+  };
+  auto prefetch_data = [&]() {
+    if (tid < 3 * n) pX = g.Xpts[3 * (long)cX + tid % 3];
+#pragma unroll
+    for (int m = 0; m < NU; m++) {
+      const int kk = tid + m * TEAM;
+      pu[m] = 0.0;
+      pa[m] = 0.0;
+      if (kk < nd) {
+        const long src = 6 * (long)cU[m] + kk % 6;
+        if (g.vars) pu[m] = g.vars[src];
+        if (g.ddvars) pa[m] = g.ddvars[src];
+      }
+    }
+    dnext = cD;
+    // the descriptor row is read in place (L1): pull its two lines in ahead of time
+    if (tid < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.desc_table + (long)kDescStride * cD + 16 * tid));
+  };
+  auto clamp_elem = [&](long e) { return e < nelem ? e : nelem - 1; };
+  {
+    const long e0 = (long)blockIdx.x * TEAMS + team_in_cta;
+    prefetch_ids(clamp_elem(e0));
+    prefetch_data();
+    prefetch_ids(clamp_elem(e0 + nteams));
+  }
+  // entries of the symmetric tying-space matrix S owned by this thread (decoded once)
+  constexpr int NTRI = nty * (nty + 1) / 2;
+  constexpr int NSA = (NTRI + TEAM - 1) / TEAM;
+  int stri[NSA];
+#pragma unroll
+  for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
+  // staging offsets of this lane's C fragments: rows 8 mt + gq, column pairs 8 nt + 2 tq (node-pair-major 6x6 blocks)
+  int ro[3], co[3];
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    const int R = 8 * t + gq, C = 8 * t + 2 * tq;
+    ro[t] = (R / 6) * (n * 36) + (R % 6) * 6;
+    co[t] = (C / 6) * 36 + C % 6;
+  }
+  __syncwarp();
+
+  for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
+    const bool live = (base + team_in_cta) < nelem;
+    const long e = live ? base + team_in_cta : nelem - 1;
+    if (tid < 3 * n) w.X()[tid] = pX;
+    const double *desc = g.desc_table + (long)kDescStride * dnext;
+    double cu[NU], ca[NU];  // the state stays in registers until the last quadrature interval
+#pragma unroll
+    for (int m = 0; m < NU; m++) {
+      cu[m] = pu[m];
+      ca[m] = pa[m];
+    }
+    __syncwarp();
+    prefetch_data();                                            // next element (ids already here)
+    prefetch_ids(clamp_elem(base + 2 * nteams + team_in_cta));  // element after next
+    if (tid < n) shell_p1_node<O>(tid, w, tab, desc);
+    __syncwarp();
+    if (tid < nty) shell_p2_tying<O>(tid, w, tab);
+    else if (tid < nty + nq) shell_unc_qgeom<O>(tid - nty, w, tab, desc);
+    __syncwarp();
+    for (int t = tid; t < 5 * nq; t += TEAM) shell_unc_G<O>(t, w, desc);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < NSA; m++)
+      if (tid + m * TEAM < NTRI) shell_unc_S_entry<O>(stri[m], w, tab);
+    // k padding of the A operand S (columns 9..11 of the rows that are used)
+    for (int t = tid; t < 3 * nty; t += TEAM) w.scr[Work::oS + (t / 3) * Work::LDS_ + nty + t % 3] = 0.0;
+    __syncwarp();
+    // Rty = S Bty on the tensor cores: M = tying row (2 tiles, rows 9..15 dropped), N = column (3 tiles), K = 12
+#pragma unroll
+    for (int el = 0; el < 2; el++) {
+      Work &x = *we[el];
+      double c[2][3][2];
+#pragma unroll
+      for (int k = 0; k < 12; k++) (&c[0][0][0])[k] = 0.0;
+      const double *S = x.scr + Work::oS;
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        const double a0 = S[gq * Work::LDS_ + 4 * ks + tq], a1 = S[(8 + gq) * Work::LDS_ + 4 * ks + tq];
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) {
+          const double b = x.Lty[ks][32 * nt + lane];
+          dmma884(c[0][nt][0], c[0][nt][1], a0, b);
+          dmma884(c[1][nt][0], c[1][nt][1], a1, b);
+        }
+      }
+      double *R = x.scr + Work::oRty;
+#pragma unroll
+      for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int col = 8 * nt + 2 * tq + h;
+          R[(gq >> 2) * LDP + 4 * col + (gq & 3)] = c[0][nt][h];
+          // rows 8..11: row 8 is the last tying row, rows 9..11 are the k padding of the next product
+          if (gq < 4) R[2 * LDP + 4 * col + gq] = (gq == 0) ? c[1][nt][h] : 0.0;
+        }
+    }
+    __syncwarp();
+    // rows of point 0 (bending + drill) go to buffer 0 while the tying rows are contracted; inside the loop the
+    // rows of point q+1 are produced in the barrier interval that contracts those of point q
+    if (tid < 3 * n) shell_unc_rows<O>(tid, 0, w, tab, desc, w.buf(0));
+    double kacc[2][3][3][2];
+#pragma unroll
+    for (int k = 0; k < 36; k++) (&kacc[0][0][0][0])[k] = 0.0;
+#pragma unroll
+    for (int el = 0; el < 2; el++) {
+      Work &x = *we[el];
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        double a[3], b[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          a[t] = x.Lty[ks][32 * t + lane];
+          b[t] = x.scr[Work::oRty + ks * LDP + 32 * t + lane];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 3; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 3; nt++) dmma884(kacc[el][mt][nt][0], kacc[el][mt][nt][1], a[mt], b[nt]);
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int q = 0; q < nq; q++) {
+      if (q + 1 < nq) {
+        if (tid < 3 * n) shell_unc_rows<O>(tid, q + 1, w, tab, desc, w.buf((q + 1) & 1));
+      } else {
+        // last interval: the state enters shared memory in the row buffer that is no longer read
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) {
+            w.uvec()[kk] = cu[m];
+            w.avec()[kk] = ca[m];
+          }
+        }
+      }
+#pragma unroll
+      for (int el = 0; el < 2; el++) {
+        const double *L = we[el]->buf(q & 1);
+        double a[3], b[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          a[t] = L[32 * t + lane];
+          b[t] = L[4 * nd + 32 * t + lane];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 3; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 3; nt++) dmma884(kacc[el][mt][nt][0], kacc[el][mt][nt][1], a[mt], b[nt]);
+      }
+      __syncwarp();
+    }
+    // finish (whole warp per element): residual K u from the fragments, alpha, tangent to the staging area
+#pragma unroll
+    for (int el = 0; el < 2; el++) {
+      Work &x = *we[el];
+      const long eo = base + (team_in_cta & ~1) + el;
+      const bool live_o = eo < nelem;
+      double2 up[3];
+#pragma unroll
+      for (int nt = 0; nt < 3; nt++) up[nt] = *reinterpret_cast<const double2 *>(x.uvec() + 8 * nt + 2 * tq);
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) {
+        double r = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) r += kacc[el][mt][nt][0] * up[nt].x + kacc[el][mt][nt][1] * up[nt].y;
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        if (tq == 0) x.scr[Work::oRes + 8 * mt + gq] = r;
+      }
+      if (live_o) {
+        double *dst = g.Ke + eo * (n * n * 36);
+#pragma unroll
+        for (int mt = 0; mt < 3; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 3; nt++)
+            *reinterpret_cast<double2 *>(dst + ro[mt] + co[nt]) =
+                make_double2(g.alpha * kacc[el][mt][nt][0], g.alpha * kacc[el][mt][nt][1]);
+      }
+    }
+    __syncwarp();
+    if (inertia) {
+      // inertial block of node pair tid = (i,j) added to the staged tangent of this team's own element
+      double M[36];
+      shell_mass_tile<O>(tid, w, tab, desc, M);
+      const int j = tid % n;
+      double *rp = w.rpart() + 6 * tid;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) sacc += M[6 * a + b] * w.avec()[6 * j + b];
+        rp[a] = sacc;
+      }
+      if (live) {
+        double2 *dst = reinterpret_cast<double2 *>(g.Ke + (e * (n * n) + tid) * 36);
+#pragma unroll
+        for (int k = 0; k < 18; k++) {
+          double2 v = dst[k];
+          v.x += g.gamma * M[2 * k];
+          v.y += g.gamma * M[2 * k + 1];
+          dst[k] = v;
+        }
+      }
+      __syncwarp();
+    }
+    if (live && g.Re) {
+      for (int k = tid; k < nd; k += TEAM) {
+        double sres = w.scr[Work::oRes + k];
+        if (inertia) {
+          const int i = k / 6, a = k % 6;
+          const double *rp = w.rpart();
+          for (int j = 0; j < n; j++) sres += rp[(i * n + j) * 6 + a];
+        }
+        g.Re[e * nd + k] = sres;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int O>
 __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
     solid_element_kernel(ElemGroupArgs g) {
@@ -561,7 +839,7 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
   if (g.nelem <= 0) return cudaSuccess;
   switch (g.kind) {
     case ELEM_QUAD4_SHELL:
-      if (g.uncoupled && g.Ke) return launch_family<ShellFamily<2, true>>(shell_element_kernel<2, true>, g, num_sms, s);
+      if (g.uncoupled && g.Ke) return launch_family<ShellQ4MmaFamily>(shell4_mma_kernel, g, num_sms, s);
       return launch_family<ShellFamily<2, false>>(shell_element_kernel<2, false>, g, num_sms, s);
     case ELEM_QUAD9_SHELL:
       if (g.uncoupled && g.Ke) return launch_family<ShellFamily<3, true>>(shell_element_kernel<3, true>, g, num_sms, s);

@@ -102,6 +102,85 @@ static void run_shell_unc(const double *Xpts, const double *vars, const double *
   delete w;
 }
 
+// Quad4 tensor-core kernel (shell4_mma_kernel): the scalar phases are the device task functions; the two MMA
+// products are replayed as plain loops over the same shared-memory panels (the lane <-> fragment mapping itself is
+// only exercised on the GPU)
+static void run_shell4_mma(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                           double alpha, double gamma, double *res, double *mat) {
+  using WK = ShellQ4MmaWork;
+  constexpr int O = 2, n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty, KS = WK::KS, LDP = WK::LDP;
+  static ShellTables<O> tab;
+  build_shell_tables<O>(tab);
+  WK *w = new WK;
+  std::memset(w, 0, sizeof(WK));  // the kernel zeroes the work area once
+  for (int k = 0; k < WK::SCR; k++) w->scr[k] = 1e300;  // stale scratch must not matter
+  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
+  const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
+  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, desc);
+  for (int t = 0; t < nty; t++) shell_p2_tying<O>(t, *w, tab);
+  for (int q = 0; q < nq; q++) shell_unc_qgeom<O>(q, *w, tab, desc);
+  for (int t = 0; t < 5 * nq; t++) shell_unc_G<O>(t, *w, desc);
+  for (int k = 0; k < nty * (nty + 1) / 2; k++) shell_unc_S_entry<O>(shell_unc_tri<O>(k), *w, tab);
+  for (int t = 0; t < 3 * nty; t++) w->scr[WK::oS + (t / 3) * WK::LDS_ + nty + t % 3] = 0.0;
+  // Rty = S Bty (rows 0..8), rows 9..11 zero
+  {
+    std::vector<double> R((size_t)KS * LDP, 0.0);
+    for (int ty = 0; ty < 12; ty++)
+      for (int col = 0; col < nd; col++) {
+        double sum = 0.0;
+        if (ty < nty)
+          for (int t = 0; t < 12; t++) sum += w->scr[WK::oS + ty * WK::LDS_ + t] * w->Lty[t >> 2][col * 4 + (t & 3)];
+        R[(ty >> 2) * LDP + col * 4 + (ty & 3)] = sum;
+      }
+    for (int k = 0; k < KS * LDP; k++) w->scr[WK::oRty + k] = R[k];
+  }
+  for (int t = 0; t < n * 3; t++) shell_unc_rows<O>(t, 0, *w, tab, desc, w->buf(0));
+  std::vector<double> K((size_t)nd * nd, 0.0);
+  for (int i = 0; i < nd; i++)
+    for (int j = 0; j < nd; j++)
+      for (int k = 0; k < 12; k++)
+        K[i * nd + j] += w->Lty[k >> 2][i * 4 + (k & 3)] * w->scr[WK::oRty + (k >> 2) * LDP + j * 4 + (k & 3)];
+  for (int q = 0; q < nq; q++) {
+    if (q + 1 < nq) {
+      for (int t = 0; t < n * 3; t++) shell_unc_rows<O>(t, q + 1, *w, tab, desc, w->buf((q + 1) & 1));
+    } else {
+      for (int k = 0; k < nd; k++) { w->uvec()[k] = vars[k]; w->avec()[k] = ddvars ? ddvars[k] : 0.0; }
+    }
+    const double *L = w->buf(q & 1);
+    for (int i = 0; i < nd; i++)
+      for (int j = 0; j < nd; j++)
+        for (int r = 0; r < 4; r++) K[i * nd + j] += L[i * 4 + r] * L[4 * nd + j * 4 + r];
+  }
+  for (int i = 0; i < nd; i++) {
+    double r = 0.0;
+    for (int j = 0; j < nd; j++) r += K[i * nd + j] * w->uvec()[j];
+    w->scr[WK::oRes + i] = r;
+    for (int j = 0; j < nd; j++) mat[i * nd + j] = alpha * K[i * nd + j];
+  }
+  if (inertia) {
+    for (int t = 0; t < n * n; t++) {
+      double M[36];
+      shell_mass_tile<O>(t, *w, tab, desc, M);
+      const int i = t / n, j = t % n;
+      for (int a = 0; a < 6; a++) {
+        double sacc = 0.0;
+        for (int b = 0; b < 6; b++) {
+          sacc += M[6 * a + b] * w->avec()[6 * j + b];
+          mat[nd * (6 * i + a) + 6 * j + b] += gamma * M[6 * a + b];
+        }
+        w->rpart()[6 * t + a] = sacc;
+      }
+    }
+  }
+  for (int k = 0; k < nd; k++) {
+    double sres = w->scr[WK::oRes + k];
+    if (inertia)
+      for (int j = 0; j < n; j++) sres += w->rpart()[((k / 6) * n + j) * 6 + k % 6];
+    res[k] = sres;
+  }
+  delete w;
+}
+
 template <int O, int QC>
 static void run_solid(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
                       double alpha, double gamma, double *res, double *mat) {
@@ -142,9 +221,10 @@ int emul_element(int kind, const double *Xpts, const double *vars, const double 
                  double alpha, double gamma, double *res, double *mat) {
   switch (kind) {
     case 1:
-      if (desc_uncoupled(desc)) run_shell_unc<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      if (desc_uncoupled(desc)) run_shell4_mma(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       else run_shell<2, 1>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       return 0;
+    case 5: run_shell_unc<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;  // generic uncoupled flow
     case 2:
       if (desc_uncoupled(desc)) run_shell_unc<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       else run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
