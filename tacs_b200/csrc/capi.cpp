@@ -42,7 +42,7 @@ static double timed(int reps, F fn) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  cudaStreamSynchronize(ctx().stream);
+  cudaStreamSynchronize(ctx().stream.s);
   cudaEventRecord(e0, ctx().stream);
   int fail = 0;
   for (int i = 0; i < reps && !fail; i++) fail = fn();
@@ -73,7 +73,7 @@ int tacsb200_comm_rank(void) { return ctx().rank; }
 int tacsb200_comm_size(void) { return ctx().size; }
 int tacsb200_synchronize(void) {
   if (ctx().device < 0) return 1;
-  return cuda_ok(cudaStreamSynchronize(ctx().stream), "synchronize") ? 0 : 1;
+  return cuda_ok(cudaStreamSynchronize(ctx().stream.s), "synchronize") ? 0 : 1;
 }
 long tacsb200_kernel_launches(int reset) {
   long n = ctx().kernel_launches;

@@ -120,7 +120,7 @@ static int exchange(DeviceExchange &dx, int chunk, const double *src, RecvBase r
   const long ns = dx.sendTotal();
   if (ns > 0) {
     if (dx.sendbuf.count < (size_t)ns * chunk && !dx.sendbuf.alloc((size_t)ns * chunk)) return 1;
-    if (s == c.stream) {
+    if (s == c.stream.s) {
       KernelTimer kt(K_HALO);  // event timing only makes sense on the stream the events are recorded on
       if (!cuda_ok(launch_pack_blocks(chunk, ns, dx.d_send_idx.ptr, src, dx.sendbuf.ptr, c.num_sms, s), "halo pack"))
         return 1;

@@ -147,6 +147,10 @@ struct alignas(16) ShellWork {
   TB2_HD double *uvec() { return u; }
   TB2_HD double *avec() { return acc; }
   TB2_HD double &bty(int ty, int col) { return Bty[ty][col]; }
+  // nodal drill row of node i: displacement / rotation columns of node j (rotation part non-zero for j == i only)
+  static constexpr bool kFullBdr = true;
+  TB2_HD double &bdr_u(int i, int j, int c) { return Bdr[i][6 * j + c]; }
+  TB2_HD double &bdr_q(int i, int c) { return Bdr[i][6 * i + 3 + c]; }
 };
 
 // phase 1, task i in [0,n): node normal, nodal frame, nodal drill-strain row
@@ -191,15 +195,15 @@ TB2_HD void shell_p1_node(int i, WK &w, const ShellTables<O> &tab, const double 
     const double g1 = d0 * XdinvT[1] + d1 * XdinvT[4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      w.Bdr[i][6 * j + c] = 0.5 * (T[3 * c + 1] * g0 - T[3 * c] * g1);
-      w.Bdr[i][6 * j + 3 + c] = 0.0;
+      w.bdr_u(i, j, c) = 0.5 * (T[3 * c + 1] * g0 - T[3 * c] * g1);
+      if (WK::kFullBdr) w.bdr_u(i, j, 3 + c) = 0.0;
     }
   }
   double t1[3] = {T[0], T[3], T[6]}, t2[3] = {T[1], T[4], T[7]}, t12[3];
   cross3(t1, t2, t12);
-  w.Bdr[i][6 * i + 3] = -t12[0];
-  w.Bdr[i][6 * i + 4] = -t12[1];
-  w.Bdr[i][6 * i + 5] = -t12[2];
+  w.bdr_q(i, 0) = -t12[0];
+  w.bdr_q(i, 1) = -t12[1];
+  w.bdr_q(i, 2) = -t12[2];
 }
 
 // phase 2, task ty in [0,nty): tying-strain row (reads fn of every node: runs after phase 1).
@@ -452,7 +456,7 @@ struct alignas(16) ShellUncWork {
   alignas(16) double Bdr[n][LDT];
   alignas(16) double Bty[nty][LDT];
   // per quadrature point: T(0,1,3,4,6,7) A(0,1,3,4) Az(0,1,3,4,6,7) -- the frame entries the bending rows use
-  alignas(16) double geo[nq][16];
+  alignas(16) double geo[nq][18];  // 16 used; the stride spreads the four lanes that fill it over the banks
   double wdet[nq];
   alignas(16) double scr[SCR];
   TB2_HD double *X() { return scr + oX; }
@@ -461,6 +465,9 @@ struct alignas(16) ShellUncWork {
   TB2_HD double *avec() { return scr + oAcc; }
   TB2_HD double *buf(int k) { return scr + k * LBUF; }
   TB2_HD double &bty(int ty, int col) { return Bty[ty][col]; }
+  static constexpr bool kFullBdr = true;
+  TB2_HD double &bdr_u(int i, int j, int c) { return Bdr[i][6 * j + c]; }
+  TB2_HD double &bdr_q(int i, int c) { return Bdr[i][6 * i + 3 + c]; }
   static constexpr int LDS_ = nty;               // row stride of S
   static constexpr bool kColMajorRows = false;   // row buffers are [row][col]
 };
@@ -472,11 +479,15 @@ struct alignas(16) ShellUncWork {
 struct alignas(16) ShellQ4MmaWork {
   static constexpr int n = 4, nd = 24, nq = 4, nty = 9;
   static constexpr int ntiles = n * n;
-  static constexpr int LDT = nd + 2;
   static constexpr int KS = 3;       // k-steps of the tying rows (9 rows padded to 12; pad rows stay zero)
   static constexpr int LDP = 100;    // panel stride (96 + 4: the C-fragment stores of two panels hit distinct banks)
   static constexpr int LDS_ = 12;    // row stride of S (A operand of S * Bty, k padded to 12 with zeros)
   static constexpr bool kColMajorRows = true;
+  // Row buffers (one k-step each, rewritten per quadrature point) split a panel into its row pairs,
+  // X[k >> 1][col][k & 1] with the two halves HS doubles apart: the producers (one lane per column pair) then store
+  // 16-byte pieces at consecutive addresses instead of 32-byte strides, and the fragment of lane (gq,tq) for tile t
+  // sits at (tq >> 1) HS + 16 t + 2 gq + (tq & 1)  (HS = 8 mod 16 keeps a half-warp conflict free).
+  static constexpr int HS = 56, LPAN = 2 * HS;
   // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S [S .. SB product];
   // Rty = S Bty [SB product .. tying contraction]; row buffer 0 [after SB product ..], row buffer 1 overlays Rty
   // [after the tying contraction ..]; u, acc, residual, Rp [last loop interval .. finish] in buffer 0.
@@ -484,14 +495,15 @@ struct alignas(16) ShellQ4MmaWork {
   static constexpr int oG = 192;             // G[nq][26]
   static constexpr int oP = 296;             // P[nq][5][6]
   static constexpr int oX = 416;             // X[3n]
-  static constexpr int LBUF = 8 * nd;        // row buffer: L[col][4] then R[col][4]
-  static constexpr int oRty = LBUF;          // Rty[KS][LDP]
+  static constexpr int LBUF = 2 * LPAN;      // row buffer: L panel then R panel
+  static constexpr int oRty = LBUF;          // Rty[KS][LDP]: clear of buffer 0 and of S
   static constexpr int oU = 0, oAcc = 24, oRes = 48, oRp = 72;
   static constexpr int SCR = oRty + KS * LDP;
   double fn[3 * n];
-  alignas(16) double Bdr[n][LDT];
+  double Bdu[n][3 * n];   // nodal drill rows, displacement columns [node i][3 j + c]
+  double Bdq[n][4];       // nodal drill rows, rotation columns of the own node [node i][c]
   alignas(16) double Lty[KS][LDP];
-  alignas(16) double geo[nq][16];
+  alignas(16) double geo[nq][18];
   double wdet[nq];
   alignas(16) double scr[SCR];
   TB2_HD double *X() { return scr + oX; }
@@ -500,8 +512,12 @@ struct alignas(16) ShellQ4MmaWork {
   TB2_HD double *avec() { return scr + oAcc; }
   TB2_HD double *buf(int k) { return scr + k * LBUF; }
   TB2_HD double &bty(int ty, int col) { return Lty[ty >> 2][col * 4 + (ty & 3)]; }
+  static constexpr bool kFullBdr = false;
+  TB2_HD double &bdr_u(int i, int j, int c) { return Bdu[i][3 * j + c]; }
+  TB2_HD double &bdr_q(int i, int c) { return Bdq[i][c]; }
 };
-static_assert(ShellQ4MmaWork::oX + 12 <= ShellQ4MmaWork::SCR && ShellQ4MmaWork::oRp + 96 <= ShellQ4MmaWork::LBUF,
+static_assert(ShellQ4MmaWork::oRp + 96 <= ShellQ4MmaWork::LBUF && ShellQ4MmaWork::oRty >= 192 &&
+                  ShellQ4MmaWork::oX + 12 <= ShellQ4MmaWork::SCR,
               "scratch overlays");
 
 // phase 2 (same barrier interval as shell_p2_tying), task q: frame, inverse Jacobian products, weighted
@@ -658,9 +674,9 @@ TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, co
   // row are non-zero at node i only
   {
     double su = 0.0;
-    for (int i = 0; i < n; i++) su += tab.Nq[q][i] * w.Bdr[i][cu];
+    for (int i = 0; i < n; i++) su += tab.Nq[q][i] * w.bdr_u(i, j, c);
     bu[3] = su;
-    bq[3] = N * w.Bdr[j][cq];
+    bq[3] = N * w.bdr_q(j, c);
   }
   // D block of the descriptor at [12..17], packed [0 1 2; 1 3 4; 2 4 5]
   const double *Dm = desc + 12;
@@ -676,23 +692,26 @@ TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, co
   const double wdr = wd * desc[21];
   ru[3] = wdr * bu[3];
   rq[3] = wdr * bq[3];
-  double *L = buf, *R = buf + 4 * nd;
-  if (WK::kColMajorRows) {
-    // panels L[col][4], R[col][4]: the four rows of a column are contiguous (two 128-bit stores each)
+  if constexpr (WK::kColMajorRows) {
+    // half-split panels X[k >> 1][col][k & 1] (ShellQ4MmaWork): four 16-byte pieces per column
+    double *L = buf, *R = buf + WK::LPAN;
 #if defined(__CUDA_ARCH__)
-    double2 *Lu = reinterpret_cast<double2 *>(L + 4 * cu), *Lq = reinterpret_cast<double2 *>(L + 4 * cq);
-    double2 *Ru = reinterpret_cast<double2 *>(R + 4 * cu), *Rq = reinterpret_cast<double2 *>(R + 4 * cq);
-    Lu[0] = make_double2(bu[0], bu[1]); Lu[1] = make_double2(bu[2], bu[3]);
-    Lq[0] = make_double2(bq[0], bq[1]); Lq[1] = make_double2(bq[2], bq[3]);
-    Ru[0] = make_double2(ru[0], ru[1]); Ru[1] = make_double2(ru[2], ru[3]);
-    Rq[0] = make_double2(rq[0], rq[1]); Rq[1] = make_double2(rq[2], rq[3]);
+    *reinterpret_cast<double2 *>(L + 2 * cu) = make_double2(bu[0], bu[1]);
+    *reinterpret_cast<double2 *>(L + WK::HS + 2 * cu) = make_double2(bu[2], bu[3]);
+    *reinterpret_cast<double2 *>(L + 2 * cq) = make_double2(bq[0], bq[1]);
+    *reinterpret_cast<double2 *>(L + WK::HS + 2 * cq) = make_double2(bq[2], bq[3]);
+    *reinterpret_cast<double2 *>(R + 2 * cu) = make_double2(ru[0], ru[1]);
+    *reinterpret_cast<double2 *>(R + WK::HS + 2 * cu) = make_double2(ru[2], ru[3]);
+    *reinterpret_cast<double2 *>(R + 2 * cq) = make_double2(rq[0], rq[1]);
+    *reinterpret_cast<double2 *>(R + WK::HS + 2 * cq) = make_double2(rq[2], rq[3]);
 #else
     for (int r = 0; r < 4; r++) {
-      L[4 * cu + r] = bu[r]; L[4 * cq + r] = bq[r];
-      R[4 * cu + r] = ru[r]; R[4 * cq + r] = rq[r];
+      L[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = bu[r]; L[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = bq[r];
+      R[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = ru[r]; R[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = rq[r];
     }
 #endif
   } else {
+    double *L = buf, *R = buf + 4 * nd;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       L[r * nd + cu] = bu[r];

@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
 #pragma unroll
   for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
   // staging offsets of this lane's C fragments: rows 8 mt + gq, column pairs 8 nt + 2 tq (node-pair-major 6x6 blocks)
+  const int fo = (tq >> 1) * Work::HS + 2 * gq + (tq & 1);  // this lane's fragment inside a half-split row panel
   int ro[3], co[3];
 #pragma unroll
   for (int t = 0; t < 3; t++) {
@@ -532,12 +533,12 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
       }
 #pragma unroll
       for (int el = 0; el < 2; el++) {
-        const double *L = we[el]->buf(q & 1);
+        const double *L = we[el]->buf(q & 1) + fo;
         double a[3], b[3];
 #pragma unroll
         for (int t = 0; t < 3; t++) {
-          a[t] = L[32 * t + lane];
-          b[t] = L[4 * nd + 32 * t + lane];
+          a[t] = L[16 * t];
+          b[t] = L[Work::LPAN + 16 * t];
         }
 #pragma unroll
         for (int mt = 0; mt < 3; mt++)

@@ -48,8 +48,10 @@ int ctx_init(int device) {
     return 1;
   }
   c.num_sms = prop.multiProcessorCount;
-  if (!cuda_ok(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&c.stream.s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   if (!cuda_ok(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  if (!cuda_ok(cudaEventCreateWithFlags(&c.tail_evt, cudaEventDisableTiming), "cudaEventCreate")) return 1;
   c.device = device;
   return 0;
 }
@@ -77,17 +79,17 @@ KernelTimer::KernelTimer(KernelId id) : slot(-1) {
   r.id = id;
   r.e0 = prof_event();
   r.e1 = prof_event();
-  cudaEventRecord(r.e0, g_ctx.stream);
+  cudaEventRecord(r.e0, g_ctx.stream.s);
   slot = (int)g_prof_log.size();
   g_prof_log.push_back(r);
 }
 KernelTimer::~KernelTimer() {
-  if (slot >= 0) cudaEventRecord(g_prof_log[slot].e1, g_ctx.stream);
+  if (slot >= 0) cudaEventRecord(g_prof_log[slot].e1, g_ctx.stream.s);
 }
 int profile_collect(double *ms, long *count) {
   for (int k = 0; k < K_COUNT; k++) { ms[k] = 0.0; count[k] = 0; }
   if (g_ctx.device < 0) return 1;
-  cudaStreamSynchronize(g_ctx.stream);
+  cudaStreamSynchronize(g_ctx.stream.s);
   for (auto &r : g_prof_log) {
     float t = 0.0f;
     cudaEventElapsedTime(&t, r.e0, r.e1);
@@ -786,19 +788,24 @@ void TACSBVec::copyValues(TACSBVec *x) {
 void TACSBVec::zeroEntries() {
   if (data.count) cuda_ok(cudaMemsetAsync(data.ptr, 0, data.count * sizeof(double), ctx().stream), "zeroEntries");
 }
+// copies between a host array and the owned slice; behind a matrix-only tail of the compute stream they overlap it
+static bool host_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, const char *what) {
+  Context &c = ctx();
+  if (c.tail_is_matrix_only()) {
+    return cuda_ok(cudaStreamWaitEvent(c.copy_stream, c.tail_evt, 0), what) &&
+           cuda_ok(cudaMemcpyAsync(dst, src, bytes, kind, c.copy_stream), what) &&
+           cuda_ok(cudaStreamSynchronize(c.copy_stream), what);
+  }
+  return cuda_ok(cudaMemcpyAsync(dst, src, bytes, kind, c.stream), what) &&
+         cuda_ok(cudaStreamSynchronize(c.stream.s), what);
+}
 int TACSBVec::getArray(double *out) {
   if (ownedSize() == 0) return 0;
-  bool ok = cuda_ok(cudaMemcpyAsync(out, owned(), ownedSize() * sizeof(double), cudaMemcpyDeviceToHost,
-                                    ctx().stream), "getArray") &&
-            cuda_ok(cudaStreamSynchronize(ctx().stream), "getArray sync");
-  return ok ? 0 : 1;
+  return host_copy(out, owned(), ownedSize() * sizeof(double), cudaMemcpyDeviceToHost, "getArray") ? 0 : 1;
 }
 int TACSBVec::setArray(const double *in) {
   if (ownedSize() == 0) return 0;
-  bool ok = cuda_ok(cudaMemcpyAsync(owned(), in, ownedSize() * sizeof(double), cudaMemcpyHostToDevice,
-                                    ctx().stream), "setArray") &&
-            cuda_ok(cudaStreamSynchronize(ctx().stream), "setArray sync");
-  return ok ? 0 : 1;
+  return host_copy(owned(), in, ownedSize() * sizeof(double), cudaMemcpyHostToDevice, "setArray") ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1014,10 +1021,17 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
   if (launchElements(alpha, gamma, true)) return 1;
   if (size > 1) staging_exchange(this, true);
   if (res) {
-    KernelTimer kt(K_GATHER_RES);
-    if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
-                                        ctx().stream), "gather residual")) return 1;
+    {
+      KernelTimer kt(K_GATHER_RES);
+      if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
+                                          ctx().stream), "gather residual")) return 1;
+    }
+    KernelTimer kt(K_BCS);
+    if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
+                                      lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
   }
+  // from here on only the staging area and the matrix are touched (Context::tail_evt)
+  cudaEventRecord(ctx().tail_evt, ctx().stream.s);
   {
     KernelTimer kt(K_GATHER_MAT);
     if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
@@ -1028,12 +1042,8 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
     if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
                                       ctx().num_sms, ctx().stream), "gather blocks")) return 1;
   }
-  if (res) {
-    KernelTimer kt(K_BCS);
-    if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
-                                      lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
-  }
   A->applyBCs();
+  ctx().tail_seq = ctx().stream.seq;
   return 0;
 }
 

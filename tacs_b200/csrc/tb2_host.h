@@ -36,11 +36,31 @@ namespace tb2 {
 // ---------------------------------------------------------------------------------------------
 // runtime context: one process drives one GPU
 // ---------------------------------------------------------------------------------------------
+// The compute stream counts its uses: every enqueue site reads it through the implicit conversion, so
+// `stream.seq` identifies the last operation put on it (see Context::tail_seq).
+struct CountedStream {
+  cudaStream_t s = nullptr;
+  mutable long seq = 0;
+  operator cudaStream_t() const {
+    ++seq;
+    return s;
+  }
+};
+
 struct Context {
   int device = -1;
   int num_sms = 0;
-  cudaStream_t stream = nullptr;       // compute stream
+  CountedStream stream;                // compute stream
   cudaStream_t comm_stream = nullptr;  // halo / collective stream
+  // Host <-> device vector copies normally ride the compute stream. assembleJacobian ends with the block gather and
+  // the matrix boundary conditions, which touch no vector: it records `tail_evt` in front of them and remembers the
+  // stream position after them, so that a getArray/setArray issued while that tail is still the last thing on the
+  // compute stream runs on `copy_stream` behind `tail_evt` only -- the residual returns to the host while the matrix
+  // is still being gathered.
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t tail_evt = nullptr;
+  long tail_seq = -1;
+  bool tail_is_matrix_only() const { return tail_seq >= 0 && stream.seq == tail_seq; }
   int rank = 0, size = 1;
   void *nccl_comm = nullptr;  // ncclComm_t when size > 1
   long kernel_launches = 0;   // launches of tacs_b200 kernels since the last reset

@@ -149,7 +149,8 @@ static void run_shell4_mma(const double *Xpts, const double *vars, const double 
     const double *L = w->buf(q & 1);
     for (int i = 0; i < nd; i++)
       for (int j = 0; j < nd; j++)
-        for (int r = 0; r < 4; r++) K[i * nd + j] += L[i * 4 + r] * L[4 * nd + j * 4 + r];
+        for (int r = 0; r < 4; r++)
+          K[i * nd + j] += L[(r >> 1) * WK::HS + 2 * i + (r & 1)] * L[WK::LPAN + (r >> 1) * WK::HS + 2 * j + (r & 1)];
   }
   for (int i = 0; i < nd; i++) {
     double r = 0.0;

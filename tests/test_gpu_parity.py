@@ -99,6 +99,28 @@ def test_jacobian_with_mass_and_scaling(lib):
     assert relerr(A.getValues(), o["A"]) < TOL and relerr(res.getArray(), o["res"]) < TOL
 
 
+def test_host_copies_overlap_the_matrix_gather(lib):
+    """getArray / setArray issued right after assembleJacobian run on the copy stream behind the residual only
+    (Context::tail_evt); results must equal the fully synchronised ones."""
+    mesh = meshgen.plate(2, 60, 50)
+    creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.iso_shell_element(T, lib, 2)])
+    A, res, u, v = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+    n = u.getSize()
+    u.setArray(meshgen.hash_vector(n))
+    asm.applyBCs(u)
+    asm.setVariables(u)
+    for _ in range(3):
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+        early = res.getArray()                       # copy stream, overlaps the block gather
+        fresh = meshgen.hash_vector(n)[::-1].copy()
+        v.setArray(fresh)                            # also behind the tail
+        lib.synchronize()
+        assert np.array_equal(early, res.getArray())
+        assert np.array_equal(v.getArray(), fresh)
+    o = oracle_port.assemble(mesh, 1, vars=u.getArray())
+    assert relerr(A.getValues(), o["A"]) < TOL and relerr(early, o["res"]) < TOL
+
+
 def test_vector_kernels(lib):
     mesh = meshgen.cube(2, 6)
     creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.solid_element(T, lib, 2)])
