@@ -861,8 +861,11 @@ struct SolidWork {
   double desc[kDescStride];
   double J[nq][9];
   double wdet[nq];
-  double G[QC][nd];        // physical shape-function gradients: G[ql][3a+dir] = dN_a/dx_dir
-  double CB[QC][NS][nd];   // w det C B; the strain rows B themselves are implied by G (3 non-zeros per column)
+  alignas(16) double G[QC][nd];  // physical shape-function gradients: G[ql][3a+dir] = dN_a/dx_dir
+  // w det C B; the strain rows B themselves are implied by G (3 non-zeros per column). Each quadrature slab is
+  // padded by 8 doubles so that the lanes of two slabs (one lane per node and slab) store to distinct banks.
+  static constexpr int CBQ = NS * nd + 8;
+  double CB[QC][CBQ];
   double rpart[ntiles][TR];
 };
 
@@ -907,9 +910,10 @@ TB2_HD void solid_p3_bcols(int task, int q0, SolidWork<O, QC> &w, const SolidTab
 #pragma unroll
   for (int r = 0; r < 6; r++) {
     // only the three structurally non-zero strain entries of each displacement column contribute
-    w.CB[ql][r][c0] = wd * (C[idx[r][0]] * gx + C[idx[r][4]] * gz + C[idx[r][5]] * gy);
-    w.CB[ql][r][c0 + 1] = wd * (C[idx[r][1]] * gy + C[idx[r][3]] * gz + C[idx[r][5]] * gx);
-    w.CB[ql][r][c0 + 2] = wd * (C[idx[r][2]] * gz + C[idx[r][3]] * gy + C[idx[r][4]] * gx);
+    double *cb = &w.CB[ql][r * SolidDims<O>::nd + c0];
+    cb[0] = wd * (C[idx[r][0]] * gx + C[idx[r][4]] * gz + C[idx[r][5]] * gy);
+    cb[1] = wd * (C[idx[r][1]] * gy + C[idx[r][3]] * gz + C[idx[r][5]] * gx);
+    cb[2] = wd * (C[idx[r][2]] * gz + C[idx[r][3]] * gy + C[idx[r][4]] * gx);
   }
 }
 
@@ -938,7 +942,7 @@ TB2_HD double solid_res_accumulate(int k, SolidWork<O, QC> &w) {
   double out = 0.0;
   for (int ql = 0; ql < QC; ql++)
 #pragma unroll
-    for (int r = 0; r < 6; r++) out += w.CB[ql][r][k] * e[6 * ql + r];
+    for (int r = 0; r < 6; r++) out += w.CB[ql][r * SolidDims<O>::nd + k] * e[6 * ql + r];
   return out;
 }
 
@@ -949,7 +953,7 @@ template <int QC, int ND, int TR, int TC>
 TB2_HD void solid_tile_accumulate(const double *G, const double *CB, int row0, int col0, double *acc) {
   for (int ql = 0; ql < QC; ql++) {
     const double *g = G + ql * ND + row0;
-    const double *cbq = CB + ql * 6 * ND + col0;
+    const double *cbq = CB + ql * (6 * ND + 8) + col0;  // SolidWork::CBQ
 #pragma unroll
     for (int bn = 0; bn < TC / 3; bn++) {
       double cb[6][3];

@@ -722,25 +722,53 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
         for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
         team_sync<TEAM>();
         if (has_tile)
-          solid_tile_accumulate<QC, nd, TR, TC>(&w.G[0][0], &w.CB[0][0][0], TR * ti, TC * tj, acc);
+          solid_tile_accumulate<QC, nd, TR, TC>(&w.G[0][0], &w.CB[0][0], TR * ti, TC * tj, acc);
         team_sync<TEAM>();
       }
-      if (has_tile) {
-        solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, inertia, acc);
-        if (live) {
-          // the tile covers (TR/3)x(TC/3) node pairs; staging is node-pair-major, 3x3 row-major inside
+      if (has_tile) solid_p6_finish<O, QC>(tid, w, tab, g.alpha, g.gamma, inertia, acc);
+      if constexpr (O == 2) {
+        // hex8: every lane owns a 2x2 patch of 3x3 node-pair blocks. Written straight from registers a warp store
+        // touches 32 different lines with 8-byte pieces (ncu: 4x sector amplification, lg throttle), so the element
+        // matrix is laid out in staging order in shared memory (G and CB are dead after the last contraction) and
+        // the team writes it with coalesced 128-bit stores. Rows of patches are 152 doubles apart (8 mod 16) for the banks.
+        double *kst = &w.G[0][0];
+        static_assert(sizeof(w.G) + sizeof(w.CB) >= 4 * 152 * sizeof(double), "element matrix fits in G + CB");
 #pragma unroll
-          for (int an = 0; an < TR / 3; an++)
+        for (int an = 0; an < 2; an++) {
+          double run[18];  // blocks (2 ti + an, 2 tj) and (2 ti + an, 2 tj + 1) are adjacent in the staging order
 #pragma unroll
-            for (int bn = 0; bn < TC / 3; bn++) {
-              const long na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
-              double *dst = g.Ke + ((e * n + na) * n + nb) * 9;
+          for (int bn = 0; bn < 2; bn++)
 #pragma unroll
-              for (int a = 0; a < 3; a++)
+            for (int a = 0; a < 3; a++)
 #pragma unroll
-                for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
-            }
+              for (int b = 0; b < 3; b++) run[9 * bn + 3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+          double2 *dst = reinterpret_cast<double2 *>(kst + ti * 152 + an * 72 + tj * 18);
+#pragma unroll
+          for (int k = 0; k < 9; k++) dst[k] = make_double2(run[2 * k], run[2 * k + 1]);
         }
+        team_sync<TEAM>();
+        if (live) {
+          const double2 *src = reinterpret_cast<const double2 *>(kst);
+          double2 *dst = reinterpret_cast<double2 *>(g.Ke + e * (long)(nd * nd));
+#pragma unroll
+          for (int it = 0; it < (nd * nd / 2) / TEAM; it++) {
+            const int p = it * TEAM + tid;  // double2 index in staging order; 72 per row of patches
+            dst[p] = src[p + (p / 72) * 4];
+          }
+        }
+      } else if (has_tile && live) {
+        // the tile covers (TR/3)x(TC/3) node pairs; staging is node-pair-major, 3x3 row-major inside
+#pragma unroll
+        for (int an = 0; an < TR / 3; an++)
+#pragma unroll
+          for (int bn = 0; bn < TC / 3; bn++) {
+            const long na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
+            double *dst = g.Ke + ((e * n + na) * n + nb) * 9;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+          }
       }
       team_sync<TEAM>();
       if (live && g.Re) {

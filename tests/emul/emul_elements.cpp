@@ -198,7 +198,7 @@ static void run_solid(const double *Xpts, const double *vars, const double *ddva
   for (int q0 = 0; q0 < nq; q0 += QC) {
     for (int t = 0; t < QC * n; t++) solid_p3_bcols<O, QC>(t, q0, *w, tab);
     for (int t = 0; t < WK::ntiles; t++)
-      solid_tile_accumulate<QC, nd, TR, TC>(&w->G[0][0], &w->CB[0][0][0], TR * (t / ntc), TC * (t % ntc),
+      solid_tile_accumulate<QC, nd, TR, TC>(&w->G[0][0], &w->CB[0][0], TR * (t / ntc), TC * (t % ntc),
                                             &acc[(size_t)TR * TC * t]);
   }
   for (int t = 0; t < WK::ntiles; t++) solid_p6_finish<O, QC>(t, *w, tab, alpha, gamma, (gamma != 0.0) || (ddvars != nullptr), &acc[(size_t)TR * TC * t]);
