@@ -499,6 +499,8 @@ struct alignas(16) ShellQ4MmaWork {
   static constexpr int oRty = LBUF;          // Rty[KS][LDP]: clear of buffer 0 and of S
   static constexpr int oU = 0, oAcc = 24, oRes = 48, oRp = 72;
   static constexpr int SCR = oRty + KS * LDP;
+  // residual-only path (no tangent): state, tying strains / stresses and row strains beyond X; only buffer 0 is used
+  static constexpr int oRu = 428, oRt = 452, oRs5 = 464, oRsty = 488, oRt4 = 500;
   double fn[3 * n];
   double Bdu[n][3 * n];   // nodal drill rows, displacement columns [node i][3 j + c]
   double Bdq[n][4];       // nodal drill rows, rotation columns of the own node [node i][c]
@@ -519,6 +521,9 @@ struct alignas(16) ShellQ4MmaWork {
 static_assert(ShellQ4MmaWork::oRp + 96 <= ShellQ4MmaWork::LBUF && ShellQ4MmaWork::oRty >= 192 &&
                   ShellQ4MmaWork::oX + 12 <= ShellQ4MmaWork::SCR,
               "scratch overlays");
+static_assert(ShellQ4MmaWork::oRt4 + 4 <= ShellQ4MmaWork::SCR && ShellQ4MmaWork::oRu >= ShellQ4MmaWork::oX + 12 &&
+                  ShellQ4MmaWork::LBUF <= ShellQ4MmaWork::oP,
+              "residual-only scratch");
 
 // phase 2 (same barrier interval as shell_p2_tying), task q: frame, inverse Jacobian products, weighted
 // determinant (as shell_p2_qgeom) and the frame products of the five tying fields,
@@ -651,7 +656,7 @@ TB2_HD void shell_unc_products(int task, ShellUncWork<O> &w) {
 // row buffer of quadrature point q, task (j, c): the columns 6j+c and 6j+3+c of
 //   L rows 0..2: bending rows 3,4,5 of B (same expressions as shell_p3_columns);  L row 3: drill row
 //   R rows 0..2: (w det D) L;                                                     R row 3: (w det drill) L3
-template <int O, class WK>
+template <int O, class WK, bool LONLY = false>
 TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, const double *desc, double *buf) {
   constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
   const int c = task % 3, j = (task / 3) % n;
@@ -700,6 +705,7 @@ TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, co
     *reinterpret_cast<double2 *>(L + WK::HS + 2 * cu) = make_double2(bu[2], bu[3]);
     *reinterpret_cast<double2 *>(L + 2 * cq) = make_double2(bq[0], bq[1]);
     *reinterpret_cast<double2 *>(L + WK::HS + 2 * cq) = make_double2(bq[2], bq[3]);
+    if (LONLY) return;
     *reinterpret_cast<double2 *>(R + 2 * cu) = make_double2(ru[0], ru[1]);
     *reinterpret_cast<double2 *>(R + WK::HS + 2 * cu) = make_double2(ru[2], ru[3]);
     *reinterpret_cast<double2 *>(R + 2 * cq) = make_double2(rq[0], rq[1]);
@@ -707,7 +713,7 @@ TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, co
 #else
     for (int r = 0; r < 4; r++) {
       L[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = bu[r]; L[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = bq[r];
-      R[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = ru[r]; R[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = rq[r];
+      if (!LONLY) { R[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = ru[r]; R[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = rq[r]; }
     }
 #endif
   } else {
@@ -720,6 +726,81 @@ TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, co
       R[r * nd + cq] = rq[r];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// residual-only path of the uncoupled shells (assembleRes): no tangent, no S; the state is pushed through the
+// tying space,  res = Bty^T r_ty + sum_q L_q^T (w det [D 0; 0 drill]) L_q u,
+//   t = Bty u;  e_q = W_q t;  s_q = w det [A 0; 0 As] e_q;  r_ty = sum_q W_q^T s_q;   W_q[ty][m] = Ntq[q][ty] P_q[f(ty)][m]
+// ------------------------------------------------------------------------------------------
+// task ty: tying strain of the state
+template <int O, class WK>
+TB2_HD void shell_unc_res_tying(int ty, WK &w, const double *u, double *tvec) {
+  constexpr int nd = ShellDims<O>::nd;
+  double s = 0.0;
+  for (int col = 0; col < nd; col++) s += w.bty(ty, col) * u[col];
+  tvec[ty] = s;
+}
+
+// task q: membrane / transverse-shear strains and stresses at quadrature point q -> s5[6 q + m]
+template <int O, class WK>
+TB2_HD void shell_unc_res_point(int q, WK &w, const ShellTables<O> &tab, const double *desc, const double *tvec,
+                                double *s5) {
+  constexpr int nty = ShellDims<O>::nty;
+  const double *P = w.scr + WK::oP + 30 * q;
+  double e[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int ty = 0; ty < nty; ty++) {
+    const double a = tab.Ntq[q][ty] * tvec[ty];
+    double p[6];
+    load6(P + 6 * shell_ty_field<O>(ty), p);
+#pragma unroll
+    for (int m = 0; m < 5; m++) e[m] += a * p[m];
+  }
+  const double wd = w.wdet[q];
+  double *so = s5 + 6 * q;
+  so[0] = wd * (desc[0] * e[0] + desc[1] * e[1] + desc[2] * e[2]);
+  so[1] = wd * (desc[1] * e[0] + desc[3] * e[1] + desc[4] * e[2]);
+  so[2] = wd * (desc[2] * e[0] + desc[4] * e[1] + desc[5] * e[2]);
+  so[3] = wd * (desc[18] * e[3] + desc[19] * e[4]);
+  so[4] = wd * (desc[19] * e[3] + desc[20] * e[4]);
+  so[5] = 0.0;
+}
+
+// task ty: stresses projected back on the tying point
+template <int O, class WK>
+TB2_HD void shell_unc_res_back(int ty, WK &w, const ShellTables<O> &tab, const double *s5, double *sty) {
+  constexpr int nq = ShellDims<O>::nq;
+  const int f = shell_ty_field<O>(ty);
+  double sum = 0.0;
+  for (int q = 0; q < nq; q++) {
+    double p[6], sv[6];
+    load6(w.scr + WK::oP + 30 * q + 6 * f, p);
+    load6(s5 + 6 * q, sv);
+    sum += tab.Ntq[q][ty] * (p[0] * sv[0] + p[1] * sv[1] + p[2] * sv[2] + p[3] * sv[3] + p[4] * sv[4]);
+  }
+  sty[ty] = sum;
+}
+
+// task r in [0,4): strain r of the row buffer (bending 0..2, drill 3) for the state
+template <int O, class WK>
+TB2_HD void shell_unc_res_rowstrain(int r, WK &w, const double *L, const double *u, double *t4) {
+  constexpr int nd = ShellDims<O>::nd;
+  const double *row = L + (r >> 1) * WK::HS + (r & 1);
+  double s = 0.0;
+  for (int col = 0; col < nd; col++) s += row[2 * col] * u[col];
+  t4[r] = s;
+}
+
+// dof `col`: contribution of the row buffer of point q, L^T (w det [D 0; 0 drill]) t4
+template <int O, class WK>
+TB2_HD double shell_unc_res_rowback(int col, int q, WK &w, const double *desc, const double *L, const double *t4) {
+  const double wd = w.wdet[q];
+  const double *Dm = desc + 12;
+  const double v0 = wd * (Dm[0] * t4[0] + Dm[1] * t4[1] + Dm[2] * t4[2]);
+  const double v1 = wd * (Dm[1] * t4[0] + Dm[3] * t4[1] + Dm[4] * t4[2]);
+  const double v2 = wd * (Dm[2] * t4[0] + Dm[4] * t4[1] + Dm[5] * t4[2]);
+  const double v3 = (wd * desc[21]) * t4[3];
+  return L[2 * col] * v0 + L[2 * col + 1] * v1 + L[WK::HS + 2 * col] * v2 + L[WK::HS + 2 * col + 1] * v3;
 }
 
 // residual-only path (assembleRes): strains of the chunk, task (ql, r): e = B u, kept in the unused CB rows

@@ -445,6 +445,8 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
     for (int m = 0; m < NU; m++) {
       cu[m] = pu[m];
       ca[m] = pa[m];
+      const int kk = tid + m * TEAM;
+      if (!g.Ke && kk < nd) w.scr[Work::oRu + kk] = pu[m];
     }
     __syncwarp();
     prefetch_data();                                            // next element (ids already here)
@@ -454,6 +456,46 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
     if (tid < nty) shell_p2_tying<O>(tid, w, tab);
     else if (tid < nty + nq) shell_unc_qgeom<O>(tid - nty, w, tab, desc);
     __syncwarp();
+    if (!g.Ke) {
+      // residual only (assembleRes without inertia): the state goes through the tying space, no tangent
+      double *sc = w.scr;
+      const double *us = sc + Work::oRu;
+      if (tid < nty) shell_unc_res_tying<O>(tid, w, us, sc + Work::oRt);
+      __syncwarp();
+      if (tid < nq) shell_unc_res_point<O>(tid, w, tab, desc, sc + Work::oRt, sc + Work::oRs5);
+      __syncwarp();
+      if (tid < nty) shell_unc_res_back<O>(tid, w, tab, sc + Work::oRs5, sc + Work::oRsty);
+      __syncwarp();
+      double racc[NU];
+#pragma unroll
+      for (int m = 0; m < NU; m++) {
+        const int kk = tid + m * TEAM;
+        racc[m] = 0.0;
+        if (kk < nd)
+          for (int ty = 0; ty < nty; ty++) racc[m] += w.bty(ty, kk) * sc[Work::oRsty + ty];
+      }
+#pragma unroll 1
+      for (int q = 0; q < nq; q++) {
+        if (tid < 3 * n) shell_unc_rows<O, Work, true>(tid, q, w, tab, desc, w.buf(0));
+        __syncwarp();
+        if (tid < 4) shell_unc_res_rowstrain<O>(tid, w, w.buf(0), us, sc + Work::oRt4);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) racc[m] += shell_unc_res_rowback<O>(kk, q, w, desc, w.buf(0), sc + Work::oRt4);
+        }
+        __syncwarp();
+      }
+      if (live && g.Re) {
+#pragma unroll
+        for (int m = 0; m < NU; m++) {
+          const int kk = tid + m * TEAM;
+          if (kk < nd) g.Re[e * nd + kk] = racc[m];
+        }
+      }
+      continue;
+    }
     for (int t = tid; t < 5 * nq; t += TEAM) shell_unc_G<O>(t, w, desc);
     __syncwarp();
 #pragma unroll
@@ -868,7 +910,10 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
   if (g.nelem <= 0) return cudaSuccess;
   switch (g.kind) {
     case ELEM_QUAD4_SHELL:
-      if (g.uncoupled && g.Ke) return launch_family<ShellQ4MmaFamily>(shell4_mma_kernel, g, num_sms, s);
+      // uncoupled constitutive matrix: tensor-core kernel (tangent + residual, or the residual alone when no
+      // inertial term is requested)
+      if (g.uncoupled && (g.Ke || (g.gamma == 0.0 && !g.ddvars)))
+        return launch_family<ShellQ4MmaFamily>(shell4_mma_kernel, g, num_sms, s);
       return launch_family<ShellFamily<2, false>>(shell_element_kernel<2, false>, g, num_sms, s);
     case ELEM_QUAD9_SHELL:
       if (g.uncoupled && g.Ke) return launch_family<ShellFamily<3, true>>(shell_element_kernel<3, true>, g, num_sms, s);

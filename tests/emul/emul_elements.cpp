@@ -182,6 +182,36 @@ static void run_shell4_mma(const double *Xpts, const double *vars, const double 
   delete w;
 }
 
+// residual-only branch of shell4_mma_kernel (assembleRes, no inertia)
+static void run_shell4_residual(const double *Xpts, const double *vars, const double *desc, double *res) {
+  using WK = ShellQ4MmaWork;
+  constexpr int O = 2, n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
+  static ShellTables<O> tab;
+  build_shell_tables<O>(tab);
+  WK *w = new WK;
+  std::memset(w, 0, sizeof(WK));
+  for (int k = 0; k < WK::SCR; k++) w->scr[k] = 1e300;
+  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
+  double *sc = w->scr;
+  for (int k = 0; k < nd; k++) sc[WK::oRu + k] = vars[k];
+  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, desc);
+  for (int t = 0; t < nty; t++) shell_p2_tying<O>(t, *w, tab);
+  for (int q = 0; q < nq; q++) shell_unc_qgeom<O>(q, *w, tab, desc);
+  for (int t = 0; t < nty; t++) shell_unc_res_tying<O>(t, *w, sc + WK::oRu, sc + WK::oRt);
+  for (int q = 0; q < nq; q++) shell_unc_res_point<O>(q, *w, tab, desc, sc + WK::oRt, sc + WK::oRs5);
+  for (int t = 0; t < nty; t++) shell_unc_res_back<O>(t, *w, tab, sc + WK::oRs5, sc + WK::oRsty);
+  for (int k = 0; k < nd; k++) {
+    res[k] = 0.0;
+    for (int ty = 0; ty < nty; ty++) res[k] += w->bty(ty, k) * sc[WK::oRsty + ty];
+  }
+  for (int q = 0; q < nq; q++) {
+    for (int t = 0; t < 3 * n; t++) shell_unc_rows<O, WK, true>(t, q, *w, tab, desc, w->buf(0));
+    for (int r = 0; r < 4; r++) shell_unc_res_rowstrain<O>(r, *w, w->buf(0), sc + WK::oRu, sc + WK::oRt4);
+    for (int k = 0; k < nd; k++) res[k] += shell_unc_res_rowback<O>(k, q, *w, desc, w->buf(0), sc + WK::oRt4);
+  }
+  delete w;
+}
+
 template <int O, int QC>
 static void run_solid(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
                       double alpha, double gamma, double *res, double *mat) {
@@ -217,6 +247,13 @@ static void run_solid(const double *Xpts, const double *vars, const double *ddva
 }
 
 extern "C" {
+// residual-only fast path (Quad4, uncoupled descriptor, no inertia): 0 when handled
+int emul_residual(int kind, const double *Xpts, const double *vars, const double *desc, double *res) {
+  if (kind != 1 || !desc_uncoupled(desc)) return 1;
+  run_shell4_residual(Xpts, vars, desc, res);
+  return 0;
+}
+
 // kind: 1 Quad4, 2 Quad9, 3 hex8, 4 hex27; desc = one 32-double descriptor row
 int emul_element(int kind, const double *Xpts, const double *vars, const double *ddvars, const double *desc,
                  double alpha, double gamma, double *res, double *mat) {

@@ -50,6 +50,7 @@ def emul():
     L = C.CDLL(so)
     DP = C.POINTER(C.c_double)
     L.emul_element.argtypes = [C.c_int, DP, DP, DP, DP, C.c_double, C.c_double, DP, DP]
+    L.emul_residual.argtypes = [C.c_int, DP, DP, DP, DP]
     return L
 
 
@@ -72,4 +73,18 @@ def test_device_phases_replayed_on_host_match_oracle(emul, kind):
                                    m2.ctypes.data_as(DP))
             assert rc == 0
             assert relerr(m2, mat.ravel()) < TOL
+            assert relerr(r2, res) < TOL
+
+
+def test_residual_only_phases_match_oracle(emul):
+    """assembleRes fast path of the Quad4 tensor-core kernel (state pushed through the tying space)."""
+    X, u, a = common.shell_batch(2, 6, seed=77)
+    DP = C.POINTER(C.c_double)
+    for desc in (oracle_port.iso_shell_desc(t=0.01, tOffset=0.0, transform=1, axis=(1, .3, .2)),
+                 oracle_port.iso_shell_desc(t=0.03, tOffset=0.0, transform=0)):
+        for e in range(X.shape[0]):
+            res, _ = oracle_port.element(1, desc, X[e], u[e], 0.0 * a[e], alpha=1.0, gamma=0.0)
+            r2 = np.zeros(res.size)
+            args = [np.ascontiguousarray(v) for v in (X[e], u[e], desc)]
+            assert emul.emul_residual(1, *[v.ctypes.data_as(DP) for v in args], r2.ctypes.data_as(DP)) == 0
             assert relerr(r2, res) < TOL

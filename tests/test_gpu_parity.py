@@ -35,6 +35,11 @@ def test_element_kernels_match_oracle(lib):
         # residual-only entry point
         res2 = elem.addResidual(X, u, None, a)
         assert relerr(res2, res) < TOL, name
+        # ... and without inertial terms (uncoupled Quad4 takes the tying-space residual path)
+        res3 = elem.addResidual(X, u, None, None)
+        for e in range(0, X.shape[0], 6):
+            r0, _ = oracle_port.element(kind, desc, X[e], u[e], 0.0 * a[e], alpha=1.0, gamma=0.0)
+            assert relerr(res3[e], r0) < TOL, (name, e)
 
 
 def test_element_kernels_match_reference(lib, ref):
