@@ -157,6 +157,15 @@ int tacsb200_assembler_assemble_res(tacsb200_handle a, tacsb200_handle res);
 int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double beta, double gamma,
                                          tacsb200_handle res, tacsb200_handle mat);
 
+/* assembleMatType(matType, A, TACS_MAT_NORMAL, lambda = 1, applyBCs) :227, src/TACSAssembler.cpp:4418-4504.
+   matType follows ElementMatrixType (src/elements/TACSElementTypes.h:113-119): 1 = TACS_STIFFNESS_MATRIX,
+   2 = TACS_MASS_MATRIX; any other type returns non-zero (not evaluated on the device). */
+int tacsb200_assembler_assemble_mat_type(tacsb200_handle a, int mat_type, tacsb200_handle mat, int apply_bcs);
+/* addJacobianVecProduct(scale, alpha, beta, gamma, x, y, TACS_MAT_NORMAL, lambda = 1, applyBCs)
+   src/TACSAssembler.cpp:5416-5496: y <- y + scale * (alpha K + gamma M) x, matrix free */
+int tacsb200_assembler_add_jacobian_vec_product(tacsb200_handle a, double scale, double alpha, double beta,
+                                                double gamma, tacsb200_handle x, tacsb200_handle y, int apply_bcs);
+
 /* ---- TACSBVec: src/bpmat/TACSBVec.h:67-163 (TACSVec interface KSM.h:91-115) ---------------------- */
 int tacsb200_vec_get_size(tacsb200_handle v);                /* length of getArray(): bs * owned nodes */
 int tacsb200_vec_get_array(tacsb200_handle v, double *out);  /* device -> host copy */

@@ -355,6 +355,19 @@ int ref_assembler_assemble_jacobian(ref_handle a, double alpha, double beta, dou
   return 0;
 }
 
+int ref_assembler_assemble_mat_type(ref_handle a, int mat_type, ref_handle mat, int apply_bcs) {
+  as<TACSAssembler>(a)->assembleMatType((ElementMatrixType)mat_type, as<TACSMat>(mat), TACS_MAT_NORMAL, 1.0,
+                                        apply_bcs != 0);
+  return 0;
+}
+
+int ref_assembler_add_jacobian_vec_product(ref_handle a, double scale, double alpha, double beta, double gamma,
+                                           ref_handle x, ref_handle y, int apply_bcs) {
+  as<TACSAssembler>(a)->addJacobianVecProduct(scale, alpha, beta, gamma, as<TACSBVec>(x), as<TACSBVec>(y),
+                                              TACS_MAT_NORMAL, 1.0, apply_bcs != 0);
+  return 0;
+}
+
 /* ---- vectors ------------------------------------------------------------- */
 int ref_vec_get_size(ref_handle v) {
   TacsScalar *x;

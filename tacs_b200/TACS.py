@@ -355,6 +355,19 @@ class Assembler(_Obj):
                "assembleJacobian")
 
 
+    def assembleMatType(self, matType, mat, applyBCs=True):
+        """matType: STIFFNESS_MATRIX (1) or MASS_MATRIX (2) (tacs/TACS.pyx ElementMatrixType)."""
+        _check(self.lib.assembler_assemble_mat_type(self.h, int(matType), mat.h, 1 if applyBCs else 0),
+               "assembleMatType")
+
+    def addJacobianVecProduct(self, scale, alpha, beta, gamma, x, y, applyBCs=True):
+        _check(self.lib.assembler_add_jacobian_vec_product(self.h, scale, alpha, beta, gamma, x.h, y.h,
+                                                           1 if applyBCs else 0), "addJacobianVecProduct")
+
+
+JACOBIAN_MATRIX, STIFFNESS_MATRIX, MASS_MATRIX, GEOMETRIC_STIFFNESS_MATRIX = 0, 1, 2, 3
+
+
 class Creator(_Obj):
     def __init__(self, lib, vars_per_node):
         super().__init__(lib, lib.creator_create(vars_per_node), "creator_create")

@@ -76,6 +76,8 @@ SIGNATURES = {
     "assembler_set_num_threads": (I, [H, I]),
     "assembler_assemble_res": (I, [H, H]),
     "assembler_assemble_jacobian": (I, [H, D, D, D, H, H]),
+    "assembler_assemble_mat_type": (I, [H, I, H, I]),
+    "assembler_add_jacobian_vec_product": (I, [H, D, D, D, D, H, H, I]),
     "vec_get_size": (I, [H]),
     "vec_get_array": (I, [H, DP]),
     "vec_set_array": (I, [H, DP]),

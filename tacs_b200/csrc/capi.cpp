@@ -407,6 +407,21 @@ int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double
   if (t->assembleJacobian(alpha, beta, gamma, as<TACSBVec>(res), A, 1.0)) return 1;
   return tacsb200_synchronize();
 }
+int tacsb200_assembler_assemble_mat_type(tacsb200_handle a, int mat_type, tacsb200_handle mat, int apply_bcs) {
+  ASM(a);
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE(A, "matrix");
+  if (t->assembleMatType(mat_type, A, apply_bcs != 0)) return 1;
+  return tacsb200_synchronize();
+}
+int tacsb200_assembler_add_jacobian_vec_product(tacsb200_handle a, double scale, double alpha, double beta,
+                                                double gamma, tacsb200_handle x, tacsb200_handle y, int apply_bcs) {
+  ASM(a);
+  TACSBVec *xv = as<TACSBVec>(x), *yv = as<TACSBVec>(y);
+  REQUIRE(xv && yv, "vector");
+  if (t->addJacobianVecProduct(scale, alpha, beta, gamma, xv, yv, apply_bcs != 0)) return 1;
+  return tacsb200_synchronize();
+}
 
 /* ---- vectors ---------------------------------------------------------------------------------- */
 #define VEC(v, name)              \

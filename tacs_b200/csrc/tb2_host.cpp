@@ -417,9 +417,7 @@ int TACSElement::addJacobianBatch(int count, double alpha, double beta, double g
   g.kind = kind; g.nelem = count; g.conn = d_conn.ptr; g.desc_index = d_desc.ptr; g.desc_table = d_table.ptr;
   g.tables = d_tab.ptr; g.Xpts = d_X.ptr; g.vars = d_u.ptr; g.ddvars = ddvars ? d_a.ptr : nullptr;
   g.alpha = alpha; g.gamma = gamma; g.Ke = mat ? d_Ke.ptr : nullptr; g.Re = d_Re.ptr;
-  g.uncoupled = 1;
-  for (int i = 6; i < 12; i++)
-    if (drow[i] != 0.0) g.uncoupled = 0;
+  g.uncoupled = (kind == ELEM_QUAD4_SHELL || kind == ELEM_QUAD9_SHELL) && shell_desc_uncoupled(drow) ? 1 : 0;
   if (!cuda_ok(launch_element_group(g, ctx().num_sms, ctx().stream), "element kernel")) return 1;
   ctx().kernel_launches++;
   if (!cuda_ok(cudaStreamSynchronize(ctx().stream), "element kernel sync")) return 1;
@@ -818,6 +816,9 @@ TACSAssembler::~TACSAssembler() {
   if (vars) vars->decref();
   if (dvars) dvars->decref();
   if (ddvars) ddvars->decref();
+  if (jvp_x) jvp_x->decref();
+  if (jvp_a) jvp_a->decref();
+  if (jvp_t) jvp_t->decref();
 }
 
 int TACSAssembler::localNode(int g) const { return plan->localNode(g); }
@@ -854,9 +855,11 @@ int TACSAssembler::finalize() {
   if (!d_desc_table.upload(table)) return 1;
   // shells whose constitutive B block (entries 6..11) vanishes take the cheaper uncoupled kernel path
   shells_uncoupled = true;
-  for (size_t row = 0; row < distinct.size(); row++)
-    for (int i = 6; i < 12; i++)
-      if (table[32 * row + i] != 0.0) shells_uncoupled = false;
+  for (size_t row = 0; row < distinct.size(); row++) {
+    const int k = distinct[row]->kernelKind();
+    if ((k == ELEM_QUAD4_SHELL || k == ELEM_QUAD9_SHELL) && !shell_desc_uncoupled(&table[32 * row]))
+      shells_uncoupled = false;
+  }
   // element groups by kernel family (local order preserved inside a group)
   groups.clear();
   for (size_t gi = 0; gi < P.group_kinds.size(); gi++) {
@@ -966,7 +969,8 @@ void TACSAssembler::setBCs(TACSBVec *v) {
 }
 void TACSAssembler::applyBCs(TACSParallelMat *m) { m->applyBCs(); }
 
-int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat) {
+int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat, const double *vars_override,
+                                  const double *ddvars_override, bool use_override) {
   if (want_mat && Ke.count < (size_t)total_blocks * bs * bs) {
     if (!Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
   }
@@ -979,8 +983,8 @@ int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat) {
     a.desc_table = d_desc_table.ptr;
     a.tables = g.d_tables.ptr;
     a.Xpts = xpts->local();
-    a.vars = vars_zero ? nullptr : vars->local();
-    a.ddvars = ddvars_zero ? nullptr : ddvars->local();
+    a.vars = use_override ? vars_override : (vars_zero ? nullptr : vars->local());
+    a.ddvars = use_override ? ddvars_override : (ddvars_zero ? nullptr : ddvars->local());
     a.alpha = alpha;
     a.gamma = gamma;
     a.uncoupled = shells_uncoupled ? 1 : 0;
@@ -1016,7 +1020,7 @@ int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
 
 // TACSAssembler::assembleJacobian (TACSAssembler.cpp:4291-4406)
 int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
-                                    double lambda) {
+                                    double lambda, bool apply_bcs) {
   (void)beta;
   if (launchElements(alpha, gamma, true)) return 1;
   if (size > 1) staging_exchange(this, true);
@@ -1042,8 +1046,61 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
     if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
                                       ctx().num_sms, ctx().stream), "gather blocks")) return 1;
   }
-  A->applyBCs();
+  if (apply_bcs) A->applyBCs();
   ctx().tail_seq = ctx().stream.seq;
+  return 0;
+}
+
+// TACSAssembler::assembleMatType (TACSAssembler.cpp:4418-4504). The element matrices come from getMatType:
+// shells TACSShellElement.h:644-660 (stiffness: alpha = 1, mass: gamma = 1), solids TACSElement3D.cpp:316-380 --
+// for the linear models of this path these are the alpha / gamma parts of addJacobian. The geometric stiffness
+// needs the nonlinear strain terms and is not on the device path: non-zero return, the caller keeps the reference.
+int TACSAssembler::assembleMatType(int matType, TACSParallelMat *A, bool apply_bcs) {
+  double alpha = 0.0, gamma = 0.0;
+  if (matType == 1) {
+    alpha = 1.0;
+  } else if (matType == 2) {
+    gamma = 1.0;
+  } else {
+    fprintf(stderr, "tacs_b200: assembleMatType(%d): only TACS_STIFFNESS_MATRIX (1) and TACS_MASS_MATRIX (2) "
+                    "are evaluated on the device\n", matType);
+    return 1;
+  }
+  return assembleJacobian(alpha, 0.0, gamma, nullptr, A, 1.0, apply_bcs);
+}
+
+// TACSAssembler::addJacobianVecProduct (TACSAssembler.cpp:5416-5496): y <- y + scale * J x without forming J.
+// Both element models are linear, J = alpha K + gamma M does not depend on the state, and the residual-only
+// element kernels evaluate K v + M a for any pair of nodal vectors: J x = K (alpha x) + M (gamma x).
+int TACSAssembler::addJacobianVecProduct(double scale, double alpha, double beta, double gamma, TACSBVec *x,
+                                         TACSBVec *y, bool apply_bcs) {
+  (void)beta;
+  if (!jvp_x) {
+    jvp_x = createVec();
+    jvp_a = createVec();
+    jvp_t = createVec();
+    jvp_x->incref();
+    jvp_a->incref();
+    jvp_t->incref();
+    if (!jvp_x->data.ptr || !jvp_a->data.ptr || !jvp_t->data.ptr) return 1;
+  }
+  jvp_x->copyValues(x);
+  jvp_x->scale(alpha);
+  if (size > 1) halo_forward(this, jvp_x);
+  if (gamma != 0.0) {
+    jvp_a->copyValues(x);
+    jvp_a->scale(gamma);
+    if (size > 1) halo_forward(this, jvp_a);
+  }
+  if (launchElements(1.0, 0.0, false, jvp_x->local(), gamma != 0.0 ? jvp_a->local() : nullptr, true)) return 1;
+  if (size > 1) staging_exchange(this, false);
+  {
+    KernelTimer kt(K_GATHER_RES);
+    if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, jvp_t->owned(), ctx().num_sms,
+                                        ctx().stream), "gather residual")) return 1;
+  }
+  y->axpy(scale, jvp_t);
+  if (apply_bcs) applyBCs(y);
   return 0;
 }
 

@@ -12,10 +12,15 @@
 
 using namespace tb2;
 
+// same rule as shell_desc_uncoupled (tacs_b200/csrc/tb2_host.h)
 static bool desc_uncoupled(const double *desc) {
-  for (int i = 6; i < 12; i++)
-    if (desc[i] != 0.0) return false;
-  return true;
+  double amax = 0.0, dmax = 0.0, bmax = 0.0;
+  for (int i = 0; i < 6; i++) {
+    amax = std::fmax(amax, std::fabs(desc[i]));
+    bmax = std::fmax(bmax, std::fabs(desc[6 + i]));
+    dmax = std::fmax(dmax, std::fabs(desc[12 + i]));
+  }
+  return bmax <= 1e-18 * std::sqrt(amax * dmax);
 }
 
 template <int O, class WK>

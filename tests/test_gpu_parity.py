@@ -104,6 +104,46 @@ def test_jacobian_with_mass_and_scaling(lib):
     assert relerr(A.getValues(), o["A"]) < TOL and relerr(res.getArray(), o["res"]) < TOL
 
 
+@pytest.mark.parametrize("name", ["quad4_plate", "quad9_cylinder", "hex8_cube", "hex27_cube"])
+def test_mat_type_and_matrix_free_product_match_reference(lib, ref, name):
+    """assembleMatType (stiffness, mass) and addJacobianVecProduct against the compiled reference
+    (TACSAssembler.cpp:4418-4504, 5416-5496), and against the oracle's alpha / gamma tangents."""
+    mesh_f, kind, elem_f = common.SMALL_MODELS[name]
+    mesh = mesh_f()
+    out = {}
+    for tag, L in (("b200", lib), ("ref", ref)):
+        creator, asm = meshgen.build_model(T, L, mesh, [elem_f(L)])
+        A, x, y, u = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+        n = x.getSize()
+        u.setArray(meshgen.hash_vector(n))
+        asm.applyBCs(u)
+        asm.setVariables(u)
+        r = {}
+        asm.assembleMatType(T.STIFFNESS_MATRIX, A)
+        r["K"] = A.getValues()
+        asm.assembleMatType(T.MASS_MATRIX, A)
+        r["M"] = A.getValues()
+        x.setArray(meshgen.hash_vector(n)[::-1].copy())
+        for key, (alpha, gamma) in (("Kx", (1.0, 0.0)), ("Jx", (0.6, 1.7))):
+            y.setArray(0.25 * meshgen.hash_vector(n))
+            asm.addJacobianVecProduct(-1.5, alpha, 0.0, gamma, x, y)
+            r[key] = y.getArray()
+        out[tag] = r
+        keep = (creator, asm, A)
+    for key in ("K", "M", "Kx", "Jx"):
+        assert relerr(out["b200"][key], out["ref"][key]) < TOL, (name, key)
+    desc = oracle_port.composite_shell_desc() if "cylinder" in name else None
+    u_np = meshgen.hash_vector(out["b200"]["Kx"].size)
+    assert relerr(out["b200"]["M"], oracle_port.assemble(mesh, kind, desc=desc, alpha=0.0, gamma=1.0)["A"]) < TOL
+
+
+def test_geometric_stiffness_is_refused(lib):
+    creator, asm = meshgen.build_model(T, lib, meshgen.plate(2, 3, 3), [meshgen.iso_shell_element(T, lib, 2)])
+    A = asm.createMat()
+    with pytest.raises(Exception):
+        asm.assembleMatType(T.GEOMETRIC_STIFFNESS_MATRIX, A)
+
+
 def test_host_copies_overlap_the_matrix_gather(lib):
     """getArray / setArray issued right after assembleJacobian run on the copy stream behind the residual only
     (Context::tail_evt); results must equal the fully synchronised ones."""
