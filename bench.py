@@ -286,6 +286,8 @@ def run_b200(args):
         launches = lib.kernel_launches(0)
         lib.profile_collect(tacs_b200.binding.dptr(ms_k),
                             cnt_k.ctypes.data_as(C.POINTER(C.c_long)))
+        lib.profile_enable(0)
+        ms_res = lib.time_assemble_res(asm.h, res.h, args.steps) / args.steps
         # SpMV loop inside the same clock window
         lib.time_mat_mult(A.h, x.h, y.h, 3)
         nsp = 50
@@ -295,6 +297,7 @@ def run_b200(args):
     assert ms > 0, "device timing failed"
     ms = max_over_ranks(ms)
     ms_spmv = max_over_ranks(ms_spmv)
+    ms_res = max_over_ranks(ms_res)
     ms_per_step = ms / args.steps
     value = nelem_total / (ms_per_step * 1e-3)
 
@@ -335,11 +338,13 @@ def run_b200(args):
     kernels = []
     if per_launch["element"]:
         t = per_launch["element"] * 1e-3
-        kernels.append({"kernel": "shell_element_kernel<2>", "ms": per_launch["element"], "bound": "fp64",
+        kernels.append({"kernel": "shell4_mma_kernel", "ms": per_launch["element"], "bound": "fp64",
                         "achieved": FLOPS_PER_ELEMENT["quad4"] * nelem_local / t * 1e-12, "peak": fp64_peak,
                         "unit": "TFLOP/s", "hbm_gbs": elem_bytes / t * 1e-9,
                         "note": "flops = SURVEY 8d minimal-algorithm count (57 kFLOP/element); peak = live DFMA "
-                                "microbenchmark (tacsb200_measure_fp64_tflops)"})
+                                "microbenchmark (tacsb200_measure_fp64_tflops); the kernel issues its two matrix "
+                                "products as DMMA m8n8k4, which shares that FP64 peak on B200 "
+                                "(profiles/r1_probe_fp64.txt: 36.5 DFMA vs 37.0 DMMA TFLOP/s)"})
     if per_launch["gather_blocks"]:
         t = per_launch["gather_blocks"] * 1e-3
         kernels.append({"kernel": "gather_blocks36_kernel", "ms": per_launch["gather_blocks"], "bound": "hbm",
@@ -380,7 +385,10 @@ def run_b200(args):
                    "elements": nelem_total, "dof": 6 * creator.num_nodes, "nnzb": int(nnzb),
                    "l2": "inputs larger than L2 (staging 4.6 GB + matrix 2.6 GB per step)",
                    "partition": "METIS element partition (TACSCreator::partitionMesh)" if world > 1 else "single rank"},
-        "roofline": roofline, "kernels": kernels, "spmv": spmv, "cpu_baseline": cpu,
+        "roofline": roofline, "kernels": kernels, "spmv": spmv,
+        "assemble_res": {"ms": ms_res, "value": nelem_total / (ms_res * 1e-3), "unit": UNIT,
+                         "note": "assembleRes alone (SURVEY 8d metric i), same mesh and state"},
+        "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8),
                 "note": "state vector from pinned host memory -> setVariables -> assembleJacobian -> residual to "
                         "pinned host memory; the BCSR matrix stays in HBM for the device-side Krylov solver"},

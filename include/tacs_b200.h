@@ -193,8 +193,19 @@ int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y); 
 int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y);
 tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m); /* TACSMat::createVec KSM.h */
 
+/* ---- TACSChebyshevSmoother: src/bpmat/TACSParallelMat.h:180-217, TACSParallelMat.cpp:871-1113 ---- */
+/* TACSChebyshevSmoother(mat, degree, lower_factor = 1/30, upper_factor = 1.1, iters = 1) */
+tacsb200_handle tacsb200_chebyshev_create(tacsb200_handle mat, int degree, double lower_factor,
+                                          double upper_factor, int iters);
+int tacsb200_chebyshev_factor(tacsb200_handle pc);                                    /* factor() :930 */
+int tacsb200_chebyshev_apply_factor(tacsb200_handle pc, tacsb200_handle x, tacsb200_handle y); /* :981 */
+double tacsb200_chebyshev_get_spectral_radius(tacsb200_handle pc);  /* Gershgorin bound used by factor() :1024 */
+
 /* ---- GMRES: src/bpmat/KSM.h:392-440, KSM.cpp:547-956 -------------------------------------------- */
 tacsb200_handle tacsb200_gmres_create(tacsb200_handle mat, int m, int nrestart);
+/* GMRES(mat, pc, m, nrestart, isFlexible) KSM.cpp:547: right preconditioning by a Chebyshev smoother */
+tacsb200_handle tacsb200_gmres_create_pc(tacsb200_handle mat, tacsb200_handle pc, int m, int nrestart,
+                                         int is_flexible);
 int tacsb200_gmres_set_tolerances(tacsb200_handle k, double rtol, double atol);
 int tacsb200_gmres_solve(tacsb200_handle k, tacsb200_handle b, tacsb200_handle x, int zero_guess);
 int tacsb200_gmres_get_iter_count(tacsb200_handle k);

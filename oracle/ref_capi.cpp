@@ -472,6 +472,20 @@ int ref_mat_mult(ref_handle m, ref_handle x, ref_handle y) {
   return 0;
 }
 
+/* ---- Chebyshev smoother ---------------------------------------------------- */
+ref_handle ref_chebyshev_create(ref_handle mat, int degree, double lower_factor, double upper_factor, int iters) {
+  return keep(new TACSChebyshevSmoother(as<TACSMat>(mat), degree, lower_factor, upper_factor, iters));
+}
+int ref_chebyshev_factor(ref_handle pc) {
+  as<TACSPc>(pc)->factor();
+  return 0;
+}
+int ref_chebyshev_apply_factor(ref_handle pc, ref_handle x, ref_handle y) {
+  as<TACSPc>(pc)->applyFactor(as<TACSBVec>(x), as<TACSBVec>(y));
+  return 0;
+}
+double ref_chebyshev_get_spectral_radius(ref_handle) { return -1.0; /* private in the reference */ }
+
 /* ---- GMRES (unpreconditioned or with the reference additive Schwarz PC) ----- */
 ref_handle ref_gmres_create(ref_handle mat, int m, int nrestart) {
   return keep(new GMRES(as<TACSMat>(mat), m, nrestart));

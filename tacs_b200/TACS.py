@@ -259,12 +259,33 @@ class Mat(_Obj):
         raise NotImplementedError
 
 
-class KSM(_Obj):
-    """GMRES (tacs/TACS.pyx:1256): KSM(mat, pc=None, m, nrestart)."""
+class ChebyshevSmoother(_Obj):
+    """TACSChebyshevSmoother (src/bpmat/TACSParallelMat.h:180): polynomial smoother used as a preconditioner."""
 
-    def __init__(self, lib, mat, m, nrestart=0):
+    def __init__(self, lib, mat, degree, lower_factor=1.0 / 30.0, upper_factor=1.1, iters=1):
         self.mat = mat
-        super().__init__(lib, lib.gmres_create(mat.h, m, nrestart), "gmres_create")
+        super().__init__(lib, lib.chebyshev_create(mat.h, degree, lower_factor, upper_factor, iters),
+                         "chebyshev_create")
+
+    def factor(self):
+        _check(self.lib.chebyshev_factor(self.h), "factor")
+
+    def applyFactor(self, x, y):
+        _check(self.lib.chebyshev_apply_factor(self.h, x.h, y.h), "applyFactor")
+
+    def getSpectralRadius(self):
+        return self.lib.chebyshev_get_spectral_radius(self.h)
+
+
+class KSM(_Obj):
+    """GMRES (tacs/TACS.pyx:1256): KSM(mat, pc, m, nrestart, isFlexible)."""
+
+    def __init__(self, lib, mat, m, nrestart=0, pc=None, isFlexible=0):
+        self.mat, self.pc = mat, pc
+        if pc is None:
+            super().__init__(lib, lib.gmres_create(mat.h, m, nrestart), "gmres_create")
+        else:
+            super().__init__(lib, lib.gmres_create_pc(mat.h, pc.h, m, nrestart, isFlexible), "gmres_create_pc")
 
     def setTolerances(self, rtol, atol):
         _check(self.lib.gmres_set_tolerances(self.h, rtol, atol), "gmres_set_tolerances")

@@ -95,7 +95,12 @@ SIGNATURES = {
     "mat_get_ext_col_nodes": (I, [H, IP]),
     "mat_zero_entries": (I, [H]),
     "mat_mult": (I, [H, H, H]),
+    "chebyshev_create": (H, [H, I, D, D, I]),
+    "chebyshev_factor": (I, [H]),
+    "chebyshev_apply_factor": (I, [H, H, H]),
+    "chebyshev_get_spectral_radius": (D, [H]),
     "gmres_create": (H, [H, I, I]),
+    "gmres_create_pc": (H, [H, H, I, I, I]),
     "gmres_set_tolerances": (I, [H, D, D]),
     "gmres_solve": (I, [H, H, H, I]),
     "gmres_get_iter_count": (I, [H]),

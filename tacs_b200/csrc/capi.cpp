@@ -526,6 +526,35 @@ tacsb200_handle tacsb200_gmres_create(tacsb200_handle mat, int m, int nrestart) 
   REQUIRE_H(A, "matrix");
   return keep(new GMRES(A, m, nrestart));
 }
+tacsb200_handle tacsb200_gmres_create_pc(tacsb200_handle mat, tacsb200_handle pc, int m, int nrestart,
+                                         int is_flexible) {
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  TACSChebyshevSmoother *P = as<TACSChebyshevSmoother>(pc);
+  REQUIRE_H(A && P, "matrix / preconditioner");
+  return keep(new GMRES(A, m, nrestart, P, is_flexible != 0));
+}
+tacsb200_handle tacsb200_chebyshev_create(tacsb200_handle mat, int degree, double lower_factor,
+                                          double upper_factor, int iters) {
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE_H(A, "matrix");
+  return keep(new TACSChebyshevSmoother(A, degree, lower_factor, upper_factor, iters));
+}
+int tacsb200_chebyshev_factor(tacsb200_handle pc) {
+  TACSChebyshevSmoother *P = as<TACSChebyshevSmoother>(pc);
+  REQUIRE(P, "Chebyshev smoother");
+  return P->factor();
+}
+int tacsb200_chebyshev_apply_factor(tacsb200_handle pc, tacsb200_handle x, tacsb200_handle y) {
+  TACSChebyshevSmoother *P = as<TACSChebyshevSmoother>(pc);
+  TACSBVec *xv = as<TACSBVec>(x), *yv = as<TACSBVec>(y);
+  REQUIRE(P && xv && yv, "Chebyshev smoother / vector");
+  P->applyFactor(xv, yv);
+  return tacsb200_synchronize();
+}
+double tacsb200_chebyshev_get_spectral_radius(tacsb200_handle pc) {
+  TACSChebyshevSmoother *P = as<TACSChebyshevSmoother>(pc);
+  return P ? P->rho : -1.0;
+}
 int tacsb200_gmres_set_tolerances(tacsb200_handle k, double rtol, double atol) {
   GMRES *g = as<GMRES>(k);
   REQUIRE(g, "GMRES");

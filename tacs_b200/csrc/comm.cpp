@@ -35,7 +35,7 @@ static struct {
   fn_errstr errstr = nullptr;
 } nccl;
 
-static const int kNcclFloat64 = 8, kNcclSum = 0;
+static const int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
 
 static int load_nccl() {
   if (nccl.lib) return 0;
@@ -97,6 +97,13 @@ int comm_allreduce_sum(double *dev_buf, int n) {
   Context &c = ctx();
   if (c.size <= 1) return 0;
   return nccl_ok(nccl.allreduce(dev_buf, dev_buf, (size_t)n, kNcclFloat64, kNcclSum, c.nccl_comm, c.stream),
+                 "ncclAllReduce") ? 0 : 1;
+}
+
+int comm_allreduce_max(double *dev_buf, int n) {
+  Context &c = ctx();
+  if (c.size <= 1) return 0;
+  return nccl_ok(nccl.allreduce(dev_buf, dev_buf, (size_t)n, kNcclFloat64, kNcclMax, c.nccl_comm, c.stream),
                  "ncclAllReduce") ? 0 : 1;
 }
 

@@ -1007,6 +1007,14 @@ __global__ void gather_residual_kernel(long nnodes, const int *__restrict__ ptr,
   }
 }
 
+static inline unsigned vec_grid_fwd(long n, int num_sms) {
+  long want = (n + 255) / 256;
+  long cap = (long)num_sms * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (unsigned)want;
+}
+
 static inline unsigned grid_for(long total, int block, int num_sms) {
   long want = (total + block - 1) / block;
   long cap = (long)num_sms * 64;  // a whole number of CTAs per SM, grid-stride beyond that
@@ -1208,6 +1216,53 @@ cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, con
   } else {
     return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Gershgorin bound of the spectral radius (TACSChebyshevSmoother::gershgorin,
+// /root/reference/src/bpmat/TACSParallelMat.cpp:1024-1113)
+// ------------------------------------------------------------------------------------------
+// One thread per scalar row: the diagonal entry enters with its sign, every other entry of the row (all blocks of
+// Aloc in storage order, then the Bext blocks of rows >= np) with its magnitude -- the reference's summation order.
+// The maximum over rows is order independent: a bit-pattern atomicMax on the non-negative result (the reference
+// starts its running maximum at 0).
+__global__ void __launch_bounds__(256) gershgorin_kernel(int bs, int nrows, const int *__restrict__ rowp,
+                                                        const int *__restrict__ cols, const double *__restrict__ A,
+                                                        int np, const int *__restrict__ browp,
+                                                        const double *__restrict__ B, unsigned long long *out) {
+  const int b2 = bs * bs;
+  double best = 0.0;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < (long)nrows * bs; g += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(g / bs), ii = (int)(g - (long)i * bs);
+    double eig = 0.0;
+    for (int jp = rowp[i]; jp < rowp[i + 1]; jp++) {
+      const double *a = A + (long)b2 * jp + bs * ii;
+      const bool diag = cols[jp] == i;
+      for (int jj = 0; jj < bs; jj++) eig += (diag && jj == ii) ? a[jj] : fabs(a[jj]);
+    }
+    if (browp && i >= np) {
+      const int ib = i - np;
+      for (int jp = browp[ib]; jp < browp[ib + 1]; jp++) {
+        const double *a = B + (long)b2 * jp + bs * ii;
+        for (int jj = 0; jj < bs; jj++) eig += fabs(a[jj]);
+      }
+    }
+    if (eig > best) best = eig;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const double o = __shfl_down_sync(0xffffffffu, best, off);
+    if (o > best) best = o;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(best));
+}
+
+cudaError_t launch_gershgorin(int bs, int nrows, const int *rowp, const int *cols, const double *A, int np,
+                              const int *browp, const double *B, double *out, int num_sms, cudaStream_t s) {
+  cudaError_t err = cudaMemsetAsync(out, 0, sizeof(double), s);
+  if (err != cudaSuccess || nrows <= 0) return err;
+  gershgorin_kernel<<<vec_grid_fwd((long)nrows * bs, num_sms), 256, 0, s>>>(
+      bs, nrows, rowp, cols, A, np, browp, B, reinterpret_cast<unsigned long long *>(out));
   return cudaGetLastError();
 }
 

@@ -55,6 +55,10 @@ cudaError_t launch_vec_set_bcs(int bs, int nbcs, const int *bc_rows, const int *
 cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
                         double *y, int add, int num_sms, cudaStream_t s);
 
+// out[0] = max over scalar rows of (signed diagonal + sum of magnitudes); browp/B: Bext rows for owned rows >= np
+cudaError_t launch_gershgorin(int bs, int nrows, const int *rowp, const int *cols, const double *A, int np,
+                              const int *browp, const double *B, double *out, int num_sms, cudaStream_t s);
+
 cudaError_t launch_axpy(long n, double alpha, const double *x, double *y, int num_sms, cudaStream_t s);
 cudaError_t launch_axpby(long n, double alpha, double beta, const double *x, double *y, int num_sms,
                          cudaStream_t s);

@@ -1201,14 +1201,102 @@ void TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
 // ---------------------------------------------------------------------------------------------
 // GMRES (KSM.cpp:547-956), modified Gram-Schmidt (:526-532)
 // ---------------------------------------------------------------------------------------------
-GMRES::GMRES(TACSParallelMat *_mat, int _m, int _nrestart) {
+int comm_allreduce_max(double *dev_buf, int n);  // comm.cpp
+
+TACSChebyshevSmoother::TACSChebyshevSmoother(TACSParallelMat *_mat, int _degree, double _lower, double _upper,
+                                             int _iters) {
   mat = _mat;
   mat->incref();
+  degree = _degree > 0 ? _degree : 1;
+  iters = _iters;
+  lower_factor = _lower;
+  upper_factor = _upper;
+  r.assign(degree, 0.0);
+  c.assign(degree + 1, 1.0);
+  res = mat->createVec();
+  t = mat->createVec();
+  h = mat->createVec();
+  res->incref();
+  t->incref();
+  h->incref();
+}
+TACSChebyshevSmoother::~TACSChebyshevSmoother() {
+  res->decref();
+  t->decref();
+  h->decref();
+  mat->decref();
+}
+
+double TACSChebyshevSmoother::gershgorin() {
+  if (!dot_buffers()) return 0.0;
+  const BCSRPattern &A = mat->Aloc, &B = mat->Bext;
+  {
+    KernelTimer kt(K_VEC);
+    cuda_ok(launch_gershgorin(A.bsize, A.nrows, A.d_rowp.ptr, A.d_cols.ptr, A.d_vals.ptr, mat->np,
+                              B.nnzb() > 0 ? B.d_rowp.ptr : nullptr, B.d_vals.ptr, g_dot_out, ctx().num_sms,
+                              ctx().stream), "gershgorin");
+  }
+  if (ctx().size > 1) comm_allreduce_max(g_dot_out, 1);
+  cuda_ok(cudaMemcpyAsync(g_dot_host, g_dot_out, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream), "gershgorin");
+  cuda_ok(cudaStreamSynchronize(ctx().stream.s), "gershgorin sync");
+  return g_dot_host[0];
+}
+
+// factor(): interval [alpha, beta] = [lower, upper] * rho, Chebyshev roots mapped onto it, monomial coefficients of
+// q(A) = 1 - p(A) A normalised to q(0) = 1 (TACSParallelMat.cpp:930-976)
+int TACSChebyshevSmoother::factor() {
+  rho = gershgorin();
+  alpha = lower_factor * rho;
+  beta = upper_factor * rho;
+  for (int k = 0; k < degree; k++) r[k] = cos(M_PI * (0.5 + k) / degree);
+  for (int k = 0; k < degree; k++) r[k] = 0.5 * (beta - alpha) * (r[k] + 1.0) + alpha;
+  std::fill(c.begin(), c.end(), 0.0);
+  c[0] = 1.0;
+  for (int j = 0; j < degree; j++)
+    for (int k = j; k >= 0; k--) c[k + 1] = c[k + 1] - r[j] * c[k];
+  for (int k = 0; k < degree; k++) c[k] = c[k] / c[degree];
+  c[degree] = 1.0;
+  return 0;
+}
+
+// applyFactor(): y <- y + p(A) (x - A y); note that y enters as the initial guess (TACSParallelMat.cpp:981-1014)
+void TACSChebyshevSmoother::applyFactor(TACSBVec *x, TACSBVec *y) {
+  for (int i = 0; i < iters; i++) {
+    res->copyValues(x);
+    mat->mult(y, t);
+    res->axpy(-1.0, t);
+    h->copyValues(res);
+    h->scale(-c[0]);
+    for (int j = 0; j < degree - 1; j++) {
+      mat->mult(h, t);
+      h->copyValues(res);
+      h->scale(-c[j + 1]);
+      h->axpy(1.0, t);
+    }
+    y->axpy(1.0, h);
+  }
+}
+
+GMRES::GMRES(TACSParallelMat *_mat, int _m, int _nrestart, TACSChebyshevSmoother *_pc, bool _flexible) {
+  mat = _mat;
+  mat->incref();
+  pc = _pc;
+  if (pc) pc->incref();
+  flexible = _flexible && pc;
   m = _m;
   nrestart = _nrestart >= 0 ? _nrestart : 0;
   for (int i = 0; i < m + 1; i++) {
     W.push_back(mat->createVec());
     W.back()->incref();
+  }
+  if (flexible) {
+    for (int i = 0; i < m; i++) {
+      Z.push_back(mat->createVec());
+      Z.back()->incref();
+    }
+  } else if (pc) {
+    work = mat->createVec();
+    work->incref();
   }
   Hptr.assign(m + 1, 0);
   for (int i = 0; i < m; i++) Hptr[i + 1] = Hptr[i] + i + 2;
@@ -1219,6 +1307,9 @@ GMRES::GMRES(TACSParallelMat *_mat, int _m, int _nrestart) {
 }
 GMRES::~GMRES() {
   for (auto w : W) w->decref();
+  for (auto z : Z) z->decref();
+  if (work) work->decref();
+  if (pc) pc->decref();
   mat->decref();
 }
 
@@ -1248,7 +1339,15 @@ int GMRES::solve(TACSBVec *b, TACSBVec *x, int zero_guess) {
       break;
     }
     for (int i = 0; i < m; i++) {
-      mat->mult(W[i], W[i + 1]);
+      if (flexible) {
+        pc->applyFactor(W[i], Z[i]);   // Z[i] = M^{-1} W[i]
+        mat->mult(Z[i], W[i + 1]);
+      } else if (pc) {
+        pc->applyFactor(W[i], work);   // work = M^{-1} W[i] (work enters as the smoother's initial guess)
+        mat->mult(work, W[i + 1]);
+      } else {
+        mat->mult(W[i], W[i + 1]);
+      }
       double *h = &H[Hptr[i]];
       for (int j = 0; j < i + 1; j++) {
         h[j] = W[i + 1]->dot(W[j]);
@@ -1285,7 +1384,16 @@ int GMRES::solve(TACSBVec *b, TACSBVec *x, int zero_guess) {
       for (int j = i + 1; j < niters; j++) res[i] = res[i] - H[i + Hptr[j]] * res[j];
       res[i] = res[i] / H[i + Hptr[i]];
     }
-    for (int i = 0; i < niters; i++) x->axpy(res[i], W[i]);
+    if (flexible) {
+      for (int i = 0; i < niters; i++) x->axpy(res[i], Z[i]);
+    } else if (!pc) {
+      for (int i = 0; i < niters; i++) x->axpy(res[i], W[i]);
+    } else {
+      work->zeroEntries();
+      for (int i = 0; i < niters; i++) work->axpy(res[i], W[i]);
+      pc->applyFactor(work, W[0]);     // M^{-1} applied to the linear combination
+      x->axpy(1.0, W[0]);
+    }
     if (solve_flag) break;
   }
   cudaStreamSynchronize(ctx().stream);

@@ -487,9 +487,25 @@ class TACSAssembler : public Object {
 
 // GMRES (src/bpmat/KSM.cpp:547-956): right-preconditioned restarted GMRES with modified
 // Gram-Schmidt; host control flow, device vectors; optional block-Jacobi-free identity PC.
+// TACSChebyshevSmoother (bpmat/TACSParallelMat.h:180-217, TACSParallelMat.cpp:871-1113): polynomial smoother /
+// preconditioner built from products with the matrix only; the spectral radius comes from Gershgorin's discs.
+class TACSChebyshevSmoother : public Object {
+ public:
+  TACSChebyshevSmoother(TACSParallelMat *mat, int degree, double lower_factor, double upper_factor, int iters);
+  ~TACSChebyshevSmoother();
+  int factor();
+  void applyFactor(TACSBVec *x, TACSBVec *y);
+  double gershgorin();
+  TACSParallelMat *mat;
+  int degree, iters;
+  double lower_factor, upper_factor, alpha = 0.0, beta = 0.0, rho = 0.0;
+  std::vector<double> r, c;
+  TACSBVec *res = nullptr, *t = nullptr, *h = nullptr;
+};
+
 class GMRES : public Object {
  public:
-  GMRES(TACSParallelMat *mat, int m, int nrestart);
+  GMRES(TACSParallelMat *mat, int m, int nrestart, TACSChebyshevSmoother *pc = nullptr, bool flexible = false);
   ~GMRES();
   void setTolerances(double rtol, double atol) { this->rtol = rtol; this->atol = atol; }
   int solve(TACSBVec *b, TACSBVec *x, int zero_guess);
@@ -498,8 +514,10 @@ class GMRES : public Object {
   TACSParallelMat *mat;
   int m, nrestart, iters = 0;
   double rtol = 1e-8, atol = 1e-30, resnorm = 0.0;
-  std::vector<TACSBVec *> W;
-  TACSBVec *work = nullptr;
+  std::vector<TACSBVec *> W, Z;   // Z: preconditioned directions of the flexible variant
+  TACSBVec *work = nullptr;       // M^{-1} W[i] of the regular variant
+  TACSChebyshevSmoother *pc = nullptr;
+  bool flexible = false;
   std::vector<double> H, res, Qsin, Qcos;
   std::vector<int> Hptr;
 };
