@@ -472,58 +472,69 @@ struct alignas(16) ShellUncWork {
   static constexpr bool kColMajorRows = false;   // row buffers are [row][col]
 };
 
-// Quad4 work area of the tensor-core (DMMA m8n8k4) kernel. Every operand of a matrix product is kept as
-// "k-step panels" X[kstep][col][4]: the four rows of one k-step are contiguous per column, so that the A / B
-// fragment of lane l for tile t of a panel is the single double at panel[32 t + l] (a warp reads 256 contiguous
-// bytes, conflict free) and the producers of the rows store 128-bit pieces.
-struct alignas(16) ShellQ4MmaWork {
-  static constexpr int n = 4, nd = 24, nq = 4, nty = 9;
+// Work area of the tensor-core (DMMA m8n8k4) kernels (Quad4: shell4_mma_kernel, Quad9: shell9_mma_kernel). Every
+// operand of a matrix product is kept as "k-step panels" X[kstep][col][4]: the four rows of one k-step are contiguous
+// per column, so that the A / B fragment of lane l for tile t of a panel is the single double at panel[32 t + l] (a
+// warp reads 256 contiguous bytes, conflict free) and the producers of the rows store 128-bit pieces. Columns are
+// padded to a whole number of 8-wide tiles (Quad9: 54 -> 56; what the products put in the pad columns is never
+// stored), tying rows to a whole number of k-steps (Quad4: 9 -> 12, the pad rows stay exactly zero).
+template <int O>
+struct alignas(16) ShellMmaWork {
+  using D = ShellDims<O>;
+  static constexpr int n = D::n, nd = D::nd, nq = D::nq, nty = D::nty;
   static constexpr int ntiles = n * n;
-  static constexpr int KS = 3;       // k-steps of the tying rows (9 rows padded to 12; pad rows stay zero)
-  static constexpr int LDP = 100;    // panel stride (96 + 4: the C-fragment stores of two panels hit distinct banks)
-  static constexpr int LDS_ = 12;    // row stride of S (A operand of S * Bty, k padded to 12 with zeros)
+  static constexpr int NT = (nd + 7) / 8, NDP = 8 * NT;   // 8x8 tiles per side, padded columns
+  static constexpr int KS = (nty + 3) / 4;                // k-steps of the tying rows
+  static constexpr int LDP = 4 * NDP + 4;  // panel stride (+4: the C-fragment stores of two panels hit distinct banks)
+  static constexpr int LDS_ = 4 * KS;      // row stride of S (A operand of S * Bty, k padded with zeros)
+  static constexpr int SROWS = 8 * ((nty + 7) / 8);  // rows >= nty are never written: their products are dropped
   static constexpr bool kColMajorRows = true;
   // Row buffers (one k-step each, rewritten per quadrature point) split a panel into its row pairs,
   // X[k >> 1][col][k & 1] with the two halves HS doubles apart: the producers (one lane per column pair) then store
   // 16-byte pieces at consecutive addresses instead of 32-byte strides, and the fragment of lane (gq,tq) for tile t
   // sits at (tq >> 1) HS + 16 t + 2 gq + (tq & 1)  (HS = 8 mod 16 keeps a half-warp conflict free).
-  static constexpr int HS = 56, LPAN = 2 * HS;
+  static constexpr int HS = 2 * NDP + 8, LPAN = 2 * HS;
+  static constexpr int LBUF = 2 * LPAN;  // row buffer: L panel then R panel
+  static constexpr int even(int x) { return x + (x & 1); }
   // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S [S .. SB product];
-  // Rty = S Bty [SB product .. tying contraction]; row buffer 0 [after SB product ..], row buffer 1 overlays Rty
-  // [after the tying contraction ..]; u, acc, residual, Rp [last loop interval .. finish] in buffer 0.
-  static constexpr int oS = 0;               // S[16][12] (rows 9..15 are never written: their products are dropped)
-  static constexpr int oG = 192;             // G[nq][26]
-  static constexpr int oP = 296;             // P[nq][5][6]
-  static constexpr int oX = 416;             // X[3n]
-  static constexpr int LBUF = 2 * LPAN;      // row buffer: L panel then R panel
-  static constexpr int oRty = LBUF;          // Rty[KS][LDP]: clear of buffer 0 and of S
-  static constexpr int oU = 0, oAcc = 24, oRes = 48, oRp = 72;
+  // Rty = S Bty [SB product .. tying contraction]; row buffer 0 [after SB product ..] overlays S, row buffer 1
+  // overlays Rty [after the tying contraction ..]; u, acc, residual, Rp [last loop interval .. finish] in the
+  // buffer the last interval does not read.
+  static constexpr int oS = 0;
+  static constexpr int oG = SROWS * LDS_;            // G[nq][26]
+  static constexpr int oP = oG + 26 * nq;            // P[nq][5][6]
+  static constexpr int oX = oP + 30 * nq;            // X[3n]
+  static constexpr int oRty = (LBUF > SROWS * LDS_) ? LBUF : SROWS * LDS_;  // Rty[KS][LDP]: clear of buffer 0 and S
   static constexpr int SCR = oRty + KS * LDP;
+  static constexpr int oU = (nq & 1) * oRty, oAcc = oU + nd, oRes = oAcc + nd, oRp = oRes + NDP;
   // residual-only path (no tangent): state, tying strains / stresses and row strains beyond X; only buffer 0 is used
-  static constexpr int oRu = 428, oRt = 452, oRs5 = 464, oRsty = 488, oRt4 = 500;
+  static constexpr int oRu = oX + even(3 * n), oRt = oRu + nd, oRs5 = oRt + LDS_, oRsty = oRs5 + 6 * nq,
+                       oRt4 = oRsty + LDS_;
   double fn[3 * n];
   double Bdu[n][3 * n];   // nodal drill rows, displacement columns [node i][3 j + c]
   double Bdq[n][4];       // nodal drill rows, rotation columns of the own node [node i][c]
   alignas(16) double Lty[KS][LDP];
   alignas(16) double geo[nq][18];
-  double wdet[nq];
+  double wdet[nq + (nq & 1)];
   alignas(16) double scr[SCR];
   TB2_HD double *X() { return scr + oX; }
   TB2_HD double *rpart() { return scr + oRp; }
   TB2_HD double *uvec() { return scr + oU; }
   TB2_HD double *avec() { return scr + oAcc; }
-  TB2_HD double *buf(int k) { return scr + k * LBUF; }
+  TB2_HD double *buf(int k) { return scr + k * oRty; }
   TB2_HD double &bty(int ty, int col) { return Lty[ty >> 2][col * 4 + (ty & 3)]; }
   static constexpr bool kFullBdr = false;
   TB2_HD double &bdr_u(int i, int j, int c) { return Bdu[i][3 * j + c]; }
   TB2_HD double &bdr_q(int i, int c) { return Bdq[i][c]; }
+  static_assert(oX + even(3 * n) <= SCR && oRt4 + 4 <= SCR && oRu >= LBUF, "setup / residual-only scratch");
+  static_assert(oRp + 6 * ntiles <= SCR && (oU != 0 || oRp + 6 * ntiles <= LBUF), "finish data");
+  static_assert(HS % 16 == 8 && LDP % 16 == 4, "bank spreading of the panels");
 };
-static_assert(ShellQ4MmaWork::oRp + 96 <= ShellQ4MmaWork::LBUF && ShellQ4MmaWork::oRty >= 192 &&
-                  ShellQ4MmaWork::oX + 12 <= ShellQ4MmaWork::SCR,
-              "scratch overlays");
-static_assert(ShellQ4MmaWork::oRt4 + 4 <= ShellQ4MmaWork::SCR && ShellQ4MmaWork::oRu >= ShellQ4MmaWork::oX + 12 &&
-                  ShellQ4MmaWork::LBUF <= ShellQ4MmaWork::oP,
-              "residual-only scratch");
+using ShellQ4MmaWork = ShellMmaWork<2>;
+using ShellQ9MmaWork = ShellMmaWork<3>;
+static_assert(ShellQ4MmaWork::LDP == 100 && ShellQ4MmaWork::oRty == 224 && ShellQ4MmaWork::SCR == 524 &&
+                  ShellQ4MmaWork::oG == 192 && ShellQ4MmaWork::oRu == 428 && ShellQ9MmaWork::SCR == 2492,
+              "work-area layouts");
 
 // phase 2 (same barrier interval as shell_p2_tying), task q: frame, inverse Jacobian products, weighted
 // determinant (as shell_p2_qgeom) and the frame products of the five tying fields,

@@ -658,6 +658,292 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Quad9 shells with an uncoupled constitutive matrix: tensor-core kernel
+// ------------------------------------------------------------------------------------------
+// Same scheme as shell4_mma_kernel with one element per CTA of three warps: the scalar phases deal their tasks over
+// the 96 threads, the MMA phases split the 7x7 grid of 8x8 tiles (54 dofs padded to 56) by tile row -- warp w owns
+// the tile rows w, w+3 (and 6 for warp 0) in the contraction, and the tile columns w, w+3 (6) of S*Bty. 28 tying
+// rows are exactly 7 k-steps, so nothing needs zero padding; what lands in the pad rows / columns 54, 55 is dropped.
+struct ShellQ9MmaFamily {
+  using Work = ShellQ9MmaWork;
+  using Tables = ShellTables<3>;
+  static constexpr int TEAM = 96, TEAMS = 1, MIN_CTAS = 3, BS = 6;
+  static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
+};
+
+// Rty = S Bty: warp W computes the tile columns W + 3 i of all four tile rows (K = 28)
+template <int W>
+__device__ __forceinline__ void q9_sb_product(ShellQ9MmaWork &x, int lane, int gq, int tq) {
+  using Work = ShellQ9MmaWork;
+  constexpr int NTS = (W == 0) ? 3 : 2, KS = Work::KS, LDP = Work::LDP, LDS_ = Work::LDS_;
+  double c[4][NTS][2];
+#pragma unroll
+  for (int k = 0; k < 8 * NTS; k++) (&c[0][0][0])[k] = 0.0;
+  const double *S = x.scr + Work::oS;
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+    double a[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) a[mt] = S[(8 * mt + gq) * LDS_ + 4 * ks + tq];
+#pragma unroll
+    for (int i = 0; i < NTS; i++) {
+      const double b = x.Lty[ks][32 * (W + 3 * i) + lane];
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) dmma884(c[mt][i][0], c[mt][i][1], a[mt], b);
+    }
+  }
+  double *R = x.scr + Work::oRty;
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int row = 8 * mt + gq;
+    if (row < Work::nty) {
+#pragma unroll
+      for (int i = 0; i < NTS; i++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int col = 8 * (W + 3 * i) + 2 * tq + h;
+          R[(row >> 2) * LDP + 4 * col + (row & 3)] = c[mt][i][h];
+        }
+    }
+  }
+}
+
+// K tile rows W + 3 i += L^T R over the KS panels of the tying rows
+template <int W>
+__device__ __forceinline__ void q9_contract_ty(ShellQ9MmaWork &x, int lane, double (&kacc)[3][7][2]) {
+  using Work = ShellQ9MmaWork;
+  constexpr int MTS = (W == 0) ? 3 : 2;
+#pragma unroll
+  for (int ks = 0; ks < Work::KS; ks++) {
+    double a[MTS], b[7];
+#pragma unroll
+    for (int i = 0; i < MTS; i++) a[i] = x.Lty[ks][32 * (W + 3 * i) + lane];
+#pragma unroll
+    for (int nt = 0; nt < 7; nt++) b[nt] = x.scr[Work::oRty + ks * Work::LDP + 32 * nt + lane];
+#pragma unroll
+    for (int i = 0; i < MTS; i++)
+#pragma unroll
+      for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
+  }
+}
+
+// ... and over one row buffer (half-split panels; fo = this lane's fragment offset inside a panel)
+template <int W>
+__device__ __forceinline__ void q9_contract_rows(const double *L, int fo, double (&kacc)[3][7][2]) {
+  using Work = ShellQ9MmaWork;
+  constexpr int MTS = (W == 0) ? 3 : 2;
+  double a[MTS], b[7];
+#pragma unroll
+  for (int i = 0; i < MTS; i++) a[i] = L[fo + 16 * (W + 3 * i)];
+#pragma unroll
+  for (int nt = 0; nt < 7; nt++) b[nt] = L[Work::LPAN + fo + 16 * nt];
+#pragma unroll
+  for (int i = 0; i < MTS; i++)
+#pragma unroll
+    for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
+}
+
+// residual rows K u of the warp's tile rows, alpha, tangent fragments to the node-pair-major staging area
+template <int W>
+__device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, double alpha, double *Ke_elem,
+                                          double (&kacc)[3][7][2]) {
+  using Work = ShellQ9MmaWork;
+  constexpr int MTS = (W == 0) ? 3 : 2, nd = Work::nd, n = Work::n;
+  double2 up[7];
+  int co[7];
+#pragma unroll
+  for (int nt = 0; nt < 7; nt++) {
+    const int C = 8 * nt + 2 * tq;
+    up[nt] = C < nd ? *reinterpret_cast<const double2 *>(x.uvec() + C) : make_double2(0.0, 0.0);
+    co[nt] = (C / 6) * 36 + C % 6;
+  }
+#pragma unroll
+  for (int i = 0; i < MTS; i++) {
+    const int R = 8 * (W + 3 * i) + gq;
+    double r = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < 7; nt++)
+      if (8 * nt + 2 * tq < nd) r += kacc[i][nt][0] * up[nt].x + kacc[i][nt][1] * up[nt].y;
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    if (R < nd) {
+      if (tq == 0) x.scr[Work::oRes + R] = r;
+      if (Ke_elem) {
+        double *dst = Ke_elem + (R / 6) * (n * 36) + (R % 6) * 6;
+#pragma unroll
+        for (int nt = 0; nt < 7; nt++)
+          if (8 * nt + 2 * tq < nd)
+            *reinterpret_cast<double2 *>(dst + co[nt]) = make_double2(alpha * kacc[i][nt][0], alpha * kacc[i][nt][1]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_CTAS)
+    shell9_mma_kernel(ElemGroupArgs g) {
+  using F = ShellQ9MmaFamily;
+  using Work = ShellQ9MmaWork;
+  constexpr int O = 3, TEAM = F::TEAM;
+  constexpr int n = Work::n, nd = Work::nd, nq = Work::nq, nty = Work::nty;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  F::Tables &tab = *reinterpret_cast<F::Tables *>(smem_raw);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(F::Tables));
+  Work &w = *reinterpret_cast<Work *>(smem_raw + sizeof(F::Tables) + 16);
+  stage_tables(&tab, g.tables, (uint32_t)sizeof(F::Tables), mbar);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int fo = (tq >> 1) * Work::HS + 2 * gq + (tq & 1);
+  for (int k = tid; k < (int)(sizeof(Work) / sizeof(double)); k += TEAM) reinterpret_cast<double *>(&w)[k] = 0.0;
+  const long nelem = g.nelem, stride = gridDim.x;
+  const bool inertia = (g.gamma != 0.0) || (g.ddvars != nullptr);
+  // two-deep input pipeline (see shell_element_kernel)
+  double pX = 0.0, pu = 0.0, pa = 0.0;
+  int cX = 0, cU = 0, cD = 0, dnext = 0;
+  auto prefetch_ids = [&](long e) {
+    const int *conn = g.conn + e * n;
+    if (tid < 3 * n) cX = __ldg(conn + tid / 3);
+    cU = tid < nd ? __ldg(conn + tid / 6) : 0;
+    cD = __ldg(g.desc_index + e);
+  };
+  auto prefetch_data = [&]() {
+    if (tid < 3 * n) pX = g.Xpts[3 * (long)cX + tid % 3];
+    pu = 0.0;
+    pa = 0.0;
+    if (tid < nd) {
+      const long src = 6 * (long)cU + tid % 6;
+      if (g.vars) pu = g.vars[src];
+      if (g.ddvars) pa = g.ddvars[src];
+    }
+    dnext = cD;
+    if (tid < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.desc_table + (long)kDescStride * cD + 16 * tid));
+  };
+  auto clamp_elem = [&](long e) { return e < nelem ? e : nelem - 1; };
+  prefetch_ids(clamp_elem(blockIdx.x));
+  prefetch_data();
+  prefetch_ids(clamp_elem(blockIdx.x + stride));
+  constexpr int NTRI = nty * (nty + 1) / 2;
+  constexpr int NSA = (NTRI + TEAM - 1) / TEAM;
+  int stri[NSA];
+#pragma unroll
+  for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
+  __syncthreads();
+
+  for (long e = blockIdx.x; e < nelem; e += stride) {
+    if (tid < 3 * n) w.X()[tid] = pX;
+    const double *desc = g.desc_table + (long)kDescStride * dnext;
+    const double cu = pu, ca = pa;  // the state stays in registers until the last quadrature interval
+    if (!g.Ke && tid < nd) w.scr[Work::oRu + tid] = pu;
+    __syncthreads();
+    prefetch_data();
+    prefetch_ids(clamp_elem(e + 2 * stride));
+    if (tid < n) shell_p1_node<O>(tid, w, tab, desc);
+    __syncthreads();
+    if (tid < nty) shell_p2_tying<O>(tid, w, tab);
+    else if (tid < nty + nq) shell_unc_qgeom<O>(tid - nty, w, tab, desc);
+    __syncthreads();
+    if (!g.Ke) {
+      // residual only (assembleRes without inertia): the state goes through the tying space, no tangent
+      double *sc = w.scr;
+      const double *us = sc + Work::oRu;
+      if (tid < nty) shell_unc_res_tying<O>(tid, w, us, sc + Work::oRt);
+      __syncthreads();
+      if (tid < nq) shell_unc_res_point<O>(tid, w, tab, desc, sc + Work::oRt, sc + Work::oRs5);
+      __syncthreads();
+      if (tid < nty) shell_unc_res_back<O>(tid, w, tab, sc + Work::oRs5, sc + Work::oRsty);
+      __syncthreads();
+      double racc = 0.0;
+      if (tid < nd)
+        for (int ty = 0; ty < nty; ty++) racc += w.bty(ty, tid) * sc[Work::oRsty + ty];
+#pragma unroll 1
+      for (int q = 0; q < nq; q++) {
+        if (tid < 3 * n) shell_unc_rows<O, Work, true>(tid, q, w, tab, desc, w.buf(0));
+        __syncthreads();
+        if (tid < 4) shell_unc_res_rowstrain<O>(tid, w, w.buf(0), us, sc + Work::oRt4);
+        __syncthreads();
+        if (tid < nd) racc += shell_unc_res_rowback<O>(tid, q, w, desc, w.buf(0), sc + Work::oRt4);
+        __syncthreads();
+      }
+      if (g.Re && tid < nd) g.Re[e * nd + tid] = racc;
+      continue;
+    }
+    for (int t = tid; t < 5 * nq; t += TEAM) shell_unc_G<O>(t, w, desc);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < NSA; m++)
+      if (tid + m * TEAM < NTRI) shell_unc_S_entry<O>(stri[m], w, tab);
+    __syncthreads();
+    if (warp == 0) q9_sb_product<0>(w, lane, gq, tq);
+    else if (warp == 1) q9_sb_product<1>(w, lane, gq, tq);
+    else q9_sb_product<2>(w, lane, gq, tq);
+    __syncthreads();
+    // rows of point 0 go to buffer 0 while the tying rows are contracted; inside the loop the rows of point q+1 are
+    // produced in the barrier interval that contracts those of point q
+    if (tid < 3 * n) shell_unc_rows<O>(tid, 0, w, tab, desc, w.buf(0));
+    double kacc[3][7][2];
+#pragma unroll
+    for (int k = 0; k < 42; k++) (&kacc[0][0][0])[k] = 0.0;
+    if (warp == 0) q9_contract_ty<0>(w, lane, kacc);
+    else if (warp == 1) q9_contract_ty<1>(w, lane, kacc);
+    else q9_contract_ty<2>(w, lane, kacc);
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < nq; q++) {
+      if (q + 1 < nq) {
+        if (tid < 3 * n) shell_unc_rows<O>(tid, q + 1, w, tab, desc, w.buf((q + 1) & 1));
+      } else if (tid < nd) {
+        w.uvec()[tid] = cu;  // last interval: the state enters shared memory in the buffer that is no longer read
+        w.avec()[tid] = ca;
+      }
+      const double *L = w.buf(q & 1);
+      if (warp == 0) q9_contract_rows<0>(L, fo, kacc);
+      else if (warp == 1) q9_contract_rows<1>(L, fo, kacc);
+      else q9_contract_rows<2>(L, fo, kacc);
+      __syncthreads();
+    }
+    double *Ke_elem = g.Ke + e * (long)(n * n * 36);
+    if (warp == 0) q9_finish<0>(w, gq, tq, g.alpha, Ke_elem, kacc);
+    else if (warp == 1) q9_finish<1>(w, gq, tq, g.alpha, Ke_elem, kacc);
+    else q9_finish<2>(w, gq, tq, g.alpha, Ke_elem, kacc);
+    __syncthreads();
+    if (inertia) {
+      if (tid < n * n) {
+        // inertial block of node pair tid = (i,j) added to the staged tangent
+        double M[36];
+        shell_mass_tile<O>(tid, w, tab, desc, M);
+        const int j = tid % n;
+        double *rp = w.rpart() + 6 * tid;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int b = 0; b < 6; b++) sacc += M[6 * a + b] * w.avec()[6 * j + b];
+          rp[a] = sacc;
+        }
+        double2 *dst = reinterpret_cast<double2 *>(Ke_elem + tid * 36);
+#pragma unroll
+        for (int k = 0; k < 18; k++) {
+          double2 v = dst[k];
+          v.x += g.gamma * M[2 * k];
+          v.y += g.gamma * M[2 * k + 1];
+          dst[k] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (g.Re && tid < nd) {
+      double sres = w.scr[Work::oRes + tid];
+      if (inertia) {
+        const int i = tid / 6, a = tid % 6;
+        const double *rp = w.rpart();
+        for (int j = 0; j < n; j++) sres += rp[(i * n + j) * 6 + a];
+      }
+      g.Re[e * nd + tid] = sres;
+    }
+    __syncthreads();
+  }
+}
+
 template <int O>
 __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
     solid_element_kernel(ElemGroupArgs g) {
@@ -916,7 +1202,8 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
         return launch_family<ShellQ4MmaFamily>(shell4_mma_kernel, g, num_sms, s);
       return launch_family<ShellFamily<2, false>>(shell_element_kernel<2, false>, g, num_sms, s);
     case ELEM_QUAD9_SHELL:
-      if (g.uncoupled && g.Ke) return launch_family<ShellFamily<3, true>>(shell_element_kernel<3, true>, g, num_sms, s);
+      if (g.uncoupled && (g.Ke || (g.gamma == 0.0 && !g.ddvars)))
+        return launch_family<ShellQ9MmaFamily>(shell9_mma_kernel, g, num_sms, s);
       return launch_family<ShellFamily<3, false>>(shell_element_kernel<3, false>, g, num_sms, s);
     case ELEM_HEX8: return launch_family<SolidFamily<2>>(solid_element_kernel<2>, g, num_sms, s);
     case ELEM_HEX27: return launch_family<SolidFamily<3>>(solid_element_kernel<3>, g, num_sms, s);

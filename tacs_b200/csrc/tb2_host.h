@@ -93,7 +93,7 @@ inline bool shell_desc_uncoupled(const double *row) {
     bmax = std::max(bmax, std::fabs(row[6 + i]));
     dmax = std::max(dmax, std::fabs(row[12 + i]));
   }
-  return bmax <= 1e-18 * std::sqrt(amax * dmax);
+  return bmax <= 1e-14 * std::sqrt(amax * dmax);
 }
 
 template <class T>

@@ -20,7 +20,7 @@ static bool desc_uncoupled(const double *desc) {
     bmax = std::fmax(bmax, std::fabs(desc[6 + i]));
     dmax = std::fmax(dmax, std::fabs(desc[12 + i]));
   }
-  return bmax <= 1e-18 * std::sqrt(amax * dmax);
+  return bmax <= 1e-14 * std::sqrt(amax * dmax);
 }
 
 template <int O, class WK>
@@ -107,13 +107,14 @@ static void run_shell_unc(const double *Xpts, const double *vars, const double *
   delete w;
 }
 
-// Quad4 tensor-core kernel (shell4_mma_kernel): the scalar phases are the device task functions; the two MMA
-// products are replayed as plain loops over the same shared-memory panels (the lane <-> fragment mapping itself is
-// only exercised on the GPU)
-static void run_shell4_mma(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
-                           double alpha, double gamma, double *res, double *mat) {
-  using WK = ShellQ4MmaWork;
-  constexpr int O = 2, n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty, KS = WK::KS, LDP = WK::LDP;
+// Tensor-core kernels (shell4_mma_kernel / shell9_mma_kernel): the scalar phases are the device task functions; the
+// two MMA products are replayed as plain loops over the same shared-memory panels (the lane <-> fragment mapping
+// itself is only exercised on the GPU)
+template <int O>
+static void run_shell_mma(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
+                          double alpha, double gamma, double *res, double *mat) {
+  using WK = ShellMmaWork<O>;
+  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty, KS = WK::KS, LDP = WK::LDP;
   static ShellTables<O> tab;
   build_shell_tables<O>(tab);
   WK *w = new WK;
@@ -126,15 +127,17 @@ static void run_shell4_mma(const double *Xpts, const double *vars, const double 
   for (int q = 0; q < nq; q++) shell_unc_qgeom<O>(q, *w, tab, desc);
   for (int t = 0; t < 5 * nq; t++) shell_unc_G<O>(t, *w, desc);
   for (int k = 0; k < nty * (nty + 1) / 2; k++) shell_unc_S_entry<O>(shell_unc_tri<O>(k), *w, tab);
-  for (int t = 0; t < 3 * nty; t++) w->scr[WK::oS + (t / 3) * WK::LDS_ + nty + t % 3] = 0.0;
-  // Rty = S Bty (rows 0..8), rows 9..11 zero
+  for (int t = 0; t < (WK::LDS_ - nty) * nty; t++)  // k padding of the A operand S
+    w->scr[WK::oS + (t / (WK::LDS_ - nty)) * WK::LDS_ + nty + t % (WK::LDS_ - nty)] = 0.0;
+  // Rty = S Bty (rows 0..nty-1), pad rows zero
   {
     std::vector<double> R((size_t)KS * LDP, 0.0);
-    for (int ty = 0; ty < 12; ty++)
+    for (int ty = 0; ty < 4 * KS; ty++)
       for (int col = 0; col < nd; col++) {
         double sum = 0.0;
         if (ty < nty)
-          for (int t = 0; t < 12; t++) sum += w->scr[WK::oS + ty * WK::LDS_ + t] * w->Lty[t >> 2][col * 4 + (t & 3)];
+          for (int t = 0; t < 4 * KS; t++)
+            sum += w->scr[WK::oS + ty * WK::LDS_ + t] * w->Lty[t >> 2][col * 4 + (t & 3)];
         R[(ty >> 2) * LDP + col * 4 + (ty & 3)] = sum;
       }
     for (int k = 0; k < KS * LDP; k++) w->scr[WK::oRty + k] = R[k];
@@ -143,7 +146,7 @@ static void run_shell4_mma(const double *Xpts, const double *vars, const double 
   std::vector<double> K((size_t)nd * nd, 0.0);
   for (int i = 0; i < nd; i++)
     for (int j = 0; j < nd; j++)
-      for (int k = 0; k < 12; k++)
+      for (int k = 0; k < 4 * KS; k++)
         K[i * nd + j] += w->Lty[k >> 2][i * 4 + (k & 3)] * w->scr[WK::oRty + (k >> 2) * LDP + j * 4 + (k & 3)];
   for (int q = 0; q < nq; q++) {
     if (q + 1 < nq) {
@@ -188,9 +191,10 @@ static void run_shell4_mma(const double *Xpts, const double *vars, const double 
 }
 
 // residual-only branch of shell4_mma_kernel (assembleRes, no inertia)
-static void run_shell4_residual(const double *Xpts, const double *vars, const double *desc, double *res) {
-  using WK = ShellQ4MmaWork;
-  constexpr int O = 2, n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
+template <int O>
+static void run_shell_mma_residual(const double *Xpts, const double *vars, const double *desc, double *res) {
+  using WK = ShellMmaWork<O>;
+  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
   static ShellTables<O> tab;
   build_shell_tables<O>(tab);
   WK *w = new WK;
@@ -254,8 +258,9 @@ static void run_solid(const double *Xpts, const double *vars, const double *ddva
 extern "C" {
 // residual-only fast path (Quad4, uncoupled descriptor, no inertia): 0 when handled
 int emul_residual(int kind, const double *Xpts, const double *vars, const double *desc, double *res) {
-  if (kind != 1 || !desc_uncoupled(desc)) return 1;
-  run_shell4_residual(Xpts, vars, desc, res);
+  if (kind > 2 || !desc_uncoupled(desc)) return 1;
+  if (kind == 1) run_shell_mma_residual<2>(Xpts, vars, desc, res);
+  else run_shell_mma_residual<3>(Xpts, vars, desc, res);
   return 0;
 }
 
@@ -264,12 +269,13 @@ int emul_element(int kind, const double *Xpts, const double *vars, const double 
                  double alpha, double gamma, double *res, double *mat) {
   switch (kind) {
     case 1:
-      if (desc_uncoupled(desc)) run_shell4_mma(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      if (desc_uncoupled(desc)) run_shell_mma<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       else run_shell<2, 1>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       return 0;
     case 5: run_shell_unc<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;  // generic uncoupled flow
+    case 6: run_shell_unc<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
     case 2:
-      if (desc_uncoupled(desc)) run_shell_unc<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
+      if (desc_uncoupled(desc)) run_shell_mma<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       else run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       return 0;
     case 3: run_solid<2, 4>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
