@@ -792,14 +792,17 @@ TB2_HD void shell_unc_res_back(int ty, WK &w, const ShellTables<O> &tab, const d
   sty[ty] = sum;
 }
 
-// task r in [0,4): strain r of the row buffer (bending 0..2, drill 3) for the state
-template <int O, class WK>
-TB2_HD void shell_unc_res_rowstrain(int r, WK &w, const double *L, const double *u, double *t4) {
+// task (r, part) with r in [0,4), part in [0,PARTS): partial strain r of the row buffer (bending 0..2, drill 3) for
+// the state over the columns part, part + PARTS, ...; the kernel sums the PARTS partials of a row with shuffles
+// (tasks of one row sit in adjacent lanes), the host replay adds them in the same order
+template <int O, class WK, int PARTS>
+TB2_HD double shell_unc_res_rowstrain(int task, WK &w, const double *L, const double *u) {
   constexpr int nd = ShellDims<O>::nd;
+  const int r = task / PARTS, part = task % PARTS;
   const double *row = L + (r >> 1) * WK::HS + (r & 1);
   double s = 0.0;
-  for (int col = 0; col < nd; col++) s += row[2 * col] * u[col];
-  t4[r] = s;
+  for (int col = part; col < nd; col += PARTS) s += row[2 * col] * u[col];
+  return s;
 }
 
 // dof `col`: contribution of the row buffer of point q, L^T (w det [D 0; 0 drill]) t4

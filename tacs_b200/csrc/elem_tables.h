@@ -47,14 +47,11 @@ struct alignas(16) ShellTables {
   double Nq[D::nq][D::n];        // shape functions at quadrature points
   double dNq[D::nq][D::n][2];    // parametric derivatives at quadrature points
   double wq[D::nq];              // quadrature weights
-  double dNn[D::n][D::n][2];     // derivatives at the node parametric points
-  double Nt[D::nty][D::n];       // shape functions at tying points
-  double dNt[D::nty][D::n][2];   // derivatives at tying points
   double Ntq[D::nq][D::nty];     // tying-strain interpolation evaluated at quadrature points
-  // transposed copies for the phases whose tasks are "one lane per tying point / node / quadrature point":
-  // the lane index is the fastest dimension, so a team's loads hit consecutive shared-memory banks
-  double Nt_T[D::n][D::nty], dNt_T[D::n][2][D::nty];
-  double dNn_T[D::n][2][D::n];   // [j][k][i] = dNn[i][j][k]
+  // tables of the phases whose tasks are "one lane per tying point / node / quadrature point" are stored with the
+  // lane index as the fastest dimension, so a team's loads hit consecutive shared-memory banks:
+  double Nt_T[D::n][D::nty], dNt_T[D::n][2][D::nty];  // shape functions / derivatives at tying points, [j][(k)][ty]
+  double dNn_T[D::n][2][D::n];   // derivatives at the node parametric points, [j][k][i] = dN_j/dxi_k at node i
   double Nq_T[D::n][D::nq], dNq_T[D::n][2][D::nq];
 };
 
@@ -149,9 +146,10 @@ inline void build_shell_tables(ShellTables<O> &t) {
     for (int j = 0; j < O - 1; j++) for (int i = 0; i < O; i++) *N++ = na[i] * nbr[j];
     for (int j = 0; j < O; j++) for (int i = 0; i < O - 1; i++) *N++ = nar[i] * nb[j];
   }
+  static double Nt[D::nty][D::n], dNt[D::nty][D::n][2], dNn[D::n][D::n][2];  // host-side staging of the tables
   for (int i = 0; i < D::n; i++) {
     double pt[2] = {-1.0 + (2.0 / (O - 1)) * (i % O), -1.0 + (2.0 / (O - 1)) * (i / O)};
-    shape2d<O>(pt, nullptr, t.dNn[i]);
+    shape2d<O>(pt, nullptr, dNn[i]);
   }
   const int cnt[5] = {D::c11, D::c22, D::c12, D::c23, D::c13};
   for (int index = 0; index < D::nty; index++) {
@@ -161,17 +159,17 @@ inline void build_shell_tables(ShellTables<O> &t) {
     if (f == 0 || f == 4) { pt[0] = red[ty % (O - 1)]; pt[1] = full[ty / (O - 1)]; }
     else if (f == 1 || f == 3) { pt[0] = full[ty % O]; pt[1] = red[ty / O]; }
     else { pt[0] = red[ty % (O - 1)]; pt[1] = red[ty / (O - 1)]; }
-    shape2d<O>(pt, t.Nt[index], t.dNt[index]);
+    shape2d<O>(pt, Nt[index], dNt[index]);
   }
   for (int j = 0; j < D::n; j++) {
     for (int ty = 0; ty < D::nty; ty++) {
-      t.Nt_T[j][ty] = t.Nt[ty][j];
-      t.dNt_T[j][0][ty] = t.dNt[ty][j][0];
-      t.dNt_T[j][1][ty] = t.dNt[ty][j][1];
+      t.Nt_T[j][ty] = Nt[ty][j];
+      t.dNt_T[j][0][ty] = dNt[ty][j][0];
+      t.dNt_T[j][1][ty] = dNt[ty][j][1];
     }
     for (int i = 0; i < D::n; i++) {
-      t.dNn_T[j][0][i] = t.dNn[i][j][0];
-      t.dNn_T[j][1][i] = t.dNn[i][j][1];
+      t.dNn_T[j][0][i] = dNn[i][j][0];
+      t.dNn_T[j][1][i] = dNn[i][j][1];
     }
     for (int q = 0; q < D::nq; q++) {
       t.Nq_T[j][q] = t.Nq[q][j];

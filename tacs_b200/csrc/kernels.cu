@@ -478,7 +478,13 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
       for (int q = 0; q < nq; q++) {
         if (tid < 3 * n) shell_unc_rows<O, Work, true>(tid, q, w, tab, desc, w.buf(0));
         __syncwarp();
-        if (tid < 4) shell_unc_res_rowstrain<O>(tid, w, w.buf(0), us, sc + Work::oRt4);
+        {
+          // 4 rows x 4 column parts on the 16 lanes of the team, partials folded with two shuffles
+          double part = shell_unc_res_rowstrain<O, Work, 4>(tid, w, w.buf(0), us);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          if ((tid & 3) == 0) sc[Work::oRt4 + (tid >> 2)] = part;
+        }
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < NU; m++) {
@@ -668,7 +674,7 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
 struct ShellQ9MmaFamily {
   using Work = ShellQ9MmaWork;
   using Tables = ShellTables<3>;
-  static constexpr int TEAM = 96, TEAMS = 1, MIN_CTAS = 3, BS = 6;
+  static constexpr int TEAM = 96, TEAMS = 1, MIN_CTAS = 4, BS = 6;
   static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
@@ -859,7 +865,14 @@ __global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_
       for (int q = 0; q < nq; q++) {
         if (tid < 3 * n) shell_unc_rows<O, Work, true>(tid, q, w, tab, desc, w.buf(0));
         __syncthreads();
-        if (tid < 4) shell_unc_res_rowstrain<O>(tid, w, w.buf(0), us, sc + Work::oRt4);
+        if (tid < 32) {
+          // 4 rows x 8 column parts on the first warp, partials folded with three shuffles
+          double part = shell_unc_res_rowstrain<O, Work, 8>(tid, w, w.buf(0), us);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+          if ((tid & 7) == 0) sc[Work::oRt4 + (tid >> 3)] = part;
+        }
         __syncthreads();
         if (tid < nd) racc += shell_unc_res_rowback<O>(tid, q, w, desc, w.buf(0), sc + Work::oRt4);
         __syncthreads();

@@ -215,7 +215,18 @@ static void run_shell_mma_residual(const double *Xpts, const double *vars, const
   }
   for (int q = 0; q < nq; q++) {
     for (int t = 0; t < 3 * n; t++) shell_unc_rows<O, WK, true>(t, q, *w, tab, desc, w->buf(0));
-    for (int r = 0; r < 4; r++) shell_unc_res_rowstrain<O>(r, *w, w->buf(0), sc + WK::oRu, sc + WK::oRt4);
+    {
+      // the kernel's butterfly: parts (0+1)+(2+3) for Quad4, ((0+1)+(2+3))+((4+5)+(6+7)) for Quad9
+      constexpr int PARTS = (O == 2) ? 4 : 8;
+      for (int r = 0; r < 4; r++) {
+        double p[PARTS];
+        for (int k = 0; k < PARTS; k++)
+          p[k] = shell_unc_res_rowstrain<O, WK, PARTS>(r * PARTS + k, *w, w->buf(0), sc + WK::oRu);
+        for (int stride = 1; stride < PARTS; stride *= 2)
+          for (int k = 0; k < PARTS; k += 2 * stride) p[k] += p[k + stride];
+        sc[WK::oRt4 + r] = p[0];
+      }
+    }
     for (int k = 0; k < nd; k++) res[k] += shell_unc_res_rowback<O>(k, q, *w, desc, w->buf(0), sc + WK::oRt4);
   }
   delete w;
