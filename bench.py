@@ -27,16 +27,24 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# keep stdout to the one JSON line: NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# Keep stdout to the one JSON line: libraries below us write there from C (NCCL prints its version banner on stdout
+# whenever NCCL_DEBUG is VERSION or above, the reference prints a banner per assembler). File descriptor 1 is pointed at
+# stderr for the whole run and the result line goes to the saved original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(os.dup(2), "w")
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "elements/sec for Jacobian+residual assembly (BCSR SpMV GB/s vs HBM peak under 'spmv')"
 UNIT = "elements/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this command at the
-# default workload (profiles/r1_d_kernels_ncu.txt); reported only when the run uses that workload on one GPU
-NCU_TRAFFIC_BYTES = {"shell_element_kernel<2>": 0.139460e9 + 4.795389e9, "gather_blocks36_kernel": 4.744171e9 + 2.586922e9,
-                     "spmv6_kernel<0>": 2.690065e9 + 0.049695e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures at the default workload
+# (profiles/r1_n_kernels_ncu.txt); reported only when the run uses that workload on one GPU
+NCU_TRAFFIC_BYTES = {"shell4_mma_kernel": 0.142545e9 + 4.742443e9, "gather_blocks36_kernel": 4.744081e9 + 2.584352e9,
+                     "spmv6_kernel<0>": 2.689707e9 + 0.050150e9}
 # minimal-algorithm flops per element used for the FP64 roofline
 FLOPS_PER_ELEMENT = {"quad4": 57e3, "quad9": 551e3, "hex8": 69e3, "hex27": 2.28e6}
 
@@ -56,7 +64,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled while the timed region runs: NVML polled in-process every few
+    milliseconds (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as fallback."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -64,49 +73,73 @@ class ClockSampler:
 
     def __init__(self, device=0):
         self.device = device
-        self.rows = []
-        self.proc = None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.device)
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.004)
+
+    def _poll_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while True:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout
+                r = [c.strip() for c in out.strip().split(",")]
+                self.sm.append(float(r[1]))
+                self.mx.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                break
+            if self.stop.is_set():
+                break
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            target = self._poll_nvml
+        except Exception:
+            self.nvml = None
+            target = self._poll_smi
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *exc):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop.set()
+        if self.thread:
+            self.thread.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)), "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def host_threads():
@@ -213,7 +246,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -395,7 +428,7 @@ def run_b200(args):
         "gpu_launches": int(launches), "clocks": clocks.summary(),
         "fp64_peak_tflops": fp64_peak,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
