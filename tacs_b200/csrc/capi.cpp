@@ -285,6 +285,9 @@ int tacsb200_plan_get_array(tacsb200_handle plan, const char *name, int *out) {
   else if (n == "a_src") v = &P.a_src;
   else if (n == "b_ptr") v = &P.b_ptr;
   else if (n == "b_src") v = &P.b_src;
+  else if (n == "g_base") v = &P.g_base;
+  else if (n == "g_pptr") v = &P.g_pptr;
+  else if (n == "g_pos") v = &P.g_pos;
   else if (n == "r_ptr") v = &P.r_ptr;
   else if (n == "r_src") v = &P.r_src;
   else if (n == "scalars") {

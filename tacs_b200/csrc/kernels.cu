@@ -1315,6 +1315,95 @@ static inline unsigned vec_grid_fwd(long n, int num_sms) {
   return (unsigned)want;
 }
 
+// Row-strip gather: one warp per owned block row. An element contributes to row r (its node i) the strip of its nn
+// staging blocks (i, 0..nn-1), contiguous in the staging area: the warp streams each strip with fully used sectors
+// (the per-block form reads 72-byte 3x3 blocks that straddle sectors), adds its blocks into the row's buffer in
+// shared memory at the planned positions and finally writes the row's Aloc (and Bext) blocks, contiguous in BCSR
+// storage. Strips are visited in ascending global element order, so every block is still summed in the order of the
+// reference's serial loop; no atomics.
+template <int B2>
+__global__ void __launch_bounds__(256) gather_rows_kernel(int nrows, const int *__restrict__ gptr,
+                                                         const int *__restrict__ gbase, const int *__restrict__ gpptr,
+                                                         const int *__restrict__ gpos, const double *__restrict__ Ke,
+                                                         const int *__restrict__ rowpA, double *__restrict__ A, int np,
+                                                         const int *__restrict__ rowpB, double *__restrict__ B,
+                                                         int row_doubles) {
+  extern __shared__ __align__(16) double rowbuf_all[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double *buf = rowbuf_all + (size_t)wib * row_doubles;
+  for (long r = (long)blockIdx.x * wpb + wib; r < nrows; r += (long)gridDim.x * wpb) {
+    const int a0 = __ldg(rowpA + r), nA = __ldg(rowpA + r + 1) - a0;
+    int b0 = 0, nB = 0;
+    if (rowpB && r >= np) {
+      b0 = __ldg(rowpB + (r - np));
+      nB = __ldg(rowpB + (r - np) + 1) - b0;
+    }
+    const int total = (nA + nB) * B2;
+    for (int i = lane; i < total; i += 32) buf[i] = 0.0;
+    __syncwarp();
+    const int p0 = __ldg(gptr + r), p1 = __ldg(gptr + r + 1);
+    for (int p = p0; p < p1; p++) {
+      const int pp = __ldg(gpptr + p), len = (__ldg(gpptr + p + 1) - pp) * B2;
+      const double *strip = Ke + (long)__ldg(gbase + p) * B2;
+      if (B2 % 2 == 0) {
+        // 6x6 blocks: 128-bit loads (a pair never straddles a block)
+        for (int i = 2 * lane; i < len; i += 64) {
+          const double2 v = __ldg(reinterpret_cast<const double2 *>(strip + i));
+          const int j = i / B2, k = i - j * B2;
+          double *d = buf + __ldg(gpos + pp + j) * B2 + k;
+          d[0] += v.x;
+          d[1] += v.y;
+        }
+      } else {
+        for (int i = lane; i < len; i += 32) {
+          const double v = __ldg(strip + i);
+          const int j = i / B2, k = i - j * B2;
+          buf[__ldg(gpos + pp + j) * B2 + k] += v;
+        }
+      }
+      __syncwarp();
+    }
+    double *dA = A + (long)a0 * B2;
+    for (int i = lane; i < nA * B2; i += 32) dA[i] = buf[i];
+    if (nB > 0) {
+      double *dB = B + (long)b0 * B2;
+      const double *sb = buf + nA * B2;
+      for (int i = lane; i < nB * B2; i += 32) dB[i] = sb[i];
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_gather_rows(int bs, int nrows, const int *gptr, const int *gbase, const int *gpptr, const int *gpos,
+                               const double *Ke, const int *rowpA, double *A, int np, const int *rowpB, double *B,
+                               int max_row_blocks, int num_sms, cudaStream_t s) {
+  if (nrows <= 0) return cudaSuccess;
+  const int b2 = bs * bs;
+  const int row_doubles = ((max_row_blocks * b2 + 15) / 16) * 16;
+  int wpb = 8;
+  while (wpb > 1 && (size_t)wpb * row_doubles * sizeof(double) > 96 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)wpb * row_doubles * sizeof(double);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  long want = ((long)nrows + wpb - 1) / wpb;
+  long cap = (long)num_sms * 32;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  cudaError_t err;
+  if (bs == 6) {
+    err = cudaFuncSetAttribute(gather_rows_kernel<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    gather_rows_kernel<36><<<grid, wpb * 32, smem, s>>>(nrows, gptr, gbase, gpptr, gpos, Ke, rowpA, A, np, rowpB, B,
+                                                       row_doubles);
+  } else if (bs == 3) {
+    err = cudaFuncSetAttribute(gather_rows_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    gather_rows_kernel<9><<<grid, wpb * 32, smem, s>>>(nrows, gptr, gbase, gpptr, gpos, Ke, rowpA, A, np, rowpB, B,
+                                                      row_doubles);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 static inline unsigned grid_for(long total, int block, int num_sms) {
   long want = (total + block - 1) / block;
   long cap = (long)num_sms * 64;  // a whole number of CTAs per SM, grid-stride beyond that

@@ -41,6 +41,11 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
 
 cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int *src, const double *Ke,
                                  double *A, int num_sms, cudaStream_t s);
+// row-strip form: gptr[nrows+1] contributions per owned row, gbase[p] first staging slot of strip p, gpptr/gpos
+// positions of the strip's blocks in the row buffer [Aloc row | Bext row]
+cudaError_t launch_gather_rows(int bs, int nrows, const int *gptr, const int *gbase, const int *gpptr, const int *gpos,
+                               const double *Ke, const int *rowpA, double *A, int np, const int *rowpB, double *B,
+                               int max_row_blocks, int num_sms, cudaStream_t s);
 cudaError_t launch_gather_residual(int bs, long nnodes, const int *ptr, const int *src, const double *Re,
                                    double *res, int num_sms, cudaStream_t s);
 

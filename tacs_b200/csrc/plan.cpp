@@ -411,6 +411,34 @@ int HostPlan::buildMatrix() {
           }
     });
   }
+  // row-strip form of the same plan
+  {
+    const size_t ncontrib = adj.size();
+    g_base.resize(ncontrib);
+    g_pptr.assign(ncontrib + 1, 0);
+    for (size_t p = 0; p < ncontrib; p++) {
+      g_base[p] = adj[p].blk_base;
+      g_pptr[p + 1] = g_pptr[p] + adj[p].nn;
+    }
+    g_pos.resize(g_pptr[ncontrib]);
+    max_row_blocks = 0;
+    for (int r = 0; r < nowned; r++) {
+      const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];
+      const int nB = (r >= np) ? Bext.rowp[r - np + 1] - Bext.rowp[r - np] : 0;
+      if (nA + nB > max_row_blocks) max_row_blocks = nA + nB;
+    }
+    plan_parallel_for(nowned, [&](long r0, long r1) {
+      for (long r = r0; r < r1; r++) {
+        const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];
+        for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++)
+          for (int j = 0; j < adj[p].nn; j++) {
+            bool is_ext;
+            long pos = locate((int)r, adj[p].conn[j], is_ext);
+            g_pos[g_pptr[p] + j] = is_ext ? nA + (int)(pos - Bext.rowp[r - np]) : (int)(pos - Aloc.rowp[r]);
+          }
+      }
+    });
+  }
   // receive side of the column halo: ext_col_nodes is sorted, each owner's columns are contiguous
   cols.recv_peers.clear();
   cols.recv_ptr.assign(1, 0);

@@ -81,6 +81,12 @@ struct HostPlan {
   int np = 0;
   std::vector<int> ext_col_nodes;
   std::vector<int> a_ptr, a_src, b_ptr, b_src;
+  // row-strip gather plan (what the device uses): contribution p of owned row r (adj_ptr order = ascending global
+  // element) is the contiguous strip of nn staging blocks starting at slot g_base[p]; block j of the strip goes to
+  // block g_pos[g_pptr[p] + j] of the row's buffer [Aloc row blocks | Bext row blocks]
+  std::vector<int> g_base, g_pptr;
+  std::vector<int> g_pos;
+  int max_row_blocks = 0;
   // neighbour exchanges (empty on one rank)
   ExchangePlan state;   // chunk = one node block of a state vector: owned node -> ext slots of peers
   ExchangePlan cols;    // chunk = one node block of x: owned node -> x_ext of peers (SpMV)

@@ -1036,15 +1036,23 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
   }
   // from here on only the staging area and the matrix are touched (Context::tail_evt)
   cudaEventRecord(ctx().tail_evt, ctx().stream.s);
-  {
+  if (A->row_gather) {
     KernelTimer kt(K_GATHER_MAT);
-    if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
-                                      ctx().num_sms, ctx().stream), "gather blocks")) return 1;
-  }
-  if (A->Bext.nnzb() > 0) {
-    KernelTimer kt(K_GATHER_MAT);
-    if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
-                                      ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+    if (!cuda_ok(launch_gather_rows(bs, nowned, r_ptr.ptr, A->g_base.ptr, A->g_pptr.ptr, A->g_pos.ptr, Ke.ptr,
+                                    A->Aloc.d_rowp.ptr, A->Aloc.d_vals.ptr, A->np,
+                                    A->Bext.nnzb() > 0 ? A->Bext.d_rowp.ptr : nullptr, A->Bext.d_vals.ptr,
+                                    A->max_row_blocks, ctx().num_sms, ctx().stream), "gather rows")) return 1;
+  } else {
+    {
+      KernelTimer kt(K_GATHER_MAT);
+      if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
+                                        ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+    }
+    if (A->Bext.nnzb() > 0) {
+      KernelTimer kt(K_GATHER_MAT);
+      if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
+                                        ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+    }
   }
   if (apply_bcs) A->applyBCs();
   ctx().tail_seq = ctx().stream.seq;
@@ -1132,11 +1140,20 @@ TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
   copy(Bext, P.Bext);
   const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
   const size_t b2 = (size_t)Aloc.bsize * Aloc.bsize;
-  bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA) &&
-            a_ptr.upload(P.a_ptr) && a_src.upload(P.a_src);
-  if (ok && nnzB > 0)
+  // gather plan on the device. The row-strip form (one warp per block row, whole-sector reads of the element strips)
+  // pays for 3x3 blocks with short rows -- hex8: 27 blocks per row, measured 1.77 -> 1.55 ms per 1M elements; it
+  // is on par for Quad4 and loses where a row buffer is large (Quad9 900, hex27 1125 doubles per warp: measured 2x
+  // slower), where the per-block form is kept.
+  max_row_blocks = P.max_row_blocks;
+  row_gather = Aloc.bsize == 3 && (size_t)max_row_blocks * b2 <= 256;
+  bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA);
+  if (ok && row_gather) ok = g_base.upload(P.g_base) && g_pptr.upload(P.g_pptr) && g_pos.upload(P.g_pos);
+  if (ok && !row_gather) ok = a_ptr.upload(P.a_ptr) && a_src.upload(P.a_src);
+  if (ok && nnzB > 0) {
     ok = Bext.d_rowp.upload(Bext.rowp) && Bext.d_cols.upload(Bext.cols) && Bext.d_vals.alloc(b2 * nnzB) &&
-         b_ptr.upload(P.b_ptr) && b_src.upload(P.b_src) && x_ext.alloc((size_t)Aloc.bsize * Bext.ncols);
+         x_ext.alloc((size_t)Aloc.bsize * Bext.ncols);
+    if (ok && !row_gather) ok = b_ptr.upload(P.b_ptr) && b_src.upload(P.b_src);
+  }
   if (ok && a->size > 1) ok = comm_setup_exchange(x_cols, P.cols) == 0;
   if (!ok) {
     Aloc.bsize = 0;

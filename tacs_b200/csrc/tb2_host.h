@@ -365,7 +365,10 @@ class TACSParallelMat : public Object {
   int np = 0;                      // first owned row with an off-rank column (rows of Bext start here)
   std::vector<int> ext_col_nodes;  // ascending global node ids of the external columns
   // gather plan: staging slots of every block, ascending element order
-  DeviceArray<int> a_ptr, a_src, b_ptr, b_src;
+  DeviceArray<int> a_ptr, a_src, b_ptr, b_src;  // per-block form (kept on the host plan; uploaded only as fallback)
+  DeviceArray<int> g_base, g_pptr, g_pos;       // row-strip form (HostPlan::g_*), rows indexed by the assembler's r_ptr
+  int max_row_blocks = 0;
+  bool row_gather = false;
   DeviceArray<double> x_ext;  // external column values for the SpMV halo
   DeviceArray<int> d_bc_rows_ext;  // Bext row (owned row - np) of each merged BC, or -1
   DeviceExchange x_cols;

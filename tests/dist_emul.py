@@ -69,6 +69,27 @@ def gather_blocks(ptr, src, Ke):
     return out
 
 
+def gather_rows(P, Ke):
+    """Replay of gather_rows_kernel: row r sums the strips of its contributions (ascending element order) into the
+    row buffer [Aloc row blocks | Bext row blocks] at the planned positions."""
+    rp, gb, gpp, gpos = P.array("r_ptr"), P.array("g_base"), P.array("g_pptr"), P.array("g_pos")
+    ar, br = P.array("Aloc_rowp"), P.array("Bext_rowp")
+    np_ = P.scalars()["np"]
+    A = np.zeros((ar[-1],) + Ke.shape[1:])
+    B = np.zeros(((br[-1] if br.size else 0),) + Ke.shape[1:])
+    for r in range(rp.size - 1):
+        nA = ar[r + 1] - ar[r]
+        nB = br[r - np_ + 1] - br[r - np_] if (br.size and r >= np_) else 0
+        buf = np.zeros((nA + nB,) + Ke.shape[1:])
+        for p in range(rp[r], rp[r + 1]):
+            for j in range(gpp[p + 1] - gpp[p]):
+                buf[gpos[gpp[p] + j]] += Ke[gb[p] + j]
+        A[ar[r]:ar[r + 1]] = buf[:nA]
+        if nB:
+            B[br[r - np_]:br[r - np_ + 1]] = buf[nA:]
+    return A, B
+
+
 def apply_bcs(plan, bc_global, A_vals, B_vals, res, u_owned, bs):
     lo, hi = plan.array("owner_range")[[plan.rank_, plan.rank_ + 1]]
     np_ = plan.scalars()["np"]
@@ -110,6 +131,9 @@ def run_rank_phase2(plans, rank, transport, st, bc_global, u_global, x_global):
         f()
     A = gather_blocks(P.array("a_ptr"), P.array("a_src"), st["Ke"])
     Bv = gather_blocks(P.array("b_ptr"), P.array("b_src"), st["Ke"])
+    # the device uses the row-strip form of the same plan: identical sums, bit for bit (same order per block)
+    A2, B2 = gather_rows(P, st["Ke"])
+    assert np.array_equal(A, A2) and (Bv.size == 0 or np.array_equal(Bv, B2)), "row-strip gather plan"
     res = gather_blocks(P.array("r_ptr"), P.array("r_src"), st["Re"])
     lo, hi = P.array("owner_range")[[rank, rank + 1]]
     P.rank_ = rank
