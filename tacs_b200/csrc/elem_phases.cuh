@@ -947,7 +947,7 @@ struct SolidWork {
   using D = SolidDims<O>;
   static constexpr int n = D::n, nd = D::nd, nq = D::nq;
   static constexpr int NS = 6;
-  static constexpr int TR = (O == 2) ? 6 : 9, TC = (O == 2) ? 6 : 9;
+  static constexpr int TR = (O == 2) ? 6 : 9, TC = (O == 2) ? 6 : 3;  // hex27: 9x3 tiles, 243 per element (8 warps)
   static constexpr int ntiles = (nd / TR) * (nd / TC);
   static constexpr int LD = nd;
   double X[3 * n];

@@ -92,8 +92,9 @@ struct SolidFamily {
   static constexpr int QC = (O == 2) ? 4 : 3;
   using Work = SolidWork<O, QC>;
   using Tables = SolidTables<O>;
-  static constexpr int TEAM = (O == 2) ? 16 : 96;
+  static constexpr int TEAM = (O == 2) ? 16 : 256;
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
+  static constexpr int MIN_CTAS = (O == 2) ? 1 : 2;
   static constexpr int BS = 3;
   static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
@@ -958,7 +959,7 @@ __global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_
 }
 
 template <int O>
-__global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS)
+__global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS, SolidFamily<O>::MIN_CTAS)
     solid_element_kernel(ElemGroupArgs g) {
   using F = SolidFamily<O>;
   using Work = typename F::Work;
