@@ -157,6 +157,11 @@ int tacsb200_assembler_assemble_res(tacsb200_handle a, tacsb200_handle res);
 int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double beta, double gamma,
                                          tacsb200_handle res, tacsb200_handle mat);
 
+/* Enqueue-only variant (SURVEY 8b "_async"): returns once the kernels are on the compute stream. A following
+   tacsb200_vec_get_array of the residual copies it to the host behind the residual kernels only, while the block
+   gather of the matrix is still running; pair with tacsb200_synchronize before the matrix is read on the host. */
+int tacsb200_assembler_assemble_jacobian_async(tacsb200_handle a, double alpha, double beta, double gamma,
+                                               tacsb200_handle res, tacsb200_handle mat);
 /* assembleMatType(matType, A, TACS_MAT_NORMAL, lambda = 1, applyBCs) :227, src/TACSAssembler.cpp:4418-4504.
    matType follows ElementMatrixType (src/elements/TACSElementTypes.h:113-119): 1 = TACS_STIFFNESS_MATRIX,
    2 = TACS_MASS_MATRIX; any other type returns non-zero (not evaluated on the device). */

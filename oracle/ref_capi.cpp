@@ -355,6 +355,11 @@ int ref_assembler_assemble_jacobian(ref_handle a, double alpha, double beta, dou
   return 0;
 }
 
+int ref_assembler_assemble_jacobian_async(ref_handle a, double alpha, double beta, double gamma, ref_handle res,
+                                          ref_handle mat) {
+  return ref_assembler_assemble_jacobian(a, alpha, beta, gamma, res, mat);  /* the CPU path has no asynchrony */
+}
+
 int ref_assembler_assemble_mat_type(ref_handle a, int mat_type, ref_handle mat, int apply_bcs) {
   as<TACSAssembler>(a)->assembleMatType((ElementMatrixType)mat_type, as<TACSMat>(mat), TACS_MAT_NORMAL, 1.0,
                                         apply_bcs != 0);

@@ -371,9 +371,11 @@ class Assembler(_Obj):
     def assembleRes(self, res):
         _check(self.lib.assembler_assemble_res(self.h, res.h), "assembleRes")
 
-    def assembleJacobian(self, alpha, beta, gamma, res, mat):
-        _check(self.lib.assembler_assemble_jacobian(self.h, alpha, beta, gamma, res.h if res else None, mat.h),
-               "assembleJacobian")
+    def assembleJacobian(self, alpha, beta, gamma, res, mat, wait=True):
+        """wait=False enqueues only (tacsb200_assembler_assemble_jacobian_async): a following res.getArray() copies
+        the residual to the host while the matrix is still being gathered."""
+        f = self.lib.assembler_assemble_jacobian if wait else self.lib.assembler_assemble_jacobian_async
+        _check(f(self.h, alpha, beta, gamma, res.h if res else None, mat.h), "assembleJacobian")
 
 
     def assembleMatType(self, matType, mat, applyBCs=True):

@@ -76,6 +76,7 @@ SIGNATURES = {
     "assembler_set_num_threads": (I, [H, I]),
     "assembler_assemble_res": (I, [H, H]),
     "assembler_assemble_jacobian": (I, [H, D, D, D, H, H]),
+    "assembler_assemble_jacobian_async": (I, [H, D, D, D, H, H]),
     "assembler_assemble_mat_type": (I, [H, I, H, I]),
     "assembler_add_jacobian_vec_product": (I, [H, D, D, D, D, H, H, I]),
     "vec_get_size": (I, [H]),

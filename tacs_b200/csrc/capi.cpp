@@ -410,6 +410,13 @@ int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double
   if (t->assembleJacobian(alpha, beta, gamma, as<TACSBVec>(res), A, 1.0)) return 1;
   return tacsb200_synchronize();
 }
+int tacsb200_assembler_assemble_jacobian_async(tacsb200_handle a, double alpha, double beta, double gamma,
+                                               tacsb200_handle res, tacsb200_handle mat) {
+  ASM(a);
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE(A, "matrix");
+  return t->assembleJacobian(alpha, beta, gamma, as<TACSBVec>(res), A, 1.0) ? 1 : 0;
+}
 int tacsb200_assembler_assemble_mat_type(tacsb200_handle a, int mat_type, tacsb200_handle mat, int apply_bcs) {
   ASM(a);
   TACSParallelMat *A = as<TACSParallelMat>(mat);
