@@ -433,45 +433,6 @@ TB2_HD void shell_p3_columns(int task, int q0, ShellWork<O, QC> &w, const ShellT
 //   S[t1][t2] = sum_q Ntq[q][t1] Ntq[q][t2] G_q[f1][f2],   G_q = w det P_q [A 0; 0 As] P_q^T   (5 x 5 per point),
 // which moves all the S arithmetic out of the quadrature loop.
 // ------------------------------------------------------------------------------------------
-template <int O>
-struct alignas(16) ShellUncWork {
-  using D = ShellDims<O>;
-  static constexpr int n = D::n, nd = D::nd, nq = D::nq, nty = D::nty;
-  static constexpr int ntiles = n * n;
-  static constexpr int LDT = nd + 2;  // padded row stride (16-byte aligned rows, lanes spread over banks)
-  static constexpr int even(int x) { return x + (x & 1); }
-  static constexpr int imax(int a, int b) { return a > b ? a : b; }
-  // scratch layout (doubles). Lifetimes: X [load .. p2]; P [p2 .. G]; G [G .. S]; S [S .. products];
-  // SB [products .. tying tile pass]; row buffers 0/1 [tying tile pass .. loop end]; u, acc, Rp [last loop
-  // iteration .. finish] in the row buffer that the last iteration does not read.
-  static constexpr int oS = 0;
-  static constexpr int oP = even(nty * nty);         // P[nq][5][6]
-  static constexpr int oG = oP + 30 * nq;            // G[nq][26]
-  static constexpr int oX = oG + 26 * nq;            // X[3n]
-  static constexpr int LBUF = 8 * nd;                // one row buffer: L[4][nd] (3 bending + drill) then R[4][nd]
-  static constexpr int oSB = imax(LBUF, oP);         // SB[nty][nd]: clear of buffer 0 and of S
-  static constexpr int oU = (nq & 1) * LBUF, oAcc = oU + nd, oRp = oAcc + nd;
-  static constexpr int SCR = imax(imax(oSB + nty * nd, oX + even(3 * n)), imax(2 * LBUF, oRp + 6 * ntiles));
-  double fn[3 * n];
-  alignas(16) double Bdr[n][LDT];
-  alignas(16) double Bty[nty][LDT];
-  // per quadrature point: T(0,1,3,4,6,7) A(0,1,3,4) Az(0,1,3,4,6,7) -- the frame entries the bending rows use
-  alignas(16) double geo[nq][18];  // 16 used; the stride spreads the four lanes that fill it over the banks
-  double wdet[nq];
-  alignas(16) double scr[SCR];
-  TB2_HD double *X() { return scr + oX; }
-  TB2_HD double *rpart() { return scr + oRp; }
-  TB2_HD double *uvec() { return scr + oU; }
-  TB2_HD double *avec() { return scr + oAcc; }
-  TB2_HD double *buf(int k) { return scr + k * LBUF; }
-  TB2_HD double &bty(int ty, int col) { return Bty[ty][col]; }
-  static constexpr bool kFullBdr = true;
-  TB2_HD double &bdr_u(int i, int j, int c) { return Bdr[i][6 * j + c]; }
-  TB2_HD double &bdr_q(int i, int c) { return Bdr[i][6 * i + 3 + c]; }
-  static constexpr int LDS_ = nty;               // row stride of S
-  static constexpr bool kColMajorRows = false;   // row buffers are [row][col]
-};
-
 // Work area of the tensor-core (DMMA m8n8k4) kernels (Quad4: shell4_mma_kernel, Quad9: shell9_mma_kernel). Every
 // operand of a matrix product is kept as "k-step panels" X[kstep][col][4]: the four rows of one k-step are contiguous
 // per column, so that the A / B fragment of lane l for tile t of a panel is the single double at panel[32 t + l] (a
@@ -488,7 +449,6 @@ struct alignas(16) ShellMmaWork {
   static constexpr int LDP = 4 * NDP + 4;  // panel stride (+4: the C-fragment stores of two panels hit distinct banks)
   static constexpr int LDS_ = 4 * KS;      // row stride of S (A operand of S * Bty, k padded with zeros)
   static constexpr int SROWS = 8 * ((nty + 7) / 8);  // rows >= nty are never written: their products are dropped
-  static constexpr bool kColMajorRows = true;
   // Row buffers (one k-step each, rewritten per quadrature point) split a panel into its row pairs,
   // X[k >> 1][col][k & 1] with the two halves HS doubles apart: the producers (one lane per column pair) then store
   // 16-byte pieces at consecutive addresses instead of 32-byte strides, and the fragment of lane (gq,tq) for tile t
@@ -644,32 +604,12 @@ TB2_HD void shell_unc_S_entry(int packed, WK &w, const ShellTables<O> &tab) {
   w.scr[WK::oS + t2 * WK::LDS_ + t1] = s;
 }
 
-// products phase, task (ty, j): six entries of SB = S Bty
-template <int O>
-TB2_HD void shell_unc_products(int task, ShellUncWork<O> &w) {
-  using WK = ShellUncWork<O>;
-  constexpr int n = WK::n, nd = WK::nd, nty = WK::nty;
-  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const int ty = task / n, j = task % n;
-  const double *S = w.scr + WK::oS + ty * nty;
-  for (int t = 0; t < nty; t++) {
-    const double s = S[t];
-    double b[6];
-    load6(&w.Bty[t][6 * j], b);
-#pragma unroll
-    for (int c = 0; c < 6; c++) out[c] += s * b[c];
-  }
-  double *dst = w.scr + WK::oSB + ty * nd + 6 * j;
-#pragma unroll
-  for (int c = 0; c < 6; c++) dst[c] = out[c];
-}
-
 // row buffer of quadrature point q, task (j, c): the columns 6j+c and 6j+3+c of
 //   L rows 0..2: bending rows 3,4,5 of B (same expressions as shell_p3_columns);  L row 3: drill row
 //   R rows 0..2: (w det D) L;                                                     R row 3: (w det drill) L3
 template <int O, class WK, bool LONLY = false>
 TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, const double *desc, double *buf) {
-  constexpr int n = ShellDims<O>::n, nd = ShellDims<O>::nd;
+  constexpr int n = ShellDims<O>::n;
   const int c = task % 3, j = (task / 3) % n;
   const int cu = 6 * j + c, cq = cu + 3;
   const double d0 = tab.dNq[q][j][0], d1 = tab.dNq[q][j][1], N = tab.Nq[q][j];
@@ -708,35 +648,24 @@ TB2_HD void shell_unc_rows(int task, int q, WK &w, const ShellTables<O> &tab, co
   const double wdr = wd * desc[21];
   ru[3] = wdr * bu[3];
   rq[3] = wdr * bq[3];
-  if constexpr (WK::kColMajorRows) {
-    // half-split panels X[k >> 1][col][k & 1] (ShellQ4MmaWork): four 16-byte pieces per column
-    double *L = buf, *R = buf + WK::LPAN;
+  // half-split panels X[k >> 1][col][k & 1] (ShellMmaWork): four 16-byte pieces per column
+  double *L = buf, *R = buf + WK::LPAN;
 #if defined(__CUDA_ARCH__)
-    *reinterpret_cast<double2 *>(L + 2 * cu) = make_double2(bu[0], bu[1]);
-    *reinterpret_cast<double2 *>(L + WK::HS + 2 * cu) = make_double2(bu[2], bu[3]);
-    *reinterpret_cast<double2 *>(L + 2 * cq) = make_double2(bq[0], bq[1]);
-    *reinterpret_cast<double2 *>(L + WK::HS + 2 * cq) = make_double2(bq[2], bq[3]);
-    if (LONLY) return;
-    *reinterpret_cast<double2 *>(R + 2 * cu) = make_double2(ru[0], ru[1]);
-    *reinterpret_cast<double2 *>(R + WK::HS + 2 * cu) = make_double2(ru[2], ru[3]);
-    *reinterpret_cast<double2 *>(R + 2 * cq) = make_double2(rq[0], rq[1]);
-    *reinterpret_cast<double2 *>(R + WK::HS + 2 * cq) = make_double2(rq[2], rq[3]);
+  *reinterpret_cast<double2 *>(L + 2 * cu) = make_double2(bu[0], bu[1]);
+  *reinterpret_cast<double2 *>(L + WK::HS + 2 * cu) = make_double2(bu[2], bu[3]);
+  *reinterpret_cast<double2 *>(L + 2 * cq) = make_double2(bq[0], bq[1]);
+  *reinterpret_cast<double2 *>(L + WK::HS + 2 * cq) = make_double2(bq[2], bq[3]);
+  if (LONLY) return;
+  *reinterpret_cast<double2 *>(R + 2 * cu) = make_double2(ru[0], ru[1]);
+  *reinterpret_cast<double2 *>(R + WK::HS + 2 * cu) = make_double2(ru[2], ru[3]);
+  *reinterpret_cast<double2 *>(R + 2 * cq) = make_double2(rq[0], rq[1]);
+  *reinterpret_cast<double2 *>(R + WK::HS + 2 * cq) = make_double2(rq[2], rq[3]);
 #else
-    for (int r = 0; r < 4; r++) {
-      L[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = bu[r]; L[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = bq[r];
-      if (!LONLY) { R[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = ru[r]; R[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = rq[r]; }
-    }
-#endif
-  } else {
-    double *L = buf, *R = buf + 4 * nd;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      L[r * nd + cu] = bu[r];
-      L[r * nd + cq] = bq[r];
-      R[r * nd + cu] = ru[r];
-      R[r * nd + cq] = rq[r];
-    }
+  for (int r = 0; r < 4; r++) {
+    L[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = bu[r]; L[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = bq[r];
+    if (!LONLY) { R[(r >> 1) * WK::HS + 2 * cu + (r & 1)] = ru[r]; R[(r >> 1) * WK::HS + 2 * cq + (r & 1)] = rq[r]; }
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -18,8 +18,6 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#include <type_traits>
-
 #include "elem_phases.cuh"
 #include "kernels.h"
 
@@ -75,10 +73,10 @@ __device__ __forceinline__ void team_sync() {
 // plus a 64-byte skew, so that the two teams of a warp hit disjoint shared-memory banks when they read the
 // same field with 128-bit loads (the tile loop reads 4 distinct 48-byte chunks per team: 16-byte bank
 // groups {0,3,6,1}+k for team 0 and {4,7,2,5}+k for team 1).
-template <int O, bool UNC = false>
+template <int O>
 struct ShellFamily {
   static constexpr int QC = (O == 2) ? 1 : 3;
-  using Work = typename std::conditional<UNC, ShellUncWork<O>, ShellWork<O, QC>>::type;
+  using Work = ShellWork<O, QC>;
   using Tables = ShellTables<O>;
   static constexpr int TEAM = (O == 2) ? 16 : 96;
   static constexpr int TEAMS = (O == 2) ? 8 : 1;
@@ -99,12 +97,12 @@ struct SolidFamily {
   static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
-// UNC: every descriptor of the group has a zero membrane-bending block and a tangent is requested
-// (the residual-only request always runs the general instantiation)
-template <int O, bool UNC>
-__global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>::TEAMS, ShellFamily<O, UNC>::MIN_CTAS)
+// General shell kernel (any constitutive matrix, FMA register tiles). Groups whose descriptors all have a zero
+// membrane-bending block run shell4_mma_kernel / shell9_mma_kernel instead (tangent, or residual without inertia).
+template <int O>
+__global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, ShellFamily<O>::MIN_CTAS)
     shell_element_kernel(ElemGroupArgs g) {
-  using F = ShellFamily<O, UNC>;
+  using F = ShellFamily<O>;
   using Work = typename F::Work;
   constexpr int TEAM = F::TEAM, TEAMS = F::TEAMS, QC = F::QC;
   constexpr int n = Work::n, nd = Work::nd, nq = Work::nq, nty = Work::nty;
@@ -123,12 +121,12 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
   // loaded into registers while the current element is being evaluated, so the dependent global loads
   // never sit on the critical path of a team.
   constexpr int NU = (nd + TEAM - 1) / TEAM;
-  constexpr int ND = UNC ? 1 : (kDescStride + TEAM - 1) / TEAM;
+  constexpr int ND = (kDescStride + TEAM - 1) / TEAM;
   double pX = 0.0, pu[NU], pa[NU], pd[ND];
   // two-deep pipeline: node ids / descriptor index of the element after next, data of the next element.
   // The data loads of iteration i use ids that were requested in iteration i-1, so no load ever waits for
   // the address it depends on.
-  int cX = 0, cU[NU], cD = 0, dnext = 0;
+  int cX = 0, cU[NU], cD = 0;
   auto prefetch_ids = [&](long e) {
     const int *conn = g.conn + e * n;
     if (tid < 3 * n) cX = __ldg(conn + tid / 3);
@@ -153,16 +151,10 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
       }
     }
     const double *drow = g.desc_table + (long)kDescStride * cD;
-    dnext = cD;
-    if constexpr (UNC) {
-      // the uncoupled kernel reads the descriptor row in place (L1): pull its two lines in ahead of time
-      if (tid < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(drow + 16 * tid));
-    } else {
 #pragma unroll
-      for (int m = 0; m < ND; m++) {
-        const int kk = tid + m * TEAM;
-        pd[m] = kk < kDescStride ? __ldg(drow + kk) : 0.0;
-      }
+    for (int m = 0; m < ND; m++) {
+      const int kk = tid + m * TEAM;
+      pd[m] = kk < kDescStride ? __ldg(drow + kk) : 0.0;
     }
   };
   auto clamp_elem = [&](long e) { return e < nelem ? e : nelem - 1; };
@@ -172,42 +164,23 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
     prefetch_data();
     prefetch_ids(clamp_elem(e0 + nteams));
   }
-  // uncoupled path: the entries of the symmetric tying-space matrix S this thread owns (decoded once)
-  constexpr int NTRI = nty * (nty + 1) / 2;
-  constexpr int NSA = UNC ? (NTRI + TEAM - 1) / TEAM : 1;
-  int stri[NSA];
-  if constexpr (UNC) {
-#pragma unroll
-    for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
-  }
   // uniform trip count inside a CTA so that barriers are reached by every thread
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
     const long e = live ? base + team_in_cta : nelem - 1;
     if (tid < 3 * n) w.X()[tid] = pX;
-    const double *desc;
-    double cu[NU], ca[NU];  // uncoupled kernel: the state stays in registers until the last quadrature interval
-    if constexpr (UNC) {
-      desc = g.desc_table + (long)kDescStride * dnext;
+    const double *desc = w.desc;
 #pragma unroll
-      for (int m = 0; m < NU; m++) {
-        cu[m] = pu[m];
-        ca[m] = pa[m];
-      }
-    } else {
-      desc = w.desc;
+    for (int m = 0; m < ND; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < kDescStride) w.desc[kk] = pd[m];
+    }
 #pragma unroll
-      for (int m = 0; m < ND; m++) {
-        const int kk = tid + m * TEAM;
-        if (kk < kDescStride) w.desc[kk] = pd[m];
-      }
-#pragma unroll
-      for (int m = 0; m < NU; m++) {
-        const int kk = tid + m * TEAM;
-        if (kk < nd) {
-          w.u[kk] = pu[m];
-          w.acc[kk] = pa[m];
-        }
+    for (int m = 0; m < NU; m++) {
+      const int kk = tid + m * TEAM;
+      if (kk < nd) {
+        w.u[kk] = pu[m];
+        w.acc[kk] = pa[m];
       }
     }
     team_sync<TEAM>();
@@ -216,12 +189,8 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
     for (int t = tid; t < n; t += TEAM) shell_p1_node<O>(t, w, tab, desc);
     team_sync<TEAM>();
     for (int t = tid; t < nty + nq; t += TEAM) {
-      if (t < nty) {
-        shell_p2_tying<O>(t, w, tab);
-      } else {
-        if constexpr (UNC) shell_unc_qgeom<O>(t - nty, w, tab, desc);
-        else shell_p2_qgeom<O>(t - nty, w, tab, desc);
-      }
+      if (t < nty) shell_p2_tying<O>(t, w, tab);
+      else shell_p2_qgeom<O>(t - nty, w, tab, desc);
     }
     team_sync<TEAM>();
     double acc[36];
@@ -231,50 +200,14 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
     const int ti = tid / n, tj = tid % n;
     if (g.Ke) {
       double *rpart = w.rpart();
-      if constexpr (UNC) {
-        // tying part in "tying space" (elem_phases.cuh), all of it outside the quadrature loop
-        for (int t = tid; t < 5 * nq; t += TEAM) shell_unc_G<O>(t, w, desc);
+      for (int q0 = 0; q0 < nq; q0 += QC) {
+        for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
+        for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
         team_sync<TEAM>();
-#pragma unroll
-        for (int m = 0; m < NSA; m++)
-          if (tid + m * TEAM < NTRI) shell_unc_S_entry<O>(stri[m], w, tab);
+        for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
         team_sync<TEAM>();
-        for (int t = tid; t < nty * n; t += TEAM) shell_unc_products<O>(t, w);
+        if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
         team_sync<TEAM>();
-        // the rows of point 0 (bending + drill) go to buffer 0 while the tying rows are contracted; inside the
-        // loop the rows of point q+1 are produced in the barrier interval that contracts those of point q
-        for (int t = tid; t < n * 3; t += TEAM) shell_unc_rows<O>(t, 0, w, tab, desc, w.buf(0));
-        if (has_tile) tile_accumulate<nty, Work::LDT, 6, 6, nd>(&w.Bty[0][0], w.scr + Work::oSB, 6 * ti, 6 * tj, acc);
-        team_sync<TEAM>();
-#pragma unroll 1
-        for (int q = 0; q < nq; q++) {
-          if (q + 1 < nq) {
-            for (int t = tid; t < n * 3; t += TEAM) shell_unc_rows<O>(t, q + 1, w, tab, desc, w.buf((q + 1) & 1));
-          } else {
-            // last interval: the state enters shared memory in the row buffer that is no longer read
-#pragma unroll
-            for (int m = 0; m < NU; m++) {
-              const int kk = tid + m * TEAM;
-              if (kk < nd) {
-                w.uvec()[kk] = cu[m];
-                w.avec()[kk] = ca[m];
-              }
-            }
-          }
-          const double *L = w.buf(q & 1);
-          if (has_tile) tile_accumulate<4, nd, 6, 6>(L, L + 4 * nd, 6 * ti, 6 * tj, acc);
-          team_sync<TEAM>();
-        }
-      } else {
-        for (int q0 = 0; q0 < nq; q0 += QC) {
-          for (int t = tid; t < QC * nty; t += TEAM) shell_p3_weights<O, QC>(t, q0, w, tab);
-          for (int t = tid; t < QC * 22; t += TEAM) shell_p3_cw<O, QC>(t, q0, w, desc);
-          team_sync<TEAM>();
-          for (int t = tid; t < QC * n * 3; t += TEAM) shell_p3_columns<O, QC>(t, q0, w, tab);
-          team_sync<TEAM>();
-          if (has_tile) tile_accumulate<QC * 9, nd, 6, 6>(&w.B[0][0][0], &w.CB[0][0][0], 6 * ti, 6 * tj, acc);
-          team_sync<TEAM>();
-        }
       }
       if (has_tile) {
         shell_p6_finish<O>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, rpart + 6 * tid);
@@ -294,7 +227,7 @@ __global__ void __launch_bounds__(ShellFamily<O, UNC>::TEAM *ShellFamily<O, UNC>
           g.Re[e * nd + k] = s;
         }
       }
-    } else if constexpr (!UNC) {
+    } else {
       // residual only (assembleRes): res = sum_q B^T (w det C) B u, no tangent tiles
       double racc[NU];
 #pragma unroll
@@ -1214,11 +1147,11 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
       // inertial term is requested)
       if (g.uncoupled && (g.Ke || (g.gamma == 0.0 && !g.ddvars)))
         return launch_family<ShellQ4MmaFamily>(shell4_mma_kernel, g, num_sms, s);
-      return launch_family<ShellFamily<2, false>>(shell_element_kernel<2, false>, g, num_sms, s);
+      return launch_family<ShellFamily<2>>(shell_element_kernel<2>, g, num_sms, s);
     case ELEM_QUAD9_SHELL:
       if (g.uncoupled && (g.Ke || (g.gamma == 0.0 && !g.ddvars)))
         return launch_family<ShellQ9MmaFamily>(shell9_mma_kernel, g, num_sms, s);
-      return launch_family<ShellFamily<3, false>>(shell_element_kernel<3, false>, g, num_sms, s);
+      return launch_family<ShellFamily<3>>(shell_element_kernel<3>, g, num_sms, s);
     case ELEM_HEX8: return launch_family<SolidFamily<2>>(solid_element_kernel<2>, g, num_sms, s);
     case ELEM_HEX27: return launch_family<SolidFamily<3>>(solid_element_kernel<3>, g, num_sms, s);
   }

@@ -43,7 +43,7 @@ static void shell_outputs(WK *w, const ShellTables<O> &tab, const double *desc, 
   }
 }
 
-// coupled path: the general kernel flow (shell_element_kernel<O, false>)
+// general kernel flow (shell_element_kernel<O>)
 template <int O, int QC>
 static void run_shell(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
                       double alpha, double gamma, double *res, double *mat) {
@@ -65,43 +65,6 @@ static void run_shell(const double *Xpts, const double *vars, const double *ddva
     for (int t = 0; t < QC * n * 3; t++) shell_p3_columns<O, QC>(t, q0, *w, tab);
     for (int t = 0; t < WK::ntiles; t++)
       tile_accumulate<QC * 9, nd, 6, 6>(&w->B[0][0][0], &w->CB[0][0][0], 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-  }
-  shell_outputs<O>(w, tab, desc, alpha, gamma, inertia, acc, res, mat);
-  delete w;
-}
-
-// membrane/bending-uncoupled path (shell_element_kernel<O, true>), same order of phases and buffers
-template <int O>
-static void run_shell_unc(const double *Xpts, const double *vars, const double *ddvars, const double *desc,
-                          double alpha, double gamma, double *res, double *mat) {
-  using WK = ShellUncWork<O>;
-  constexpr int n = WK::n, nd = WK::nd, nq = WK::nq, nty = WK::nty;
-  static ShellTables<O> tab;
-  build_shell_tables<O>(tab);
-  WK *w = new WK;
-  for (int k = 0; k < WK::SCR; k++) w->scr[k] = std::nan("");  // stale scratch must never be consumed
-  for (int k = 0; k < 3 * n; k++) w->X()[k] = Xpts[k];
-  const bool inertia = (gamma != 0.0) || (ddvars != nullptr);
-  for (int i = 0; i < n; i++) shell_p1_node<O>(i, *w, tab, desc);
-  for (int t = 0; t < nty; t++) shell_p2_tying<O>(t, *w, tab);
-  for (int q = 0; q < nq; q++) shell_unc_qgeom<O>(q, *w, tab, desc);
-  for (int t = 0; t < 5 * nq; t++) shell_unc_G<O>(t, *w, desc);
-  for (int k = 0; k < nty * (nty + 1) / 2; k++) shell_unc_S_entry<O>(shell_unc_tri<O>(k), *w, tab);
-  for (int t = 0; t < nty * n; t++) shell_unc_products<O>(t, *w);
-  std::vector<double> acc((size_t)WK::ntiles * 36, 0.0);
-  for (int t = 0; t < n * 3; t++) shell_unc_rows<O>(t, 0, *w, tab, desc, w->buf(0));
-  for (int t = 0; t < WK::ntiles; t++)
-    tile_accumulate<nty, WK::LDT, 6, 6, nd>(&w->Bty[0][0], w->scr + WK::oSB, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
-  for (int q = 0; q < nq; q++) {
-    if (q + 1 < nq) {
-      for (int t = 0; t < n * 3; t++) shell_unc_rows<O>(t, q + 1, *w, tab, desc, w->buf((q + 1) & 1));
-    } else {
-      // the state enters shared memory in the last interval, in the row buffer that is no longer read
-      for (int k = 0; k < nd; k++) { w->uvec()[k] = vars[k]; w->avec()[k] = ddvars ? ddvars[k] : 0.0; }
-    }
-    const double *L = w->buf(q & 1);
-    for (int t = 0; t < WK::ntiles; t++)
-      tile_accumulate<4, nd, 6, 6>(L, L + 4 * nd, 6 * (t / n), 6 * (t % n), &acc[36 * t]);
   }
   shell_outputs<O>(w, tab, desc, alpha, gamma, inertia, acc, res, mat);
   delete w;
@@ -283,8 +246,6 @@ int emul_element(int kind, const double *Xpts, const double *vars, const double 
       if (desc_uncoupled(desc)) run_shell_mma<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       else run_shell<2, 1>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       return 0;
-    case 5: run_shell_unc<2>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;  // generic uncoupled flow
-    case 6: run_shell_unc<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat); return 0;
     case 2:
       if (desc_uncoupled(desc)) run_shell_mma<3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);
       else run_shell<3, 3>(Xpts, vars, ddvars, desc, alpha, gamma, res, mat);

@@ -90,19 +90,3 @@ def test_residual_only_phases_match_oracle(emul, kind):
             args = [np.ascontiguousarray(v) for v in (X[e], u[e], desc)]
             assert emul.emul_residual(kind, *[v.ctypes.data_as(DP) for v in args], r2.ctypes.data_as(DP)) == 0
             assert relerr(r2, res) < TOL
-
-
-@pytest.mark.parametrize("kind", [5, 6])
-def test_generic_uncoupled_flow_matches_oracle(emul, kind):
-    """shell_element_kernel<O, true> (FMA version of the uncoupled path, kept for reference / fallback sizes)."""
-    X, u, a = common.shell_batch(kind - 3, 4, seed=31)
-    DP = C.POINTER(C.c_double)
-    desc = oracle_port.iso_shell_desc(t=0.02, tOffset=0.0, transform=0)
-    for e in range(X.shape[0]):
-        res, mat = oracle_port.element(kind - 4, desc, X[e], u[e], a[e], alpha=1.3, gamma=0.7)
-        nv = res.size
-        r2, m2 = np.zeros(nv), np.zeros(nv * nv)
-        args = [np.ascontiguousarray(v) for v in (X[e], u[e], a[e], desc)]
-        assert emul.emul_element(kind, *[v.ctypes.data_as(DP) for v in args], 1.3, 0.7, r2.ctypes.data_as(DP),
-                                 m2.ctypes.data_as(DP)) == 0
-        assert relerr(m2, mat.ravel()) < TOL and relerr(r2, res) < TOL
