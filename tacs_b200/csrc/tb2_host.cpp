@@ -1141,11 +1141,12 @@ TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
   const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
   const size_t b2 = (size_t)Aloc.bsize * Aloc.bsize;
   // gather plan on the device. The row-strip form (one warp per block row, whole-sector reads of the element strips)
-  // pays for 3x3 blocks with short rows -- hex8: 27 blocks per row, measured 1.77 -> 1.55 ms per 1M elements; it
-  // is on par for Quad4 and loses where a row buffer is large (Quad9 900, hex27 1125 doubles per warp: measured 2x
-  // slower), where the per-block form is kept.
+  // pays for 3x3 blocks with short rows on one rank -- hex8: 27 blocks per row, measured 1.77 -> 1.55 ms per 1M
+  // elements. It is on par for Quad4, loses where a row buffer is large (Quad9 900, hex27 1125 doubles per warp:
+  // measured 2x slower) and on METIS partitions, whose local row order scatters the strips of consecutive rows
+  // (200^3 hex8 on 8 GPUs: assembly 4.82 -> 5.81 ms); the per-block form is kept there.
   max_row_blocks = P.max_row_blocks;
-  row_gather = Aloc.bsize == 3 && (size_t)max_row_blocks * b2 <= 256;
+  row_gather = a->size == 1 && Aloc.bsize == 3 && (size_t)max_row_blocks * b2 <= 256;
   bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA);
   if (ok && row_gather) ok = g_base.upload(P.g_base) && g_pptr.upload(P.g_pptr) && g_pos.upload(P.g_pos);
   if (ok && !row_gather) ok = a_ptr.upload(P.a_ptr) && a_src.upload(P.a_src);
