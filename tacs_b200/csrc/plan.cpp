@@ -412,7 +412,13 @@ int HostPlan::buildMatrix() {
     });
   }
   // row-strip form of the same plan
-  {
+  max_row_blocks = 0;
+  for (int r = 0; r < nowned; r++) {
+    const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];
+    const int nB = (r >= np) ? Bext.rowp[r - np + 1] - Bext.rowp[r - np] : 0;
+    if (nA + nB > max_row_blocks) max_row_blocks = nA + nB;
+  }
+  if (force_row_plan || rowPlanEligible()) {
     const size_t ncontrib = adj.size();
     g_base.resize(ncontrib);
     g_pptr.assign(ncontrib + 1, 0);
@@ -421,12 +427,6 @@ int HostPlan::buildMatrix() {
       g_pptr[p + 1] = g_pptr[p] + adj[p].nn;
     }
     g_pos.resize(g_pptr[ncontrib]);
-    max_row_blocks = 0;
-    for (int r = 0; r < nowned; r++) {
-      const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];
-      const int nB = (r >= np) ? Bext.rowp[r - np + 1] - Bext.rowp[r - np] : 0;
-      if (nA + nB > max_row_blocks) max_row_blocks = nA + nB;
-    }
     plan_parallel_for(nowned, [&](long r0, long r1) {
       for (long r = r0; r < r1; r++) {
         const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];

@@ -87,6 +87,10 @@ struct HostPlan {
   std::vector<int> g_base, g_pptr;
   std::vector<int> g_pos;
   int max_row_blocks = 0;
+  // The row-strip arrays are built only where the device uses them (one rank, 3x3 blocks, short rows -- see
+  // TACSParallelMat) or when a test asks for them: for C5 they would be 729 M host integers nobody reads.
+  bool force_row_plan = false;
+  bool rowPlanEligible() const { return size == 1 && bs == 3 && max_row_blocks * bs * bs <= 256; }
   // neighbour exchanges (empty on one rank)
   ExchangePlan state;   // chunk = one node block of a state vector: owned node -> ext slots of peers
   ExchangePlan cols;    // chunk = one node block of x: owned node -> x_ext of peers (SpMV)

@@ -643,6 +643,7 @@ PlanObject *TACSCreator::createPlan(int rank, int size) {
   std::vector<int> kinds;
   if (prepareMesh(rank, size, gm, kinds)) return nullptr;
   PlanObject *po = new PlanObject();
+  po->plan.force_row_plan = true;  // test / inspection path: small meshes, every form of the plan is exported
   if (po->plan.build(gm, vars_per_node, rank, kinds) || po->plan.buildMatrix()) {
     delete po;
     return nullptr;
@@ -1146,7 +1147,7 @@ TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
   // measured 2x slower) and on METIS partitions, whose local row order scatters the strips of consecutive rows
   // (200^3 hex8 on 8 GPUs: assembly 4.82 -> 5.81 ms); the per-block form is kept there.
   max_row_blocks = P.max_row_blocks;
-  row_gather = a->size == 1 && Aloc.bsize == 3 && (size_t)max_row_blocks * b2 <= 256;
+  row_gather = P.rowPlanEligible() && !P.g_base.empty();
   bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA);
   if (ok && row_gather) ok = g_base.upload(P.g_base) && g_pptr.upload(P.g_pptr) && g_pos.upload(P.g_pos);
   if (ok && !row_gather) ok = a_ptr.upload(P.a_ptr) && a_src.upload(P.a_src);

@@ -52,7 +52,7 @@ def serial_reference(mesh, kind, desc, new_nodes):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("size", [2, 3, 4])
+@pytest.mark.parametrize("size", [1, 2, 3, 4])
 def test_plans_replay_matches_serial(name, size):
     import tacs_b200
 
