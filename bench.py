@@ -4,18 +4,29 @@
     python bench.py --gpus N --steps K --warmup W            # tacs_b200 (CUDA, sm_100a)
     python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path
 
-Workload (BASELINE.json configs[1]): synthetic 1000x1000 Quad4 MITC shell plate, 6 dof/node
+Headline workload (BASELINE.json configs[1]): synthetic 1000x1000 Quad4 MITC shell plate, 6 dof/node
 (~6M dof), isotropic, all edges clamped.  At N > 1 GPUs the plate grows to (1000*N) x 1000 elements
 (weak scaling: 1M elements per GPU), partitioned by the reference's METIS call.
 
-A step is one `assembleJacobian(1, 0, 0, res, A)`: element residuals + tangents, atomic-free
-gather into the BCSR matrix and the residual, boundary conditions.  `value` is elements/s with
-everything resident in HBM (CUDA events on the library's stream); `e2e` repeats the step through the
-C ABI with the state vector arriving from pinned host memory and the residual going back to it.
-The BCSR SpMV (the other half of the metric) is timed in its own loop and reported under `spmv`.
+A step is one `assembleJacobian(1, 0, 0, res, A)`: element residuals + tangents, atomic-free gather into the
+BCSR matrix and the residual, boundary conditions.  `value` is elements/s with everything resident in HBM
+(CUDA events on the library's stream); `e2e` repeats the step through the C ABI with the state vector
+arriving from pinned host memory and the residual going back to it.  The BCSR SpMV (the other half of the
+metric) is timed in its own loop and reported under `spmv`.
+
+Besides the headline the line carries
+  parity   (N > 1) the distributed path checked against the serial oracle on small METIS-partitioned meshes
+           before anything is timed; the run fails when an error exceeds 1e-12
+  fullsize the full-size result of this run against known answers of the unmodified reference
+           (tests/golden/fullsize_norms.json)
+  c4       BASELINE configs[3], 200^3 hex8 solid, a FIXED problem partitioned over the N GPUs (strong scaling:
+           the north_star's >= 6x target is c4.jac_ms at N=1 over c4.jac_ms at N=8)
+  c3, c5   BASELINE configs[2] / [4] (Quad9 composite cylinder 2M elements, 100^3 hex27), same treatment
+  gmres    time per GMRES(m) iteration on the assembled C2 / C4 operators
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -41,12 +52,16 @@ def emit(line):
 
 METRIC = "elements/sec for Jacobian+residual assembly (BCSR SpMV GB/s vs HBM peak under 'spmv')"
 UNIT = "elements/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures at the default workload
-# (profiles/r1_n_kernels_ncu.txt); reported only when the run uses that workload on one GPU
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed `ncu --set full` capture of this
+# same command at the default workload (TRAFFIC_SOURCE); reported only when the run uses that workload on one GPU.
+TRAFFIC_SOURCE = "profiles/r1_n_kernels_ncu.txt"
 NCU_TRAFFIC_BYTES = {"shell4_mma_kernel": 0.142545e9 + 4.742443e9, "gather_blocks36_kernel": 4.744081e9 + 2.584352e9,
                      "spmv6_kernel<0>": 2.689707e9 + 0.050150e9}
 # minimal-algorithm flops per element used for the FP64 roofline
-FLOPS_PER_ELEMENT = {"quad4": 57e3, "quad9": 551e3, "hex8": 69e3, "hex27": 2.28e6}
+FLOPS_PER_ELEMENT = {1: 57e3, 2: 551e3, 3: 69e3, 4: 2.28e6}
+KIND_NN = {1: 4, 2: 9, 3: 8, 4: 27}
+KIND_BS = {1: 6, 2: 6, 3: 3, 4: 3}
+PARITY_TOL = 1e-12
 
 
 def spmv_bytes(bs, nrows, nnzb):
@@ -146,24 +161,35 @@ def host_threads():
     return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
 
 
-def time_reference(nx, ny, steps, warmup):
-    """Reference CPU implementation (oracle/_ref, compiled from the unmodified sources) on an nx x ny plate.
-    The reference's intra-rank parallelism is its pthread work queue, capped at 16 threads
-    (src/TACSObject.h:150); MPI is not available in this image."""
+# ------------------------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref = the unmodified reference compiled where it lies)
+# ------------------------------------------------------------------------------------------------------------
+def _quiet_stdout():
+    class Q:
+        def __enter__(self):
+            self.devnull = os.open(os.devnull, os.O_WRONLY)
+            self.saved = os.dup(1)
+            os.dup2(self.devnull, 1)  # the reference prints a banner on stdout; keep ours one JSON line
+
+        def __exit__(self, *exc):
+            os.dup2(self.saved, 1)
+            os.close(self.devnull)
+            os.close(self.saved)
+
+    return Q()
+
+
+def time_reference(nx, ny, steps, warmup, gmres_m=0):
+    """Reference CPU implementation on an nx x ny Quad4 plate. The reference's intra-rank parallelism is its pthread
+    work queue, capped at 16 threads (src/TACSObject.h:150)."""
     from tacs_b200 import TACS as T
     from tacs_b200 import binding, meshgen
 
     so = os.path.join(ROOT, "oracle", "_ref", "libtacs_ref.so")
     ref = binding.Lib(so, "ref_")
     mesh = meshgen.plate(2, nx, ny)
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)  # the reference prints a banner on stdout; keep ours one JSON line
-    try:
+    with _quiet_stdout():
         creator, asm = meshgen.build_model(T, ref, mesh, [meshgen.iso_shell_element(T, ref, 2)])
-    finally:
-        os.dup2(saved, 1)
-        os.close(devnull)
     A, res, x, y = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
     x.setArray(meshgen.hash_vector(x.getSize()))
     asm.applyBCs(x)
@@ -177,15 +203,27 @@ def time_reference(nx, ny, steps, warmup):
         asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
     dt = (time.perf_counter() - t0) / steps
     # bs=6 SpMV is threaded in the reference as well
-    A.mult(x, y)
+    xr = asm.createVec()
+    xr.setArray(meshgen.hash_vector(x.getSize())[::-1].copy())
+    asm.applyBCs(xr)
+    A.mult(xr, y)
     t1 = time.perf_counter()
-    nsp = 10
+    nsp = 5
     for _ in range(nsp):
-        A.mult(x, y)
+        A.mult(xr, y)
     dts = (time.perf_counter() - t1) / nsp
     bs, nrows, ncols, nnzb = A.getSizes()
-    return dict(elements=nx * ny, seconds_per_step=dt, threads=threads,
-                spmv_gbs=spmv_bytes(bs, nrows, nnzb) / dts * 1e-9, ynorm=y.norm())
+    out = dict(elements=nx * ny, seconds_per_step=dt, threads=threads,
+               spmv_gbs=spmv_bytes(bs, nrows, nnzb) / dts * 1e-9, ynorm=y.norm(), resnorm=res.norm())
+    if gmres_m > 0:
+        ksm = T.KSM(ref, A, gmres_m, 0)
+        ksm.setTolerances(1e-30, 1e-300)
+        sol = asm.createVec()
+        t2 = time.perf_counter()
+        ksm.solve(res, sol)
+        out["gmres_ms_per_iter"] = (time.perf_counter() - t2) * 1e3 / max(ksm.getIterCount(), 1)
+        out["gmres_iters"] = ksm.getIterCount()
+    return out
 
 
 def time_reference_mpi(nx, ny, nranks, reps):
@@ -199,14 +237,15 @@ def time_reference_mpi(nx, ny, nranks, reps):
     return summary
 
 
-def best_cpu_baseline(n, steps, warmup):
+def best_cpu_baseline(n, steps, warmup, gmres_m=0):
     """Fastest of the reference's two CPU parallel modes on this box: pthreads (<= 16) and MPI ranks."""
     cores = host_threads()
-    r = time_reference(n, n, steps, warmup)
+    r = time_reference(n, n, steps, warmup, gmres_m)
     best = {"value": r["elements"] / r["seconds_per_step"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
             "sample": f"{n}x{n} Quad4 plate ({r['elements']} elements per step), assembleJacobian(1,0,0), "
                       f"oracle/_ref, 1 rank x {r['threads']} pthreads (setNumThreads)",
-            "spmv_gbs": r["spmv_gbs"], "seconds_per_step": r["seconds_per_step"]}
+            "spmv_gbs": r["spmv_gbs"], "seconds_per_step": r["seconds_per_step"], "ynorm": r["ynorm"],
+            "resnorm": r["resnorm"], "gmres_ms_per_iter": r.get("gmres_ms_per_iter"), "gmres_iters": r.get("gmres_iters")}
     try:
         from oracle import ref_mpi
 
@@ -214,11 +253,13 @@ def best_cpu_baseline(n, steps, warmup):
             nranks = min(cores, 64)
             m = time_reference_mpi(n, n, nranks, max(steps, 2))
             if m and m["elements_per_s"] > best["value"]:
-                best = {"value": m["elements_per_s"], "unit": UNIT, "cores": nranks, "kind": "reference",
-                        "sample": f"{n}x{n} Quad4 plate ({m['elements']} elements per step), assembleJacobian(1,0,0), "
-                                  f"oracle/_ref ref_driver, {nranks} MPI ranks (forked-rank stand-in, METIS partition)",
-                        "spmv_gbs": None, "seconds_per_step": m["jac_s"],
-                        "pthreads_value": best["value"], "pthreads_cores": best["cores"]}
+                best.update({"value": m["elements_per_s"], "cores": nranks,
+                             "sample": f"{n}x{n} Quad4 plate ({m['elements']} elements per step), "
+                                       f"assembleJacobian(1,0,0), oracle/_ref ref_driver, {nranks} MPI ranks "
+                                       f"(forked-rank stand-in, METIS partition)",
+                             "seconds_per_step": m["jac_s"], "pthreads_value": best["value"],
+                             "pthreads_cores": best["cores"], "spmv_gbs_mpi": m.get("spmv_gbs"),
+                             "spmv_note": "spmv_gbs: the reference's threaded bs=6 product on 1 rank x pthreads"})
             else:
                 best["mpi_value"] = m["elements_per_s"] if m else None
                 best["mpi_ranks"] = nranks
@@ -232,107 +273,368 @@ def run_reference(args):
     if rank != 0:
         return
     nx = ny = args.ref_n
-    cpu = best_cpu_baseline(nx, args.steps, args.warmup)
+    cpu = best_cpu_baseline(nx, args.steps, args.warmup, gmres_m=args.gmres_m)
     value = cpu["value"]
+    same = nx == args.nx and ny == args.ny
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": cpu["seconds_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic 1000x1000 Quad4Shell plate (BASELINE configs[1])",
-                   "sample": f"{nx}x{ny} Quad4 plate of the same generator ({nx * ny} elements per step)",
-                   "timing": "host wall clock"},
+                   "sample": f"{nx}x{ny} Quad4 plate of the same generator ({nx * ny} elements per step)"
+                             + (" = the full configuration" if same else ""),
+                   "same_config": bool(same), "timing": "host wall clock"},
         "cpu_baseline": cpu,
-        "spmv": {"gbs": cpu.get("spmv_gbs")},
+        "spmv": {"gbs": cpu.get("spmv_gbs"), "ynorm": cpu.get("ynorm")},
+        "gmres": {"ms_per_iter": cpu.get("gmres_ms_per_iter"), "m": args.gmres_m, "iters": cpu.get("gmres_iters")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# tacs_b200 arm
+# ------------------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed is the bootstrap only (broadcasts of the ncclUniqueId and of rank 0's METIS partition,
+    the closing max-over-ranks); the data path of the library uses its own NCCL communicator."""
+
+    def __init__(self, lib):
+        import torch
+
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.lib = lib
+        if lib.init(self.local_rank) != 0:
+            raise SystemExit("tacs_b200: no usable GPU")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            import tacs_b200
+
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            buf = np.zeros(128, np.uint8)
+            if self.rank == 0:
+                assert lib.comm_unique_id(buf.ctypes.data_as(tacs_b200.binding.UP)) == 0
+            uid = torch.from_numpy(buf.copy()).cuda()
+            dist.broadcast(uid, 0)
+            buf = uid.cpu().numpy().copy()
+            assert lib.comm_init(self.rank, self.world, buf.ctypes.data_as(tacs_b200.binding.UP)) == 0
+
+    def barrier(self):
+        self.lib.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, v, op):
+        if not self.dist:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, v):
+        return self._reduce(v, self.dist.ReduceOp.MAX) if self.dist else v
+
+    def sum(self, v):
+        return self._reduce(v, self.dist.ReduceOp.SUM) if self.dist else v
+
+    def bcast_i32(self, arr, n):
+        """rank 0's int32 array of length n on every rank"""
+        if not self.dist:
+            return arr
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, np.int32)).cuda() if self.rank == 0 else \
+            self.torch.empty(n, dtype=self.torch.int32, device="cuda")
+        self.dist.broadcast(t, 0)
+        return t.cpu().numpy()
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def build_partitioned(D, T, meshgen, lib, mesh, elements):
+    """Creator -> Assembler; on several ranks rank 0 alone runs METIS (the reference's root does the same,
+    TACSCreator.cpp:1104-1125) and the partition is broadcast, instead of every rank partitioning the global mesh."""
+    t0 = time.time()
+    part = None
+    if D.world > 1:
+        ne = int(mesh["elem_ids"].size)
+        if D.rank == 0:
+            c0 = T.Creator(lib, mesh["vars_per_node"])
+            c0.setGlobalConnectivity(mesh["num_nodes"], mesh["ptr"], mesh["conn"], mesh["elem_ids"])
+            c0.partitionMesh()
+            part = c0.getElementPartition()
+            del c0
+        part = D.bcast_i32(part, ne)
+    t1 = time.time()
+    creator, asm = meshgen.build_model(T, lib, mesh, elements, part=part, split_size=D.world if part is not None else 0)
+    return creator, asm, {"partition": t1 - t0, "create_tacs": time.time() - t1}
+
+
+def collect_profile(lib, steps):
+    """{kernel name as launched: (launches per step, ms per step)} from the library's event log."""
+    import tacs_b200
+
+    ms_k, cnt_k = np.zeros(8), np.zeros(8, np.int64)
+    lib.profile_collect(tacs_b200.binding.dptr(ms_k), cnt_k.ctypes.data_as(C.POINTER(C.c_long)))
+    out = {}
+    for line in (lib.profile_named() or b"").decode().splitlines():
+        name, cnt, ms = line.rsplit("|", 2)
+        out[name] = (int(cnt) / steps, float(ms) / steps)
+    return out
+
+
+def kernel_rooflines(kind, nelem_local, nnzb_local, prof, fp64_peak, hbm_peak, world, default_workload):
+    """Roofline entries of the kernels of one assembleJacobian step, named by what was launched."""
+    nn, bs = KIND_NN[kind], KIND_BS[kind]
+    b2 = bs * bs
+    # algorithmic HBM bytes per launch (DESIGN.md): the element kernel reads X/u/conn and writes the staging
+    # blocks + residual slots; the block gather reads the staging blocks and the plan and writes A once.
+    elem_bytes = nelem_local * (nn * (3 + bs) * 8 + nn * 4 + 4 + nn * nn * b2 * 8 + nn * bs * 8)
+    gather_bytes = nelem_local * nn * nn * (b2 * 8 + 4) + nnzb_local * (b2 * 8 + 4)
+    kernels = []
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        entry = {"kernel": name, "ms": ms, "launches_per_step": cnt}
+        t = ms * 1e-3
+        if "element_kernel" in name or "_mma_kernel" in name:
+            entry.update({"bound": "fp64", "achieved": FLOPS_PER_ELEMENT[kind] * nelem_local / t * 1e-12,
+                          "peak": fp64_peak, "unit": "TFLOP/s", "hbm_gbs": elem_bytes / t * 1e-9,
+                          "algorithmic_bytes": elem_bytes,
+                          "note": "flops = SURVEY 8d minimal-algorithm count; peak = live DFMA microbenchmark "
+                                  "(tacsb200_measure_fp64_tflops; DMMA m8n8k4 shares that FP64 peak on B200, "
+                                  "profiles/r1_probe_fp64.txt)"})
+        elif name.startswith("gather_blocks") or name.startswith("gather_rows"):
+            entry.update({"bound": "hbm", "achieved": gather_bytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                          "algorithmic_bytes": gather_bytes})
+        else:
+            continue
+        entry["frac"] = entry["achieved"] / entry["peak"] if entry["peak"] else None
+        entry["traffic"] = NCU_TRAFFIC_BYTES.get(name) if default_workload else None
+        entry["traffic_source"] = TRAFFIC_SOURCE if entry["traffic"] else None
+        kernels.append(entry)
+    return kernels
+
+
+def time_config(D, lib, asm, A, res, x, y, kind, nelem_total, steps, fp64_peak, hbm_peak, default_workload=False,
+                with_res=True):
+    """Device-timed assembleJacobian / assembleRes / SpMV of one assembled configuration (max over ranks)."""
+    nelem_local = asm.getNumElements()
+    for _ in range(3):
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+    lib.profile_enable(1)
+    collect_profile(lib, 1)
+    D.barrier()
+    lib.kernel_launches(1)
+    ms = lib.time_assemble_jacobian(asm.h, 1.0, 0.0, 0.0, res.h, A.h, steps)
+    launches = lib.kernel_launches(0)
+    prof = collect_profile(lib, steps)
+    lib.profile_enable(0)
+    ms_res = lib.time_assemble_res(asm.h, res.h, steps) / steps if with_res else None
+    lib.time_mat_mult(A.h, x.h, y.h, 3)
+    D.barrier()
+    nsp = 30
+    ms_spmv = lib.time_mat_mult(A.h, x.h, y.h, nsp) / nsp
+    D.barrier()
+    assert ms > 0 and ms_spmv > 0, "device timing failed"
+    ms = D.max(ms) / steps
+    ms_spmv = D.max(ms_spmv)
+    if with_res:
+        ms_res = D.max(ms_res)
+    sizes_a, sizes_b = A.getSizes(0), A.getSizes(1)
+    bs = sizes_a[0]
+    sp_bytes_local = spmv_bytes(bs, sizes_a[1], sizes_a[3] + sizes_b[3])
+    sp_bytes = D.sum(float(sp_bytes_local))
+    kernels = kernel_rooflines(kind, nelem_local, sizes_a[3] + sizes_b[3], prof, fp64_peak, hbm_peak, D.world,
+                               default_workload)
+    spmv_names = sorted(n for n in prof if n.startswith("spmv")) or [f"spmv{bs}_kernel<0>"]
+    spmv = {"kernel": "spmv6_kernel<0>" if bs == 6 else "spmv3_kernel<0>", "ms": ms_spmv, "bound": "hbm",
+            "achieved": sp_bytes / (ms_spmv * 1e-3) * 1e-9, "peak": hbm_peak * D.world, "unit": "GB/s",
+            "bytes_per_launch": sp_bytes, "note": "aggregate over all ranks; peak = ranks x measured HBM peak"}
+    spmv["frac"] = spmv["achieved"] / spmv["peak"]
+    return {"ms": ms, "ms_res": ms_res, "ms_spmv": ms_spmv, "launches": int(launches), "kernels": kernels,
+            "spmv": spmv, "value": nelem_total / (ms * 1e-3), "spmv_kernel_names": spmv_names}
+
+
+def serial_dof_index(D, T, lib, mesh, creator, lo, hi):
+    """Index of every owned dof of this rank in the SERIAL (one-rank, first-touch) numbering of the reference, so that
+    the deterministic state / input vectors are the same physical vectors on any number of ranks (and the ones the
+    known answers in tests/golden/fullsize_norms.json were computed for)."""
+    bs = mesh["vars_per_node"]
+    if D.world == 1:
+        return None
+    c1 = T.Creator(lib, bs)
+    c1.setGlobalConnectivity(mesh["num_nodes"], mesh["ptr"], mesh["conn"], mesh["elem_ids"])
+    c1.partitionMesh(1, np.zeros(mesh["elem_ids"].size, np.int32))
+    serial = c1.getNodeNums().astype(np.int64)       # original node -> serial number
+    dist_nodes = creator.getNodeNums().astype(np.int64)  # original node -> number on this partition
+    inv = np.empty(creator.num_nodes, np.int64)
+    inv[dist_nodes] = np.arange(creator.num_nodes)
+    own = serial[inv[lo:hi]]
+    return (bs * own[:, None] + np.arange(bs)[None, :]).ravel()
+
+
+def fullsize_check(D, name, res, y, dof_index):
+    """This run's residual / A*x against the known answers of the unmodified reference for the same configuration
+    (tests/golden/fullsize_norms.json, generated by tests/golden/make_fullsize_norms.py). On several ranks the norms
+    and the weighted checksum are reduced over the ranks; the sampled entries are compared on one rank only."""
+    path = os.path.join(ROOT, "tests", "golden", "fullsize_norms.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        gold = json.load(f).get(name)
+    if not gold:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_fullsize_norms import checksum_weights
+
+    out = {"against": f"tests/golden/fullsize_norms.json[{name}] (unmodified reference, oracle/_ref)"}
+    w = checksum_weights(gold["dof"])
+    for key, v in (("res", res), ("y", y)):
+        g = gold[key]
+        vec = v.getArray()
+        if D.world == 1 and vec.size != gold["dof"]:
+            return {"error": f"size mismatch {vec.size} vs {gold['dof']}"}
+        wl = w if dof_index is None else w[dof_index]
+        out[key] = {"norm2_rel": abs(v.norm() - g["norm2"]) / g["norm2"],
+                    "checksum_rel": abs(D.sum(float(np.dot(wl, vec))) - g["checksum"]) / (g["norm2"] * np.sqrt(gold["dof"]))}
+        if D.world == 1:
+            idx = np.asarray(g["sample_idx"])
+            out[key]["sample_rel_max"] = float(np.abs(vec[idx] - np.asarray(g["sample"])).max() / g["max"])
+    out["tol"] = 1e-10
+    out["ok"] = all(val < 1e-10 for k in ("res", "y") for val in out[k].values())
+    return out
+
+
+def time_gmres(D, lib, T, asm, A, b, m):
+    """ms per GMRES(m) iteration on the assembled operator: one cycle of m iterations, tolerances that cannot be met."""
+    ksm = T.KSM(lib, A, m, 0)
+    ksm.setTolerances(1e-30, 1e-300)
+    sol = asm.createVec()
+    ksm.solve(b, sol)  # warm-up (allocations, graph capture)
+    D.barrier()
+    t0 = time.perf_counter()
+    ksm.solve(b, sol)
+    lib.synchronize()
+    dt = D.max(time.perf_counter() - t0)
+    it = max(ksm.getIterCount(), 1)
+    return {"ms_per_iter": dt * 1e3 / it, "m": m, "iters": it, "timing": "host wall clock around solve(), max over ranks"}
+
+
+EXTRA_CONFIGS = {
+    # name: (kind, mesh factory, element factory, description)
+    "c3": (2, lambda mg: mg.cylinder(3, 1000, 2000), lambda mg, T, lib: mg.composite_shell_element(T, lib, 3),
+           "BASELINE configs[2]: Quad9Shell composite-laminate cylinder, 1000x2000 = 2M elements, 48M dof"),
+    "c4": (3, lambda mg: mg.cube(2, 200), lambda mg, T, lib: mg.solid_element(T, lib, 2),
+           "BASELINE configs[3]: 200^3 hex8 solid, 8M elements, 24.4M dof"),
+    "c5": (4, lambda mg: mg.cube(3, 100), lambda mg, T, lib: mg.solid_element(T, lib, 3),
+           "BASELINE configs[4]: 100^3 hex27 solid, 1M elements, 24.4M dof"),
+}
+
+
+def run_extra(D, lib, T, meshgen, name, steps, fp64_peak, hbm_peak, gmres_m):
+    kind, mesh_f, elem_f, what = EXTRA_CONFIGS[name]
+    t0 = time.time()
+    mesh = mesh_f(meshgen)
+    creator, asm, setup = build_partitioned(D, T, meshgen, lib, mesh, [elem_f(meshgen, T, lib)])
+    t1 = time.time()
+    A = asm.createMat()
+    setup["create_mat"] = time.time() - t1
+    setup["mesh"] = t1 - t0 - setup["partition"] - setup["create_tacs"]
+    res, u, x, y = asm.createVec(), asm.createVec(), asm.createVec(), asm.createVec()
+    bs = mesh["vars_per_node"]
+    lo, hi = asm.getOwnerRange()
+    h = meshgen.hash_vector(bs * creator.num_nodes)
+    idx = serial_dof_index(D, T, lib, mesh, creator, lo, hi)
+    u.setArray(h if idx is None else h[idx])
+    x.setArray(h[::-1].copy() if idx is None else h[::-1][idx])
+    asm.applyBCs(u)
+    asm.applyBCs(x)
+    asm.setVariables(u)
+    nelem_total = int(mesh["elem_ids"].size)
+    r = time_config(D, lib, asm, A, res, x, y, kind, nelem_total, steps, fp64_peak, hbm_peak)
+    A.mult(x, y)
+    out = {"workload": what, "n_gpus": D.world, "scaling": "strong (fixed problem partitioned over the GPUs)",
+           "partition": "METIS (rank 0, broadcast)" if D.world > 1 else "single rank",
+           "elements": nelem_total, "jac_ms": r["ms"], "elements_per_s": r["value"], "res_ms": r["ms_res"],
+           "spmv_ms": r["ms_spmv"], "spmv_gbs_aggregate": r["spmv"]["achieved"], "spmv_frac_of_hbm_peak": r["spmv"]["frac"],
+           "kernels": r["kernels"], "ynorm": y.norm(), "resnorm": res.norm(), "setup_s": setup,
+           "local_elements_rank0": asm.getNumElements()}
+    if name == "c4":
+        out["fullsize"] = fullsize_check(D, "c4", res, y, idx)
+    if gmres_m > 0 and name == "c4":
+        out["gmres"] = time_gmres(D, lib, T, asm, A, res, gmres_m)
+    del A, asm, creator, res, u, x, y
+    gc.collect()
+    return out
+
+
 def run_b200(args):
     import torch
-    import torch.distributed as dist
 
     import tacs_b200
     from tacs_b200 import TACS as T
     from tacs_b200 import meshgen
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     lib = tacs_b200.load()  # raises when libtacs_b200.so is missing: there is no fallback
-    if lib.init(local_rank) != 0:
-        raise SystemExit("tacs_b200: no usable GPU")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (np.zeros(128, np.uint8))
-            assert lib.comm_unique_id(buf.ctypes.data_as(tacs_b200.binding.UP)) == 0
-            uid = torch.from_numpy(buf.copy())
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        buf = uid.cpu().numpy().copy()
-        assert lib.comm_init(rank, world, buf.ctypes.data_as(tacs_b200.binding.UP)) == 0
+    D = Dist(lib)
+    world, rank = D.world, D.rank
 
+    # ---- multi-GPU parity gate: distributed assembly + SpMV against the serial oracle, before anything is timed ----
+    parity = None
+    if world > 1:
+        from tests import dist_check  # checker only (oracle/tacs_oracle.c through tests/oracle_port.py)
+
+        errs = dist_check.check_all(lib)
+        worst = {k: D.max(v) for k, v in errs["max"].items()}
+        exact = D.max(0.0 if errs["pattern_exact"] else 1.0) == 0.0
+        parity = {"A": worst["A"], "res": worst["res"], "y": worst["y"], "res_only": worst["res_only"],
+                  "norm": worst["norm"], "dot": worst["dot"], "pattern_exact": exact, "tol": PARITY_TOL,
+                  "cases": sorted(k for k in errs if k not in ("max", "pattern_exact")),
+                  "what": "every owned row of the METIS-partitioned matrix / residual / A*x on every rank (NCCL halo and "
+                          "off-rank staging rows included) vs the serial oracle in the same numbering; max over ranks"}
+        parity["ok"] = bool(exact and all(worst[k] < PARITY_TOL for k in ("A", "res", "y", "res_only", "norm")))
+        if not parity["ok"]:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity": parity,
+                      "error": "multi-GPU parity check failed; nothing was timed"})
+            D.close()
+            raise SystemExit(2)
+
+    hbm_peak, hbm_src = measured_peaks()
+    fp64_peak = lib.measure_fp64_tflops()
+
+    # ---- headline: C2 plate, 1M elements per GPU -------------------------------------------------------------------
     nx, ny = args.nx * world, args.ny
     mesh = meshgen.plate(2, nx, ny)
-    creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.iso_shell_element(T, lib, 2)])
-    A, res, x, y = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+    creator, asm, setup = build_partitioned(D, T, meshgen, lib, mesh, [meshgen.iso_shell_element(T, lib, 2)])
+    A, res, x, y, xr = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec(), asm.createVec()
     n = x.getSize()
     state = torch.empty(n, dtype=torch.float64).pin_memory()
     out = torch.empty(n, dtype=torch.float64).pin_memory()
     state_np, out_np = state.numpy(), out.numpy()
     lo, hi = asm.getOwnerRange()
-    state_np[:] = meshgen.hash_vector(6 * creator.num_nodes)[6 * lo:6 * hi] if world > 1 else meshgen.hash_vector(n)
+    h = meshgen.hash_vector(6 * creator.num_nodes)
+    idx = serial_dof_index(D, T, lib, mesh, creator, lo, hi)
+    state_np[:] = h if idx is None else h[idx]
     x.setArray(state_np)
     asm.applyBCs(x)
     asm.setVariables(x)
-    nelem_local = asm.getNumElements()
+    xr.setArray(h[::-1].copy() if idx is None else h[::-1][idx])
+    asm.applyBCs(xr)
     nelem_total = nx * ny
     bs, nrows, ncols, nnzb = A.getSizes()
+    default_workload = world == 1 and args.nx == 1000 and args.ny == 1000
 
-    def barrier():
-        lib.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident timing --------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
-    lib.profile_enable(1)
-    ms_k, cnt_k = np.zeros(8), np.zeros(8, np.int64)
-    lib.profile_collect(tacs_b200.binding.dptr(ms_k), cnt_k.ctypes.data_as(C.POINTER(C.c_long)))
-    barrier()
-    lib.kernel_launches(1)
-    with ClockSampler(local_rank) as clocks:
-        ms = lib.time_assemble_jacobian(asm.h, 1.0, 0.0, 0.0, res.h, A.h, args.steps)
-        launches = lib.kernel_launches(0)
-        lib.profile_collect(tacs_b200.binding.dptr(ms_k),
-                            cnt_k.ctypes.data_as(C.POINTER(C.c_long)))
-        lib.profile_enable(0)
-        ms_res = lib.time_assemble_res(asm.h, res.h, args.steps) / args.steps
-        # SpMV loop inside the same clock window
-        lib.time_mat_mult(A.h, x.h, y.h, 3)
-        nsp = 50
-        ms_spmv = lib.time_mat_mult(A.h, x.h, y.h, nsp) / nsp
-    lib.profile_enable(0)
-    barrier()
-    assert ms > 0, "device timing failed"
-    ms = max_over_ranks(ms)
-    ms_spmv = max_over_ranks(ms_spmv)
-    ms_res = max_over_ranks(ms_res)
-    ms_per_step = ms / args.steps
-    value = nelem_total / (ms_per_step * 1e-3)
+    with ClockSampler(D.local_rank) as clocks:
+        r = time_config(D, lib, asm, A, res, xr, y, 1, nelem_total, args.steps, fp64_peak, hbm_peak, default_workload)
+    ms_per_step, value = r["ms"], r["value"]
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     def e2e_step():
@@ -343,62 +645,51 @@ def run_b200(args):
 
     for _ in range(2):
         e2e_step()
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    lib.synchronize()  # the last step's block gather and matrix BCs are inside the timed region
+    D.barrier()
+    e2e_s = D.max((time.perf_counter() - t0) / args.steps)
     e2e_value = nelem_total / e2e_s
 
+    fullsize = None
+    if default_workload:
+        A.mult(xr, y)
+        fullsize = fullsize_check(D, "c2", res, y, idx)
+    gmres = time_gmres(D, lib, T, asm, A, res, args.gmres_m) if args.gmres_m > 0 else None
+    del A, asm, creator, res, x, y, xr
+    gc.collect()
+
+    # ---- the other BASELINE configurations: fixed problems partitioned over the N GPUs (strong scaling) ------------
+    extra = {}
+    for name in [c for c in args.configs.split(",") if c]:
+        try:
+            extra[name] = run_extra(D, lib, T, meshgen, name, max(3, args.steps // 3), fp64_peak, hbm_peak, args.gmres_m)
+        except Exception as exc:  # a configuration that does not fit must not take the headline down
+            extra[name] = {"error": str(exc)[:300]}
+            if world > 1:
+                raise
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.close()
         return
 
-    # ---- roofline of the kernels in the step ----------------------------------------------------------
-    hbm_peak, hbm_src = measured_peaks()
-    fp64_peak = lib.measure_fp64_tflops()
-    names = ["element", "gather_residual", "gather_blocks", "boundary_conditions", "spmv", "vector", "dot", "halo"]
-    # per-step device time of each kernel family (a family may launch more than once per step, e.g. the
-    # Aloc and Bext gathers on several ranks)
-    per_launch = {names[k]: (ms_k[k] / args.steps if cnt_k[k] else None) for k in range(8)}
-    nn, b2 = 4, 36
-    # algorithmic HBM bytes per launch: element kernel reads X/u/conn and writes the staging
-    # blocks + residual slots; block gather reads the staging blocks and the plan, writes A once.
-    elem_bytes = nelem_local * (nn * (3 + 6) * 8 + nn * 4 + 4 + nn * nn * b2 * 8 + nn * 6 * 8)
-    gather_bytes = nelem_local * nn * nn * (b2 * 8 + 4) + nnzb * (b2 * 8 + 4)
-    kernels = []
-    if per_launch["element"]:
-        t = per_launch["element"] * 1e-3
-        kernels.append({"kernel": "shell4_mma_kernel", "ms": per_launch["element"], "bound": "fp64",
-                        "achieved": FLOPS_PER_ELEMENT["quad4"] * nelem_local / t * 1e-12, "peak": fp64_peak,
-                        "unit": "TFLOP/s", "hbm_gbs": elem_bytes / t * 1e-9,
-                        "note": "flops = SURVEY 8d minimal-algorithm count (57 kFLOP/element); peak = live DFMA "
-                                "microbenchmark (tacsb200_measure_fp64_tflops); the kernel issues its two matrix "
-                                "products as DMMA m8n8k4, which shares that FP64 peak on B200 "
-                                "(profiles/r1_probe_fp64.txt: 36.5 DFMA vs 37.0 DMMA TFLOP/s)"})
-    if per_launch["gather_blocks"]:
-        t = per_launch["gather_blocks"] * 1e-3
-        kernels.append({"kernel": "gather_blocks36_kernel", "ms": per_launch["gather_blocks"], "bound": "hbm",
-                        "achieved": gather_bytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s"})
-    default_workload = world == 1 and args.nx == 1000 and args.ny == 1000
-    for k in kernels:
-        k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
-        k["traffic"] = NCU_TRAFFIC_BYTES.get(k["kernel"]) if default_workload else None
+    kernels = r["kernels"]
     dominant = max(kernels, key=lambda k: k["ms"]) if kernels else None
     roofline = None
     if dominant:
         roofline = {"kernel": dominant["kernel"], "bound": dominant["bound"], "achieved": dominant["achieved"],
                     "peak": dominant["peak"], "unit": dominant["unit"], "frac": dominant["frac"],
-                    "traffic": dominant["traffic"], "algorithmic_bytes": elem_bytes if dominant["bound"] == "fp64" else gather_bytes,
+                    "traffic": dominant["traffic"], "traffic_source": dominant["traffic_source"],
+                    "algorithmic_bytes": dominant["algorithmic_bytes"],
                     "peak_source": hbm_src if dominant["bound"] == "hbm" else "live DFMA microbenchmark",
                     "share_of_step": dominant["ms"] / ms_per_step}
-    sp_bytes = spmv_bytes(bs, nrows, nnzb)
-    spmv = {"kernel": "spmv6_kernel<0>", "ms": ms_spmv, "bound": "hbm", "achieved": sp_bytes / (ms_spmv * 1e-3) * 1e-9,
-            "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "bytes_per_launch": sp_bytes}
-    spmv["frac"] = spmv["achieved"] / spmv["peak"]
-    spmv["traffic"] = NCU_TRAFFIC_BYTES["spmv6_kernel<0>"] if default_workload else None
+    spmv = r["spmv"]
+    spmv["peak_source"] = hbm_src
+    spmv["traffic"] = NCU_TRAFFIC_BYTES.get(spmv["kernel"]) if default_workload else None
+    spmv["traffic_source"] = TRAFFIC_SOURCE if spmv["traffic"] else None
 
     # ---- CPU baseline: the reference's own implementation on this box's host cores ---------------------
     cpu = None
@@ -415,24 +706,33 @@ def run_b200(args):
         "config": {"workload": f"synthetic {nx}x{ny} Quad4Shell plate (6 dof/node), isotropic, edges clamped: "
                                f"assembleJacobian(1,0,0,res,A) per step; BASELINE configs[1] at 1 GPU, "
                                f"{args.nx}x{args.ny} elements per GPU",
-                   "elements": nelem_total, "dof": 6 * creator.num_nodes, "nnzb": int(nnzb),
-                   "l2": "inputs larger than L2 (staging 4.6 GB + matrix 2.6 GB per step)",
-                   "partition": "METIS element partition (TACSCreator::partitionMesh)" if world > 1 else "single rank"},
+                   "elements": nelem_total, "dof": 6 * (nx + 1) * (ny + 1), "nnzb": int(nnzb),
+                   "l2": "inputs larger than L2 (staging + matrix of several GB per step)",
+                   "partition": "METIS element partition (TACSCreator::partitionMesh on rank 0, broadcast)"
+                   if world > 1 else "single rank",
+                   "strong_scaling": "see c4 / c3 / c5: fixed problems partitioned over the N GPUs"},
         "roofline": roofline, "kernels": kernels, "spmv": spmv,
-        "assemble_res": {"ms": ms_res, "value": nelem_total / (ms_res * 1e-3), "unit": UNIT,
+        "assemble_res": {"ms": r["ms_res"], "value": nelem_total / (r["ms_res"] * 1e-3), "unit": UNIT,
                          "note": "assembleRes alone (SURVEY 8d metric i), same mesh and state"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8),
+                "ms_per_step": e2e_s * 1e3,
                 "note": "state vector from pinned host memory -> setVariables -> assembleJacobian (enqueue-only C ABI "
                         "entry) -> residual to pinned host memory on the copy stream while the block gather still runs; "
                         "the region ends with a device synchronize; the BCSR matrix stays in HBM for the device-side "
                         "Krylov solver"},
-        "gpu_launches": int(launches), "clocks": clocks.summary(),
-        "fp64_peak_tflops": fp64_peak,
+        "gpu_launches": r["launches"], "clocks": clocks.summary(),
+        "fp64_peak_tflops": fp64_peak, "setup_s": setup,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if fullsize is not None:
+        line["fullsize"] = fullsize
+    if gmres is not None:
+        line["gmres"] = gmres
+    line.update(extra)
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():
@@ -443,7 +743,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=1000, help="plate elements per GPU along x")
     ap.add_argument("--ny", type=int, default=1000)
-    ap.add_argument("--ref-n", type=int, default=300, help="edge of the bounded CPU-baseline sample plate")
+    ap.add_argument("--ref-n", type=int, default=1000, help="edge of the CPU-baseline plate (1000 = the full config)")
+    ap.add_argument("--configs", default="c4,c3,c5", help="extra BASELINE configurations to run after the headline")
+    ap.add_argument("--gmres-m", type=int, default=30, help="GMRES subspace size of the per-iteration timing (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -231,6 +231,9 @@ double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_han
    and clears it. */
 int tacsb200_profile_enable(int on);
 int tacsb200_profile_collect(double *ms, long *count);
+/* The same log by kernel as launched: lines "kernel name|launches|ms" of the last collect() (library-owned
+   string, valid until the next collect). */
+const char *tacsb200_profile_named(void);
 /* Roofline denominators measured on this device: FP64 FMA throughput (TFLOP/s, 2 flop per FMA) of a
    register-resident DFMA stream, and device-to-device copy bandwidth (GB/s, read + write bytes). */
 double tacsb200_measure_fp64_tflops(void);

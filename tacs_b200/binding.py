@@ -126,6 +126,7 @@ PRODUCT_ONLY = {
     "plan_get_array": (I, [H, C.c_char_p, IP]),
     "profile_enable": (I, [I]),
     "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
+    "profile_named": (C.c_char_p, []),
     "measure_fp64_tflops": (D, []),
     "measure_copy_gbs": (D, []),
 }

@@ -364,13 +364,11 @@ int tacsb200_assembler_set_nodes(tacsb200_handle a, tacsb200_handle X) {
   ASM(a);
   TACSBVec *v = as<TACSBVec>(X);
   REQUIRE(v, "vector");
-  t->setNodes(v);
-  return 0;
+  return t->setNodes(v);
 }
 int tacsb200_assembler_set_variables(tacsb200_handle a, tacsb200_handle q, tacsb200_handle qd, tacsb200_handle qdd) {
   ASM(a);
-  t->setVariables(as<TACSBVec>(q), as<TACSBVec>(qd), as<TACSBVec>(qdd));
-  return 0;
+  return t->setVariables(as<TACSBVec>(q), as<TACSBVec>(qd), as<TACSBVec>(qdd));
 }
 int tacsb200_assembler_zero_variables(tacsb200_handle a) { ASM(a); t->zeroVariables(); return 0; }
 int tacsb200_assembler_apply_bcs_vec(tacsb200_handle a, tacsb200_handle v) {
@@ -459,8 +457,7 @@ int tacsb200_vec_mdot(tacsb200_handle v, int n, tacsb200_handle *ys, double *out
     y[i] = as<TACSBVec>(ys[i]);
     REQUIRE(y[i], "vector");
   }
-  x->mdot(y.data(), out, n);
-  return 0;
+  return x->mdot(y.data(), out, n);
 }
 int tacsb200_vec_axpy(tacsb200_handle yv, double alpha, tacsb200_handle xv) {
   VEC(yv, y); VEC(xv, x);
@@ -517,8 +514,7 @@ int tacsb200_mat_zero_entries(tacsb200_handle m) { MAT(m); A->zeroEntries(); ret
 int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
   MAT(m);
   VEC(xv, x); VEC(yv, y);
-  A->mult(x, y);
-  return 0;
+  return A->mult(x, y);
 }
 int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
   if (tacsb200_mat_mult_async(m, xv, yv)) return 1;
@@ -605,10 +601,7 @@ double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_ha
   TACSParallelMat *A = as<TACSParallelMat>(m);
   TACSBVec *x = as<TACSBVec>(xv), *y = as<TACSBVec>(yv);
   if (!A || !x || !y) return -1.0;
-  return timed(reps, [&]() {
-    A->mult(x, y);
-    return 0;
-  });
+  return timed(reps, [&]() { return A->mult(x, y); });
 }
 
 int tacsb200_profile_enable(int on) {
@@ -616,6 +609,7 @@ int tacsb200_profile_enable(int on) {
   return 0;
 }
 int tacsb200_profile_collect(double *ms, long *count) { return profile_collect(ms, count); }
+const char *tacsb200_profile_named(void) { return profile_named(); }
 
 double tacsb200_measure_fp64_tflops(void) {
   if (ctx_init(-1)) return -1.0;

@@ -153,11 +153,11 @@ static int exchange(DeviceExchange &dx, int chunk, const double *src, RecvBase r
 
 // TACSBVecDistribute::beginForward/endForward for the assembler's external nodes: the ext blocks of a
 // local-order vector are [ext < range | owned | ext >= range]; each owner's nodes are contiguous.
-void halo_forward(TACSAssembler *a, TACSBVec *v) {
-  if (a->size <= 1) return;
+int halo_forward(TACSAssembler *a, TACSBVec *v) {
+  if (a->size <= 1) return 0;
   DeviceExchange &dx = a->x_state;
   const int chunk = v->bsize, eb = a->ext_before, no = a->nowned;
-  exchange(dx, chunk, v->owned(),
+  return exchange(dx, chunk, v->owned(),
            [&](int k) {
              const int first = dx.recv_ptr[k];  // position in the sorted external list
              const long local = first < eb ? first : (long)no + first;
@@ -169,23 +169,25 @@ void halo_forward(TACSAssembler *a, TACSBVec *v) {
 // Off-rank rows (TACSMatDistribute::beginAssembly/endAssembly, TACSBVecDistribute reverse): rows of the
 // residual staging (and the matching block rows of the matrix staging) that belong to nodes owned by a
 // neighbour are sent to it and land in the tail of its staging arrays, where its gather plans find them.
-void staging_exchange(TACSAssembler *a, bool with_blocks) {
-  if (a->size <= 1) return;
+int staging_exchange(TACSAssembler *a, bool with_blocks) {
+  if (a->size <= 1) return 0;
   HostPlan &P = *a->plan;
   const int bs = a->bs;
-  exchange(a->x_rows, bs, a->Re.ptr,
-           [&](int k) { return a->Re.ptr + ((size_t)P.local_node_slots + a->x_rows.recv_ptr[k]) * bs; },
-           ctx().stream);
+  if (exchange(a->x_rows, bs, a->Re.ptr,
+               [&](int k) { return a->Re.ptr + ((size_t)P.local_node_slots + a->x_rows.recv_ptr[k]) * bs; },
+               ctx().stream))
+    return 1;
   if (with_blocks)
-    exchange(a->x_blocks, bs * bs, a->Ke.ptr,
-             [&](int k) { return a->Ke.ptr + ((size_t)P.local_blocks + a->x_blocks.recv_ptr[k]) * bs * bs; },
-             ctx().stream);
+    return exchange(a->x_blocks, bs * bs, a->Ke.ptr,
+                    [&](int k) { return a->Ke.ptr + ((size_t)P.local_blocks + a->x_blocks.recv_ptr[k]) * bs * bs; },
+                    ctx().stream);
+  return 0;
 }
 
 // SpMV halo (TACSParallelMat::mult, TACSParallelMat.cpp:248-265): gather the external columns on the
 // communication stream while the compute stream runs the local product.
 static cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
-void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x) {
+int spmv_halo_begin(TACSParallelMat *A, TACSBVec *x) {
   Context &c = ctx();
   if (!ev_x_ready) {
     cudaEventCreateWithFlags(&ev_x_ready, cudaEventDisableTiming);
@@ -195,9 +197,10 @@ void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x) {
   cudaStreamWaitEvent(c.comm_stream, ev_x_ready, 0);
   DeviceExchange &dx = A->x_cols;
   const int chunk = A->Aloc.bsize;
-  exchange(dx, chunk, x->owned(), [&](int k) { return A->x_ext.ptr + (size_t)dx.recv_ptr[k] * chunk; },
-           c.comm_stream);
+  const int rc = exchange(dx, chunk, x->owned(), [&](int k) { return A->x_ext.ptr + (size_t)dx.recv_ptr[k] * chunk; },
+                          c.comm_stream);
   cudaEventRecord(ev_halo_done, c.comm_stream);
+  return rc;
 }
 void spmv_halo_end(TACSParallelMat *A) {
   (void)A;

@@ -1139,6 +1139,18 @@ static cudaError_t launch_family(K kernel, const ElemGroupArgs &g, int num_sms, 
   return cudaGetLastError();
 }
 
+// name of the kernel launch_element_group picks for a group (for the launch log / profile)
+const char *element_kernel_name(const ElemGroupArgs &g) {
+  const bool mma = g.uncoupled && (g.Ke || (g.gamma == 0.0 && !g.ddvars));
+  switch (g.kind) {
+    case ELEM_QUAD4_SHELL: return mma ? "shell4_mma_kernel" : "shell_element_kernel<2>";
+    case ELEM_QUAD9_SHELL: return mma ? "shell9_mma_kernel" : "shell_element_kernel<3>";
+    case ELEM_HEX8: return "solid_element_kernel<2>";
+    case ELEM_HEX27: return "solid_element_kernel<3>";
+  }
+  return "?";
+}
+
 cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream_t s) {
   if (g.nelem <= 0) return cudaSuccess;
   switch (g.kind) {

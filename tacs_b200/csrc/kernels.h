@@ -38,6 +38,13 @@ struct ElemGroupArgs {
 size_t elem_tables_bytes(int kind);
 void elem_tables_build(int kind, void *host_dst);
 cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream_t s);
+const char *element_kernel_name(const ElemGroupArgs &g);
+inline const char *gather_blocks_kernel_name(int bs) { return bs == 6 ? "gather_blocks36_kernel" : "gather_blocks_kernel<9>"; }
+inline const char *gather_rows_kernel_name(int bs) { return bs == 6 ? "gather_rows_kernel<36>" : "gather_rows_kernel<9>"; }
+inline const char *gather_residual_kernel_name(int bs) { return bs == 6 ? "gather_residual_kernel<6>" : "gather_residual_kernel<3>"; }
+inline const char *spmv_kernel_name(int bs, int add) {
+  return bs == 6 ? (add ? "spmv6_kernel<1>" : "spmv6_kernel<0>") : (add ? "spmv3_kernel<1>" : "spmv3_kernel<0>");
+}
 
 cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int *src, const double *Ke,
                                  double *A, int num_sms, cudaStream_t s);

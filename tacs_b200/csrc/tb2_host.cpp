@@ -38,7 +38,12 @@ int ctx_init(int device) {
     return 1;
   }
   if (device < 0) device = 0;
-  if (device >= ndev) device = device % ndev;
+  if (device >= ndev) {
+    // a wrong LOCAL_RANK must not silently put two ranks on one GPU (ncclCommInitRank would fail much later)
+    fprintf(stderr, "tacs_b200: device index %d is out of range (%d visible device%s)\n", device, ndev,
+            ndev == 1 ? "" : "s");
+    return 1;
+  }
   if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return 1;
   cudaDeviceProp prop;
   if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return 1;
@@ -58,7 +63,7 @@ int ctx_init(int device) {
 
 // ---- event profiler ------------------------------------------------------------------------
 static bool g_prof_on = false;
-struct ProfRec { KernelId id; cudaEvent_t e0, e1; };
+struct ProfRec { KernelId id; const char *name; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_prof_log;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {
@@ -72,11 +77,12 @@ static cudaEvent_t prof_event() {
   return e;
 }
 void profile_enable(int on) { g_prof_on = on != 0; }
-KernelTimer::KernelTimer(KernelId id) : slot(-1) {
+KernelTimer::KernelTimer(KernelId id, const char *name) : slot(-1) {
   g_ctx.kernel_launches++;
   if (!g_prof_on) return;
   ProfRec r;
   r.id = id;
+  r.name = name;
   r.e0 = prof_event();
   r.e1 = prof_event();
   cudaEventRecord(r.e0, g_ctx.stream.s);
@@ -86,19 +92,32 @@ KernelTimer::KernelTimer(KernelId id) : slot(-1) {
 KernelTimer::~KernelTimer() {
   if (slot >= 0) cudaEventRecord(g_prof_log[slot].e1, g_ctx.stream.s);
 }
+// per-name totals of the last collect: "name|launches|ms" lines (kernel names as launched, not literals of the caller)
+static std::string g_prof_named;
+const char *profile_named() { return g_prof_named.c_str(); }
 int profile_collect(double *ms, long *count) {
   for (int k = 0; k < K_COUNT; k++) { ms[k] = 0.0; count[k] = 0; }
   if (g_ctx.device < 0) return 1;
   cudaStreamSynchronize(g_ctx.stream.s);
+  std::map<std::string, std::pair<long, double>> named;
   for (auto &r : g_prof_log) {
     float t = 0.0f;
     cudaEventElapsedTime(&t, r.e0, r.e1);
     ms[r.id] += t;
     count[r.id]++;
+    auto &slot = named[r.name ? r.name : "(unnamed)"];
+    slot.first++;
+    slot.second += t;
     g_prof_pool.push_back(r.e0);
     g_prof_pool.push_back(r.e1);
   }
   g_prof_log.clear();
+  g_prof_named.clear();
+  for (auto &kv : named) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s|%ld|%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    g_prof_named += line;
+  }
   return 0;
 }
 
@@ -738,24 +757,30 @@ static bool dot_buffers() {
 
 int comm_allreduce_sum(double *dev_buf, int n);  // comm.cpp
 
-void TACSBVec::mdot(TACSBVec **ys, double *out, int n) {
-  dot_buffers();
+int TACSBVec::mdot(TACSBVec **ys, double *out, int n) {
+  if (!dot_buffers()) {
+    for (int v = 0; v < n; v++) out[v] = NAN;
+    return 1;
+  }
+  int rc = 0;
   for (int done = 0; done < n; done += 8) {
     const int nv = std::min(8, n - done);
     const double *ptrs[8];
     for (int v = 0; v < nv; v++) ptrs[v] = ys[done + v]->owned();
     {
       KernelTimer kt(K_DOT);
-      cuda_ok(launch_mdot(ownedSize(), owned(), nv, ptrs, g_dot_partial, g_dot_out, ctx().num_sms, ctx().stream),
-              "mdot");
+      if (!cuda_ok(launch_mdot(ownedSize(), owned(), nv, ptrs, g_dot_partial, g_dot_out, ctx().num_sms, ctx().stream),
+                   "mdot")) rc = 1;
       ctx().kernel_launches++;
     }
-    if (ctx().size > 1) comm_allreduce_sum(g_dot_out, nv);
-    cuda_ok(cudaMemcpyAsync(g_dot_host, g_dot_out, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream),
-            "mdot D2H");
-    cuda_ok(cudaStreamSynchronize(ctx().stream), "mdot sync");
-    for (int v = 0; v < nv; v++) out[done + v] = g_dot_host[v];
+    if (ctx().size > 1 && comm_allreduce_sum(g_dot_out, nv)) rc = 1;
+    if (!cuda_ok(cudaMemcpyAsync(g_dot_host, g_dot_out, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream),
+                 "mdot D2H") ||
+        !cuda_ok(cudaStreamSynchronize(ctx().stream), "mdot sync"))
+      rc = 1;
+    for (int v = 0; v < nv; v++) out[done + v] = rc ? NAN : g_dot_host[v];
   }
+  return rc;
 }
 double TACSBVec::dot(TACSBVec *y) {
   double r = 0.0;
@@ -931,20 +956,21 @@ int TACSAssembler::finalize() {
 TACSBVec *TACSAssembler::createVec() { return new TACSBVec(bs, nowned, ext_before, ext_after); }
 TACSBVec *TACSAssembler::createNodeVec() { return new TACSBVec(3, nowned, ext_before, ext_after); }
 
-void halo_forward(TACSAssembler *a, TACSBVec *v);  // comm.cpp: fill the external blocks of v
+int halo_forward(TACSAssembler *a, TACSBVec *v);  // comm.cpp: fill the external blocks of v; non-zero on failure
 
-void TACSAssembler::setVariables(TACSBVec *q, TACSBVec *qdot, TACSBVec *qddot) {
+int TACSAssembler::setVariables(TACSBVec *q, TACSBVec *qdot, TACSBVec *qddot) {
   if (q) {
     vars->copyValues(q);
     vars_zero = false;
-    if (size > 1) halo_forward(this, vars);
+    if (size > 1 && halo_forward(this, vars)) return 1;
   }
   if (qdot) dvars->copyValues(qdot);
   if (qddot) {
     ddvars->copyValues(qddot);
     ddvars_zero = false;
-    if (size > 1) halo_forward(this, ddvars);
+    if (size > 1 && halo_forward(this, ddvars)) return 1;
   }
+  return 0;
 }
 void TACSAssembler::zeroVariables() {
   vars->zeroEntries();
@@ -953,9 +979,9 @@ void TACSAssembler::zeroVariables() {
   vars_zero = ddvars_zero = true;
 }
 void TACSAssembler::getNodes(TACSBVec *X) { X->copyValues(xpts); }
-void TACSAssembler::setNodes(TACSBVec *X) {
+int TACSAssembler::setNodes(TACSBVec *X) {
   xpts->copyValues(X);
-  if (size > 1) halo_forward(this, xpts);
+  return size > 1 ? halo_forward(this, xpts) : 0;
 }
 
 void TACSAssembler::applyBCs(TACSBVec *v) {
@@ -992,26 +1018,26 @@ int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat, con
     a.Ke = want_mat ? Ke.ptr + (size_t)g.block_base * bs * bs : nullptr;
     a.Re = Re.ptr + (size_t)g.node_base * bs;
     {
-      KernelTimer kt(K_ELEMENT);
+      KernelTimer kt(K_ELEMENT, element_kernel_name(a));
       if (!cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel")) return 1;
     }
   }
   return 0;
 }
 
-void staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank rows of Re (and Ke)
+int staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank rows of Re (and Ke)
 
 // TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
   if (launchElements(1.0, 0.0, false)) return 1;
-  if (size > 1) staging_exchange(this, false);
+  if (size > 1 && staging_exchange(this, false)) return 1;
   {
-    KernelTimer kt(K_GATHER_RES);
+    KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
     if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
                                         ctx().stream), "gather residual")) return 1;
   }
   {
-    KernelTimer kt(K_BCS);
+    KernelTimer kt(K_BCS, "vec_apply_bcs_kernel");
     if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
                                       lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
   }
@@ -1024,33 +1050,33 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
                                     double lambda, bool apply_bcs) {
   (void)beta;
   if (launchElements(alpha, gamma, true)) return 1;
-  if (size > 1) staging_exchange(this, true);
+  if (size > 1 && staging_exchange(this, true)) return 1;
   if (res) {
     {
-      KernelTimer kt(K_GATHER_RES);
+      KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
       if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
                                           ctx().stream), "gather residual")) return 1;
     }
-    KernelTimer kt(K_BCS);
+    KernelTimer kt(K_BCS, "vec_apply_bcs_kernel");
     if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
                                       lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
   }
   // from here on only the staging area and the matrix are touched (Context::tail_evt)
   cudaEventRecord(ctx().tail_evt, ctx().stream.s);
   if (A->row_gather) {
-    KernelTimer kt(K_GATHER_MAT);
+    KernelTimer kt(K_GATHER_MAT, gather_rows_kernel_name(bs));
     if (!cuda_ok(launch_gather_rows(bs, nowned, r_ptr.ptr, A->g_base.ptr, A->g_pptr.ptr, A->g_pos.ptr, Ke.ptr,
                                     A->Aloc.d_rowp.ptr, A->Aloc.d_vals.ptr, A->np,
                                     A->Bext.nnzb() > 0 ? A->Bext.d_rowp.ptr : nullptr, A->Bext.d_vals.ptr,
                                     A->max_row_blocks, ctx().num_sms, ctx().stream), "gather rows")) return 1;
   } else {
     {
-      KernelTimer kt(K_GATHER_MAT);
+      KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs));
       if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
                                         ctx().num_sms, ctx().stream), "gather blocks")) return 1;
     }
     if (A->Bext.nnzb() > 0) {
-      KernelTimer kt(K_GATHER_MAT);
+      KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs));
       if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
                                         ctx().num_sms, ctx().stream), "gather blocks")) return 1;
     }
@@ -1095,16 +1121,16 @@ int TACSAssembler::addJacobianVecProduct(double scale, double alpha, double beta
   }
   jvp_x->copyValues(x);
   jvp_x->scale(alpha);
-  if (size > 1) halo_forward(this, jvp_x);
+  if (size > 1 && halo_forward(this, jvp_x)) return 1;
   if (gamma != 0.0) {
     jvp_a->copyValues(x);
     jvp_a->scale(gamma);
-    if (size > 1) halo_forward(this, jvp_a);
+    if (size > 1 && halo_forward(this, jvp_a)) return 1;
   }
   if (launchElements(1.0, 0.0, false, jvp_x->local(), gamma != 0.0 ? jvp_a->local() : nullptr, true)) return 1;
-  if (size > 1) staging_exchange(this, false);
+  if (size > 1 && staging_exchange(this, false)) return 1;
   {
-    KernelTimer kt(K_GATHER_RES);
+    KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
     if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, jvp_t->owned(), ctx().num_sms,
                                         ctx().stream), "gather residual")) return 1;
   }
@@ -1187,34 +1213,40 @@ TACSBVec *TACSParallelMat::createVec() { return new TACSBVec(Aloc.bsize, Aloc.nr
 // TACSParallelMat::applyBCs (TACSParallelMat.cpp:343-374)
 void TACSParallelMat::applyBCs() {
   TACSAssembler *a = assembler;
-  KernelTimer kt(K_BCS);
+  KernelTimer kt(K_BCS, "mat_apply_bcs_kernel");
   cuda_ok(launch_mat_apply_bcs(Aloc.bsize, a->nbc_dev, a->d_bc_rows.ptr, a->d_bc_vars.ptr, Aloc.d_rowp.ptr,
                                Aloc.d_cols.ptr, Aloc.d_vals.ptr, 0, ctx().stream), "mat applyBCs");
   if (Bext.nnzb() > 0) {
-    KernelTimer kt2(K_BCS);
+    KernelTimer kt2(K_BCS, "mat_apply_bcs_kernel");
     cuda_ok(launch_mat_apply_bcs(Bext.bsize, a->nbc_dev, d_bc_rows_ext.ptr, a->d_bc_vars.ptr, Bext.d_rowp.ptr,
                                  Bext.d_cols.ptr, Bext.d_vals.ptr, -1, ctx().stream), "mat applyBCs ext");
   }
 }
 
-void spmv_halo_begin(TACSParallelMat *A, TACSBVec *x);  // comm.cpp
+int spmv_halo_begin(TACSParallelMat *A, TACSBVec *x);  // comm.cpp
 void spmv_halo_end(TACSParallelMat *A);
 
 // TACSParallelMat::mult (TACSParallelMat.cpp:248-265): y = Aloc x + Bext x_ext, halo overlapped
-void TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
-  const bool dist = assembler->size > 1 && Bext.nnzb() > 0;
-  if (dist) spmv_halo_begin(this, x);
+int TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
+  const bool dist = assembler->size > 1;
+  int rc = 0;
+  // every rank takes part in the column halo (a rank without external columns may still have to send)
+  if (dist) rc = spmv_halo_begin(this, x);
   {
-    KernelTimer kt(K_SPMV);
-    cuda_ok(launch_spmv(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr, x->owned(),
-                        y->owned(), 0, ctx().num_sms, ctx().stream), "spmv");
+    KernelTimer kt(K_SPMV, spmv_kernel_name(Aloc.bsize, 0));
+    if (!cuda_ok(launch_spmv(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr, x->owned(),
+                             y->owned(), 0, ctx().num_sms, ctx().stream), "spmv")) rc = 1;
   }
   if (dist) {
     spmv_halo_end(this);
-    KernelTimer kt(K_SPMV);
-    cuda_ok(launch_spmv(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr, x_ext.ptr,
-                        y->owned() + (size_t)Bext.bsize * np, 1, ctx().num_sms, ctx().stream), "spmv ext");
+    if (Bext.nnzb() > 0) {
+      KernelTimer kt(K_SPMV, spmv_kernel_name(Bext.bsize, 1));
+      if (!cuda_ok(launch_spmv(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr, x_ext.ptr,
+                               y->owned() + (size_t)Bext.bsize * np, 1, ctx().num_sms, ctx().stream), "spmv ext"))
+        rc = 1;
+    }
   }
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

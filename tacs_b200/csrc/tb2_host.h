@@ -73,13 +73,14 @@ Context &ctx();
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
 enum KernelId { K_ELEMENT = 0, K_GATHER_RES, K_GATHER_MAT, K_BCS, K_SPMV, K_VEC, K_DOT, K_HALO, K_COUNT };
 struct KernelTimer {
-  explicit KernelTimer(KernelId id);
+  explicit KernelTimer(KernelId id, const char *name = nullptr);  // name: static string of the kernel launched
   ~KernelTimer();
   int slot;
 };
 void profile_enable(int on);
 // sums the recorded launches: ms[K_COUNT], count[K_COUNT]; clears the log
 int profile_collect(double *ms, long *count);
+const char *profile_named();  // "kernel name|launches|ms" lines of the last profile_collect
 int ctx_init(int device);  // 0 ok; prints to stderr and returns non-zero when no usable GPU is present
 bool cuda_ok(cudaError_t err, const char *what);
 
@@ -346,7 +347,7 @@ class TACSBVec : public Object {
   // TACSVec interface (KSM.h:91-115); reductions are over owned entries and all ranks
   double norm();
   double dot(TACSBVec *y);
-  void mdot(TACSBVec **ys, double *out, int n);
+  int mdot(TACSBVec **ys, double *out, int n);  // non-zero (and NaN results) when a launch / reduction failed
   void axpy(double alpha, TACSBVec *x);
   void axpby(double alpha, double beta, TACSBVec *x);
   void scale(double alpha);
@@ -373,7 +374,7 @@ class TACSParallelMat : public Object {
   DeviceArray<int> d_bc_rows_ext;  // Bext row (owned row - np) of each merged BC, or -1
   DeviceExchange x_cols;
   void zeroEntries();
-  void mult(TACSBVec *x, TACSBVec *y);
+  int mult(TACSBVec *x, TACSBVec *y);
   void applyBCs();
   TACSBVec *createVec();
 };
@@ -437,10 +438,10 @@ class TACSAssembler : public Object {
   TACSBVec *createVec();
   TACSBVec *createNodeVec();
   TACSParallelMat *createMat();
-  void setVariables(TACSBVec *q, TACSBVec *qdot, TACSBVec *qddot);
+  int setVariables(TACSBVec *q, TACSBVec *qdot, TACSBVec *qddot);
   void zeroVariables();
   void getNodes(TACSBVec *X);
-  void setNodes(TACSBVec *X);
+  int setNodes(TACSBVec *X);
   void applyBCs(TACSBVec *v);
   void applyBCs(TACSParallelMat *m);
   void setBCs(TACSBVec *v);
