@@ -31,28 +31,39 @@ struct ElemGroupArgs {
   const double *ddvars;      // [nlocal][bs] or null
   double alpha, gamma;
   int uncoupled;             // 1: every shell descriptor of the group has a zero membrane-bending block
-  double *Ke;                // staging [nelem][nn][nn][bs*bs] or null (residual only)
+  double *Ke;                // matrix staging or null (residual only); layout selected by `upper`
   double *Re;                // staging [nelem][nn*bs] or null
+  // upper = 0: Ke is [nelem][nn][nn][bs*bs], every directed node pair (element-level interface).
+  // upper = 1: Ke is [nelem][nn(nn+1)/2][bs*bs], node pairs i <= j only (plan.h upper_index); a directed pair (i, j)
+  //            whose dmap entry is >= 0 is written to block dmap[..] of `direct` instead (the BCSR value array) and
+  //            pairs i > j without a direct target are not written at all: the gather reads the mirror transposed.
+  int upper;
+  const int *dmap;           // [nelem][nn*nn] or null (no direct targets)
+  double *direct;            // value array of the matrix being assembled
 };
+
+// destination of the bs x bs block of the directed node pair (i, j) of element e; null: not stored
+template <int NN, int B2>
+__host__ __device__ inline double *pair_block_dst(const ElemGroupArgs &g, long e, int i, int j, int dm) {
+  if (!g.upper) return g.Ke + ((e * NN + i) * NN + j) * B2;
+  if (dm >= 0) return g.direct + (long)dm * B2;
+  if (i <= j) return g.Ke + (e * (NN * (NN + 1) / 2) + (i * NN - i * (i - 1) / 2 + (j - i))) * B2;
+  return nullptr;
+}
 
 size_t elem_tables_bytes(int kind);
 void elem_tables_build(int kind, void *host_dst);
 cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream_t s);
 const char *element_kernel_name(const ElemGroupArgs &g);
-inline const char *gather_blocks_kernel_name(int bs) { return bs == 6 ? "gather_blocks36_kernel" : "gather_blocks_kernel<9>"; }
-inline const char *gather_rows_kernel_name(int bs) { return bs == 6 ? "gather_rows_kernel<36>" : "gather_rows_kernel<9>"; }
+inline const char *gather_blocks_kernel_name(int bs) { return bs == 6 ? "gather_blocks36_kernel" : "gather_blocks9_kernel"; }
 inline const char *gather_residual_kernel_name(int bs) { return bs == 6 ? "gather_residual_kernel<6>" : "gather_residual_kernel<3>"; }
 inline const char *spmv_kernel_name(int bs, int add) {
   return bs == 6 ? (add ? "spmv6_kernel<1>" : "spmv6_kernel<0>") : (add ? "spmv3_kernel<1>" : "spmv3_kernel<0>");
 }
 
-cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int *src, const double *Ke,
-                                 double *A, int num_sms, cudaStream_t s);
-// row-strip form: gptr[nrows+1] contributions per owned row, gbase[p] first staging slot of strip p, gpptr/gpos
-// positions of the strip's blocks in the row buffer [Aloc row | Bext row]
-cudaError_t launch_gather_rows(int bs, int nrows, const int *gptr, const int *gbase, const int *gpptr, const int *gpos,
-                               const double *Ke, const int *rowpA, double *A, int np, const int *rowpB, double *B,
-                               int max_row_blocks, int num_sms, cudaStream_t s);
+// blocks gb_blk[0..nblocks) of A sum their staging sources src[ptr[g]..ptr[g+1]) (2*slot + transposed flag)
+cudaError_t launch_gather_blocks(int bs, long nblocks, const int *blk, const int *ptr, const int *src,
+                                 const double *Ke, double *A, int num_sms, cudaStream_t s);
 cudaError_t launch_gather_residual(int bs, long nnodes, const int *ptr, const int *src, const double *Re,
                                    double *res, int num_sms, cudaStream_t s);
 

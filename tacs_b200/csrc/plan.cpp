@@ -22,6 +22,22 @@ int kind_nodes(int kind) {
   return 0;
 }
 
+int shipped_pairs(int nn, unsigned mask) {
+  const int rest = nn - __builtin_popcount(mask);
+  return upper_pairs(nn) - upper_pairs(rest);
+}
+
+int shipped_rank(int nn, unsigned mask, int i, int j) {
+  int r = 0;
+  for (int a = 0; a < i; a++) {
+    if (mask & (1u << a)) r += nn - a;                           // every pair (a, a..nn-1) touches the mask
+    else r += __builtin_popcount(mask >> a);                     // pairs (a, b > a) with b masked
+  }
+  if (mask & (1u << i)) r += j - i;
+  else r += __builtin_popcount((mask >> i) & ((1u << (j - i)) - 1u));
+  return r;
+}
+
 int GlobalMesh::ownerOf(int node) const {
   return (int)(std::upper_bound(owner_range.begin(), owner_range.end(), node) - owner_range.begin()) - 1;
 }
@@ -123,17 +139,21 @@ int HostPlan::build(std::shared_ptr<const GlobalMesh> mesh, int _bs, int _rank, 
     }
     elem_block_base.assign(nelems, 0);
     elem_node_base.assign(nelems, 0);
-    local_blocks = local_node_slots = 0;
+    elem_pair_base.assign(nelems, 0);
+    local_blocks = local_node_slots = local_pairs = 0;
     for (size_t gi = 0; gi < group_kinds.size(); gi++) {
-      const long nn = kind_nodes(group_kinds[gi]);
+      const long nn = kind_nodes(group_kinds[gi]), nu = upper_pairs((int)nn);
       group_block_base.push_back(local_blocks);
       group_node_base.push_back(local_node_slots);
+      group_pair_base.push_back(local_pairs);
       for (size_t k = 0; k < group_elems[gi].size(); k++) {
-        elem_block_base[group_elems[gi][k]] = local_blocks + (long)k * nn * nn;
+        elem_block_base[group_elems[gi][k]] = local_blocks + (long)k * nu;
         elem_node_base[group_elems[gi][k]] = local_node_slots + (long)k * nn;
+        elem_pair_base[group_elems[gi][k]] = local_pairs + (long)k * nn * nn;
       }
-      local_blocks += (long)group_elems[gi].size() * nn * nn;
+      local_blocks += (long)group_elems[gi].size() * nu;
       local_node_slots += (long)group_elems[gi].size() * nn;
+      local_pairs += (long)group_elems[gi].size() * nn * nn;
     }
   }
 
@@ -153,12 +173,22 @@ int HostPlan::build(std::shared_ptr<const GlobalMesh> mesh, int _bs, int _rank, 
         else other = true;
       }
       if (p == rank) {
-        // rows of nodes owned elsewhere are shipped to their owners (TACSMatDistribute :801-834, 1154-1267)
+        // rows of nodes owned elsewhere are shipped to their owners (TACSMatDistribute :801-834, 1154-1267):
+        // the residual row of each such node, and once per owner the upper node-pair blocks that touch its nodes
         for (int k = 0; k < nn; k++)
           if (owners[k] != rank) {
             rows_send[owners[k]].push_back((int)(elem_node_base[local_index] + k));
-            for (int j = 0; j < nn; j++)
-              blocks_send[owners[k]].push_back((int)(elem_block_base[local_index] + (long)k * nn + j));
+            bool first = true;
+            for (int m = 0; m < k; m++)
+              if (owners[m] == owners[k]) { first = false; break; }
+            if (!first) continue;
+            unsigned mask = 0;
+            for (int m = k; m < nn; m++)
+              if (owners[m] == owners[k]) mask |= 1u << m;
+            for (int i = 0; i < nn; i++)
+              for (int j = i; j < nn; j++)
+                if ((mask >> i | mask >> j) & 1u)
+                  blocks_send[owners[k]].push_back((int)(elem_block_base[local_index] + upper_index(nn, i, j)));
           }
         local_index++;
       } else if (mine) {
@@ -219,28 +249,40 @@ int HostPlan::build(std::shared_ptr<const GlobalMesh> mesh, int _bs, int _rank, 
   std::vector<int> remote_node, remote_i;
   for (int p = 0; p < size; p++) {
     if (remote[p].empty()) continue;
+    int cur_elem = -1, cur_base = 0;
+    unsigned cur_mask = 0;
     for (const RemoteRow &rr : remote[p]) {
       const int b = g.ptr[rr.gelem], nn = g.ptr[rr.gelem + 1] - b;
+      if (rr.gelem != cur_elem) {
+        // the sender ships the element's blocks once: the upper pairs that touch my nodes (shipped_pairs / _rank)
+        cur_elem = rr.gelem;
+        cur_mask = 0;
+        for (int m = 0; m < nn; m++)
+          if (g.conn[b + m] >= lo && g.conn[b + m] < hi) cur_mask |= 1u << m;
+        cur_base = (int)(local_blocks + recv_blocks);
+        recv_blocks += shipped_pairs(nn, cur_mask);
+      }
       RowContribution rc;
       rc.gelem = rr.gelem;
       rc.nn = nn;
       rc.conn = &g.conn[b];
       rc.res_slot = (int)(local_node_slots + recv_node_slots);
-      rc.blk_base = (int)(local_blocks + recv_blocks);
+      rc.slot_base = cur_base;
+      rc.lelem = -1;
+      rc.mask = cur_mask;
       remote_rc.push_back(rc);
       remote_node.push_back(g.conn[b + rr.i] - lo);
       remote_i.push_back(rr.i);
       recv_node_slots += 1;
-      recv_blocks += nn;
     }
     rows.recv_peers.push_back(p);
     rows.recv_ptr.push_back((int)recv_node_slots);
     blocks.recv_peers.push_back(p);
     blocks.recv_ptr.push_back((int)recv_blocks);
   }
-  if (local_blocks + recv_blocks >= (1L << 31)) {
-    fprintf(stderr, "[%d] tacs_b200: %ld staging blocks exceed the 32-bit gather index\n", rank,
-            local_blocks + recv_blocks);
+  if (local_blocks + recv_blocks >= (1L << 30) || local_pairs >= (1L << 31)) {
+    fprintf(stderr, "[%d] tacs_b200: %ld staging blocks / %ld node pairs exceed the 32-bit gather index\n", rank,
+            local_blocks + recv_blocks, local_pairs);
     return 1;
   }
 
@@ -268,7 +310,9 @@ int HostPlan::build(std::shared_ptr<const GlobalMesh> mesh, int _bs, int _rank, 
         rc.nn = nn;
         rc.conn = &elem_conn_global[elem_ptr[e]];
         rc.res_slot = (int)(elem_node_base[e] + k);
-        rc.blk_base = (int)(elem_block_base[e] + (long)k * nn);
+        rc.slot_base = (int)elem_block_base[e];
+        rc.lelem = e;
+        rc.mask = 0;
         int pos = cursor[n - lo]++;
         adj[pos] = rc;
         adj_i[pos] = k;
@@ -370,73 +414,80 @@ int HostPlan::buildMatrix() {
     Aloc.rowp[r + 1] = (int)Aloc.cols.size();
     if (r >= np) Bext.rowp[r - np + 1] = (int)Bext.cols.size();
   }
-  // gather plan: staging slots of every block in ascending global element order
-  const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
-  a_ptr.assign(nnzA + 1, 0);
-  b_ptr.assign(nnzB + 1, 0);
-  auto locate = [&](int r, int gcol, bool &is_ext) -> long {
+  // Direct map and gather plan. Block index space: [Aloc blocks | Bext blocks].
+  const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb(), nnz = nnzA + nnzB;
+  auto locate = [&](int r, int gcol) -> long {
     if (gcol >= lo && gcol < hi) {
-      is_ext = false;
       const int *b = &Aloc.cols[0] + Aloc.rowp[r], *e = &Aloc.cols[0] + Aloc.rowp[r + 1];
       return std::lower_bound(b, e, gcol - lo) - &Aloc.cols[0];
     }
-    is_ext = true;
     int c = (int)(std::lower_bound(ext_col_nodes.begin(), ext_col_nodes.end(), gcol) - ext_col_nodes.begin());
     const int *b = &Bext.cols[0] + Bext.rowp[r - np], *e = &Bext.cols[0] + Bext.rowp[r - np + 1];
-    return std::lower_bound(b, e, c) - &Bext.cols[0];
+    return nnzA + (std::lower_bound(b, e, c) - &Bext.cols[0]);
   };
+  // pass 1: contributions per block; target block of every directed pair of the local elements. A block belongs to
+  // one row, so the row-parallel loop has a single writer per counter and per dmap entry.
+  std::vector<int> cnt(nnz, 0);
+  dmap.assign(local_pairs, -1);
   plan_parallel_for(nowned, [&](long r0, long r1) {
     for (long r = r0; r < r1; r++)
-      for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++)
-        for (int j = 0; j < adj[p].nn; j++) {
-          bool is_ext;
-          long pos = locate((int)r, adj[p].conn[j], is_ext);
-          (is_ext ? b_ptr : a_ptr)[pos + 1]++;
+      for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++) {
+        const RowContribution &rc = adj[p];
+        const int k = adj_i[p];
+        for (int j = 0; j < rc.nn; j++) {
+          const long t = locate((int)r, rc.conn[j]);
+          cnt[t]++;
+          if (rc.lelem >= 0) dmap[elem_pair_base[rc.lelem] + (long)k * rc.nn + j] = (int)t;
         }
+      }
   });
-  for (long k = 0; k < nnzA; k++) a_ptr[k + 1] += a_ptr[k];
-  for (long k = 0; k < nnzB; k++) b_ptr[k + 1] += b_ptr[k];
-  a_src.resize(a_ptr[nnzA]);
-  b_src.resize(b_ptr[nnzB]);
+  // pass 2: a pair is written directly when its block and the mirror block are fed by this element alone
+  std::vector<unsigned char> is_direct(nnz, 0);
+  plan_parallel_for(nelems, [&](long e0, long e1) {
+    for (long e = e0; e < e1; e++) {
+      const int nn = elem_ptr[e + 1] - elem_ptr[e];
+      int *dm = &dmap[elem_pair_base[e]];
+      for (int k = 0; k < nn; k++)
+        for (int j = k; j < nn; j++) {
+          const int t = dm[k * nn + j], t2 = dm[j * nn + k];
+          const bool direct = t >= 0 && t2 >= 0 && cnt[t] == 1 && cnt[t2] == 1;
+          if (direct) {
+            is_direct[t] = 1;
+            is_direct[t2] = 1;
+          } else {
+            dm[k * nn + j] = -1;
+            dm[j * nn + k] = -1;
+          }
+        }
+    }
+  });
+  // pass 3: gather lists of the remaining blocks, sources in (row, ascending global element, k, j) order
+  std::vector<int> gidx(nnz, -1);
+  gb_blk.clear();
+  gb_ptr.assign(1, 0);
+  direct_blocks = 0;
+  for (long t = 0; t < nnz; t++) {
+    if (is_direct[t]) {
+      direct_blocks++;
+      continue;
+    }
+    gidx[t] = (int)gb_blk.size();
+    gb_blk.push_back((int)t);
+    gb_ptr.push_back(gb_ptr.back() + cnt[t]);
+  }
+  gb_src.resize(gb_ptr.back());
   {
-    std::vector<int> acur(a_ptr.begin(), a_ptr.end() - 1), bcur(b_ptr.begin(), b_ptr.end() - 1);
+    std::vector<int> cur(gb_ptr.begin(), gb_ptr.end() - 1);
     plan_parallel_for(nowned, [&](long r0, long r1) {
       for (long r = r0; r < r1; r++)
-        for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++)
-          for (int j = 0; j < adj[p].nn; j++) {
-            bool is_ext;
-            long pos = locate((int)r, adj[p].conn[j], is_ext);
-            if (is_ext) b_src[bcur[pos]++] = adj[p].blk_base + j;
-            else a_src[acur[pos]++] = adj[p].blk_base + j;
+        for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++) {
+          const RowContribution &rc = adj[p];
+          const int k = adj_i[p];
+          for (int j = 0; j < rc.nn; j++) {
+            const int gi = gidx[locate((int)r, rc.conn[j])];
+            if (gi >= 0) gb_src[cur[gi]++] = rc.source(k, j);
           }
-    });
-  }
-  // row-strip form of the same plan
-  max_row_blocks = 0;
-  for (int r = 0; r < nowned; r++) {
-    const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];
-    const int nB = (r >= np) ? Bext.rowp[r - np + 1] - Bext.rowp[r - np] : 0;
-    if (nA + nB > max_row_blocks) max_row_blocks = nA + nB;
-  }
-  if (force_row_plan || rowPlanEligible()) {
-    const size_t ncontrib = adj.size();
-    g_base.resize(ncontrib);
-    g_pptr.assign(ncontrib + 1, 0);
-    for (size_t p = 0; p < ncontrib; p++) {
-      g_base[p] = adj[p].blk_base;
-      g_pptr[p + 1] = g_pptr[p] + adj[p].nn;
-    }
-    g_pos.resize(g_pptr[ncontrib]);
-    plan_parallel_for(nowned, [&](long r0, long r1) {
-      for (long r = r0; r < r1; r++) {
-        const int nA = Aloc.rowp[r + 1] - Aloc.rowp[r];
-        for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++)
-          for (int j = 0; j < adj[p].nn; j++) {
-            bool is_ext;
-            long pos = locate((int)r, adj[p].conn[j], is_ext);
-            g_pos[g_pptr[p] + j] = is_ext ? nA + (int)(pos - Bext.rowp[r - np]) : (int)(pos - Aloc.rowp[r]);
-          }
-      }
+        }
     });
   }
   // receive side of the column halo: ext_col_nodes is sorted, each owner's columns are contiguous

@@ -45,13 +45,31 @@ struct HostBCSR {
   long nnzb() const { return rowp.empty() ? 0 : rowp[nrows]; }
 };
 
+// Matrix staging keeps the node pairs (i, j) with i <= j of an element only (the element matrices of the path are
+// symmetric: K = sum B^T C B with a symmetric C, likewise the mass matrix): nn(nn+1)/2 slots per element, row-major
+// over the upper triangle. The block of the directed pair (k, j) with k > j is the transpose of slot (j, k).
+inline int upper_pairs(int nn) { return nn * (nn + 1) / 2; }
+inline int upper_index(int nn, int i, int j) { return i * nn - i * (i - 1) / 2 + (j - i); }  // i <= j
+// Blocks shipped to the owner of some of an element's nodes (bit set `mask`): the upper pairs that touch a masked
+// node, in ascending upper_index order. Both ends of the exchange evaluate these two functions.
+int shipped_pairs(int nn, unsigned mask);
+int shipped_rank(int nn, unsigned mask, int i, int j);  // position of pair (i <= j) inside the shipped set
+
 // one (element, local node) pair that contributes to an owned matrix/residual row
 struct RowContribution {
   int gelem;        // global element id (summation order key)
   int nn;           // nodes of the element
   const int *conn;  // its connectivity in global (new) numbering
   int res_slot;     // residual staging slot (units of one node block)
-  int blk_base;     // staging slot of block (i, 0) (units of one bs x bs block); +j for column node j
+  int slot_base;    // first matrix staging slot of the element (local) / of its shipped set (received)
+  int lelem;        // local element index, or -1 when the element belongs to another rank
+  unsigned mask;    // received contributions: the element's nodes owned by this rank (defines the shipped set)
+  // staging source of the directed pair (k, j) of this element: 2 * slot + (1 when the slot holds the transpose)
+  int source(int k, int j) const {
+    const int i0 = k < j ? k : j, j0 = k < j ? j : k;
+    const int off = lelem >= 0 ? upper_index(nn, i0, j0) : shipped_rank(nn, mask, i0, j0);
+    return 2 * (slot_base + off) + (k > j ? 1 : 0);
+  }
 };
 
 struct HostPlan {
@@ -65,8 +83,9 @@ struct HostPlan {
   std::vector<int> elem_kind;                // per local element (ElemKind)
   std::vector<int> group_kinds;              // distinct kinds in first-appearance order
   std::vector<std::vector<int>> group_elems; // local element ids of each group
-  std::vector<long> group_block_base, group_node_base;
-  std::vector<long> elem_block_base, elem_node_base;  // per local element
+  std::vector<long> group_block_base, group_node_base, group_pair_base;
+  std::vector<long> elem_block_base, elem_node_base, elem_pair_base;  // per local element (pair_base: units of nn^2)
+  long local_pairs = 0;                               // sum of nn^2 over the local elements
   long local_blocks = 0, local_node_slots = 0;        // staging produced by this rank's element kernels
   long recv_blocks = 0, recv_node_slots = 0;          // staging received from other ranks (tail region)
   // contributions to owned rows, ascending (owned row, global element)
@@ -80,17 +99,15 @@ struct HostPlan {
   HostBCSR Aloc, Bext;
   int np = 0;
   std::vector<int> ext_col_nodes;
-  std::vector<int> a_ptr, a_src, b_ptr, b_src;
-  // row-strip gather plan (what the device uses): contribution p of owned row r (adj_ptr order = ascending global
-  // element) is the contiguous strip of nn staging blocks starting at slot g_base[p]; block j of the strip goes to
-  // block g_pos[g_pptr[p] + j] of the row's buffer [Aloc row blocks | Bext row blocks]
-  std::vector<int> g_base, g_pptr;
-  std::vector<int> g_pos;
-  int max_row_blocks = 0;
-  // The row-strip arrays are built only where the device uses them (one rank, 3x3 blocks, short rows -- see
-  // TACSParallelMat) or when a test asks for them: for C5 they would be 729 M host integers nobody reads.
-  bool force_row_plan = false;
-  bool rowPlanEligible() const { return size == 1 && bs == 3 && max_row_blocks * bs * bs <= 256; }
+  // Matrix values live in one array [Aloc blocks | Bext blocks]; "block index" below is an index into it.
+  // direct map: for the directed node pair (k, j) of local element e, dmap[elem_pair_base[e] + k*nn + j] is the
+  // block index the element kernel writes straight into -- possible when that block and its mirror (j, k) each have
+  // exactly one contribution and both rows are owned here -- or -1 (the pair goes through the staging area).
+  std::vector<int> dmap;
+  // gather plan of all other blocks: block gb_blk[g] sums the staging sources gb_src[gb_ptr[g] .. gb_ptr[g+1])
+  // (RowContribution::source encoding) in ascending global element order -- the order of the reference's serial loop
+  std::vector<int> gb_blk, gb_ptr, gb_src;
+  long direct_blocks = 0;
   // neighbour exchanges (empty on one rank)
   ExchangePlan state;   // chunk = one node block of a state vector: owned node -> ext slots of peers
   ExchangePlan cols;    // chunk = one node block of x: owned node -> x_ext of peers (SpMV)

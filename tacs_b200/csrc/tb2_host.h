@@ -327,7 +327,12 @@ struct BCSRPattern {
   int bsize = 0, nrows = 0, ncols = 0;
   std::vector<int> rowp, cols;  // host copies (bit-exact parity target)
   DeviceArray<int> d_rowp, d_cols;
-  DeviceArray<double> d_vals;  // bsize^2 * nnzb, 64-bit offsets
+  // bsize^2 * nnzb values, 64-bit offsets: a view into the owning matrix's single value array [Aloc | Bext]
+  struct ValuesView {
+    double *ptr = nullptr;
+    size_t count = 0;
+    bool download(double *host, size_t n) const;
+  } d_vals;
   long nnzb() const { return rowp.empty() ? 0 : rowp[nrows]; }
 };
 
@@ -365,11 +370,7 @@ class TACSParallelMat : public Object {
   BCSRPattern Aloc, Bext;
   int np = 0;                      // first owned row with an off-rank column (rows of Bext start here)
   std::vector<int> ext_col_nodes;  // ascending global node ids of the external columns
-  // gather plan: staging slots of every block, ascending element order
-  DeviceArray<int> a_ptr, a_src, b_ptr, b_src;  // per-block form (kept on the host plan; uploaded only as fallback)
-  DeviceArray<int> g_base, g_pptr, g_pos;       // row-strip form (HostPlan::g_*), rows indexed by the assembler's r_ptr
-  int max_row_blocks = 0;
-  bool row_gather = false;
+  DeviceArray<double> vals_all;  // [Aloc blocks | Bext blocks]: the block index space of the direct map / gather plan
   DeviceArray<double> x_ext;  // external column values for the SpMV halo
   DeviceArray<int> d_bc_rows_ext;  // Bext row (owned row - np) of each merged BC, or -1
   DeviceExchange x_cols;
@@ -422,6 +423,7 @@ struct ElemGroup {
   long nelem = 0;
   std::vector<int> local_elems;  // local element indices in this group (ascending)
   DeviceArray<int> d_conn, d_desc;
+  DeviceArray<int> d_dmap;  // [nelem][nn*nn] direct map (HostPlan::dmap), uploaded with the first matrix
   DeviceArray<unsigned char> d_tables;
   long block_base = 0;  // first staging slot (units of one bs x bs block) of this group
   long node_base = 0;   // first residual staging slot (units of one node block)
@@ -481,6 +483,11 @@ class TACSAssembler : public Object {
   DeviceArray<double> Ke, Re;
   long total_blocks = 0, total_node_slots = 0;
   DeviceArray<int> r_ptr, r_src;
+  // matrix gather plan (HostPlan::gb_*), shared by every matrix of this assembler; uploaded with the first matrix
+  DeviceArray<int> gb_blk, gb_ptr, gb_src;
+  long num_gather_blocks = 0;
+  bool mat_plan_ready = false;
+  int uploadMatPlan();
   std::unique_ptr<HostPlan> plan;
   DeviceExchange x_state, x_rows, x_blocks;
   int localNode(int global) const;
