@@ -55,8 +55,7 @@ UNIT = "elements/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed `ncu --set full` capture of this
 # same command at the default workload (TRAFFIC_SOURCE); reported only when the run uses that workload on one GPU.
 TRAFFIC_SOURCE = "profiles/r1_n_kernels_ncu.txt"
-NCU_TRAFFIC_BYTES = {"shell4_mma_kernel": 0.142545e9 + 4.742443e9, "gather_blocks36_kernel": 4.744081e9 + 2.584352e9,
-                     "spmv6_kernel<0>": 2.689707e9 + 0.050150e9}
+NCU_TRAFFIC_BYTES = {"spmv6_kernel<0>": 2.689707e9 + 0.050150e9}
 # minimal-algorithm flops per element used for the FP64 roofline
 FLOPS_PER_ELEMENT = {1: 57e3, 2: 551e3, 3: 69e3, 4: 2.28e6}
 KIND_NN = {1: 4, 2: 9, 3: 8, 4: 27}
@@ -395,14 +394,24 @@ def collect_profile(lib, steps):
     return out
 
 
-def kernel_rooflines(kind, nelem_local, nnzb_local, prof, fp64_peak, hbm_peak, world, default_workload):
+def plan_stats(lib, asm):
+    out = (C.c_long * 8)()
+    lib.assembler_get_plan_stats(asm.h, out)
+    names = ["local_slots", "recv_slots", "direct_blocks", "staged_blocks", "gather_blocks", "gather_sources",
+             "blocks", "node_pairs"]
+    return dict(zip(names, (int(v) for v in out)))
+
+
+def kernel_rooflines(kind, nelem_local, stats, prof, fp64_peak, hbm_peak, world, default_workload):
     """Roofline entries of the kernels of one assembleJacobian step, named by what was launched."""
     nn, bs = KIND_NN[kind], KIND_BS[kind]
     b2 = bs * bs
-    # algorithmic HBM bytes per launch (DESIGN.md): the element kernel reads X/u/conn and writes the staging
-    # blocks + residual slots; the block gather reads the staging blocks and the plan and writes A once.
-    elem_bytes = nelem_local * (nn * (3 + bs) * 8 + nn * 4 + 4 + nn * nn * b2 * 8 + nn * bs * 8)
-    gather_bytes = nelem_local * nn * nn * (b2 * 8 + 4) + nnzb_local * (b2 * 8 + 4)
+    # algorithmic HBM bytes per launch (DESIGN.md): the element kernel reads X/u/conn/direct map and writes the upper
+    # node-pair blocks that need staging, the blocks it owns alone straight into the matrix, and the residual slots;
+    # the block gather reads its sources (staging blocks + 4-byte source codes) and writes each remaining block once.
+    elem_bytes = (nelem_local * (nn * (3 + bs) * 8 + nn * 4 + 4 + nn * bs * 8) + stats["node_pairs"] * 4 +
+                  (stats["staged_blocks"] + stats["direct_blocks"]) * b2 * 8)
+    gather_bytes = stats["gather_sources"] * (b2 * 8 + 4) + stats["gather_blocks"] * (b2 * 8 + 8)
     kernels = []
     for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         entry = {"kernel": name, "ms": ms, "launches_per_step": cnt}
@@ -455,14 +464,15 @@ def time_config(D, lib, asm, A, res, x, y, kind, nelem_total, steps, fp64_peak, 
     bs = sizes_a[0]
     sp_bytes_local = spmv_bytes(bs, sizes_a[1], sizes_a[3] + sizes_b[3])
     sp_bytes = D.sum(float(sp_bytes_local))
-    kernels = kernel_rooflines(kind, nelem_local, sizes_a[3] + sizes_b[3], prof, fp64_peak, hbm_peak, D.world,
-                               default_workload)
+    stats = plan_stats(lib, asm)
+    kernels = kernel_rooflines(kind, nelem_local, stats, prof, fp64_peak, hbm_peak, D.world, default_workload)
     spmv_names = sorted(n for n in prof if n.startswith("spmv")) or [f"spmv{bs}_kernel<0>"]
     spmv = {"kernel": "spmv6_kernel<0>" if bs == 6 else "spmv3_kernel<0>", "ms": ms_spmv, "bound": "hbm",
             "achieved": sp_bytes / (ms_spmv * 1e-3) * 1e-9, "peak": hbm_peak * D.world, "unit": "GB/s",
             "bytes_per_launch": sp_bytes, "note": "aggregate over all ranks; peak = ranks x measured HBM peak"}
     spmv["frac"] = spmv["achieved"] / spmv["peak"]
     return {"ms": ms, "ms_res": ms_res, "ms_spmv": ms_spmv, "launches": int(launches), "kernels": kernels,
+            "plan": stats,
             "spmv": spmv, "value": nelem_total / (ms * 1e-3), "spmv_kernel_names": spmv_names}
 
 
@@ -568,7 +578,7 @@ def run_extra(D, lib, T, meshgen, name, steps, fp64_peak, hbm_peak, gmres_m):
            "partition": "METIS (rank 0, broadcast)" if D.world > 1 else "single rank",
            "elements": nelem_total, "jac_ms": r["ms"], "elements_per_s": r["value"], "res_ms": r["ms_res"],
            "spmv_ms": r["ms_spmv"], "spmv_gbs_aggregate": r["spmv"]["achieved"], "spmv_frac_of_hbm_peak": r["spmv"]["frac"],
-           "kernels": r["kernels"], "ynorm": y.norm(), "resnorm": res.norm(), "setup_s": setup,
+           "kernels": r["kernels"], "plan": r["plan"], "ynorm": y.norm(), "resnorm": res.norm(), "setup_s": setup,
            "local_elements_rank0": asm.getNumElements()}
     if name == "c4":
         out["fullsize"] = fullsize_check(D, "c4", res, y, idx)
@@ -718,7 +728,7 @@ def run_b200(args):
                    "partition": "METIS element partition (TACSCreator::partitionMesh on rank 0, broadcast)"
                    if world > 1 else "single rank",
                    "strong_scaling": "see c4 / c3 / c5: fixed problems partitioned over the N GPUs"},
-        "roofline": roofline, "kernels": kernels, "spmv": spmv,
+        "roofline": roofline, "kernels": kernels, "plan": r["plan"], "spmv": spmv,
         "assemble_res": {"ms": r["ms_res"], "value": nelem_total / (r["ms_res"] * 1e-3), "unit": UNIT,
                          "note": "assembleRes alone (SURVEY 8d metric i), same mesh and state"},
         "cpu_baseline": cpu,

@@ -225,6 +225,11 @@ double tacsb200_time_assemble_res(tacsb200_handle a, tacsb200_handle res, int re
 double tacsb200_time_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y, int reps);
 
 
+/* Plan statistics behind bench.py's algorithmic byte counts, valid after the first createMat: out[8] =
+   {local staging slots, received staging slots, blocks written directly by the element kernels, upper node-pair
+   blocks staged by the element kernels, gathered blocks, gather sources, blocks of [Aloc | Bext], local node pairs}. */
+int tacsb200_assembler_get_plan_stats(tacsb200_handle assembler, long *out);
+
 /* Per-kernel device timing: when enabled every launch is bracketed by CUDA events on the launching
    stream. collect() synchronises, sums the log into ms[8] / count[8] indexed by
    {0 element, 1 residual gather, 2 block gather, 3 boundary conditions, 4 SpMV, 5 vector, 6 dot, 7 halo}

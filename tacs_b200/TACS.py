@@ -454,5 +454,5 @@ class Plan(_Obj):
 
     def scalars(self):
         names = ["nelems", "nowned", "nlocal", "ext_before", "ext_after", "np", "local_blocks", "recv_blocks",
-                 "local_node_slots", "recv_node_slots"]
+                 "local_node_slots", "recv_node_slots", "direct_blocks"]
         return dict(zip(names, (int(v) for v in self.array("scalars"))))

@@ -124,6 +124,7 @@ PRODUCT_ONLY = {
     "time_mat_mult": (D, [H, H, H, I]),
     "creator_create_plan": (H, [H, I, I]),
     "plan_get_array": (I, [H, C.c_char_p, IP]),
+    "assembler_get_plan_stats": (I, [H, C.POINTER(C.c_long)]),
     "profile_enable": (I, [I]),
     "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
     "profile_named": (C.c_char_p, []),

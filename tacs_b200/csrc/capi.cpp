@@ -281,18 +281,17 @@ int tacsb200_plan_get_array(tacsb200_handle plan, const char *name, int *out) {
   else if (n == "Bext_rowp") v = &P.Bext.rowp;
   else if (n == "Bext_cols") v = &P.Bext.cols;
   else if (n == "ext_col_nodes") v = &P.ext_col_nodes;
-  else if (n == "a_ptr") v = &P.a_ptr;
-  else if (n == "a_src") v = &P.a_src;
-  else if (n == "b_ptr") v = &P.b_ptr;
-  else if (n == "b_src") v = &P.b_src;
-  else if (n == "g_base") v = &P.g_base;
-  else if (n == "g_pptr") v = &P.g_pptr;
-  else if (n == "g_pos") v = &P.g_pos;
+  else if (n == "dmap") v = &P.dmap;
+  else if (n == "gb_blk") v = &P.gb_blk;
+  else if (n == "gb_ptr") v = &P.gb_ptr;
+  else if (n == "gb_src") v = &P.gb_src;
+  else if (n == "elem_block_base") { tmp.assign(P.elem_block_base.begin(), P.elem_block_base.end()); v = &tmp; }
+  else if (n == "elem_pair_base") { tmp.assign(P.elem_pair_base.begin(), P.elem_pair_base.end()); v = &tmp; }
   else if (n == "r_ptr") v = &P.r_ptr;
   else if (n == "r_src") v = &P.r_src;
   else if (n == "scalars") {
     tmp = {P.nelems, P.nowned, P.nlocal, P.ext_before, P.ext_after, P.np, (int)P.local_blocks, (int)P.recv_blocks,
-           (int)P.local_node_slots, (int)P.recv_node_slots};
+           (int)P.local_node_slots, (int)P.recv_node_slots, (int)P.direct_blocks};
     v = &tmp;
   } else if (!(v = ex("state", P.state)) && !(v = ex("cols", P.cols)) && !(v = ex("rows", P.rows)) &&
              !(v = ex("blocks", P.blocks))) {
@@ -311,6 +310,22 @@ int tacsb200_assembler_get_vars_per_node(tacsb200_handle a) { ASM(a); return t->
 int tacsb200_assembler_get_num_nodes(tacsb200_handle a) { ASM(a); return t->getNumNodes(); }
 int tacsb200_assembler_get_num_owned_nodes(tacsb200_handle a) { ASM(a); return t->getNumOwnedNodes(); }
 int tacsb200_assembler_get_num_elements(tacsb200_handle a) { ASM(a); return t->getNumElements(); }
+/* plan statistics behind the roofline byte counts: {staging slots (local), staging slots (received), blocks written
+   directly by the element kernels, upper node-pair blocks staged by the element kernels, gathered blocks, gather
+   sources, total blocks [Aloc | Bext], local node pairs}; valid after the first createMat */
+int tacsb200_assembler_get_plan_stats(tacsb200_handle a, long *out) {
+  ASM(a);
+  HostPlan &P = *t->plan;
+  out[0] = P.local_blocks;
+  out[1] = P.recv_blocks;
+  out[2] = P.direct_blocks;
+  out[3] = P.staged_blocks;
+  out[4] = (long)P.gb_blk.size();
+  out[5] = (long)P.gb_src.size();
+  out[6] = P.Aloc.nnzb() + P.Bext.nnzb();
+  out[7] = P.local_pairs;
+  return P.has_matrix ? 0 : 1;
+}
 int tacsb200_assembler_get_owner_range(tacsb200_handle a, int *lo, int *hi) {
   ASM(a);
   *lo = t->owner_range[t->rank];

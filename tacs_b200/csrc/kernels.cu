@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
     for (int k = 0; k < 36; k++) acc[k] = 0.0;
     const bool has_tile = tid < n * n;
     const int ti = tid / n, tj = tid % n;
+    // direct target of this thread's node pair (requested now, used after the quadrature loop)
+    const int dm = (g.Ke && g.dmap && has_tile) ? __ldg(g.dmap + e * (n * n) + tid) : -1;
     if (g.Ke) {
       double *rpart = w.rpart();
       for (int q0 = 0; q0 < nq; q0 += QC) {
@@ -211,8 +213,8 @@ __global__ void __launch_bounds__(ShellFamily<O>::TEAM *ShellFamily<O>::TEAMS, S
       }
       if (has_tile) {
         shell_p6_finish<O>(tid, w, tab, desc, g.alpha, g.gamma, inertia, acc, rpart + 6 * tid);
-        if (live) {
-          double2 *dst = reinterpret_cast<double2 *>(g.Ke + ((e * n + ti) * n + tj) * 36);
+        double2 *dst = live ? reinterpret_cast<double2 *>(pair_block_dst<n, 36>(g, e, ti, tj, dm)) : nullptr;
+        if (dst) {
 #pragma unroll
           for (int k = 0; k < 18; k++) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
         }
@@ -360,13 +362,31 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
   for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
   // staging offsets of this lane's C fragments: rows 8 mt + gq, column pairs 8 nt + 2 tq (node-pair-major 6x6 blocks)
   const int fo = (tq >> 1) * Work::HS + 2 * gq + (tq & 1);  // this lane's fragment inside a half-split row panel
-  int ro[3], co[3];
+  // Store plan of this lane's nine C fragments (row tile mt: rows 8 mt + gq, column tile nt: column pair 8 nt + 2 tq).
+  // A fragment lies inside one node pair (i, j) = (row / 6, col / 6). Its offset in the element's staging image is
+  // separable, rowS[mt] + colS[nt]: the upper layout puts pair (i <= j) at slot f(i) + j (plan.h upper_index), the
+  // element-level layout at 4 i + j. upmask: fragments that are staged at all (i <= j; all of them for the
+  // element-level layout). Direct targets are looked up for the diagonal pairs i + j = 3 only -- the plan offers no
+  // others for this family (HostPlan direct candidates) -- at dmap[16 e + dmo[mt]]; candmask marks those fragments.
+  int rowS[3], colS[3], rowD[3], colD[3], dmo[3];
+  unsigned upmask = 0, candmask = 0;
 #pragma unroll
   for (int t = 0; t < 3; t++) {
-    const int R = 8 * t + gq, C = 8 * t + 2 * tq;
-    ro[t] = (R / 6) * (n * 36) + (R % 6) * 6;
-    co[t] = (C / 6) * 36 + C % 6;
+    const int R = 8 * t + gq, C = 8 * t + 2 * tq, i = R / 6, j = C / 6;
+    rowD[t] = (R % 6) * 6;
+    colD[t] = C % 6;
+    rowS[t] = (g.upper ? (i * n - ((i * (i - 1)) >> 1) - i) : i * n) * 36 + rowD[t];
+    colS[t] = j * 36 + colD[t];
+    dmo[t] = i * n + (n - 1 - i);
   }
+#pragma unroll
+  for (int mt = 0; mt < 3; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 3; nt++) {
+      const int i = (8 * mt + gq) / 6, j = (8 * nt + 2 * tq) / 6;
+      if (i <= j || !g.upper) upmask |= 1u << (3 * mt + nt);
+      if (i + j == n - 1) candmask |= 1u << (3 * mt + nt);
+    }
   __syncwarp();
 
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
@@ -385,6 +405,8 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
     __syncwarp();
     prefetch_data();                                            // next element (ids already here)
     prefetch_ids(clamp_elem(base + 2 * nteams + team_in_cta));  // element after next
+    if (g.dmap && g.Ke && tid == 15)  // the 64-byte direct-map row of the next element (read at its store phase)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(g.dmap + clamp_elem(base + nteams + team_in_cta) * (n * n)));
     if (tid < n) shell_p1_node<O>(tid, w, tab, desc);
     __syncwarp();
     if (tid < nty) shell_p2_tying<O>(tid, w, tab);
@@ -548,13 +570,22 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
         if (tq == 0) x.scr[Work::oRes + 8 * mt + gq] = r;
       }
       if (live_o) {
-        double *dst = g.Ke + eo * (n * n * 36);
+        double *const kbase = g.Ke + eo * (g.upper ? (n * (n + 1) / 2) * 36 : n * n * 36);
 #pragma unroll
-        for (int mt = 0; mt < 3; mt++)
+        for (int mt = 0; mt < 3; mt++) {
+          const int dmi = g.dmap ? __ldg(g.dmap + eo * (n * n) + dmo[mt]) : -1;
+          double *const drow = g.direct + (long)dmi * 36 + rowD[mt];
+          double *const srow = kbase + rowS[mt];
 #pragma unroll
-          for (int nt = 0; nt < 3; nt++)
-            *reinterpret_cast<double2 *>(dst + ro[mt] + co[nt]) =
-                make_double2(g.alpha * kacc[el][mt][nt][0], g.alpha * kacc[el][mt][nt][1]);
+          for (int nt = 0; nt < 3; nt++) {
+            const unsigned bit = 1u << (3 * mt + nt);
+            const bool direct = (candmask & bit) && dmi >= 0;
+            double *dst = direct ? drow + colD[nt] : srow + colS[nt];
+            if (direct || (upmask & bit))
+              *reinterpret_cast<double2 *>(dst) =
+                  make_double2(g.alpha * kacc[el][mt][nt][0], g.alpha * kacc[el][mt][nt][1]);
+          }
+        }
       }
     }
     __syncwarp();
@@ -571,8 +602,11 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
         for (int b = 0; b < 6; b++) sacc += M[6 * a + b] * w.avec()[6 * j + b];
         rp[a] = sacc;
       }
-      if (live) {
-        double2 *dst = reinterpret_cast<double2 *>(g.Ke + (e * (n * n) + tid) * 36);
+      double2 *dst = nullptr;
+      if (live)
+        dst = reinterpret_cast<double2 *>(
+            pair_block_dst<n, 36>(g, e, tid / n, j, g.dmap ? __ldg(g.dmap + e * (n * n) + tid) : -1));
+      if (dst) {
 #pragma unroll
         for (int k = 0; k < 18; k++) {
           double2 v = dst[k];
@@ -686,17 +720,15 @@ __device__ __forceinline__ void q9_contract_rows(const double *L, int fo, double
 
 // residual rows K u of the warp's tile rows, alpha, tangent fragments to the node-pair-major staging area
 template <int W>
-__device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, double alpha, double *Ke_elem,
-                                          double (&kacc)[3][7][2]) {
+__device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, double alpha, const ElemGroupArgs &g,
+                                          long e, double (&kacc)[3][7][2]) {
   using Work = ShellQ9MmaWork;
   constexpr int MTS = (W == 0) ? 3 : 2, nd = Work::nd, n = Work::n;
   double2 up[7];
-  int co[7];
 #pragma unroll
   for (int nt = 0; nt < 7; nt++) {
     const int C = 8 * nt + 2 * tq;
     up[nt] = C < nd ? *reinterpret_cast<const double2 *>(x.uvec() + C) : make_double2(0.0, 0.0);
-    co[nt] = (C / 6) * 36 + C % 6;
   }
 #pragma unroll
   for (int i = 0; i < MTS; i++) {
@@ -709,12 +741,18 @@ __device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, dou
     r += __shfl_xor_sync(0xffffffffu, r, 2);
     if (R < nd) {
       if (tq == 0) x.scr[Work::oRes + R] = r;
-      if (Ke_elem) {
-        double *dst = Ke_elem + (R / 6) * (n * 36) + (R % 6) * 6;
+      const int ni = R / 6;
+      const int *dmrow = g.dmap ? g.dmap + e * (n * n) + ni * n : nullptr;
 #pragma unroll
-        for (int nt = 0; nt < 7; nt++)
-          if (8 * nt + 2 * tq < nd)
-            *reinterpret_cast<double2 *>(dst + co[nt]) = make_double2(alpha * kacc[i][nt][0], alpha * kacc[i][nt][1]);
+      for (int nt = 0; nt < 7; nt++) {
+        const int C = 8 * nt + 2 * tq;
+        if (C < nd) {
+          const int nj = C / 6;
+          double *dst = pair_block_dst<n, 36>(g, e, ni, nj, dmrow ? __ldg(dmrow + nj) : -1);
+          if (dst)
+            *reinterpret_cast<double2 *>(dst + (R % 6) * 6 + C % 6) =
+                make_double2(alpha * kacc[i][nt][0], alpha * kacc[i][nt][1]);
+        }
       }
     }
   }
@@ -848,10 +886,9 @@ __global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_
       else q9_contract_rows<2>(L, fo, kacc);
       __syncthreads();
     }
-    double *Ke_elem = g.Ke + e * (long)(n * n * 36);
-    if (warp == 0) q9_finish<0>(w, gq, tq, g.alpha, Ke_elem, kacc);
-    else if (warp == 1) q9_finish<1>(w, gq, tq, g.alpha, Ke_elem, kacc);
-    else q9_finish<2>(w, gq, tq, g.alpha, Ke_elem, kacc);
+    if (warp == 0) q9_finish<0>(w, gq, tq, g.alpha, g, e, kacc);
+    else if (warp == 1) q9_finish<1>(w, gq, tq, g.alpha, g, e, kacc);
+    else q9_finish<2>(w, gq, tq, g.alpha, g, e, kacc);
     __syncthreads();
     if (inertia) {
       if (tid < n * n) {
@@ -867,13 +904,16 @@ __global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_
           for (int b = 0; b < 6; b++) sacc += M[6 * a + b] * w.avec()[6 * j + b];
           rp[a] = sacc;
         }
-        double2 *dst = reinterpret_cast<double2 *>(Ke_elem + tid * 36);
+        double2 *dst = reinterpret_cast<double2 *>(
+            pair_block_dst<n, 36>(g, e, tid / n, j, g.dmap ? __ldg(g.dmap + e * (n * n) + tid) : -1));
+        if (dst) {
 #pragma unroll
-        for (int k = 0; k < 18; k++) {
-          double2 v = dst[k];
-          v.x += g.gamma * M[2 * k];
-          v.y += g.gamma * M[2 * k + 1];
-          dst[k] = v;
+          for (int k = 0; k < 18; k++) {
+            double2 v = dst[k];
+            v.x += g.gamma * M[2 * k];
+            v.y += g.gamma * M[2 * k + 1];
+            dst[k] = v;
+          }
         }
       }
       __syncthreads();
@@ -1005,30 +1045,72 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS, S
         // hex8: every lane owns a 2x2 patch of 3x3 node-pair blocks. Written straight from registers a warp store
         // touches 32 different lines with 8-byte pieces (ncu: 4x sector amplification, lg throttle), so the element
         // matrix is laid out in staging order in shared memory (G and CB are dead after the last contraction) and
-        // the team writes it with coalesced 128-bit stores. Rows of patches are 152 doubles apart (8 mod 16) for the banks.
+        // the team writes it with coalesced 128-bit stores.
         double *kst = &w.G[0][0];
         static_assert(sizeof(w.G) + sizeof(w.CB) >= 4 * 152 * sizeof(double), "element matrix fits in G + CB");
+        if (!g.upper) {
+          // every node pair (element-level interface); rows of patches are 152 doubles apart (8 mod 16) for the banks
 #pragma unroll
-        for (int an = 0; an < 2; an++) {
-          double run[18];  // blocks (2 ti + an, 2 tj) and (2 ti + an, 2 tj + 1) are adjacent in the staging order
+          for (int an = 0; an < 2; an++) {
+            double run[18];  // blocks (2 ti + an, 2 tj) and (2 ti + an, 2 tj + 1) are adjacent in the staging order
 #pragma unroll
-          for (int bn = 0; bn < 2; bn++)
+            for (int bn = 0; bn < 2; bn++)
 #pragma unroll
-            for (int a = 0; a < 3; a++)
+              for (int a = 0; a < 3; a++)
 #pragma unroll
-              for (int b = 0; b < 3; b++) run[9 * bn + 3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
-          double2 *dst = reinterpret_cast<double2 *>(kst + ti * 152 + an * 72 + tj * 18);
+                for (int b = 0; b < 3; b++) run[9 * bn + 3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+            double2 *dst = reinterpret_cast<double2 *>(kst + ti * 152 + an * 72 + tj * 18);
 #pragma unroll
-          for (int k = 0; k < 9; k++) dst[k] = make_double2(run[2 * k], run[2 * k + 1]);
-        }
-        team_sync<TEAM>();
-        if (live) {
-          const double2 *src = reinterpret_cast<const double2 *>(kst);
-          double2 *dst = reinterpret_cast<double2 *>(g.Ke + e * (long)(nd * nd));
+            for (int k = 0; k < 9; k++) dst[k] = make_double2(run[2 * k], run[2 * k + 1]);
+          }
+          team_sync<TEAM>();
+          if (live) {
+            const double2 *src = reinterpret_cast<const double2 *>(kst);
+            double2 *dst = reinterpret_cast<double2 *>(g.Ke + e * (long)(nd * nd));
 #pragma unroll
-          for (int it = 0; it < (nd * nd / 2) / TEAM; it++) {
-            const int p = it * TEAM + tid;  // double2 index in staging order; 72 per row of patches
-            dst[p] = src[p + (p / 72) * 4];
+            for (int it = 0; it < (nd * nd / 2) / TEAM; it++) {
+              const int p = it * TEAM + tid;  // double2 index in staging order; 72 per row of patches
+              dst[p] = src[p + (p / 72) * 4];
+            }
+          }
+        } else {
+          // assembler layout: the upper node pairs form one contiguous image of 36 blocks (2592 bytes) per element;
+          // a pair with a direct target goes from the registers of its lane straight into the matrix (both the pair and
+          // its mirror are held by some lane), the remaining lower pairs are dropped. The slot of a direct upper pair
+          // is a hole the gather never reads; the coalesced copy writes whatever the image holds there.
+          constexpr int NU = n * (n + 1) / 2;
+          const int *dmp = (g.dmap && live) ? g.dmap + e * (n * n) : nullptr;
+          int dmv[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            // the plan offers direct targets for the body diagonals only (plan.h direct_candidate)
+            const int i = 2 * ti + (q >> 1), j = 2 * tj + (q & 1);
+            dmv[q] = (dmp && i + j == n - 1) ? __ldg(dmp + i * n + j) : -1;
+          }
+#pragma unroll
+          for (int an = 0; an < 2; an++)
+#pragma unroll
+            for (int bn = 0; bn < 2; bn++) {
+              const int i = 2 * ti + an, j = 2 * tj + bn, dm = dmv[2 * an + bn];
+              if (dm >= 0) {
+                double *dst = g.direct + (long)dm * 9;  // global
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                  for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+              } else if (i <= j) {
+                double *dst = kst + (i * n - i * (i - 1) / 2 + (j - i)) * 9;  // shared
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                  for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+              }
+            }
+          team_sync<TEAM>();
+          if (live) {
+            const double2 *src = reinterpret_cast<const double2 *>(kst);
+            double2 *dst = reinterpret_cast<double2 *>(g.Ke + e * (long)(NU * 9));
+            for (int p = tid; p < NU * 9 / 2; p += TEAM) dst[p] = src[p];
           }
         }
       } else if (has_tile && live) {
@@ -1037,12 +1119,14 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS, S
         for (int an = 0; an < TR / 3; an++)
 #pragma unroll
           for (int bn = 0; bn < TC / 3; bn++) {
-            const long na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
-            double *dst = g.Ke + ((e * n + na) * n + nb) * 9;
+            const int na = (TR / 3) * ti + an, nb = (TC / 3) * tj + bn;
+            double *dst = pair_block_dst<n, 9>(g, e, na, nb, g.dmap ? __ldg(g.dmap + (e * n + na) * n + nb) : -1);
+            if (dst) {
 #pragma unroll
-            for (int a = 0; a < 3; a++)
+              for (int a = 0; a < 3; a++)
 #pragma unroll
-              for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+                for (int b = 0; b < 3; b++) dst[3 * a + b] = acc[(3 * an + a) * TC + 3 * bn + b];
+            }
           }
       }
       team_sync<TEAM>();
@@ -1173,52 +1257,69 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
 // ------------------------------------------------------------------------------------------
 // gather: staging -> BCSR values / residual
 // ------------------------------------------------------------------------------------------
-// One thread per scalar entry of a block; the threads of a block read consecutive staging
-// addresses (coalesced) and every block is written exactly once.
-template <int B2>
-__global__ void __launch_bounds__(256) gather_blocks_kernel(long nblocks, const int *__restrict__ ptr,
-                                                           const int *__restrict__ src, const double *__restrict__ Ke,
-                                                           double *__restrict__ A) {
-  const long total = nblocks * B2;
+// Every block that is not written directly by the element kernels sums its staging sources. A source is
+// 2 * slot + t: slot = staging block of the upper node pair (i <= j) of a contributing element, t = 1 when the target
+// is the mirror pair (j, i) and the slot has to be read transposed. Sources are listed in ascending global element
+// order (the reference's summation order) and every block is written exactly once.
+//
+// 3x3 blocks: one thread per scalar entry, the nine threads of a block read one 72-byte staging block per step.
+__global__ void __launch_bounds__(256) gather_blocks9_kernel(long nblocks, const int *__restrict__ blk,
+                                                            const int *__restrict__ ptr, const int *__restrict__ src,
+                                                            const double *__restrict__ Ke, double *__restrict__ A) {
+  const long total = nblocks * 9;
   for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const long b = g / B2;
-    const int entry = (int)(g - b * B2);
+    const long b = g / 9;
+    const int entry = (int)(g - b * 9);
+    const int et = (entry % 3) * 3 + entry / 3;  // the same entry of the transposed block
     const int beg = __ldg(ptr + b), end = __ldg(ptr + b + 1);
     double s = 0.0;
     int k = beg;
-    // request the slots and then the values of four contributions before consuming any (memory-level
+    // request the sources and then the values of four contributions before consuming any (memory-level
     // parallelism); the sum is still formed in ascending element order
     for (; k + 4 <= end; k += 4) {
       const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1), s2 = __ldg(src + k + 2), s3 = __ldg(src + k + 3);
-      const double v0 = __ldg(Ke + (long)s0 * B2 + entry), v1 = __ldg(Ke + (long)s1 * B2 + entry);
-      const double v2 = __ldg(Ke + (long)s2 * B2 + entry), v3 = __ldg(Ke + (long)s3 * B2 + entry);
+      const double v0 = __ldg(Ke + (long)(s0 >> 1) * 9 + ((s0 & 1) ? et : entry));
+      const double v1 = __ldg(Ke + (long)(s1 >> 1) * 9 + ((s1 & 1) ? et : entry));
+      const double v2 = __ldg(Ke + (long)(s2 >> 1) * 9 + ((s2 & 1) ? et : entry));
+      const double v3 = __ldg(Ke + (long)(s3 >> 1) * 9 + ((s3 & 1) ? et : entry));
       s += v0;
       s += v1;
       s += v2;
       s += v3;
     }
-    for (; k < end; k++) s += __ldg(Ke + (long)__ldg(src + k) * B2 + entry);
-    A[g] = s;
+    for (; k < end; k++) {
+      const int s0 = __ldg(src + k);
+      s += __ldg(Ke + (long)(s0 >> 1) * 9 + ((s0 & 1) ? et : entry));
+    }
+    A[(long)__ldg(blk + b) * 9 + entry] = s;
   }
 }
 
-// 6x6 blocks: one thread per pair of entries (128-bit accesses); the slot indices and then the values of up
-// to four contributions are requested before any of them is consumed (memory-level parallelism), and the
-// sum is still formed in ascending element order.
-__global__ void __launch_bounds__(256) gather_blocks36_kernel(long nblocks, const int *__restrict__ ptr,
+// 6x6 blocks: one thread per pair of entries (row a, columns 2c and 2c+1). A plain source is one 128-bit load, a
+// transposed one two 64-bit loads from the same 288-byte block (rows 2c and 2c+1, column a).
+__device__ __forceinline__ double2 gather36_load(const double *__restrict__ Ke, int s, int direct_off, int trans_off) {
+  const double *base = Ke + (long)(s >> 1) * 36;
+  if (s & 1) return make_double2(__ldg(base + trans_off), __ldg(base + trans_off + 6));
+  return __ldg(reinterpret_cast<const double2 *>(base + direct_off));
+}
+
+__global__ void __launch_bounds__(256) gather_blocks36_kernel(long nblocks, const int *__restrict__ blk,
+                                                             const int *__restrict__ ptr,
                                                              const int *__restrict__ src,
-                                                             const double2 *__restrict__ Ke, double2 *__restrict__ A) {
+                                                             const double *__restrict__ Ke, double *__restrict__ A) {
   const long total = nblocks * 18;
   for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
     const long b = g / 18;
     const int entry = (int)(g - b * 18);
+    const int a = entry / 3, c = entry - 3 * a;
+    const int doff = 6 * a + 2 * c, toff = 12 * c + a;
     const int beg = __ldg(ptr + b), end = __ldg(ptr + b + 1);
     double2 s = make_double2(0.0, 0.0);
     int k = beg;
     for (; k + 4 <= end; k += 4) {
       const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1), s2 = __ldg(src + k + 2), s3 = __ldg(src + k + 3);
-      const double2 v0 = __ldg(Ke + (long)s0 * 18 + entry), v1 = __ldg(Ke + (long)s1 * 18 + entry);
-      const double2 v2 = __ldg(Ke + (long)s2 * 18 + entry), v3 = __ldg(Ke + (long)s3 * 18 + entry);
+      const double2 v0 = gather36_load(Ke, s0, doff, toff), v1 = gather36_load(Ke, s1, doff, toff);
+      const double2 v2 = gather36_load(Ke, s2, doff, toff), v3 = gather36_load(Ke, s3, doff, toff);
       s.x += v0.x; s.y += v0.y;
       s.x += v1.x; s.y += v1.y;
       s.x += v2.x; s.y += v2.y;
@@ -1226,16 +1327,16 @@ __global__ void __launch_bounds__(256) gather_blocks36_kernel(long nblocks, cons
     }
     if (k + 2 <= end) {
       const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1);
-      const double2 v0 = __ldg(Ke + (long)s0 * 18 + entry), v1 = __ldg(Ke + (long)s1 * 18 + entry);
+      const double2 v0 = gather36_load(Ke, s0, doff, toff), v1 = gather36_load(Ke, s1, doff, toff);
       s.x += v0.x; s.y += v0.y;
       s.x += v1.x; s.y += v1.y;
       k += 2;
     }
     if (k < end) {
-      const double2 v0 = __ldg(Ke + (long)__ldg(src + k) * 18 + entry);
+      const double2 v0 = gather36_load(Ke, __ldg(src + k), doff, toff);
       s.x += v0.x; s.y += v0.y;
     }
-    A[g] = s;
+    *reinterpret_cast<double2 *>(A + (long)__ldg(blk + b) * 36 + doff) = s;
   }
 }
 
@@ -1261,95 +1362,6 @@ static inline unsigned vec_grid_fwd(long n, int num_sms) {
   return (unsigned)want;
 }
 
-// Row-strip gather: one warp per owned block row. An element contributes to row r (its node i) the strip of its nn
-// staging blocks (i, 0..nn-1), contiguous in the staging area: the warp streams each strip with fully used sectors
-// (the per-block form reads 72-byte 3x3 blocks that straddle sectors), adds its blocks into the row's buffer in
-// shared memory at the planned positions and finally writes the row's Aloc (and Bext) blocks, contiguous in BCSR
-// storage. Strips are visited in ascending global element order, so every block is still summed in the order of the
-// reference's serial loop; no atomics.
-template <int B2>
-__global__ void __launch_bounds__(256) gather_rows_kernel(int nrows, const int *__restrict__ gptr,
-                                                         const int *__restrict__ gbase, const int *__restrict__ gpptr,
-                                                         const int *__restrict__ gpos, const double *__restrict__ Ke,
-                                                         const int *__restrict__ rowpA, double *__restrict__ A, int np,
-                                                         const int *__restrict__ rowpB, double *__restrict__ B,
-                                                         int row_doubles) {
-  extern __shared__ __align__(16) double rowbuf_all[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  double *buf = rowbuf_all + (size_t)wib * row_doubles;
-  for (long r = (long)blockIdx.x * wpb + wib; r < nrows; r += (long)gridDim.x * wpb) {
-    const int a0 = __ldg(rowpA + r), nA = __ldg(rowpA + r + 1) - a0;
-    int b0 = 0, nB = 0;
-    if (rowpB && r >= np) {
-      b0 = __ldg(rowpB + (r - np));
-      nB = __ldg(rowpB + (r - np) + 1) - b0;
-    }
-    const int total = (nA + nB) * B2;
-    for (int i = lane; i < total; i += 32) buf[i] = 0.0;
-    __syncwarp();
-    const int p0 = __ldg(gptr + r), p1 = __ldg(gptr + r + 1);
-    for (int p = p0; p < p1; p++) {
-      const int pp = __ldg(gpptr + p), len = (__ldg(gpptr + p + 1) - pp) * B2;
-      const double *strip = Ke + (long)__ldg(gbase + p) * B2;
-      if (B2 % 2 == 0) {
-        // 6x6 blocks: 128-bit loads (a pair never straddles a block)
-        for (int i = 2 * lane; i < len; i += 64) {
-          const double2 v = __ldg(reinterpret_cast<const double2 *>(strip + i));
-          const int j = i / B2, k = i - j * B2;
-          double *d = buf + __ldg(gpos + pp + j) * B2 + k;
-          d[0] += v.x;
-          d[1] += v.y;
-        }
-      } else {
-        for (int i = lane; i < len; i += 32) {
-          const double v = __ldg(strip + i);
-          const int j = i / B2, k = i - j * B2;
-          buf[__ldg(gpos + pp + j) * B2 + k] += v;
-        }
-      }
-      __syncwarp();
-    }
-    double *dA = A + (long)a0 * B2;
-    for (int i = lane; i < nA * B2; i += 32) dA[i] = buf[i];
-    if (nB > 0) {
-      double *dB = B + (long)b0 * B2;
-      const double *sb = buf + nA * B2;
-      for (int i = lane; i < nB * B2; i += 32) dB[i] = sb[i];
-    }
-    __syncwarp();
-  }
-}
-
-cudaError_t launch_gather_rows(int bs, int nrows, const int *gptr, const int *gbase, const int *gpptr, const int *gpos,
-                               const double *Ke, const int *rowpA, double *A, int np, const int *rowpB, double *B,
-                               int max_row_blocks, int num_sms, cudaStream_t s) {
-  if (nrows <= 0) return cudaSuccess;
-  const int b2 = bs * bs;
-  const int row_doubles = ((max_row_blocks * b2 + 15) / 16) * 16;
-  int wpb = 8;
-  while (wpb > 1 && (size_t)wpb * row_doubles * sizeof(double) > 96 * 1024) wpb >>= 1;
-  const size_t smem = (size_t)wpb * row_doubles * sizeof(double);
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  long want = ((long)nrows + wpb - 1) / wpb;
-  long cap = (long)num_sms * 32;
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  cudaError_t err;
-  if (bs == 6) {
-    err = cudaFuncSetAttribute(gather_rows_kernel<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    gather_rows_kernel<36><<<grid, wpb * 32, smem, s>>>(nrows, gptr, gbase, gpptr, gpos, Ke, rowpA, A, np, rowpB, B,
-                                                       row_doubles);
-  } else if (bs == 3) {
-    err = cudaFuncSetAttribute(gather_rows_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    gather_rows_kernel<9><<<grid, wpb * 32, smem, s>>>(nrows, gptr, gbase, gpptr, gpos, Ke, rowpA, A, np, rowpB, B,
-                                                      row_doubles);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
-}
-
 static inline unsigned grid_for(long total, int block, int num_sms) {
   long want = (total + block - 1) / block;
   long cap = (long)num_sms * 64;  // a whole number of CTAs per SM, grid-stride beyond that
@@ -1358,15 +1370,14 @@ static inline unsigned grid_for(long total, int block, int num_sms) {
   return (unsigned)want;
 }
 
-cudaError_t launch_gather_blocks(int bs, long nblocks, const int *ptr, const int *src, const double *Ke,
-                                 double *A, int num_sms, cudaStream_t s) {
+cudaError_t launch_gather_blocks(int bs, long nblocks, const int *blk, const int *ptr, const int *src,
+                                 const double *Ke, double *A, int num_sms, cudaStream_t s) {
   if (nblocks <= 0) return cudaSuccess;
   const int block = 256;
   if (bs == 6)
-    gather_blocks36_kernel<<<grid_for(nblocks * 18, block, num_sms), block, 0, s>>>(
-        nblocks, ptr, src, reinterpret_cast<const double2 *>(Ke), reinterpret_cast<double2 *>(A));
+    gather_blocks36_kernel<<<grid_for(nblocks * 18, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
   else if (bs == 3)
-    gather_blocks_kernel<9><<<grid_for(nblocks * 9, block, num_sms), block, 0, s>>>(nblocks, ptr, src, Ke, A);
+    gather_blocks9_kernel<<<grid_for(nblocks * 9, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

@@ -3,6 +3,7 @@
 #include "plan.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -441,16 +442,21 @@ int HostPlan::buildMatrix() {
         }
       }
   });
-  // pass 2: a pair is written directly when its block and the mirror block are fed by this element alone
+  // pass 2: a pair is written directly when its block and the mirror block are fed by this element alone.
+  // TACSB200_DIRECT_KINDS (bit k-1 = element kind k, default all) limits this to some families (measurements).
+  unsigned direct_kinds = 0xffffffffu;
+  if (const char *env = getenv("TACSB200_DIRECT_KINDS")) direct_kinds = (unsigned)strtoul(env, nullptr, 0);
   std::vector<unsigned char> is_direct(nnz, 0);
   plan_parallel_for(nelems, [&](long e0, long e1) {
     for (long e = e0; e < e1; e++) {
       const int nn = elem_ptr[e + 1] - elem_ptr[e];
+      const bool kind_on = (direct_kinds >> (elem_kind[e] - 1)) & 1u;
       int *dm = &dmap[elem_pair_base[e]];
       for (int k = 0; k < nn; k++)
         for (int j = k; j < nn; j++) {
           const int t = dm[k * nn + j], t2 = dm[j * nn + k];
-          const bool direct = t >= 0 && t2 >= 0 && cnt[t] == 1 && cnt[t2] == 1;
+          const bool direct = kind_on && t >= 0 && t2 >= 0 && cnt[t] == 1 && cnt[t2] == 1 &&
+                              direct_candidate(elem_kind[e], nn, k, j);
           if (direct) {
             is_direct[t] = 1;
             is_direct[t2] = 1;
@@ -461,19 +467,57 @@ int HostPlan::buildMatrix() {
         }
     }
   });
-  // pass 3: gather lists of the remaining blocks, sources in (row, ascending global element, k, j) order
+  // pass 3: gather lists of the remaining blocks, sources in (row, ascending global element, k, j) order.
+  // The gathered blocks are processed in the order of their first staging slot (bucketed, block order inside a
+  // bucket), not in matrix order: a block and its mirror read the same slots and so sit next to each other, and
+  // every staging slot comes from DRAM once; the element-ordered walk also streams the staging area front to back.
+  std::vector<int> first_slot(nnz, 0x7fffffff);
+  plan_parallel_for(nowned, [&](long r0, long r1) {
+    for (long r = r0; r < r1; r++)
+      for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++) {
+        const RowContribution &rc = adj[p];
+        const int k = adj_i[p];
+        for (int j = 0; j < rc.nn; j++) {
+          const long t = locate((int)r, rc.conn[j]);
+          const int slot = rc.source(k, j) >> 1;
+          if (slot < first_slot[t]) first_slot[t] = slot;
+        }
+      }
+  });
   std::vector<int> gidx(nnz, -1);
   gb_blk.clear();
   gb_ptr.assign(1, 0);
   direct_blocks = 0;
-  for (long t = 0; t < nnz; t++) {
-    if (is_direct[t]) {
-      direct_blocks++;
-      continue;
+  {
+    const int kBucketShift = 6;  // 64 staging slots per bucket
+    const long nbuckets = ((local_blocks + recv_blocks) >> kBucketShift) + 2;
+    std::vector<int> bstart(nbuckets + 1, 0);
+    long ngather = 0;
+    for (long t = 0; t < nnz; t++) {
+      if (is_direct[t]) { direct_blocks++; continue; }
+      bstart[(first_slot[t] >> kBucketShift) + 1]++;
+      ngather++;
     }
-    gidx[t] = (int)gb_blk.size();
-    gb_blk.push_back((int)t);
-    gb_ptr.push_back(gb_ptr.back() + cnt[t]);
+    for (long b = 0; b < nbuckets; b++) bstart[b + 1] += bstart[b];
+    gb_blk.resize(ngather);
+    for (long t = 0; t < nnz; t++) {
+      if (is_direct[t]) continue;
+      gb_blk[bstart[first_slot[t] >> kBucketShift]++] = (int)t;
+    }
+    gb_ptr.resize(ngather + 1);
+    for (long g = 0; g < ngather; g++) {
+      gidx[gb_blk[g]] = (int)g;
+      gb_ptr[g + 1] = gb_ptr[g] + cnt[gb_blk[g]];
+    }
+  }
+  std::vector<int>().swap(first_slot);
+  staged_blocks = 0;
+  for (int e = 0; e < nelems; e++) {
+    const int nn = elem_ptr[e + 1] - elem_ptr[e];
+    const int *dm = &dmap[elem_pair_base[e]];
+    for (int k = 0; k < nn; k++)
+      for (int j = k; j < nn; j++)
+        if (dm[k * nn + j] < 0) staged_blocks++;
   }
   gb_src.resize(gb_ptr.back());
   {

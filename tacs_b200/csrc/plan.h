@@ -50,6 +50,14 @@ struct HostBCSR {
 // over the upper triangle. The block of the directed pair (k, j) with k > j is the transpose of slot (j, k).
 inline int upper_pairs(int nn) { return nn * (nn + 1) / 2; }
 inline int upper_index(int nn, int i, int j) { return i * nn - i * (i - 1) / 2 + (j - i); }  // i <= j
+// Node pairs the element kernel of a family looks up a direct target for (HostPlan::dmap): the low-order kernels
+// test only the pairs that are alone in their block on a regular mesh -- the diagonal of a quadrilateral, the body
+// diagonals of a hexahedron (node i against nn-1-i in the tensor-product node order) -- so that their store code
+// stays cheap; the quadratic families look up every pair. kind = ElemKind (kernels.h).
+inline bool direct_candidate(int kind, int nn, int i, int j) {
+  return (kind == 1 || kind == 3) ? (i + j == nn - 1) : true;
+}
+
 // Blocks shipped to the owner of some of an element's nodes (bit set `mask`): the upper pairs that touch a masked
 // node, in ascending upper_index order. Both ends of the exchange evaluate these two functions.
 int shipped_pairs(int nn, unsigned mask);
@@ -107,7 +115,8 @@ struct HostPlan {
   // gather plan of all other blocks: block gb_blk[g] sums the staging sources gb_src[gb_ptr[g] .. gb_ptr[g+1])
   // (RowContribution::source encoding) in ascending global element order -- the order of the reference's serial loop
   std::vector<int> gb_blk, gb_ptr, gb_src;
-  long direct_blocks = 0;
+  long direct_blocks = 0;   // blocks written by the element kernels
+  long staged_blocks = 0;   // upper node-pair blocks the local element kernels write to the staging area
   // neighbour exchanges (empty on one rank)
   ExchangePlan state;   // chunk = one node block of a state vector: owned node -> ext slots of peers
   ExchangePlan cols;    // chunk = one node block of x: owned node -> x_ext of peers (SpMV)

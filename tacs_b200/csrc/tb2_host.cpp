@@ -436,6 +436,7 @@ int TACSElement::addJacobianBatch(int count, double alpha, double beta, double g
   g.kind = kind; g.nelem = count; g.conn = d_conn.ptr; g.desc_index = d_desc.ptr; g.desc_table = d_table.ptr;
   g.tables = d_tab.ptr; g.Xpts = d_X.ptr; g.vars = d_u.ptr; g.ddvars = ddvars ? d_a.ptr : nullptr;
   g.alpha = alpha; g.gamma = gamma; g.Ke = mat ? d_Ke.ptr : nullptr; g.Re = d_Re.ptr;
+  g.upper = 0; g.dmap = nullptr; g.direct = nullptr;  // element-level interface: every node pair is returned
   g.uncoupled = (kind == ELEM_QUAD4_SHELL || kind == ELEM_QUAD9_SHELL) && shell_desc_uncoupled(drow) ? 1 : 0;
   if (!cuda_ok(launch_element_group(g, ctx().num_sms, ctx().stream), "element kernel")) return 1;
   ctx().kernel_launches++;
@@ -662,7 +663,6 @@ PlanObject *TACSCreator::createPlan(int rank, int size) {
   std::vector<int> kinds;
   if (prepareMesh(rank, size, gm, kinds)) return nullptr;
   PlanObject *po = new PlanObject();
-  po->plan.force_row_plan = true;  // test / inspection path: small meshes, every form of the plan is exported
   if (po->plan.build(gm, vars_per_node, rank, kinds) || po->plan.buildMatrix()) {
     delete po;
     return nullptr;
@@ -996,8 +996,9 @@ void TACSAssembler::setBCs(TACSBVec *v) {
 }
 void TACSAssembler::applyBCs(TACSParallelMat *m) { m->applyBCs(); }
 
-int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat, const double *vars_override,
+int TACSAssembler::launchElements(double alpha, double gamma, TACSParallelMat *mat, const double *vars_override,
                                   const double *ddvars_override, bool use_override) {
+  const bool want_mat = mat != nullptr;
   if (want_mat && Ke.count < (size_t)total_blocks * bs * bs) {
     if (!Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
   }
@@ -1017,6 +1018,9 @@ int TACSAssembler::launchElements(double alpha, double gamma, bool want_mat, con
     a.uncoupled = shells_uncoupled ? 1 : 0;
     a.Ke = want_mat ? Ke.ptr + (size_t)g.block_base * bs * bs : nullptr;
     a.Re = Re.ptr + (size_t)g.node_base * bs;
+    a.upper = 1;
+    a.dmap = want_mat ? g.d_dmap.ptr : nullptr;
+    a.direct = want_mat ? mat->vals_all.ptr : nullptr;
     {
       KernelTimer kt(K_ELEMENT, element_kernel_name(a));
       if (!cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel")) return 1;
@@ -1029,7 +1033,7 @@ int staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank
 
 // TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
-  if (launchElements(1.0, 0.0, false)) return 1;
+  if (launchElements(1.0, 0.0, nullptr)) return 1;
   if (size > 1 && staging_exchange(this, false)) return 1;
   {
     KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
@@ -1049,7 +1053,7 @@ int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
 int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
                                     double lambda, bool apply_bcs) {
   (void)beta;
-  if (launchElements(alpha, gamma, true)) return 1;
+  if (launchElements(alpha, gamma, A)) return 1;
   if (size > 1 && staging_exchange(this, true)) return 1;
   if (res) {
     {
@@ -1063,23 +1067,10 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
   }
   // from here on only the staging area and the matrix are touched (Context::tail_evt)
   cudaEventRecord(ctx().tail_evt, ctx().stream.s);
-  if (A->row_gather) {
-    KernelTimer kt(K_GATHER_MAT, gather_rows_kernel_name(bs));
-    if (!cuda_ok(launch_gather_rows(bs, nowned, r_ptr.ptr, A->g_base.ptr, A->g_pptr.ptr, A->g_pos.ptr, Ke.ptr,
-                                    A->Aloc.d_rowp.ptr, A->Aloc.d_vals.ptr, A->np,
-                                    A->Bext.nnzb() > 0 ? A->Bext.d_rowp.ptr : nullptr, A->Bext.d_vals.ptr,
-                                    A->max_row_blocks, ctx().num_sms, ctx().stream), "gather rows")) return 1;
-  } else {
-    {
-      KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs));
-      if (!cuda_ok(launch_gather_blocks(bs, A->Aloc.nnzb(), A->a_ptr.ptr, A->a_src.ptr, Ke.ptr, A->Aloc.d_vals.ptr,
-                                        ctx().num_sms, ctx().stream), "gather blocks")) return 1;
-    }
-    if (A->Bext.nnzb() > 0) {
-      KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs));
-      if (!cuda_ok(launch_gather_blocks(bs, A->Bext.nnzb(), A->b_ptr.ptr, A->b_src.ptr, Ke.ptr, A->Bext.d_vals.ptr,
-                                        ctx().num_sms, ctx().stream), "gather blocks")) return 1;
-    }
+  {
+    KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs));
+    if (!cuda_ok(launch_gather_blocks(bs, num_gather_blocks, gb_blk.ptr, gb_ptr.ptr, gb_src.ptr, Ke.ptr,
+                                      A->vals_all.ptr, ctx().num_sms, ctx().stream), "gather blocks")) return 1;
   }
   if (apply_bcs) A->applyBCs();
   ctx().tail_seq = ctx().stream.seq;
@@ -1127,7 +1118,7 @@ int TACSAssembler::addJacobianVecProduct(double scale, double alpha, double beta
     jvp_a->scale(gamma);
     if (size > 1 && halo_forward(this, jvp_a)) return 1;
   }
-  if (launchElements(1.0, 0.0, false, jvp_x->local(), gamma != 0.0 ? jvp_a->local() : nullptr, true)) return 1;
+  if (launchElements(1.0, 0.0, nullptr, jvp_x->local(), gamma != 0.0 ? jvp_a->local() : nullptr, true)) return 1;
   if (size > 1 && staging_exchange(this, false)) return 1;
   {
     KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
@@ -1167,21 +1158,17 @@ TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
   copy(Bext, P.Bext);
   const long nnzA = Aloc.nnzb(), nnzB = Bext.nnzb();
   const size_t b2 = (size_t)Aloc.bsize * Aloc.bsize;
-  // gather plan on the device. The row-strip form (one warp per block row, whole-sector reads of the element strips)
-  // pays for 3x3 blocks with short rows on one rank -- hex8: 27 blocks per row, measured 1.77 -> 1.55 ms per 1M
-  // elements. It is on par for Quad4, loses where a row buffer is large (Quad9 900, hex27 1125 doubles per warp:
-  // measured 2x slower) and on METIS partitions, whose local row order scatters the strips of consecutive rows
-  // (200^3 hex8 on 8 GPUs: assembly 4.82 -> 5.81 ms); the per-block form is kept there.
-  max_row_blocks = P.max_row_blocks;
-  row_gather = P.rowPlanEligible() && !P.g_base.empty();
-  bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && Aloc.d_vals.alloc(b2 * nnzA);
-  if (ok && row_gather) ok = g_base.upload(P.g_base) && g_pptr.upload(P.g_pptr) && g_pos.upload(P.g_pos);
-  if (ok && !row_gather) ok = a_ptr.upload(P.a_ptr) && a_src.upload(P.a_src);
-  if (ok && nnzB > 0) {
-    ok = Bext.d_rowp.upload(Bext.rowp) && Bext.d_cols.upload(Bext.cols) && Bext.d_vals.alloc(b2 * nnzB) &&
-         x_ext.alloc((size_t)Aloc.bsize * Bext.ncols);
-    if (ok && !row_gather) ok = b_ptr.upload(P.b_ptr) && b_src.upload(P.b_src);
+  // one value array [Aloc | Bext]: the direct map of the element kernels and the gather plan index into it
+  bool ok = Aloc.d_rowp.upload(Aloc.rowp) && Aloc.d_cols.upload(Aloc.cols) && vals_all.alloc(b2 * (nnzA + nnzB));
+  if (ok) {
+    Aloc.d_vals.ptr = vals_all.ptr;
+    Aloc.d_vals.count = b2 * nnzA;
+    Bext.d_vals.ptr = vals_all.ptr + b2 * nnzA;
+    Bext.d_vals.count = b2 * nnzB;
   }
+  if (ok && nnzB > 0)
+    ok = Bext.d_rowp.upload(Bext.rowp) && Bext.d_cols.upload(Bext.cols) && x_ext.alloc((size_t)Aloc.bsize * Bext.ncols);
+  if (ok) ok = a->uploadMatPlan() == 0;
   if (ok && a->size > 1) ok = comm_setup_exchange(x_cols, P.cols) == 0;
   if (!ok) {
     Aloc.bsize = 0;
@@ -1202,10 +1189,29 @@ TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
 TACSParallelMat::~TACSParallelMat() { assembler->decref(); }
 
 void TACSParallelMat::zeroEntries() {
-  if (Aloc.d_vals.count)
-    cuda_ok(cudaMemsetAsync(Aloc.d_vals.ptr, 0, Aloc.d_vals.count * sizeof(double), ctx().stream), "zeroEntries");
-  if (Bext.d_vals.count)
-    cuda_ok(cudaMemsetAsync(Bext.d_vals.ptr, 0, Bext.d_vals.count * sizeof(double), ctx().stream), "zeroEntries");
+  if (vals_all.count)
+    cuda_ok(cudaMemsetAsync(vals_all.ptr, 0, vals_all.count * sizeof(double), ctx().stream), "zeroEntries");
+}
+
+bool BCSRPattern::ValuesView::download(double *host, size_t n) const {
+  if (n == 0) return true;
+  return cuda_ok(cudaMemcpyAsync(host, ptr, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream), "D2H") &&
+         cuda_ok(cudaStreamSynchronize(ctx().stream), "D2H sync");
+}
+
+// device copies of the direct map and the gather plan (HostPlan::buildMatrix), shared by all matrices
+int TACSAssembler::uploadMatPlan() {
+  if (mat_plan_ready) return 0;
+  HostPlan &P = *plan;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    ElemGroup &g = groups[gi];
+    const size_t count = (size_t)g.nelem * g.nn * g.nn;
+    if (!g.d_dmap.upload(P.dmap.data() + P.group_pair_base[gi], count)) return 1;
+  }
+  if (!gb_blk.upload(P.gb_blk) || !gb_ptr.upload(P.gb_ptr) || !gb_src.upload(P.gb_src)) return 1;
+  num_gather_blocks = (long)P.gb_blk.size();
+  mat_plan_ready = true;
+  return 0;
 }
 
 TACSBVec *TACSParallelMat::createVec() { return new TACSBVec(Aloc.bsize, Aloc.nrows, 0, 0); }

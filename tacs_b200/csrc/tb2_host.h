@@ -492,7 +492,7 @@ class TACSAssembler : public Object {
   DeviceExchange x_state, x_rows, x_blocks;
   int localNode(int global) const;
   int finalize();  // build device data after the creator filled the host arrays
-  int launchElements(double alpha, double gamma, bool want_mat, const double *vars_override = nullptr,
+  int launchElements(double alpha, double gamma, TACSParallelMat *mat, const double *vars_override = nullptr,
                      const double *ddvars_override = nullptr, bool use_override = false);
 };
 

@@ -25,24 +25,43 @@ class LocalTransport:
         return self.box[(src, dst, tag)].reshape(shape)
 
 
+def upper_index(nn, i, j):
+    return i * nn - i * (i - 1) // 2 + (j - i)
+
+
 def rank_staging(plan, mesh, kind, desc, new_nodes, u_global):
-    """Element matrices / residuals of this rank's elements in staging layout (+ empty tail for received rows)."""
+    """Element matrices / residuals of this rank's elements in staging layout (+ empty tail for received rows):
+    upper node pairs (i <= j) only; pairs with a direct target go straight into the value array [Aloc | Bext]."""
     s = plan.scalars()
     nn = KIND_NN[kind]
+    nu = nn * (nn + 1) // 2
     bs = 6 if kind <= 2 else 3
     Ke = np.zeros((s["local_blocks"] + s["recv_blocks"], bs, bs))
     Re = np.zeros((s["local_node_slots"] + s["recv_node_slots"], bs))
+    nnz = plan.array("Aloc_rowp")[-1] + (plan.array("Bext_rowp")[-1] if plan.array("Bext_rowp").size else 0)
+    Avals = np.full((nnz, bs, bs), np.nan)  # every block must be written exactly once (directly or by the gather)
+    written = np.zeros(nnz, np.int32)
+    dmap = plan.array("dmap").reshape(-1, nn * nn)
     X = np.zeros((mesh["num_nodes"], 3))
     X[new_nodes] = mesh["Xpts"]
     conn_g = plan.array("elem_conn_global").reshape(-1, nn)
+    assert s["local_blocks"] == s["nelems"] * nu
     for e in range(s["nelems"]):  # single element family: staging order == local element order
         nodes = conn_g[e]
         uu = u_global.reshape(-1, bs)[nodes].ravel()
         res, mat = oracle_port.element(kind, desc, X[nodes].ravel(), uu)
-        blk = mat.reshape(nn, bs, nn, bs).transpose(0, 2, 1, 3).reshape(nn * nn, bs, bs)
-        Ke[e * nn * nn:(e + 1) * nn * nn] = blk
+        blk = mat.reshape(nn, bs, nn, bs).transpose(0, 2, 1, 3)
+        for i in range(nn):
+            for j in range(nn):
+                d = dmap[e, i * nn + j]
+                if d >= 0:
+                    assert dmap[e, j * nn + i] >= 0, "direct targets come in mirror pairs"
+                    Avals[d] = blk[i, j]
+                    written[d] += 1
+                elif i <= j:
+                    Ke[e * nu + upper_index(nn, i, j)] = blk[i, j]
         Re[e * nn:(e + 1) * nn] = res.reshape(nn, bs)
-    return Ke, Re
+    return Ke, Re, Avals, written
 
 
 def exchange(plans, rank, transport, name, src_of, dst_of, tag):
@@ -61,33 +80,26 @@ def exchange(plans, rank, transport, name, src_of, dst_of, tag):
     return finish
 
 
-def gather_blocks(ptr, src, Ke):
-    out = np.zeros((ptr.size - 1,) + Ke.shape[1:])
+def gather_sum(ptr, src, Re):
+    out = np.zeros((ptr.size - 1,) + Re.shape[1:])
     for b in range(ptr.size - 1):
         for k in range(ptr[b], ptr[b + 1]):  # ascending element order, like the device kernel
-            out[b] += Ke[src[k]]
+            out[b] += Re[src[k]]
     return out
 
 
-def gather_rows(P, Ke):
-    """Replay of gather_rows_kernel: row r sums the strips of its contributions (ascending element order) into the
-    row buffer [Aloc row blocks | Bext row blocks] at the planned positions."""
-    rp, gb, gpp, gpos = P.array("r_ptr"), P.array("g_base"), P.array("g_pptr"), P.array("g_pos")
-    ar, br = P.array("Aloc_rowp"), P.array("Bext_rowp")
-    np_ = P.scalars()["np"]
-    A = np.zeros((ar[-1],) + Ke.shape[1:])
-    B = np.zeros(((br[-1] if br.size else 0),) + Ke.shape[1:])
-    for r in range(rp.size - 1):
-        nA = ar[r + 1] - ar[r]
-        nB = br[r - np_ + 1] - br[r - np_] if (br.size and r >= np_) else 0
-        buf = np.zeros((nA + nB,) + Ke.shape[1:])
-        for p in range(rp[r], rp[r + 1]):
-            for j in range(gpp[p + 1] - gpp[p]):
-                buf[gpos[gpp[p] + j]] += Ke[gb[p] + j]
-        A[ar[r]:ar[r + 1]] = buf[:nA]
-        if nB:
-            B[br[r - np_]:br[r - np_ + 1]] = buf[nA:]
-    return A, B
+def gather_blocks(P, Ke, Avals, written):
+    """Replay of gather_blocks*_kernel: block gb_blk[g] sums its sources 2*slot + transposed flag in list order."""
+    blk, ptr, src = P.array("gb_blk"), P.array("gb_ptr"), P.array("gb_src")
+    for g in range(blk.size):
+        acc = np.zeros(Ke.shape[1:])
+        for k in range(ptr[g], ptr[g + 1]):
+            v = Ke[src[k] >> 1]
+            acc += v.T if (src[k] & 1) else v
+        Avals[blk[g]] = acc
+        written[blk[g]] += 1
+    assert np.all(written == 1), "every block is written exactly once"
+    assert int((written == 1).sum()) - blk.size == P.scalars()["direct_blocks"]
 
 
 def apply_bcs(plan, bc_global, A_vals, B_vals, res, u_owned, bs):
@@ -110,7 +122,7 @@ def apply_bcs(plan, bc_global, A_vals, B_vals, res, u_owned, bs):
 def run_rank_phase1(plans, rank, transport, mesh, kind, desc, new_nodes, u_global):
     P = plans[rank]
     bs = 6 if kind <= 2 else 3
-    Ke, Re = rank_staging(P, mesh, kind, desc, new_nodes, u_global)
+    Ke, Re, Avals, written = rank_staging(P, mesh, kind, desc, new_nodes, u_global)
     s = P.scalars()
 
     def put_blocks(off, n, data):
@@ -121,7 +133,7 @@ def run_rank_phase1(plans, rank, transport, mesh, kind, desc, new_nodes, u_globa
 
     f1 = exchange(plans, rank, transport, "blocks", Ke, put_blocks, "K")
     f2 = exchange(plans, rank, transport, "rows", Re, put_rows, "R")
-    return dict(Ke=Ke, Re=Re, finish=(f1, f2), bs=bs)
+    return dict(Ke=Ke, Re=Re, Avals=Avals, written=written, finish=(f1, f2), bs=bs)
 
 
 def run_rank_phase2(plans, rank, transport, st, bc_global, u_global, x_global):
@@ -129,12 +141,10 @@ def run_rank_phase2(plans, rank, transport, st, bc_global, u_global, x_global):
     bs = st["bs"]
     for f in st["finish"]:
         f()
-    A = gather_blocks(P.array("a_ptr"), P.array("a_src"), st["Ke"])
-    Bv = gather_blocks(P.array("b_ptr"), P.array("b_src"), st["Ke"])
-    # the device uses the row-strip form of the same plan: identical sums, bit for bit (same order per block)
-    A2, B2 = gather_rows(P, st["Ke"])
-    assert np.array_equal(A, A2) and (Bv.size == 0 or np.array_equal(Bv, B2)), "row-strip gather plan"
-    res = gather_blocks(P.array("r_ptr"), P.array("r_src"), st["Re"])
+    gather_blocks(P, st["Ke"], st["Avals"], st["written"])
+    nnzA = P.array("Aloc_rowp")[-1]
+    A, Bv = st["Avals"][:nnzA], st["Avals"][nnzA:]
+    res = gather_sum(P.array("r_ptr"), P.array("r_src"), st["Re"])
     lo, hi = P.array("owner_range")[[rank, rank + 1]]
     P.rank_ = rank
     apply_bcs(P, bc_global, A, Bv, res, u_global.reshape(-1, bs)[lo:hi], bs)
