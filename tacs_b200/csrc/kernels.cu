@@ -362,32 +362,42 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
   for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
   // staging offsets of this lane's C fragments: rows 8 mt + gq, column pairs 8 nt + 2 tq (node-pair-major 6x6 blocks)
   const int fo = (tq >> 1) * Work::HS + 2 * gq + (tq & 1);  // this lane's fragment inside a half-split row panel
-  // Store plan of this lane's nine C fragments (row tile mt: rows 8 mt + gq, column tile nt: column pair 8 nt + 2 tq).
+  // Store plan of a lane's nine C fragments (row tile mt: rows 8 mt + gq, column tile nt: column pair 8 nt + 2 tq).
   // A fragment lies inside one node pair (i, j) = (row / 6, col / 6). Its offset in the element's staging image is
   // separable, rowS[mt] + colS[nt]: the upper layout puts pair (i <= j) at slot f(i) + j (plan.h upper_index), the
   // element-level layout at 4 i + j. upmask: fragments that are staged at all (i <= j; all of them for the
   // element-level layout). Direct targets are looked up for the diagonal pairs i + j = 3 only -- the plan offers no
-  // others for this family (HostPlan direct candidates) -- at dmap[16 e + dmo[mt]]; candmask marks those fragments.
-  int rowS[3], colS[3], rowD[3], colD[3], dmo[3];
-  unsigned upmask = 0, candmask = 0;
+  // others for this family (plan.h direct_candidate) -- at dmap[16 e + dmo[mt]]; candmask marks those fragments.
+  // The plan depends on the lane alone: it lives in shared memory (17 words per lane) and is read back at the store
+  // phase, where the 72 accumulator registers leave no room for it.
+  __shared__ int4 stplan[5][32];
+  if (threadIdx.x < 32) {
+    int rowS[3], colS[3], rowD[3], colD[3], dmo[3];
+    unsigned upmask = 0, candmask = 0;
 #pragma unroll
-  for (int t = 0; t < 3; t++) {
-    const int R = 8 * t + gq, C = 8 * t + 2 * tq, i = R / 6, j = C / 6;
-    rowD[t] = (R % 6) * 6;
-    colD[t] = C % 6;
-    rowS[t] = (g.upper ? (i * n - ((i * (i - 1)) >> 1) - i) : i * n) * 36 + rowD[t];
-    colS[t] = j * 36 + colD[t];
-    dmo[t] = i * n + (n - 1 - i);
-  }
-#pragma unroll
-  for (int mt = 0; mt < 3; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 3; nt++) {
-      const int i = (8 * mt + gq) / 6, j = (8 * nt + 2 * tq) / 6;
-      if (i <= j || !g.upper) upmask |= 1u << (3 * mt + nt);
-      if (i + j == n - 1) candmask |= 1u << (3 * mt + nt);
+    for (int t = 0; t < 3; t++) {
+      const int R = 8 * t + gq, C = 8 * t + 2 * tq, i = R / 6, j = C / 6;
+      rowD[t] = (R % 6) * 6;
+      colD[t] = C % 6;
+      rowS[t] = (g.upper ? (i * n - ((i * (i - 1)) >> 1) - i) : i * n) * 36 + rowD[t];
+      colS[t] = j * 36 + colD[t];
+      dmo[t] = i * n + (n - 1 - i);
     }
-  __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 3; nt++) {
+        const int i = (8 * mt + gq) / 6, j = (8 * nt + 2 * tq) / 6;
+        if (i <= j || !g.upper) upmask |= 1u << (3 * mt + nt);
+        if (i + j == n - 1) candmask |= 1u << (3 * mt + nt);
+      }
+    stplan[0][lane] = make_int4(rowS[0], rowS[1], rowS[2], (int)upmask);
+    stplan[1][lane] = make_int4(colS[0], colS[1], colS[2], (int)candmask);
+    stplan[2][lane] = make_int4(rowD[0], rowD[1], rowD[2], 0);
+    stplan[3][lane] = make_int4(colD[0], colD[1], colD[2], 0);
+    stplan[4][lane] = make_int4(dmo[0], dmo[1], dmo[2], 0);
+  }
+  __syncthreads();
 
   for (long base = (long)blockIdx.x * TEAMS; base < nelem; base += nteams) {
     const bool live = (base + team_in_cta) < nelem;
@@ -571,6 +581,11 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
       }
       if (live_o) {
         double *const kbase = g.Ke + eo * (g.upper ? (n * (n + 1) / 2) * 36 : n * n * 36);
+        const int4 pRS = stplan[0][lane], pCS = stplan[1][lane], pRD = stplan[2][lane], pCD = stplan[3][lane],
+                   pDM = stplan[4][lane];
+        const unsigned upmask = (unsigned)pRS.w, candmask = (unsigned)pCS.w;
+        const int rowS[3] = {pRS.x, pRS.y, pRS.z}, colS[3] = {pCS.x, pCS.y, pCS.z};
+        const int rowD[3] = {pRD.x, pRD.y, pRD.z}, colD[3] = {pCD.x, pCD.y, pCD.z}, dmo[3] = {pDM.x, pDM.y, pDM.z};
 #pragma unroll
         for (int mt = 0; mt < 3; mt++) {
           const int dmi = g.dmap ? __ldg(g.dmap + eo * (n * n) + dmo[mt]) : -1;
