@@ -321,7 +321,7 @@ int tacsb200_assembler_get_plan_stats(tacsb200_handle a, long *out) {
   out[2] = P.direct_blocks;
   out[3] = P.staged_blocks;
   out[4] = (long)P.gb_blk.size();
-  out[5] = (long)P.gb_src.size();
+  out[5] = P.gb_ptr.empty() ? 0 : (long)P.gb_ptr.back();
   out[6] = P.Aloc.nnzb() + P.Bext.nnzb();
   out[7] = P.local_pairs;
   return P.has_matrix ? 0 : 1;

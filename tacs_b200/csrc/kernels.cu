@@ -733,18 +733,28 @@ __device__ __forceinline__ void q9_contract_rows(const double *L, int fo, double
     for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
 }
 
-// residual rows K u of the warp's tile rows, alpha, tangent fragments to the node-pair-major staging area
+// residual rows K u of the warp's tile rows, alpha, tangent fragments to the staging area / the matrix.
+// A fragment (row R, column pair C) lies in the node pair (R / 6, C / 6); its offset in the element's staging image
+// is separable -- the upper layout puts pair (i <= j) at slot f(i) + j (plan.h upper_index), the element-level layout
+// at 9 i + j -- so the row and column parts are formed once per tile row / tile column. A pair with a direct target
+// (dmap >= 0, one 324-byte row set per element, L1 resident after the prefetch at the top of the element) goes to
+// that block of the matrix instead; lower pairs without one are not stored.
 template <int W>
 __device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, double alpha, const ElemGroupArgs &g,
                                           long e, double (&kacc)[3][7][2]) {
   using Work = ShellQ9MmaWork;
   constexpr int MTS = (W == 0) ? 3 : 2, nd = Work::nd, n = Work::n;
   double2 up[7];
+  int nj[7], colS[7];
 #pragma unroll
   for (int nt = 0; nt < 7; nt++) {
     const int C = 8 * nt + 2 * tq;
     up[nt] = C < nd ? *reinterpret_cast<const double2 *>(x.uvec() + C) : make_double2(0.0, 0.0);
+    nj[nt] = (C * 43) >> 8;  // C / 6 for C < 64
+    colS[nt] = nj[nt] * 36 + (C - 6 * nj[nt]);
   }
+  double *const kbase = g.Ke ? g.Ke + e * (g.upper ? (n * (n + 1) / 2) * 36 : n * n * 36) : nullptr;
+  const int *const dme = g.dmap ? g.dmap + e * (n * n) : nullptr;
 #pragma unroll
   for (int i = 0; i < MTS; i++) {
     const int R = 8 * (W + 3 * i) + gq;
@@ -756,17 +766,19 @@ __device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, dou
     r += __shfl_xor_sync(0xffffffffu, r, 2);
     if (R < nd) {
       if (tq == 0) x.scr[Work::oRes + R] = r;
-      const int ni = R / 6;
-      const int *dmrow = g.dmap ? g.dmap + e * (n * n) + ni * n : nullptr;
+      if (kbase) {
+        const int ni = (R * 43) >> 8, rowD = (R - 6 * ni) * 6;
+        const int rowS = (g.upper ? ni * n - ((ni * (ni - 1)) >> 1) - ni : ni * n) * 36 + rowD;
+        const int *const dmrow = dme ? dme + ni * n : nullptr;
 #pragma unroll
-      for (int nt = 0; nt < 7; nt++) {
-        const int C = 8 * nt + 2 * tq;
-        if (C < nd) {
-          const int nj = C / 6;
-          double *dst = pair_block_dst<n, 36>(g, e, ni, nj, dmrow ? __ldg(dmrow + nj) : -1);
-          if (dst)
-            *reinterpret_cast<double2 *>(dst + (R % 6) * 6 + C % 6) =
-                make_double2(alpha * kacc[i][nt][0], alpha * kacc[i][nt][1]);
+        for (int nt = 0; nt < 7; nt++) {
+          if (8 * nt + 2 * tq < nd) {
+            const int dm = dmrow ? __ldg(dmrow + nj[nt]) : -1;
+            double *dst = dm >= 0 ? g.direct + (long)dm * 36 + (rowD + colS[nt] - nj[nt] * 36)
+                                  : kbase + (rowS + colS[nt]);
+            if (dm >= 0 || ni <= nj[nt] || !g.upper)
+              *reinterpret_cast<double2 *>(dst) = make_double2(alpha * kacc[i][nt][0], alpha * kacc[i][nt][1]);
+          }
         }
       }
     }
@@ -824,6 +836,8 @@ __global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_
 
   for (long e = blockIdx.x; e < nelem; e += stride) {
     if (tid < 3 * n) w.X()[tid] = pX;
+    // the element's direct map (81 ints, three lines) is read at the very end: pull it into L1 now
+    if (g.dmap && g.Ke && tid >= 93) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.dmap + e * (n * n) + 32 * (tid - 93)));
     const double *desc = g.desc_table + (long)kDescStride * dnext;
     const double cu = pu, ca = pa;  // the state stays in registers until the last quadrature interval
     if (!g.Ke && tid < nd) w.scr[Work::oRu + tid] = pu;
@@ -1277,36 +1291,92 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
 // is the mirror pair (j, i) and the slot has to be read transposed. Sources are listed in ascending global element
 // order (the reference's summation order) and every block is written exactly once.
 //
-// 3x3 blocks: one thread per scalar entry, the nine threads of a block read one 72-byte staging block per step.
+// 3x3 blocks: one thread per block row -- three doubles per source (row a of the staging block, or its column a when
+// the source is the mirror pair), up to four sources requested before any is consumed: twelve 8-byte loads in flight
+// per thread. (One thread per scalar entry left the kernel latency bound: most blocks of a hexahedral mesh have two or
+// four sources, and 2048 threads x 8 bytes in flight per SM sustain only half of the HBM bandwidth.)
+struct Row3 {
+  double x, y, z;
+};
+__device__ __forceinline__ Row3 gather9_load(const double *__restrict__ Ke, int s, int a) {
+  const double *base = Ke + (long)(s >> 1) * 9;
+  Row3 r;
+  if (s & 1) {
+    r.x = __ldg(base + a);
+    r.y = __ldg(base + 3 + a);
+    r.z = __ldg(base + 6 + a);
+  } else {
+    r.x = __ldg(base + 3 * a);
+    r.y = __ldg(base + 3 * a + 1);
+    r.z = __ldg(base + 3 * a + 2);
+  }
+  return r;
+}
+
 __global__ void __launch_bounds__(256) gather_blocks9_kernel(long nblocks, const int *__restrict__ blk,
                                                             const int *__restrict__ ptr, const int *__restrict__ src,
                                                             const double *__restrict__ Ke, double *__restrict__ A) {
-  const long total = nblocks * 9;
-  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const long b = g / 9;
-    const int entry = (int)(g - b * 9);
-    const int et = (entry % 3) * 3 + entry / 3;  // the same entry of the transposed block
-    const int beg = __ldg(ptr + b), end = __ldg(ptr + b + 1);
-    double s = 0.0;
+  const long total = nblocks * 3, stride = (long)gridDim.x * blockDim.x;
+  // The index loads of the next item (list bounds, target block, first four sources) are issued before the values of
+  // the current one are consumed: an item costs one DRAM round trip instead of three dependent ones.
+  long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int nbeg = 0, nend = 0, nblk = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+  auto prefetch = [&](long gi) {
+    if (gi < total) {
+      const long b = gi / 3;
+      nbeg = __ldg(ptr + b);
+      nend = __ldg(ptr + b + 1);
+      nblk = __ldg(blk + b);
+      // sources of a block are contiguous; reading up to three entries past a short list stays inside the array
+      // (the last list is followed by the padding the host adds)
+      n0 = __ldg(src + nbeg);
+      n1 = __ldg(src + nbeg + 1);
+      n2 = __ldg(src + nbeg + 2);
+      n3 = __ldg(src + nbeg + 3);
+    }
+  };
+  prefetch(g);
+  for (; g < total; g += stride) {
+    const int a = (int)(g % 3);
+    const int beg = nbeg, end = nend;
+    const long dst = (long)nblk * 9 + 3 * a;
+    int s0 = n0, s1 = n1, s2 = n2, s3 = n3;
+    prefetch(g + stride);
+    double sx = 0.0, sy = 0.0, sz = 0.0;
     int k = beg;
-    // request the sources and then the values of four contributions before consuming any (memory-level
-    // parallelism); the sum is still formed in ascending element order
     for (; k + 4 <= end; k += 4) {
-      const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1), s2 = __ldg(src + k + 2), s3 = __ldg(src + k + 3);
-      const double v0 = __ldg(Ke + (long)(s0 >> 1) * 9 + ((s0 & 1) ? et : entry));
-      const double v1 = __ldg(Ke + (long)(s1 >> 1) * 9 + ((s1 & 1) ? et : entry));
-      const double v2 = __ldg(Ke + (long)(s2 >> 1) * 9 + ((s2 & 1) ? et : entry));
-      const double v3 = __ldg(Ke + (long)(s3 >> 1) * 9 + ((s3 & 1) ? et : entry));
-      s += v0;
-      s += v1;
-      s += v2;
-      s += v3;
+      if (k != beg) {
+        s0 = __ldg(src + k);
+        s1 = __ldg(src + k + 1);
+        s2 = __ldg(src + k + 2);
+        s3 = __ldg(src + k + 3);
+      }
+      const Row3 v0 = gather9_load(Ke, s0, a), v1 = gather9_load(Ke, s1, a), v2 = gather9_load(Ke, s2, a),
+                 v3 = gather9_load(Ke, s3, a);
+      sx += v0.x; sy += v0.y; sz += v0.z;
+      sx += v1.x; sy += v1.y; sz += v1.z;
+      sx += v2.x; sy += v2.y; sz += v2.z;
+      sx += v3.x; sy += v3.y; sz += v3.z;
     }
-    for (; k < end; k++) {
-      const int s0 = __ldg(src + k);
-      s += __ldg(Ke + (long)(s0 >> 1) * 9 + ((s0 & 1) ? et : entry));
+    if (k + 2 <= end) {
+      if (k != beg) {
+        s0 = __ldg(src + k);
+        s1 = __ldg(src + k + 1);
+      }
+      const Row3 v0 = gather9_load(Ke, s0, a), v1 = gather9_load(Ke, s1, a);
+      sx += v0.x; sy += v0.y; sz += v0.z;
+      sx += v1.x; sy += v1.y; sz += v1.z;
+      k += 2;
+      s0 = s2;  // a list of three: its last source was prefetched as the third entry
     }
-    A[(long)__ldg(blk + b) * 9 + entry] = s;
+    if (k < end) {
+      if (k != beg && k != beg + 2) s0 = __ldg(src + k);
+      const Row3 v0 = gather9_load(Ke, s0, a);
+      sx += v0.x; sy += v0.y; sz += v0.z;
+    }
+    A[dst] = sx;
+    A[dst + 1] = sy;
+    A[dst + 2] = sz;
   }
 }
 
@@ -1331,6 +1401,7 @@ __global__ void __launch_bounds__(256) gather_blocks36_kernel(long nblocks, cons
     const int beg = __ldg(ptr + b), end = __ldg(ptr + b + 1);
     double2 s = make_double2(0.0, 0.0);
     int k = beg;
+    // (a software pipeline of these index loads, as in gather_blocks9_kernel, measured slower here: 0.85 -> 0.94 ms)
     for (; k + 4 <= end; k += 4) {
       const int s0 = __ldg(src + k), s1 = __ldg(src + k + 1), s2 = __ldg(src + k + 2), s3 = __ldg(src + k + 3);
       const double2 v0 = gather36_load(Ke, s0, doff, toff), v1 = gather36_load(Ke, s1, doff, toff);
@@ -1392,7 +1463,7 @@ cudaError_t launch_gather_blocks(int bs, long nblocks, const int *blk, const int
   if (bs == 6)
     gather_blocks36_kernel<<<grid_for(nblocks * 18, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
   else if (bs == 3)
-    gather_blocks9_kernel<<<grid_for(nblocks * 9, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
+    gather_blocks9_kernel<<<grid_for(nblocks * 3, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

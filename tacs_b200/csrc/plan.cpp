@@ -355,6 +355,14 @@ int HostPlan::build(std::shared_ptr<const GlobalMesh> mesh, int _bs, int _rank, 
   return 0;
 }
 
+// number of gathered blocks (a prefix of gb_blk) that are complete once every staging slot below `slot` is written
+long HostPlan::gatherEnd(long slot) const {
+  if (gb_bucket_start.empty()) return 0;
+  long b = slot >> kGatherBucketShift;  // buckets [0, b) hold last slots < b * bucket <= slot
+  if (b >= (long)gb_bucket_start.size()) b = (long)gb_bucket_start.size() - 1;
+  return gb_bucket_start[b];
+}
+
 int HostPlan::buildMatrix() {
   if (has_matrix) return 0;
   const int lo = owner_range[rank], hi = owner_range[rank + 1];
@@ -468,10 +476,13 @@ int HostPlan::buildMatrix() {
     }
   });
   // pass 3: gather lists of the remaining blocks, sources in (row, ascending global element, k, j) order.
-  // The gathered blocks are processed in the order of their first staging slot (bucketed, block order inside a
-  // bucket), not in matrix order: a block and its mirror read the same slots and so sit next to each other, and
-  // every staging slot comes from DRAM once; the element-ordered walk also streams the staging area front to back.
-  std::vector<int> first_slot(nnz, 0x7fffffff);
+  // The gathered blocks are processed in the order of their LAST staging slot (bucketed by kGatherBucket slots, block
+  // order inside a bucket), not in matrix order: (1) a block and its mirror read the same slots and so sit next to
+  // each other -- every staging slot comes from DRAM once; (2) the walk streams the staging area front to back; and
+  // (3) every block whose last slot lies below a slot s is complete once the elements that own the slots below s
+  // have been evaluated: the gather of a chunk of elements can run while the next chunk is being computed
+  // (gatherEnd). Blocks fed by received slots (the tail region) come last, after the exchange.
+  std::vector<int> first_slot(nnz, -1);  // (holds the last slot)
   plan_parallel_for(nowned, [&](long r0, long r1) {
     for (long r = r0; r < r1; r++)
       for (int p = adj_ptr[r]; p < adj_ptr[r + 1]; p++) {
@@ -480,7 +491,7 @@ int HostPlan::buildMatrix() {
         for (int j = 0; j < rc.nn; j++) {
           const long t = locate((int)r, rc.conn[j]);
           const int slot = rc.source(k, j) >> 1;
-          if (slot < first_slot[t]) first_slot[t] = slot;
+          if (slot > first_slot[t]) first_slot[t] = slot;
         }
       }
   });
@@ -489,7 +500,7 @@ int HostPlan::buildMatrix() {
   gb_ptr.assign(1, 0);
   direct_blocks = 0;
   {
-    const int kBucketShift = 6;  // 64 staging slots per bucket
+    const int kBucketShift = kGatherBucketShift;
     const long nbuckets = ((local_blocks + recv_blocks) >> kBucketShift) + 2;
     std::vector<int> bstart(nbuckets + 1, 0);
     long ngather = 0;
@@ -499,6 +510,7 @@ int HostPlan::buildMatrix() {
       ngather++;
     }
     for (long b = 0; b < nbuckets; b++) bstart[b + 1] += bstart[b];
+    gb_bucket_start = bstart;  // first gathered block of every bucket (before the fill below advances bstart)
     gb_blk.resize(ngather);
     for (long t = 0; t < nnz; t++) {
       if (is_direct[t]) continue;
@@ -519,7 +531,7 @@ int HostPlan::buildMatrix() {
       for (int j = k; j < nn; j++)
         if (dm[k * nn + j] < 0) staged_blocks++;
   }
-  gb_src.resize(gb_ptr.back());
+  gb_src.assign((size_t)gb_ptr.back() + 4, 0);  // + 4: the gather kernels prefetch four sources per list
   {
     std::vector<int> cur(gb_ptr.begin(), gb_ptr.end() - 1);
     plan_parallel_for(nowned, [&](long r0, long r1) {

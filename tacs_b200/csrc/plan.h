@@ -115,6 +115,9 @@ struct HostPlan {
   // gather plan of all other blocks: block gb_blk[g] sums the staging sources gb_src[gb_ptr[g] .. gb_ptr[g+1])
   // (RowContribution::source encoding) in ascending global element order -- the order of the reference's serial loop
   std::vector<int> gb_blk, gb_ptr, gb_src;
+  static constexpr int kGatherBucketShift = 6;  // gathered blocks are ordered by (last staging slot >> 6)
+  std::vector<int> gb_bucket_start;             // first gathered block of every bucket of 64 staging slots
+  long gatherEnd(long slot) const;
   long direct_blocks = 0;   // blocks written by the element kernels
   long staged_blocks = 0;   // upper node-pair blocks the local element kernels write to the staging area
   // neighbour exchanges (empty on one rank)

@@ -56,6 +56,8 @@ int ctx_init(int device) {
   if (!cuda_ok(cudaStreamCreateWithFlags(&c.stream.s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   if (!cuda_ok(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   if (!cuda_ok(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&c.gather_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  if (!cuda_ok(cudaEventCreateWithFlags(&c.gather_evt, cudaEventDisableTiming), "cudaEventCreate")) return 1;
   if (!cuda_ok(cudaEventCreateWithFlags(&c.tail_evt, cudaEventDisableTiming), "cudaEventCreate")) return 1;
   c.device = device;
   return 0;
@@ -77,7 +79,7 @@ static cudaEvent_t prof_event() {
   return e;
 }
 void profile_enable(int on) { g_prof_on = on != 0; }
-KernelTimer::KernelTimer(KernelId id, const char *name) : slot(-1) {
+KernelTimer::KernelTimer(KernelId id, const char *name, cudaStream_t st) : slot(-1), stream(st ? st : g_ctx.stream.s) {
   g_ctx.kernel_launches++;
   if (!g_prof_on) return;
   ProfRec r;
@@ -85,12 +87,12 @@ KernelTimer::KernelTimer(KernelId id, const char *name) : slot(-1) {
   r.name = name;
   r.e0 = prof_event();
   r.e1 = prof_event();
-  cudaEventRecord(r.e0, g_ctx.stream.s);
+  cudaEventRecord(r.e0, stream);
   slot = (int)g_prof_log.size();
   g_prof_log.push_back(r);
 }
 KernelTimer::~KernelTimer() {
-  if (slot >= 0) cudaEventRecord(g_prof_log[slot].e1, g_ctx.stream.s);
+  if (slot >= 0) cudaEventRecord(g_prof_log[slot].e1, stream);
 }
 // per-name totals of the last collect: "name|launches|ms" lines (kernel names as launched, not literals of the caller)
 static std::string g_prof_named;
@@ -99,6 +101,7 @@ int profile_collect(double *ms, long *count) {
   for (int k = 0; k < K_COUNT; k++) { ms[k] = 0.0; count[k] = 0; }
   if (g_ctx.device < 0) return 1;
   cudaStreamSynchronize(g_ctx.stream.s);
+  cudaStreamSynchronize(g_ctx.gather_stream);
   std::map<std::string, std::pair<long, double>> named;
   for (auto &r : g_prof_log) {
     float t = 0.0f;
@@ -996,36 +999,41 @@ void TACSAssembler::setBCs(TACSBVec *v) {
 }
 void TACSAssembler::applyBCs(TACSParallelMat *m) { m->applyBCs(); }
 
+int TACSAssembler::launchGroupRange(const ElemGroup &g, long e0, long e1, double alpha, double gamma,
+                                    TACSParallelMat *mat, const double *vars_p, const double *ddvars_p) {
+  const bool want_mat = mat != nullptr;
+  const long b2 = (long)bs * bs, nu = upper_pairs(g.nn);
+  ElemGroupArgs a;
+  a.kind = g.kind;
+  a.nelem = e1 - e0;
+  a.conn = g.d_conn.ptr + e0 * g.nn;
+  a.desc_index = g.d_desc.ptr + e0;
+  a.desc_table = d_desc_table.ptr;
+  a.tables = g.d_tables.ptr;
+  a.Xpts = xpts->local();
+  a.vars = vars_p;
+  a.ddvars = ddvars_p;
+  a.alpha = alpha;
+  a.gamma = gamma;
+  a.uncoupled = shells_uncoupled ? 1 : 0;
+  a.Ke = want_mat ? Ke.ptr + ((size_t)g.block_base + (size_t)e0 * nu) * b2 : nullptr;
+  a.Re = Re.ptr + ((size_t)g.node_base + (size_t)e0 * g.nn) * bs;
+  a.upper = 1;
+  a.dmap = want_mat ? g.d_dmap.ptr + e0 * g.nn * g.nn : nullptr;
+  a.direct = want_mat ? mat->vals_all.ptr : nullptr;
+  KernelTimer kt(K_ELEMENT, element_kernel_name(a));
+  return cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel") ? 0 : 1;
+}
+
 int TACSAssembler::launchElements(double alpha, double gamma, TACSParallelMat *mat, const double *vars_override,
                                   const double *ddvars_override, bool use_override) {
-  const bool want_mat = mat != nullptr;
-  if (want_mat && Ke.count < (size_t)total_blocks * bs * bs) {
+  if (mat && Ke.count < (size_t)total_blocks * bs * bs) {
     if (!Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
   }
-  for (auto &g : groups) {
-    ElemGroupArgs a;
-    a.kind = g.kind;
-    a.nelem = g.nelem;
-    a.conn = g.d_conn.ptr;
-    a.desc_index = g.d_desc.ptr;
-    a.desc_table = d_desc_table.ptr;
-    a.tables = g.d_tables.ptr;
-    a.Xpts = xpts->local();
-    a.vars = use_override ? vars_override : (vars_zero ? nullptr : vars->local());
-    a.ddvars = use_override ? ddvars_override : (ddvars_zero ? nullptr : ddvars->local());
-    a.alpha = alpha;
-    a.gamma = gamma;
-    a.uncoupled = shells_uncoupled ? 1 : 0;
-    a.Ke = want_mat ? Ke.ptr + (size_t)g.block_base * bs * bs : nullptr;
-    a.Re = Re.ptr + (size_t)g.node_base * bs;
-    a.upper = 1;
-    a.dmap = want_mat ? g.d_dmap.ptr : nullptr;
-    a.direct = want_mat ? mat->vals_all.ptr : nullptr;
-    {
-      KernelTimer kt(K_ELEMENT, element_kernel_name(a));
-      if (!cuda_ok(launch_element_group(a, ctx().num_sms, ctx().stream), "element kernel")) return 1;
-    }
-  }
+  const double *vp = use_override ? vars_override : (vars_zero ? nullptr : vars->local());
+  const double *ap = use_override ? ddvars_override : (ddvars_zero ? nullptr : ddvars->local());
+  for (auto &g : groups)
+    if (launchGroupRange(g, 0, g.nelem, alpha, gamma, mat, vp, ap)) return 1;
   return 0;
 }
 
@@ -1050,30 +1058,61 @@ int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
 
 
 // TACSAssembler::assembleJacobian (TACSAssembler.cpp:4291-4406)
+//
+// The elements are evaluated in chunks on the compute stream. The block gather is ordered by the last staging slot
+// a block reads (HostPlan::buildMatrix), so the blocks completed by chunk c can be summed on the gather stream while
+// chunk c+1 is being computed: the element kernels are FP64 / shared-memory bound, the gather is HBM bound. Blocks that
+// need rows of other ranks are gathered after the exchange.
 int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
                                     double lambda, bool apply_bcs) {
   (void)beta;
-  if (launchElements(alpha, gamma, A)) return 1;
+  Context &c = ctx();
+  if (Ke.count < (size_t)total_blocks * bs * bs && !Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
+  const double *vp = vars_zero ? nullptr : vars->local(), *ap = ddvars_zero ? nullptr : ddvars->local();
+  auto gather = [&](long g0, long g1, cudaStream_t st) -> int {
+    if (g1 <= g0) return 0;
+    KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs), st);
+    return cuda_ok(launch_gather_blocks(bs, g1 - g0, gb_blk.ptr + g0, gb_ptr.ptr + g0, gb_src.ptr, Ke.ptr,
+                                        A->vals_all.ptr, c.num_sms, st), "gather blocks") ? 0 : 1;
+  };
+  long gdone = 0;
+  bool forked = false;
+  for (size_t k = 0; k < chunks.size(); k++) {
+    const ElemChunk &ch = chunks[k];
+    if (launchGroupRange(groups[ch.group], ch.e0, ch.e1, alpha, gamma, A, vp, ap)) return 1;
+    if (overlap_gather && k + 1 < chunks.size() && ch.gather_end > gdone) {
+      if (c.chunk_evt.size() <= k) {
+        c.chunk_evt.resize(k + 1, nullptr);
+      }
+      if (!c.chunk_evt[k] && !cuda_ok(cudaEventCreateWithFlags(&c.chunk_evt[k], cudaEventDisableTiming), "event"))
+        return 1;
+      cudaEventRecord(c.chunk_evt[k], c.stream.s);
+      cudaStreamWaitEvent(c.gather_stream, c.chunk_evt[k], 0);
+      if (gather(gdone, ch.gather_end, c.gather_stream)) return 1;
+      gdone = ch.gather_end;
+      forked = true;
+    }
+  }
   if (size > 1 && staging_exchange(this, true)) return 1;
   if (res) {
     {
       KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
-      if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), ctx().num_sms,
-                                          ctx().stream), "gather residual")) return 1;
+      if (!cuda_ok(launch_gather_residual(bs, nowned, r_ptr.ptr, r_src.ptr, Re.ptr, res->owned(), c.num_sms,
+                                          c.stream), "gather residual")) return 1;
     }
     KernelTimer kt(K_BCS, "vec_apply_bcs_kernel");
     if (!cuda_ok(launch_vec_apply_bcs(bs, nbc_dev, d_bc_rows.ptr, d_bc_vars.ptr, d_bc_vals.ptr, vars->owned(),
-                                      lambda, res->owned(), ctx().stream), "residual BCs")) return 1;
+                                      lambda, res->owned(), c.stream), "residual BCs")) return 1;
   }
   // from here on only the staging area and the matrix are touched (Context::tail_evt)
-  cudaEventRecord(ctx().tail_evt, ctx().stream.s);
-  {
-    KernelTimer kt(K_GATHER_MAT, gather_blocks_kernel_name(bs));
-    if (!cuda_ok(launch_gather_blocks(bs, num_gather_blocks, gb_blk.ptr, gb_ptr.ptr, gb_src.ptr, Ke.ptr,
-                                      A->vals_all.ptr, ctx().num_sms, ctx().stream), "gather blocks")) return 1;
+  cudaEventRecord(c.tail_evt, c.stream.s);
+  if (gather(gdone, num_gather_blocks, c.stream)) return 1;
+  if (forked) {
+    cudaEventRecord(c.gather_evt, c.gather_stream);
+    cudaStreamWaitEvent(c.stream.s, c.gather_evt, 0);
   }
   if (apply_bcs) A->applyBCs();
-  ctx().tail_seq = ctx().stream.seq;
+  c.tail_seq = c.stream.seq;
   return 0;
 }
 
@@ -1210,6 +1249,31 @@ int TACSAssembler::uploadMatPlan() {
   }
   if (!gb_blk.upload(P.gb_blk) || !gb_ptr.upload(P.gb_ptr) || !gb_src.upload(P.gb_src)) return 1;
   num_gather_blocks = (long)P.gb_blk.size();
+  // Element chunks. TACSB200_CHUNKS: chunks per group (default 8; chunks of fewer than 32768 elements are merged).
+  // TACSB200_OVERLAP_KINDS: element families (bit kind-1) whose gather overlaps the element kernel. Default hex8
+  // only: its kernel leaves room for a gather CTA on every SM (2 CTAs x 128 threads x 222 registers); the kernels of
+  // the other families fill the register file, and a co-resident gather would cost them a CTA per SM.
+  int nchunk = 8;
+  unsigned overlap_kinds = 1u << (ELEM_HEX8 - 1);
+  if (const char *env = getenv("TACSB200_CHUNKS")) nchunk = std::max(1, atoi(env));
+  if (const char *env = getenv("TACSB200_OVERLAP_KINDS")) overlap_kinds = (unsigned)strtoul(env, nullptr, 0);
+  chunks.clear();
+  overlap_gather = false;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const ElemGroup &g = groups[gi];
+    const bool ov = (overlap_kinds >> (g.kind - 1)) & 1u;
+    long n = ov ? std::min<long>(nchunk, std::max<long>(1, g.nelem / 32768)) : 1;
+    const long nu = upper_pairs(g.nn);
+    for (long k = 0; k < n; k++) {
+      ElemChunk ch;
+      ch.group = (int)gi;
+      ch.e0 = g.nelem * k / n;
+      ch.e1 = g.nelem * (k + 1) / n;
+      ch.gather_end = P.gatherEnd(g.block_base + ch.e1 * nu);
+      if (ch.e1 > ch.e0) chunks.push_back(ch);
+    }
+    if (n > 1) overlap_gather = true;
+  }
   mat_plan_ready = true;
   return 0;
 }

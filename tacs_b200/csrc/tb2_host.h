@@ -61,6 +61,11 @@ struct Context {
   // compute stream runs on `copy_stream` behind `tail_evt` only -- the residual returns to the host while the matrix
   // is still being gathered.
   cudaStream_t copy_stream = nullptr;
+  // The block gather of a chunk of elements runs on `gather_stream` while the compute stream evaluates the next chunk
+  // (TACSAssembler::assembleJacobian); chunk_evt orders the two, gather_evt joins them again.
+  cudaStream_t gather_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_evt;
+  cudaEvent_t gather_evt = nullptr;
   cudaEvent_t tail_evt = nullptr;
   long tail_seq = -1;
   bool tail_is_matrix_only() const { return tail_seq >= 0 && stream.seq == tail_seq; }
@@ -73,7 +78,9 @@ Context &ctx();
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
 enum KernelId { K_ELEMENT = 0, K_GATHER_RES, K_GATHER_MAT, K_BCS, K_SPMV, K_VEC, K_DOT, K_HALO, K_COUNT };
 struct KernelTimer {
-  explicit KernelTimer(KernelId id, const char *name = nullptr);  // name: static string of the kernel launched
+  // name: static string of the kernel launched; stream: where it is launched (default: the compute stream)
+  explicit KernelTimer(KernelId id, const char *name = nullptr, cudaStream_t stream = nullptr);
+  cudaStream_t stream;
   ~KernelTimer();
   int slot;
 };
@@ -487,6 +494,13 @@ class TACSAssembler : public Object {
   DeviceArray<int> gb_blk, gb_ptr, gb_src;
   long num_gather_blocks = 0;
   bool mat_plan_ready = false;
+  // element chunks of assembleJacobian: [e0, e1) of group `group`; every gathered block below gather_end is complete
+  // once the chunk (and all chunks before it) has been evaluated
+  struct ElemChunk { int group; long e0, e1, gather_end; };
+  std::vector<ElemChunk> chunks;
+  bool overlap_gather = false;
+  int launchGroupRange(const ElemGroup &g, long e0, long e1, double alpha, double gamma, TACSParallelMat *mat,
+                       const double *vars_p, const double *ddvars_p);
   int uploadMatPlan();
   std::unique_ptr<HostPlan> plan;
   DeviceExchange x_state, x_rows, x_blocks;
