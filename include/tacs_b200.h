@@ -213,6 +213,12 @@ tacsb200_handle tacsb200_gmres_create_pc(tacsb200_handle mat, tacsb200_handle pc
                                          int is_flexible);
 int tacsb200_gmres_set_tolerances(tacsb200_handle k, double rtol, double atol);
 int tacsb200_gmres_solve(tacsb200_handle k, tacsb200_handle b, tacsb200_handle x, int zero_guess);
+/* GMRES::setOrthoType KSM.cpp:747-756 (classical != 0: one mdot sweep + one update sweep per iteration; default
+   modified Gram-Schmidt, the reference's default), setMonitor with a KSMPrintStdout(descript, rank, freq)
+   KSM.cpp:239-283, setTimeMonitor KSM.cpp:765 */
+int tacsb200_gmres_set_ortho_type(tacsb200_handle k, int classical);
+int tacsb200_gmres_set_monitor(tacsb200_handle k, const char *descript, int freq);
+int tacsb200_gmres_set_time_monitor(tacsb200_handle k);
 int tacsb200_gmres_get_iter_count(tacsb200_handle k);
 double tacsb200_gmres_get_residual_norm(tacsb200_handle k);
 

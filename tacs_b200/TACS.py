@@ -293,6 +293,17 @@ class KSM(_Obj):
     def solve(self, b, x, zero_guess=1):
         return self.lib.gmres_solve(self.h, b.h, x.h, zero_guess)
 
+    def setOrthoType(self, classical):
+        """GMRES::setOrthoType: classical Gram-Schmidt (True) or modified (False, the default)."""
+        _check(self.lib.gmres_set_ortho_type(self.h, 1 if classical else 0), "gmres_set_ortho_type")
+
+    def setMonitor(self, descript="GMRES", freq=1):
+        """KSMPrintStdout(descript, rank, freq) attached with setMonitor."""
+        _check(self.lib.gmres_set_monitor(self.h, descript.encode(), freq), "gmres_set_monitor")
+
+    def setTimeMonitor(self):
+        _check(self.lib.gmres_set_time_monitor(self.h), "gmres_set_time_monitor")
+
     def getIterCount(self):
         return self.lib.gmres_get_iter_count(self.h)
 

@@ -128,6 +128,9 @@ PRODUCT_ONLY = {
     "profile_enable": (I, [I]),
     "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
     "profile_named": (C.c_char_p, []),
+    "gmres_set_ortho_type": (I, [H, I]),
+    "gmres_set_monitor": (I, [H, C.c_char_p, I]),
+    "gmres_set_time_monitor": (I, [H]),
     "measure_fp64_tflops": (D, []),
     "measure_copy_gbs": (D, []),
 }

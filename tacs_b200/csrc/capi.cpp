@@ -569,7 +569,7 @@ int tacsb200_chebyshev_apply_factor(tacsb200_handle pc, tacsb200_handle x, tacsb
   TACSChebyshevSmoother *P = as<TACSChebyshevSmoother>(pc);
   TACSBVec *xv = as<TACSBVec>(x), *yv = as<TACSBVec>(y);
   REQUIRE(P && xv && yv, "Chebyshev smoother / vector");
-  P->applyFactor(xv, yv);
+  if (P->applyFactor(xv, yv)) return 1;
   return tacsb200_synchronize();
 }
 double tacsb200_chebyshev_get_spectral_radius(tacsb200_handle pc) {
@@ -587,6 +587,24 @@ int tacsb200_gmres_solve(tacsb200_handle k, tacsb200_handle b, tacsb200_handle x
   TACSBVec *bv = as<TACSBVec>(b), *xv = as<TACSBVec>(x);
   if (!g || !bv || !xv) return -1;
   return g->solve(bv, xv, zero_guess);
+}
+int tacsb200_gmres_set_ortho_type(tacsb200_handle k, int classical) {
+  GMRES *g = as<GMRES>(k);
+  REQUIRE(g, "GMRES");
+  g->setOrthoType(classical ? GMRES::CLASSICAL_GRAM_SCHMIDT : GMRES::MODIFIED_GRAM_SCHMIDT);
+  return 0;
+}
+int tacsb200_gmres_set_monitor(tacsb200_handle k, const char *descript, int freq) {
+  GMRES *g = as<GMRES>(k);
+  REQUIRE(g, "GMRES");
+  g->setMonitor(descript, freq);
+  return 0;
+}
+int tacsb200_gmres_set_time_monitor(tacsb200_handle k) {
+  GMRES *g = as<GMRES>(k);
+  REQUIRE(g, "GMRES");
+  g->setTimeMonitor();
+  return 0;
 }
 int tacsb200_gmres_get_iter_count(tacsb200_handle k) {
   GMRES *g = as<GMRES>(k);

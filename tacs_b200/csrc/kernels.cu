@@ -1571,15 +1571,18 @@ __device__ __forceinline__ double2 ldg2(const double *p) {
   return __ldg(reinterpret_cast<const double2 *>(p));
 }
 
+// ADD = 2 / 3 are the fused forms used by the polynomial smoother and the Krylov residuals:
+//   2: y = zs * z + sign * (A x)     3: y = y + sign * (A x)     (the product is summed first, as a separate mult would)
 template <int ADD>
 __global__ void __launch_bounds__(256) spmv6_kernel(int nrows, const int *__restrict__ rowp,
                                                    const int *__restrict__ cols, const double *__restrict__ A,
-                                                   const double *__restrict__ x, double *__restrict__ y) {
+                                                   const double *__restrict__ x, double *__restrict__ y,
+                                                   double sign, double zs, const double *__restrict__ z) {
   const long total = (long)nrows * 6;
   for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
     const int row = (int)(g / 6), r = (int)(g - (long)row * 6);
     const int beg = rowp[row], end = rowp[row + 1];
-    double acc = ADD ? y[g] : 0.0;
+    double acc = ADD == 1 ? y[g] : 0.0;
     const double *a = A + (long)36 * beg + 6 * r;
     int k = beg;
     for (; k + 1 < end; k += 2, a += 72) {
@@ -1605,6 +1608,8 @@ __global__ void __launch_bounds__(256) spmv6_kernel(int nrows, const int *__rest
       s += a0.y * x0.y; s += a1.x * x1.x; s += a1.y * x1.y; s += a2.x * x2.x; s += a2.y * x2.y;
       acc += s;
     }
+    if (ADD == 2) acc = zs * z[g] + sign * acc;
+    if (ADD == 3) acc = y[g] + sign * acc;
     y[g] = acc;
   }
 }
@@ -1612,12 +1617,13 @@ __global__ void __launch_bounds__(256) spmv6_kernel(int nrows, const int *__rest
 template <int ADD>
 __global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__restrict__ rowp,
                                                    const int *__restrict__ cols, const double *__restrict__ A,
-                                                   const double *__restrict__ x, double *__restrict__ y) {
+                                                   const double *__restrict__ x, double *__restrict__ y,
+                                                   double sign, double zs, const double *__restrict__ z) {
   const long total = (long)nrows * 3;
   for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
     const int row = (int)(g / 3), r = (int)(g - (long)row * 3);
     const int beg = rowp[row], end = rowp[row + 1];
-    double acc = ADD ? y[g] : 0.0;
+    double acc = ADD == 1 ? y[g] : 0.0;
     const double *a = A + (long)9 * beg + 3 * r;
     int k = beg;
 #pragma unroll 4
@@ -1628,27 +1634,47 @@ __global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__rest
       s += __ldg(a + 2) * __ldg(xp + 2);
       acc += s;
     }
+    if (ADD == 2) acc = zs * z[g] + sign * acc;
+    if (ADD == 3) acc = y[g] + sign * acc;
     y[g] = acc;
   }
 }
 
-cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
-                        double *y, int add, int num_sms, cudaStream_t s) {
+cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
+                              double *y, int mode, double sign, double zs, const double *z, int num_sms,
+                              cudaStream_t s) {
   if (nrows <= 0) return cudaSuccess;
   const int block = 256;
   long want = ((long)nrows * bs + block - 1) / block;
   long cap = (long)num_sms * 8 * 64;
   unsigned grid = (unsigned)(want < cap ? want : cap);
+#define TB2_SPMV(K, M) K<M><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y, sign, zs, z)
   if (bs == 6) {
-    if (add) spmv6_kernel<1><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
-    else spmv6_kernel<0><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
+    switch (mode) {
+      case 0: TB2_SPMV(spmv6_kernel, 0); break;
+      case 1: TB2_SPMV(spmv6_kernel, 1); break;
+      case 2: TB2_SPMV(spmv6_kernel, 2); break;
+      case 3: TB2_SPMV(spmv6_kernel, 3); break;
+      default: return cudaErrorInvalidValue;
+    }
   } else if (bs == 3) {
-    if (add) spmv3_kernel<1><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
-    else spmv3_kernel<0><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y);
+    switch (mode) {
+      case 0: TB2_SPMV(spmv3_kernel, 0); break;
+      case 1: TB2_SPMV(spmv3_kernel, 1); break;
+      case 2: TB2_SPMV(spmv3_kernel, 2); break;
+      case 3: TB2_SPMV(spmv3_kernel, 3); break;
+      default: return cudaErrorInvalidValue;
+    }
   } else {
     return cudaErrorInvalidValue;
   }
+#undef TB2_SPMV
   return cudaGetLastError();
+}
+
+cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
+                        double *y, int add, int num_sms, cudaStream_t s) {
+  return launch_spmv_fused(bs, nrows, rowp, cols, A, x, y, add ? 1 : 0, 1.0, 0.0, nullptr, num_sms, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1812,6 +1838,184 @@ cudaError_t launch_mdot(long n, const double *x, int nv, const double *const *ys
     case 8: dot_partial_kernel<8><<<grid, kDotBlock, 0, s>>>(n, x, p, partial); break;
   }
   dot_final_kernel<<<1, kDotBlock, 0, s>>>(nv, grid, partial, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Krylov building blocks with device-resident scalars (GMRES, krylov.cpp)
+// ------------------------------------------------------------------------------------------
+// One Gram-Schmidt step in one sweep: w <- w - (*coef) vprev (skipped when vprev is null), and with the updated w
+// out[0] = w . vnext (vnext given) or w . w (vnext null). The coefficient is read from device memory -- it is the
+// result the previous step left there -- so a whole orthogonalisation is a chain of launches without a host round
+// trip. Reduction: fixed grid, per-block partials, the last block to finish (ticket) sums them in index order:
+// deterministic, no floating-point atomics.
+__global__ void __launch_bounds__(kDotBlock) orth_step_kernel(long n, double *__restrict__ w,
+                                                             const double *__restrict__ vprev,
+                                                             const double *__restrict__ coef,
+                                                             const double *__restrict__ vnext,
+                                                             double *__restrict__ partial, unsigned *ticket,
+                                                             double *__restrict__ out) {
+  const double c = vprev ? *coef : 0.0;
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    if (vprev) {
+      wi -= c * vprev[i];
+      w[i] = wi;
+    }
+    acc += wi * (vnext ? vnext[i] : wi);
+  }
+  __shared__ double sh[kDotBlock / 32];
+  __shared__ bool last;
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < kDotBlock / 32; k++) t += sh[k];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) t += __ldcg(partial + k);
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int k = 0; k < kDotBlock / 32; k++) r += sh[k];
+      out[0] = r;
+      *ticket = 0u;
+    }
+  }
+}
+
+cudaError_t launch_orth_step(long n, double *w, const double *vprev, const double *coef, const double *vnext,
+                             double *partial, unsigned *ticket, double *out, int num_sms, cudaStream_t s) {
+  orth_step_kernel<<<dot_num_partials(num_sms), kDotBlock, 0, s>>>(n, w, vprev, coef, vnext, partial, ticket, out);
+  return cudaGetLastError();
+}
+
+// v <- v * (sign / sqrt(*sumsq))   (the reference scales by the reciprocal of the norm, KSM.cpp:804, 849)
+__global__ void scale_rsqrt_kernel(long n, double *__restrict__ v, const double *__restrict__ sumsq, double sign) {
+  const double f = sign * (1.0 / sqrt(*sumsq));
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) v[i] *= f;
+}
+cudaError_t launch_scale_rsqrt(long n, double *v, const double *sumsq, double sign, int num_sms, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  scale_rsqrt_kernel<<<vec_grid(n, num_sms), 256, 0, s>>>(n, v, sumsq, sign);
+  return cudaGetLastError();
+}
+
+// x <- x + scale * sum_j coef[j] v_j, the terms added one after the other in index order (per entry the same
+// rounding sequence as nv successive axpy calls); coefficients in device memory
+template <int NV>
+__global__ void __launch_bounds__(256) multi_axpy_kernel(long n, double *__restrict__ x, DotPtrs vs,
+                                                        const double *__restrict__ coef, double scale) {
+  double c[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) c[v] = scale * coef[v];
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double xi = x[i];
+#pragma unroll
+    for (int v = 0; v < NV; v++) xi += c[v] * vs.y[v][i];
+    x[i] = xi;
+  }
+}
+
+cudaError_t launch_multi_axpy(long n, double *x, int nv, const double *const *vs, const double *coef, double scale,
+                              int num_sms, cudaStream_t s) {
+  if (nv < 1 || nv > kDotMaxVecs) return cudaErrorInvalidValue;
+  if (n <= 0) return cudaSuccess;
+  DotPtrs p;
+  for (int v = 0; v < kDotMaxVecs; v++) p.y[v] = vs[v < nv ? v : 0];
+  const unsigned grid = vec_grid(n, num_sms);
+  switch (nv) {
+    case 1: multi_axpy_kernel<1><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 2: multi_axpy_kernel<2><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 3: multi_axpy_kernel<3><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 4: multi_axpy_kernel<4><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 5: multi_axpy_kernel<5><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 6: multi_axpy_kernel<6><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 7: multi_axpy_kernel<7><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+    case 8: multi_axpy_kernel<8><<<grid, 256, 0, s>>>(n, x, p, coef, scale); break;
+  }
+  return cudaGetLastError();
+}
+
+// Least-squares side of GMRES for column i of the Hessenberg matrix, one thread. hcol[0..i] holds the projections
+// of A v_i on v_0..v_i, hcol[i+1] the squared norm of what is left. The earlier plane rotations are applied to the
+// column, the rotation that annihilates its subdiagonal entry is formed and applied to the right-hand side g; the
+// rotated column goes to column i of R (ldr rows per column) and |g[i+1]|, the residual norm of the iterate, to
+// resnorm[i]. (Same recurrences as every GMRES; the reference's are KSM.cpp:863-885.)
+__global__ void gmres_rotate_kernel(int i, int ldr, const double *__restrict__ hcol, double *__restrict__ R,
+                                    double *__restrict__ cs, double *__restrict__ sn, double *__restrict__ g,
+                                    double *__restrict__ resnorm) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double *col = R + (long)i * ldr;
+  for (int k = 0; k <= i; k++) col[k] = hcol[k];
+  col[i + 1] = sqrt(hcol[i + 1]);
+  for (int k = 0; k < i; k++) {
+    const double a = col[k], b = col[k + 1];
+    col[k] = a * cs[k] + b * sn[k];
+    col[k + 1] = -a * sn[k] + b * cs[k];
+  }
+  const double a = col[i], b = col[i + 1];
+  const double r = sqrt(a * a + b * b);
+  cs[i] = a / r;
+  sn[i] = b / r;
+  col[i] = a * cs[i] + b * sn[i];
+  col[i + 1] = -a * sn[i] + b * cs[i];
+  const double gi = g[i];
+  g[i] = gi * cs[i];
+  g[i + 1] = -gi * sn[i];
+  resnorm[i] = fabs(g[i + 1]);
+}
+cudaError_t launch_gmres_rotate(int i, int ldr, const double *hcol, double *R, double *cs, double *sn, double *g,
+                                double *resnorm, cudaStream_t s) {
+  gmres_rotate_kernel<<<1, 32, 0, s>>>(i, ldr, hcol, R, cs, sn, g, resnorm);
+  return cudaGetLastError();
+}
+
+// y = R(0:k,0:k)^{-1} g(0:k), upper triangular, one thread
+__global__ void gmres_backsolve_kernel(int k, int ldr, const double *__restrict__ R, const double *__restrict__ g,
+                                       double *__restrict__ y) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = k - 1; i >= 0; i--) {
+    double t = g[i];
+    for (int j = i + 1; j < k; j++) t = t - R[(long)j * ldr + i] * y[j];
+    y[i] = t / R[(long)i * ldr + i];
+  }
+}
+cudaError_t launch_gmres_backsolve(int k, int ldr, const double *R, const double *g, double *y, cudaStream_t s) {
+  if (k <= 0) return cudaSuccess;
+  gmres_backsolve_kernel<<<1, 32, 0, s>>>(k, ldr, R, g, y);
+  return cudaGetLastError();
+}
+
+// g[0] = sqrt(sumsq[0]) (start of a cycle): keeps the initial residual norm on the device
+__global__ void gmres_start_kernel(const double *__restrict__ sumsq, double *__restrict__ g, int m) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  g[0] = sqrt(sumsq[0]);
+  for (int k = 1; k <= m; k++) g[k] = 0.0;
+}
+cudaError_t launch_gmres_start(const double *sumsq, double *g, int m, cudaStream_t s) {
+  gmres_start_kernel<<<1, 32, 0, s>>>(sumsq, g, m);
+  return cudaGetLastError();
+}
+
+// y <- zs * z + ys * y   (polynomial smoother start: h = -c0 r, and the like)
+__global__ void axpbz_kernel(long n, double zs, const double *__restrict__ z, double ys, double *__restrict__ y) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = zs * z[i] + (ys != 0.0 ? ys * y[i] : 0.0);
+}
+cudaError_t launch_axpbz(long n, double zs, const double *z, double ys, double *y, int num_sms, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  axpbz_kernel<<<vec_grid(n, num_sms), 256, 0, s>>>(n, zs, z, ys, y);
   return cudaGetLastError();
 }
 

@@ -78,6 +78,23 @@ cudaError_t launch_vec_set_bcs(int bs, int nbcs, const int *bc_rows, const int *
 cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
                         double *y, int add, int num_sms, cudaStream_t s);
 
+// mode 0: y = A x; 1: y += A x (block by block, the multAdd order); 2: y = zs z + sign (A x); 3: y = y + sign (A x)
+cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
+                              double *y, int mode, double sign, double zs, const double *z, int num_sms,
+                              cudaStream_t s);
+
+// Krylov building blocks with device-resident scalars (kernels.cu): see the kernels for the contracts
+cudaError_t launch_orth_step(long n, double *w, const double *vprev, const double *coef, const double *vnext,
+                             double *partial, unsigned *ticket, double *out, int num_sms, cudaStream_t s);
+cudaError_t launch_scale_rsqrt(long n, double *v, const double *sumsq, double sign, int num_sms, cudaStream_t s);
+cudaError_t launch_multi_axpy(long n, double *x, int nv, const double *const *vs, const double *coef, double scale,
+                              int num_sms, cudaStream_t s);
+cudaError_t launch_gmres_rotate(int i, int ldr, const double *hcol, double *R, double *cs, double *sn, double *g,
+                                double *resnorm, cudaStream_t s);
+cudaError_t launch_gmres_backsolve(int k, int ldr, const double *R, const double *g, double *y, cudaStream_t s);
+cudaError_t launch_gmres_start(const double *sumsq, double *g, int m, cudaStream_t s);
+cudaError_t launch_axpbz(long n, double zs, const double *z, double ys, double *y, int num_sms, cudaStream_t s);
+
 // out[0] = max over scalar rows of (signed diagonal + sum of magnitudes); browp/B: Bext rows for owned rows >= np
 cudaError_t launch_gershgorin(int bs, int nrows, const int *rowp, const int *cols, const double *A, int np,
                               const int *browp, const double *B, double *out, int num_sms, cudaStream_t s);

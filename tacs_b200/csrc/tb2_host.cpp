@@ -749,8 +749,8 @@ TACSBVec::TACSBVec(int bs, int no, int eb, int ea) {
   zeroEntries();
 }
 
-static double *g_dot_partial = nullptr, *g_dot_out = nullptr, *g_dot_host = nullptr;
-static bool dot_buffers() {
+double *g_dot_partial = nullptr, *g_dot_out = nullptr, *g_dot_host = nullptr;
+bool dot_buffers() {
   if (g_dot_partial) return true;
   const size_t np = (size_t)dot_num_partials(ctx().num_sms) * 8;
   return cuda_ok(cudaMalloc(&g_dot_partial, np * sizeof(double)), "cudaMalloc") &&
@@ -1296,6 +1296,29 @@ void TACSParallelMat::applyBCs() {
 int spmv_halo_begin(TACSParallelMat *A, TACSBVec *x);  // comm.cpp
 void spmv_halo_end(TACSParallelMat *A);
 
+// y = zs z + sign (A x): the product with the vector update in its epilogue (smoother steps, Krylov residuals)
+int TACSParallelMat::multFused(TACSBVec *x, TACSBVec *y, double sign, double zs, TACSBVec *z) {
+  const bool dist = assembler->size > 1;
+  int rc = 0;
+  if (dist) rc = spmv_halo_begin(this, x);
+  {
+    KernelTimer kt(K_SPMV, Aloc.bsize == 6 ? "spmv6_kernel<2>" : "spmv3_kernel<2>");
+    if (!cuda_ok(launch_spmv_fused(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr,
+                                   x->owned(), y->owned(), 2, sign, zs, z->owned(), ctx().num_sms, ctx().stream),
+                 "spmv fused")) rc = 1;
+  }
+  if (dist) {
+    spmv_halo_end(this);
+    if (Bext.nnzb() > 0) {
+      KernelTimer kt(K_SPMV, Bext.bsize == 6 ? "spmv6_kernel<3>" : "spmv3_kernel<3>");
+      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
+                                     x_ext.ptr, y->owned() + (size_t)Bext.bsize * np, 3, sign, 0.0, nullptr,
+                                     ctx().num_sms, ctx().stream), "spmv ext fused")) rc = 1;
+    }
+  }
+  return rc;
+}
+
 // TACSParallelMat::mult (TACSParallelMat.cpp:248-265): y = Aloc x + Bext x_ext, halo overlapped
 int TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
   const bool dist = assembler->size > 1;
@@ -1317,208 +1340,6 @@ int TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
     }
   }
   return rc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// GMRES (KSM.cpp:547-956), modified Gram-Schmidt (:526-532)
-// ---------------------------------------------------------------------------------------------
-int comm_allreduce_max(double *dev_buf, int n);  // comm.cpp
-
-TACSChebyshevSmoother::TACSChebyshevSmoother(TACSParallelMat *_mat, int _degree, double _lower, double _upper,
-                                             int _iters) {
-  mat = _mat;
-  mat->incref();
-  degree = _degree > 0 ? _degree : 1;
-  iters = _iters;
-  lower_factor = _lower;
-  upper_factor = _upper;
-  r.assign(degree, 0.0);
-  c.assign(degree + 1, 1.0);
-  res = mat->createVec();
-  t = mat->createVec();
-  h = mat->createVec();
-  res->incref();
-  t->incref();
-  h->incref();
-}
-TACSChebyshevSmoother::~TACSChebyshevSmoother() {
-  res->decref();
-  t->decref();
-  h->decref();
-  mat->decref();
-}
-
-double TACSChebyshevSmoother::gershgorin() {
-  if (!dot_buffers()) return 0.0;
-  const BCSRPattern &A = mat->Aloc, &B = mat->Bext;
-  {
-    KernelTimer kt(K_VEC);
-    cuda_ok(launch_gershgorin(A.bsize, A.nrows, A.d_rowp.ptr, A.d_cols.ptr, A.d_vals.ptr, mat->np,
-                              B.nnzb() > 0 ? B.d_rowp.ptr : nullptr, B.d_vals.ptr, g_dot_out, ctx().num_sms,
-                              ctx().stream), "gershgorin");
-  }
-  if (ctx().size > 1) comm_allreduce_max(g_dot_out, 1);
-  cuda_ok(cudaMemcpyAsync(g_dot_host, g_dot_out, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream), "gershgorin");
-  cuda_ok(cudaStreamSynchronize(ctx().stream.s), "gershgorin sync");
-  return g_dot_host[0];
-}
-
-// factor(): interval [alpha, beta] = [lower, upper] * rho, Chebyshev roots mapped onto it, monomial coefficients of
-// q(A) = 1 - p(A) A normalised to q(0) = 1 (TACSParallelMat.cpp:930-976)
-int TACSChebyshevSmoother::factor() {
-  rho = gershgorin();
-  alpha = lower_factor * rho;
-  beta = upper_factor * rho;
-  for (int k = 0; k < degree; k++) r[k] = cos(M_PI * (0.5 + k) / degree);
-  for (int k = 0; k < degree; k++) r[k] = 0.5 * (beta - alpha) * (r[k] + 1.0) + alpha;
-  std::fill(c.begin(), c.end(), 0.0);
-  c[0] = 1.0;
-  for (int j = 0; j < degree; j++)
-    for (int k = j; k >= 0; k--) c[k + 1] = c[k + 1] - r[j] * c[k];
-  for (int k = 0; k < degree; k++) c[k] = c[k] / c[degree];
-  c[degree] = 1.0;
-  return 0;
-}
-
-// applyFactor(): y <- y + p(A) (x - A y); note that y enters as the initial guess (TACSParallelMat.cpp:981-1014)
-void TACSChebyshevSmoother::applyFactor(TACSBVec *x, TACSBVec *y) {
-  for (int i = 0; i < iters; i++) {
-    res->copyValues(x);
-    mat->mult(y, t);
-    res->axpy(-1.0, t);
-    h->copyValues(res);
-    h->scale(-c[0]);
-    for (int j = 0; j < degree - 1; j++) {
-      mat->mult(h, t);
-      h->copyValues(res);
-      h->scale(-c[j + 1]);
-      h->axpy(1.0, t);
-    }
-    y->axpy(1.0, h);
-  }
-}
-
-GMRES::GMRES(TACSParallelMat *_mat, int _m, int _nrestart, TACSChebyshevSmoother *_pc, bool _flexible) {
-  mat = _mat;
-  mat->incref();
-  pc = _pc;
-  if (pc) pc->incref();
-  flexible = _flexible && pc;
-  m = _m;
-  nrestart = _nrestart >= 0 ? _nrestart : 0;
-  for (int i = 0; i < m + 1; i++) {
-    W.push_back(mat->createVec());
-    W.back()->incref();
-  }
-  if (flexible) {
-    for (int i = 0; i < m; i++) {
-      Z.push_back(mat->createVec());
-      Z.back()->incref();
-    }
-  } else if (pc) {
-    work = mat->createVec();
-    work->incref();
-  }
-  Hptr.assign(m + 1, 0);
-  for (int i = 0; i < m; i++) Hptr[i + 1] = Hptr[i] + i + 2;
-  H.assign(Hptr[m], 0.0);
-  res.assign(m + 1, 0.0);
-  Qsin.assign(m, 0.0);
-  Qcos.assign(m, 0.0);
-}
-GMRES::~GMRES() {
-  for (auto w : W) w->decref();
-  for (auto z : Z) z->decref();
-  if (work) work->decref();
-  if (pc) pc->decref();
-  mat->decref();
-}
-
-int GMRES::solve(TACSBVec *b, TACSBVec *x, int zero_guess) {
-  double rhs_norm = 0.0;
-  int solve_flag = 0;
-  iters = 0;
-  for (int count = 0; count < nrestart + 1; count++) {
-    if (zero_guess && count == 0) {
-      x->zeroEntries();
-      W[0]->copyValues(b);
-      res[0] = W[0]->norm();
-      W[0]->scale(1.0 / res[0]);
-    } else {
-      mat->mult(x, W[0]);
-      W[0]->axpy(-1.0, b);
-      res[0] = W[0]->norm();
-      W[0]->scale(-1.0 / res[0]);
-    }
-    if (count == 0) {
-      rhs_norm = res[0];
-      resnorm = rhs_norm;
-    }
-    int niters = 0;
-    if (res[0] < atol) {
-      solve_flag = 1;
-      break;
-    }
-    for (int i = 0; i < m; i++) {
-      if (flexible) {
-        pc->applyFactor(W[i], Z[i]);   // Z[i] = M^{-1} W[i]
-        mat->mult(Z[i], W[i + 1]);
-      } else if (pc) {
-        pc->applyFactor(W[i], work);   // work = M^{-1} W[i] (work enters as the smoother's initial guess)
-        mat->mult(work, W[i + 1]);
-      } else {
-        mat->mult(W[i], W[i + 1]);
-      }
-      double *h = &H[Hptr[i]];
-      for (int j = 0; j < i + 1; j++) {
-        h[j] = W[i + 1]->dot(W[j]);
-        W[i + 1]->axpy(-h[j], W[j]);
-      }
-      h[i + 1] = W[i + 1]->norm();
-      W[i + 1]->scale(1.0 / h[i + 1]);
-      double h1, h2;
-      for (int k = 0; k < i; k++) {
-        h1 = h[k];
-        h2 = h[k + 1];
-        h[k] = h1 * Qcos[k] + h2 * Qsin[k];
-        h[k + 1] = -h1 * Qsin[k] + h2 * Qcos[k];
-      }
-      h1 = h[i];
-      h2 = h[i + 1];
-      double sq = sqrt(h1 * h1 + h2 * h2);
-      Qcos[i] = h1 / sq;
-      Qsin[i] = h2 / sq;
-      h[i] = h1 * Qcos[i] + h2 * Qsin[i];
-      h[i + 1] = -h1 * Qsin[i] + h2 * Qcos[i];
-      h1 = res[i];
-      res[i] = h1 * Qcos[i];
-      res[i + 1] = -h1 * Qsin[i];
-      niters++;
-      resnorm = fabs(res[i + 1]);
-      if (resnorm < atol || resnorm < rtol * rhs_norm) {
-        solve_flag = 1;
-        break;
-      }
-    }
-    iters += niters;
-    for (int i = niters - 1; i >= 0; i--) {
-      for (int j = i + 1; j < niters; j++) res[i] = res[i] - H[i + Hptr[j]] * res[j];
-      res[i] = res[i] / H[i + Hptr[i]];
-    }
-    if (flexible) {
-      for (int i = 0; i < niters; i++) x->axpy(res[i], Z[i]);
-    } else if (!pc) {
-      for (int i = 0; i < niters; i++) x->axpy(res[i], W[i]);
-    } else {
-      work->zeroEntries();
-      for (int i = 0; i < niters; i++) work->axpy(res[i], W[i]);
-      pc->applyFactor(work, W[0]);     // M^{-1} applied to the linear combination
-      x->axpy(1.0, W[0]);
-    }
-    if (solve_flag) break;
-  }
-  cudaStreamSynchronize(ctx().stream);
-  return solve_flag;
 }
 
 }  // namespace tb2

@@ -383,6 +383,7 @@ class TACSParallelMat : public Object {
   DeviceExchange x_cols;
   void zeroEntries();
   int mult(TACSBVec *x, TACSBVec *y);
+  int multFused(TACSBVec *x, TACSBVec *y, double sign, double zs, TACSBVec *z);  // y = zs z + sign (A x)
   void applyBCs();
   TACSBVec *createVec();
 };
@@ -510,41 +511,74 @@ class TACSAssembler : public Object {
                      const double *ddvars_override = nullptr, bool use_override = false);
 };
 
-// GMRES (src/bpmat/KSM.cpp:547-956): right-preconditioned restarted GMRES with modified
-// Gram-Schmidt; host control flow, device vectors; optional block-Jacobi-free identity PC.
+// reduction scratch shared by the vector kernels (tb2_host.cpp)
+extern double *g_dot_partial, *g_dot_out, *g_dot_host;
+bool dot_buffers();
+
 // TACSChebyshevSmoother (bpmat/TACSParallelMat.h:180-217, TACSParallelMat.cpp:871-1113): polynomial smoother /
 // preconditioner built from products with the matrix only; the spectral radius comes from Gershgorin's discs.
+// applyFactor runs as a chain of SpMV launches whose epilogues carry the vector updates (krylov.cpp).
 class TACSChebyshevSmoother : public Object {
  public:
   TACSChebyshevSmoother(TACSParallelMat *mat, int degree, double lower_factor, double upper_factor, int iters);
   ~TACSChebyshevSmoother();
   int factor();
-  void applyFactor(TACSBVec *x, TACSBVec *y);
+  int applyFactor(TACSBVec *x, TACSBVec *y);
   double gershgorin();
   TACSParallelMat *mat;
   int degree, iters;
   double lower_factor, upper_factor, alpha = 0.0, beta = 0.0, rho = 0.0;
-  std::vector<double> r, c;
-  TACSBVec *res = nullptr, *t = nullptr, *h = nullptr;
+  std::vector<double> roots, coef;  // roots of the shifted Chebyshev polynomial, monomial coefficients of q
+  TACSBVec *res = nullptr, *h0 = nullptr, *h1 = nullptr;
 };
 
+// GMRES (reference interface: src/bpmat/KSM.h:392-440): restarted, right-preconditioned (optionally flexible)
+// GMRES. Device-resident design (krylov.cpp): the Hessenberg column, the plane rotations and the least-squares
+// right-hand side live in device memory, every Gram-Schmidt coefficient is consumed by the next kernel through a
+// device pointer, the body of an iteration is a CUDA graph, and the host reads the residual history once every
+// `check_every` iterations.
 class GMRES : public Object {
  public:
+  enum OrthoType { CLASSICAL_GRAM_SCHMIDT = 0, MODIFIED_GRAM_SCHMIDT = 1 };
   GMRES(TACSParallelMat *mat, int m, int nrestart, TACSChebyshevSmoother *pc = nullptr, bool flexible = false);
   ~GMRES();
   void setTolerances(double rtol, double atol) { this->rtol = rtol; this->atol = atol; }
+  void setOrthoType(int t) { ortho = t; dropGraphs(); }
+  // KSMPrintStdout(descript, rank, freq) (KSM.cpp:239-283): "%s[%3d]: %15.8e" lines on rank 0 every freq iterations
+  void setMonitor(const char *descript, int freq);
+  // GMRES::setTimeMonitor (KSM.cpp:765): per-solve device times of the preconditioner / orthogonalisation / total
+  void setTimeMonitor() { monitor_time = true; }
   int solve(TACSBVec *b, TACSBVec *x, int zero_guess);
   int getIterCount() { return iters; }
   double getResidualNorm() { return resnorm; }
   TACSParallelMat *mat;
   int m, nrestart, iters = 0;
   double rtol = 1e-8, atol = 1e-30, resnorm = 0.0;
-  std::vector<TACSBVec *> W, Z;   // Z: preconditioned directions of the flexible variant
+  int ortho = MODIFIED_GRAM_SCHMIDT;
+  int check_every = 4;            // iterations between reads of the residual history (TACSB200_GMRES_CHECK)
+  bool use_graphs = true;         // TACSB200_GMRES_GRAPHS=0 launches the kernels one by one
+  std::vector<TACSBVec *> W, Z;   // Krylov basis; Z: preconditioned directions of the flexible variant
   TACSBVec *work = nullptr;       // M^{-1} W[i] of the regular variant
   TACSChebyshevSmoother *pc = nullptr;
   bool flexible = false;
-  std::vector<double> H, res, Qsin, Qcos;
-  std::vector<int> Hptr;
+  // device state of the least-squares problem: hcol[m+2], R[(m+1) x m] column major, cs/sn[m], g[m+1], resnorm[m],
+  // y[m], sumsq[1]; pinned host mirror of the residual history
+  DeviceArray<double> d_state;
+  DeviceArray<unsigned> d_ticket;
+  double *d_hcol = nullptr, *d_R = nullptr, *d_cs = nullptr, *d_sn = nullptr, *d_g = nullptr, *d_res = nullptr,
+         *d_y = nullptr, *d_sumsq = nullptr;
+  double *h_res = nullptr;  // pinned
+  std::vector<cudaGraphExec_t> graphs;  // one per iteration index, captured on first use
+  std::vector<int> graph_launches;      // kernels inside each graph (for the launch counter)
+  std::string monitor_name;
+  int monitor_freq = 0;
+  bool monitor_time = false;
+  double t_pc = 0.0, t_ortho = 0.0, t_total = 0.0;  // ms, last solve (setTimeMonitor)
+
+ private:
+  int iterationBody(int i);   // enqueue iteration i on the compute stream
+  int runIteration(int i);    // through its graph when enabled
+  void dropGraphs();
 };
 
 }  // namespace tb2

@@ -380,3 +380,58 @@ def test_gmres_linear_static_matches_reference(lib, ref):
     assert sol["b200"][0] == 1 and sol["ref"][0] == 1
     assert abs(sol["b200"][1] - sol["ref"][1]) <= 1
     assert relerr(sol["b200"][2], sol["ref"][2]) < 1e-10
+
+
+def test_gmres_device_design_variants(lib, ref, capfd):
+    """The device-resident GMRES gives the same iterates whether an iteration runs as a CUDA graph or kernel by
+    kernel, and whatever the interval at which the host reads the residual history (iterations past convergence are
+    discarded); iteration count and solution match the reference (KSM.cpp:785-956). Classical Gram-Schmidt
+    (GMRES::setOrthoType) converges to the same solution; the monitor prints the reference's KSMPrintStdout lines."""
+    import os
+
+    mesh = meshgen.cube(2, 6)
+    n_ref = None
+    sols = {}
+    for tag, L, env in (("ref", ref, {}), ("graphs_check4", lib, {}),
+                        ("direct_check1", lib, {"TACSB200_GMRES_GRAPHS": "0", "TACSB200_GMRES_CHECK": "1"}),
+                        ("graphs_check7", lib, {"TACSB200_GMRES_CHECK": "7"})):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            creator, asm = meshgen.build_model(T, L, mesh, [meshgen.solid_element(T, L, 2)])
+            A, res, b, x = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+            asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+            b.setArray(meshgen.hash_vector(b.getSize()) - 0.3)
+            asm.applyBCs(b)
+            ksm = T.KSM(L, A, 25, 20)
+            ksm.setTolerances(1e-10, 1e-30)
+            for _ in range(3):  # first solve direct, second captures the graphs, third replays them
+                flag = ksm.solve(b, x)
+            sols[tag] = (x.getArray(), ksm.getIterCount(), flag, ksm.getResidualNorm())
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    xr, itr, flagr, rn = sols["ref"]
+    assert flagr == 1
+    for tag in ("graphs_check4", "direct_check1", "graphs_check7"):
+        xs, its, flag, rs = sols[tag]
+        assert flag == 1 and its == itr, (tag, its, itr)
+        assert relerr(xs, xr) < 1e-10, (tag, relerr(xs, xr))
+        assert abs(rs - rn) <= 1e-2 * rn  # a residual estimate 1e-10 below the start: a few digits are all there is
+    assert np.array_equal(sols["graphs_check4"][0], sols["direct_check1"][0])
+    assert np.array_equal(sols["graphs_check4"][0], sols["graphs_check7"][0])
+    # classical Gram-Schmidt + monitor
+    creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.solid_element(T, lib, 2)])
+    A, res, b, x = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+    asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+    b.setArray(meshgen.hash_vector(b.getSize()) - 0.3)
+    asm.applyBCs(b)
+    ksm = T.KSM(lib, A, 25, 20)
+    ksm.setTolerances(1e-10, 1e-30)
+    ksm.setOrthoType(True)
+    ksm.setMonitor("GMRES", 5)
+    capfd.readouterr()
+    assert ksm.solve(b, x) == 1
+    out = capfd.readouterr().out
+    assert "GMRES[  0]:" in out and "GMRES[  5]:" in out
+    assert relerr(x.getArray(), xr) < 1e-8
