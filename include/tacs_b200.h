@@ -66,6 +66,13 @@ tacsb200_handle tacsb200_composite_shell_constitutive_create(int num_plies, tacs
 /* TACSSolidConstitutive(properties, t)  TACSSolidConstitutive.h:34 */
 tacsb200_handle tacsb200_solid_constitutive_create(tacsb200_handle props, double t);
 /* TACSShellConstitutive::setDrillingRegularization  TACSShellConstitutive.cpp:66 */
+/* Constitutive objects given by their constant values: the 22-entry shell tangent stiffness [A B D As drill] and
+   mass moments, or the 21-entry solid tangent stiffness and density -- what TACSShellConstitutive::
+   evalTangentStiffness / evalMassMoments (src/constitutive/TACSShellConstitutive.h:100-115) and
+   TACSSolidConstitutive::evalTangentStiffness / evalDensity (TACSSolidConstitutive.cpp:104-178) return for the classes
+   of this path. The reference-side shim (shim/) reads them off the caller's own objects. */
+tacsb200_handle tacsb200_shell_constitutive_create_raw(const double *C22, const double *moments3);
+tacsb200_handle tacsb200_solid_constitutive_create_raw(const double *C21, double density);
 void tacsb200_shell_set_drilling_regularization(double k);
 /* TACSConstitutive::evalTangentStiffness  TACSConstitutive.h:340 (22 values shell, 21 solid) */
 int tacsb200_constitutive_eval_tangent_stiffness(tacsb200_handle con, double *C);
@@ -110,6 +117,9 @@ int tacsb200_creator_set_boundary_conditions(tacsb200_handle c, int num_bcs, con
 int tacsb200_creator_set_nodes(tacsb200_handle c, const double *Xpts);
 int tacsb200_creator_set_elements(tacsb200_handle c, int num_elems, tacsb200_handle *elems);
 /* partitionMesh(split_size, part): part == NULL runs METIS exactly as TACSCreator.cpp:1104-1125 */
+/* Adopt the caller's node numbering as final (no first-touch renumbering, one rank): the mesh comes from an existing
+   TACSAssembler (getElementConnectivity, src/TACSAssembler.h:90) whose vectors and matrices the caller keeps using. */
+int tacsb200_creator_set_keep_numbering(tacsb200_handle creator, int keep_numbering);
 int tacsb200_creator_partition_mesh(tacsb200_handle c, int split_size, const int *part);
 int tacsb200_creator_get_node_nums(tacsb200_handle c, int *new_nodes);
 int tacsb200_creator_get_element_partition(tacsb200_handle c, int *partition);
@@ -192,6 +202,10 @@ int tacsb200_mat_get_pattern(tacsb200_handle m, int which, int *rowp, int *cols)
 int tacsb200_mat_get_values(tacsb200_handle m, int which, double *out);
 double *tacsb200_mat_device_values(tacsb200_handle m, int which);
 int tacsb200_mat_get_ext_col_nodes(tacsb200_handle m, int *nodes); /* getExtColMap :107 */
+/* TACSParallelMat::copyValues / scale / axpy (src/bpmat/TACSParallelMat.cpp:198-246), same non-zero pattern */
+int tacsb200_mat_copy_values(tacsb200_handle mat, tacsb200_handle other);
+int tacsb200_mat_scale(tacsb200_handle mat, double alpha);
+int tacsb200_mat_axpy(tacsb200_handle mat, double alpha, tacsb200_handle other);
 int tacsb200_mat_zero_entries(tacsb200_handle m);
 int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y); /* mult :248 */
 /* asynchronous variant for benchmarking: enqueue only, pair with tacsb200_synchronize */

@@ -128,6 +128,12 @@ PRODUCT_ONLY = {
     "profile_enable": (I, [I]),
     "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
     "profile_named": (C.c_char_p, []),
+    "mat_copy_values": (I, [H, H]),
+    "mat_scale": (I, [H, D]),
+    "mat_axpy": (I, [H, D, H]),
+    "shell_constitutive_create_raw": (H, [DP, DP]),
+    "solid_constitutive_create_raw": (H, [DP, D]),
+    "creator_set_keep_numbering": (I, [H, I]),
     "gmres_set_ortho_type": (I, [H, I]),
     "gmres_set_monitor": (I, [H, C.c_char_p, I]),
     "gmres_set_time_monitor": (I, [H]),

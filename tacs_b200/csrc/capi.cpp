@@ -120,6 +120,14 @@ tacsb200_handle tacsb200_solid_constitutive_create(tacsb200_handle props, double
   REQUIRE_H(p, "material properties");
   return keep(new TACSSolidConstitutive(p, t));
 }
+tacsb200_handle tacsb200_shell_constitutive_create_raw(const double *C22, const double *moments3) {
+  if (!C22 || !moments3) return nullptr;
+  return keep(new TACSRawShellConstitutive(C22, moments3));
+}
+tacsb200_handle tacsb200_solid_constitutive_create_raw(const double *C21, double density) {
+  if (!C21) return nullptr;
+  return keep(new TACSSolidConstitutive(C21, density));
+}
 void tacsb200_shell_set_drilling_regularization(double k) { TACSShellConstitutive::setDrillingRegularization(k); }
 int tacsb200_constitutive_eval_tangent_stiffness(tacsb200_handle con, double *C) {
   TACSConstitutive *c = as<TACSConstitutive>(con);
@@ -219,6 +227,16 @@ int tacsb200_creator_set_elements(tacsb200_handle c, int n, tacsb200_handle *ele
     REQUIRE(e[i], "element");
   }
   cr->setElements(n, e.data());
+  return 0;
+}
+int tacsb200_creator_set_keep_numbering(tacsb200_handle c, int keep_numbering) {
+  TACSCreator *cr = as<TACSCreator>(c);
+  REQUIRE(cr, "creator");
+  if (keep_numbering && cr->comm_size() > 1) {
+    fprintf(stderr, "tacs_b200: keep_numbering adopts the numbering of a single-rank assembler only\n");
+    return 1;
+  }
+  cr->keep_numbering = keep_numbering != 0;
   return 0;
 }
 int tacsb200_creator_partition_mesh(tacsb200_handle c, int split, const int *part) {
@@ -526,6 +544,15 @@ int tacsb200_mat_get_ext_col_nodes(tacsb200_handle m, int *nodes) {
   return (int)A->ext_col_nodes.size();
 }
 int tacsb200_mat_zero_entries(tacsb200_handle m) { MAT(m); A->zeroEntries(); return 0; }
+int tacsb200_mat_copy_values(tacsb200_handle m, tacsb200_handle other) {
+  MAT(m);
+  return A->copyValues(as<TACSParallelMat>(other));
+}
+int tacsb200_mat_scale(tacsb200_handle m, double alpha) { MAT(m); return A->scale(alpha); }
+int tacsb200_mat_axpy(tacsb200_handle m, double alpha, tacsb200_handle other) {
+  MAT(m);
+  return A->axpy(alpha, as<TACSParallelMat>(other));
+}
 int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
   MAT(m);
   VEC(xv, x); VEC(yv, y);

@@ -343,8 +343,30 @@ TACSSolidConstitutive::TACSSolidConstitutive(TACSMaterialProperties *props, doub
 TACSSolidConstitutive::~TACSSolidConstitutive() {
   if (properties) properties->decref();
 }
+TACSSolidConstitutive::TACSSolidConstitutive(const double C[21], double density) {
+  properties = nullptr;
+  t = 1.0;
+  raw = true;
+  memcpy(Craw, C, sizeof(Craw));
+  rho_raw = density;
+}
+TACSRawShellConstitutive::TACSRawShellConstitutive(const double C[22], const double moments[3]) {
+  memcpy(Cs, C, sizeof(Cs));
+  memcpy(mom, moments, sizeof(mom));
+}
+void TACSRawShellConstitutive::evalTangentStiffness(double C[]) { memcpy(C, Cs, sizeof(Cs)); }
+void TACSRawShellConstitutive::evalMassMoments(double moments[3]) { memcpy(moments, mom, sizeof(mom)); }
+void TACSRawShellConstitutive::fillDescriptor(double d[]) {
+  memcpy(d, Cs, sizeof(Cs));
+  memcpy(d + 22, mom, sizeof(mom));
+}
+
 // TACSSolidConstitutive.cpp:166-178
 void TACSSolidConstitutive::evalTangentStiffness(double C[]) {
+  if (raw) {
+    memcpy(C, Craw, sizeof(Craw));
+    return;
+  }
   if (!properties) {
     memset(C, 0, 21 * sizeof(double));
     return;
@@ -354,7 +376,7 @@ void TACSSolidConstitutive::evalTangentStiffness(double C[]) {
 }
 void TACSSolidConstitutive::fillDescriptor(double d[]) {
   evalTangentStiffness(d);
-  d[21] = properties ? evalDensity() : 0.0;
+  d[21] = raw ? rho_raw : (properties ? evalDensity() : 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -574,6 +596,17 @@ int TACSCreator::partitionMesh(int split_size, const int *part) {
         METIS_PartGraphKway(&ne, &ncon, elem_ptr.data(), elem_conn.data(), NULL, NULL, NULL, &nparts, NULL, NULL,
                             options, &objval, partition.data());
     }
+  }
+  if (keep_numbering) {
+    // the caller's numbering is final (single rank): every node and element belongs to rank 0 as numbered
+    new_nodes.resize(num_nodes);
+    for (int i = 0; i < num_nodes; i++) new_nodes[i] = i;
+    owned_elements.assign(mpi_size, 0);
+    owned_nodes.assign(mpi_size, 0);
+    owned_elements[0] = num_elements;
+    owned_nodes[0] = num_nodes;
+    std::fill(partition.begin(), partition.end(), 0);
+    return 0;
   }
   // first-touch numbering (TACSCreator.cpp:1141-1205)
   new_nodes.assign(num_nodes, 0);
@@ -1230,6 +1263,28 @@ TACSParallelMat::~TACSParallelMat() { assembler->decref(); }
 void TACSParallelMat::zeroEntries() {
   if (vals_all.count)
     cuda_ok(cudaMemsetAsync(vals_all.ptr, 0, vals_all.count * sizeof(double), ctx().stream), "zeroEntries");
+}
+
+int TACSParallelMat::copyValues(TACSParallelMat *o) {
+  if (!o || o->vals_all.count != vals_all.count) {
+    fprintf(stderr, "tacs_b200: copyValues: matrices do not share a non-zero pattern\n");
+    return 1;
+  }
+  return cuda_ok(cudaMemcpyAsync(vals_all.ptr, o->vals_all.ptr, vals_all.count * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx().stream), "copyValues") ? 0 : 1;
+}
+int TACSParallelMat::scale(double alpha) {
+  KernelTimer kt(K_VEC, "scale_kernel");
+  return cuda_ok(launch_scale((long)vals_all.count, alpha, vals_all.ptr, ctx().num_sms, ctx().stream), "scale") ? 0 : 1;
+}
+int TACSParallelMat::axpy(double alpha, TACSParallelMat *o) {
+  if (!o || o->vals_all.count != vals_all.count) {
+    fprintf(stderr, "tacs_b200: axpy: matrices do not share a non-zero pattern\n");
+    return 1;
+  }
+  KernelTimer kt(K_VEC, "axpy_kernel");
+  return cuda_ok(launch_axpy((long)vals_all.count, alpha, o->vals_all.ptr, vals_all.ptr, ctx().num_sms, ctx().stream),
+                 "axpy") ? 0 : 1;
 }
 
 bool BCSRPattern::ValuesView::download(double *host, size_t n) const {

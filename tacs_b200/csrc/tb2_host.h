@@ -237,16 +237,33 @@ class TACSCompositeShellConstitutive : public TACSShellConstitutive {
   double kcorr, tOffset;
 };
 
+// A shell constitutive object given by its constant tangent stiffness (22 entries A, B, D, As, drill) and mass moments:
+// what any TACSShellConstitutive of the reference evaluates to on this path (evalTangentStiffness / evalMassMoments
+// do not depend on the point for the classes of the path). Used by the reference-side shim, which reads these numbers
+// off the caller's own constitutive objects.
+class TACSRawShellConstitutive : public TACSShellConstitutive {
+ public:
+  TACSRawShellConstitutive(const double C[22], const double moments[3]);
+  void evalTangentStiffness(double C[]);
+  void evalMassMoments(double moments[3]);
+  void fillDescriptor(double d[]);
+  double Cs[22], mom[3];
+};
+
 class TACSSolidConstitutive : public TACSConstitutive {
  public:
   TACSSolidConstitutive(TACSMaterialProperties *props, double t);
   ~TACSSolidConstitutive();
   int getNumStresses() { return 6; }
   void evalTangentStiffness(double C[]);
-  double evalDensity() { return t * properties->getDensity(); }
+  double evalDensity() { return raw ? rho_raw : t * properties->getDensity(); }
   void fillDescriptor(double d[]);
-  TACSMaterialProperties *properties;
+  TACSMaterialProperties *properties;  // null: raw form, stiffness and density given directly
   double t;
+  // raw form (shim): constant 21-entry tangent stiffness and density
+  TACSSolidConstitutive(const double C[21], double density);
+  bool raw = false;
+  double Craw[21], rho_raw = 0.0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -382,6 +399,10 @@ class TACSParallelMat : public Object {
   DeviceArray<int> d_bc_rows_ext;  // Bext row (owned row - np) of each merged BC, or -1
   DeviceExchange x_cols;
   void zeroEntries();
+  // TACSParallelMat::copyValues / scale / axpy / addDiag (TACSParallelMat.cpp:198-246): same-pattern matrices only
+  int copyValues(TACSParallelMat *other);
+  int scale(double alpha);
+  int axpy(double alpha, TACSParallelMat *other);
   int mult(TACSBVec *x, TACSBVec *y);
   int multFused(TACSBVec *x, TACSBVec *y, double sign, double zs, TACSBVec *z);  // y = zs z + sign (A x)
   void applyBCs();
@@ -402,6 +423,8 @@ class TACSCreator : public Object {
   void setNodes(const double *Xpts);
   void setElements(int num_elems, TACSElement **elems);
   int partitionMesh(int split_size, const int *part);
+  // The mesh is already in its final numbering (an existing single-rank TACSAssembler): no first-touch renumbering
+  bool keep_numbering = false;
   int getNodeNums(const int **new_nodes);
   int getElementPartition(const int **part);
   TACSAssembler *createTACS();

@@ -1,0 +1,354 @@
+// Test driver of the reference-side binding (shim/): a TACS application written against the reference's own C++ API
+// that builds a model exactly like the reference's example drivers do --
+//   plate / plate9 : TACSCreator, Quad4 / Quad9 MITC shell plate, all edges clamped (examples/plate/plate.cpp:29-131)
+//   direct         : TACSAssembler built by hand, node ranges and connectivity set directly
+//                    (examples/tutorial/tutorial.cpp:120-290)
+//   cube / cube27  : hexahedral solid through TACSCreator (tests/integration_tests/test_elast_linhexa_element_3d.py)
+// -- runs assembleJacobian / mult / a linear-static solve once on the reference's CPU classes and once on the device
+// through TACSB200Assembler / TACSB200Mat / TACSB200Vec, and compares the two. The reference's own GMRES class is also
+// run unchanged on the device matrix, vectors and preconditioner (it only sees TACSMat / TACSVec / TACSPc).
+//
+// Linked against oracle/_ref/libtacs_ref.so (the unmodified reference) + shim/_build/libtacs_b200_shim.so.
+// Prints one line per check and exits non-zero when a tolerance is exceeded:
+//   pattern bit-exact; A, res, A*x within 1e-12 relative (max-norm); displacements within 1e-10 relative.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "TACSAssembler.h"
+#include "TACSCreator.h"
+#include "TACSElement3D.h"
+#include "TACSHexaBasis.h"
+#include "TACSIsoShellConstitutive.h"
+#include "TACSLinearElasticity.h"
+#include "TACSShellElementDefs.h"
+#include "TACSSolidConstitutive.h"
+#include "tacs_b200_shim.h"
+
+static int failures = 0;
+
+static void check(const char *what, double err, double tol) {
+  const bool ok = err <= tol;  // NaN fails
+  printf("  %-44s %.3e  (tol %.0e)  %s\n", what, err, tol, ok ? "ok" : "FAIL");
+  if (!ok) failures++;
+}
+
+static double hash_entry(long i) { return 1e-3 * (double)(((unsigned long)i * 2654435761UL % 4294967296UL) % 1000UL) / 1000.0; }
+
+static double relerr(const std::vector<double> &got, const TacsScalar *want, size_t n) {
+  double scale = 0.0, err = 0.0;
+  for (size_t i = 0; i < n; i++) {
+    scale = fmax(scale, fabs(want[i]));
+    const double d = fabs(got[i] - want[i]);
+    if (!(d <= err)) err = d;  // propagates NaN
+  }
+  return err / (scale > 0.0 ? scale : 1.0);
+}
+
+static TACSMaterialProperties *aluminium() {
+  return new TACSMaterialProperties(2700.0, 921.096, 70e3, 0.3, 270.0, 24.0e-6, 230.0);
+}
+
+// ---- model builders (reference API only) ------------------------------------------------------------------------
+static TACSAssembler *shell_plate(int order, int nx, int ny) {
+  const int vpn = 6, nnx = (order - 1) * nx + 1, nny = (order - 1) * ny + 1, npe = order * order;
+  const int nnodes = nnx * nny, nelems = nx * ny;
+  std::vector<int> ptr(nelems + 1), conn((size_t)npe * nelems), ids(nelems, 0), bcs;
+  std::vector<TacsScalar> X(3 * (size_t)nnodes, 0.0);
+  for (int j = 0, e = 0; j < ny; j++)
+    for (int i = 0; i < nx; i++, e++) {
+      ptr[e] = npe * e;
+      for (int jj = 0; jj < order; jj++)
+        for (int ii = 0; ii < order; ii++)
+          conn[npe * e + ii + order * jj] = (order - 1) * i + ii + ((order - 1) * j + jj) * nnx;
+    }
+  ptr[nelems] = npe * nelems;
+  for (int j = 0; j < nny; j++)
+    for (int i = 0; i < nnx; i++) {
+      X[3 * (i + j * nnx)] = (double)i / (nnx - 1);
+      X[3 * (i + j * nnx) + 1] = (double)j / (nny - 1);
+      if (i == 0 || j == 0 || i == nnx - 1 || j == nny - 1) bcs.push_back(i + j * nnx);
+    }
+  TACSCreator *creator = new TACSCreator(MPI_COMM_WORLD, vpn);
+  creator->incref();
+  creator->setGlobalConnectivity(nnodes, nelems, ptr.data(), conn.data(), ids.data());
+  creator->setBoundaryConditions((int)bcs.size(), bcs.data());
+  creator->setNodes(X.data());
+  TacsScalar axis[3] = {1.0, 0.0, 0.0};
+  TACSShellTransform *transform = new TACSShellRefAxisTransform(axis);
+  TACSShellConstitutive *con = new TACSIsoShellConstitutive(aluminium(), 0.01);
+  TACSElement *element = order == 2 ? (TACSElement *)new TACSQuad4Shell(transform, con)
+                                    : (TACSElement *)new TACSQuad9Shell(transform, con);
+  creator->setElements(1, &element);
+  TACSAssembler *assembler = creator->createTACS();
+  assembler->incref();
+  creator->decref();
+  return assembler;
+}
+
+static TACSAssembler *solid_cube(int order, int n) {
+  const int vpn = 3, m = (order - 1) * n + 1, npe = order * order * order;
+  const int nnodes = m * m * m, nelems = n * n * n;
+  std::vector<int> ptr(nelems + 1), conn((size_t)npe * nelems), ids(nelems, 0), bcs;
+  std::vector<TacsScalar> X(3 * (size_t)nnodes);
+  for (int k = 0, e = 0; k < n; k++)
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++, e++) {
+        ptr[e] = npe * e;
+        for (int kk = 0, a = 0; kk < order; kk++)
+          for (int jj = 0; jj < order; jj++)
+            for (int ii = 0; ii < order; ii++, a++)
+              conn[npe * e + a] = (order - 1) * i + ii + m * ((order - 1) * j + jj + m * ((order - 1) * k + kk));
+      }
+  ptr[nelems] = npe * nelems;
+  for (int k = 0; k < m; k++)
+    for (int j = 0; j < m; j++)
+      for (int i = 0; i < m; i++) {
+        const int node = i + m * (j + m * k);
+        X[3 * node] = (double)i / (m - 1);
+        X[3 * node + 1] = (double)j / (m - 1);
+        X[3 * node + 2] = (double)k / (m - 1);
+        if (i == 0) bcs.push_back(node);
+      }
+  TACSCreator *creator = new TACSCreator(MPI_COMM_WORLD, vpn);
+  creator->incref();
+  creator->setGlobalConnectivity(nnodes, nelems, ptr.data(), conn.data(), ids.data());
+  creator->setBoundaryConditions((int)bcs.size(), bcs.data());
+  creator->setNodes(X.data());
+  TACSSolidConstitutive *con = new TACSSolidConstitutive(aluminium(), 1.0);
+  TACSLinearElasticity3D *model = new TACSLinearElasticity3D(con, TACS_LINEAR_STRAIN);
+  TACSElementBasis *basis = order == 2 ? (TACSElementBasis *)new TACSLinearHexaBasis()
+                                       : (TACSElementBasis *)new TACSQuadraticHexaBasis();
+  TACSElement *element = new TACSElement3D(model, basis);
+  creator->setElements(1, &element);
+  TACSAssembler *assembler = creator->createTACS();
+  assembler->incref();
+  creator->decref();
+  return assembler;
+}
+
+// the way of examples/tutorial/tutorial.cpp: no creator, the application numbers the nodes itself
+static TACSAssembler *direct_plate(int nx, int ny) {
+  const int vpn = 6, nnx = nx + 1, nnodes = (nx + 1) * (ny + 1), nelems = nx * ny;
+  TACSAssembler *assembler = new TACSAssembler(MPI_COMM_WORLD, vpn, nnodes, nelems);
+  assembler->incref();
+  std::vector<int> ptr(nelems + 1), conn(4 * (size_t)nelems);
+  for (int j = 0, e = 0; j < ny; j++)
+    for (int i = 0; i < nx; i++, e++) {
+      ptr[e] = 4 * e;
+      conn[4 * e] = i + j * nnx;
+      conn[4 * e + 1] = i + 1 + j * nnx;
+      conn[4 * e + 2] = i + (j + 1) * nnx;
+      conn[4 * e + 3] = i + 1 + (j + 1) * nnx;
+    }
+  ptr[nelems] = 4 * nelems;
+  assembler->setElementConnectivity(ptr.data(), conn.data());
+  // two element objects of different thickness, alternating by row (distinct descriptors on the device)
+  TacsScalar axis[3] = {0.0, 1.0, 0.0};
+  TACSShellTransform *transform = new TACSShellRefAxisTransform(axis);
+  TACSElement *thin = new TACSQuad4Shell(transform, new TACSIsoShellConstitutive(aluminium(), 0.01));
+  TACSElement *thick = new TACSQuad4Shell(new TACSShellNaturalTransform(),
+                                          new TACSIsoShellConstitutive(aluminium(), 0.025));
+  std::vector<TACSElement *> elems(nelems);
+  for (int e = 0; e < nelems; e++) elems[e] = ((e / nx) % 2) ? thick : thin;
+  assembler->setElements(elems.data());
+  // clamp the edge x = 0 fully, pin w on the edge x = Lx
+  for (int j = 0; j <= ny; j++) {
+    int node = j * nnx;
+    assembler->addBCs(1, &node);
+    node = nx + j * nnx;
+    int dof = 2;
+    assembler->addBCs(1, &node, 1, &dof);
+  }
+  assembler->initialize();
+  TACSBVec *X = assembler->createNodeVec();
+  X->incref();
+  TacsScalar *xp = NULL;
+  X->getArray(&xp);
+  for (int j = 0; j <= ny; j++)
+    for (int i = 0; i <= nx; i++) {
+      const int node = i + j * nnx;
+      xp[3 * node] = 2.0 * i / nx;
+      xp[3 * node + 1] = 1.0 * j / ny;
+      xp[3 * node + 2] = 0.05 * sin(3.0 * i / nx) * cos(2.0 * j / ny);  // a shallow curved panel
+    }
+  assembler->setNodes(X);
+  X->decref();
+  return assembler;
+}
+
+// ---- the comparison ---------------------------------------------------------------------------------------------
+static void run_case(const char *name, TACSAssembler *assembler, int with_solve) {
+  printf("case %s: %d nodes, %d elements, %d dof per node\n", name, assembler->getNumNodes(),
+         assembler->getNumElements(), assembler->getVarsPerNode());
+  const int vpn = assembler->getVarsPerNode();
+
+  // reference path
+  TACSParallelMat *Aref = assembler->createMat();
+  Aref->incref();
+  TACSBVec *u = assembler->createVec(), *x = assembler->createVec(), *res = assembler->createVec(),
+           *y = assembler->createVec();
+  u->incref(); x->incref(); res->incref(); y->incref();
+  TacsScalar *ua = NULL, *xa = NULL;
+  const int n = u->getArray(&ua);
+  x->getArray(&xa);
+  for (int i = 0; i < n; i++) {
+    ua[i] = hash_entry(i);
+    xa[i] = hash_entry(n - 1 - i);
+  }
+  assembler->applyBCs(u);
+  assembler->applyBCs(x);
+  assembler->setVariables(u);
+  assembler->assembleJacobian(1.0, 0.0, 0.0, res, Aref);
+  Aref->mult(x, y);
+
+  // device path
+  TACSB200Assembler *dev = TACSB200Assembler::create(assembler);
+  if (!dev) {
+    printf("  TACSB200Assembler::create returned NULL  FAIL\n");
+    failures++;
+    return;
+  }
+  dev->incref();
+  TACSB200Mat *Adev = dev->createMat();
+  Adev->incref();
+  TACSB200Vec *dres = dev->createVec(), *dx = dev->createVec(), *dy = dev->createVec();
+  dres->incref(); dx->incref(); dy->incref();
+  dev->setVariables(u);  // host vector of the reference, uploaded
+  dev->assembleJacobian(1.0, 0.0, 0.0, dres, Adev);
+  dx->copyValues(x);
+  Adev->mult(dx, dy);
+
+  // sparsity pattern (bit-exact) and values of the owned block rows
+  BCSRMat *Aloc = NULL, *Bext = NULL;
+  Aref->getBCSRMat(&Aloc, &Bext);
+  int bs = 0, nrows = 0, ncols = 0;
+  const int *rowp = NULL, *cols = NULL;
+  TacsScalar *vals = NULL;
+  Aloc->getArrays(&bs, &nrows, &ncols, &rowp, &cols, &vals);
+  int dbs = 0, dnrows = 0, dnnzb = 0, *drowp = NULL, *dcols = NULL;
+  TacsScalar *dvals = NULL;
+  Adev->getArrays(&dbs, &dnrows, &dnnzb, &drowp, &dcols, &dvals);
+  const bool same = dbs == bs && dnrows == nrows && dnnzb == rowp[nrows] &&
+                    memcmp(drowp, rowp, (nrows + 1) * sizeof(int)) == 0 &&
+                    memcmp(dcols, cols, (size_t)dnnzb * sizeof(int)) == 0;
+  check("sparsity pattern (rowp / cols) differs", same ? 0.0 : 1.0, 0.0);
+  if (same) {
+    std::vector<double> dv(dvals, dvals + (size_t)dnnzb * bs * bs);
+    check("Jacobian blocks, relative max-norm", relerr(dv, vals, dv.size()), 1e-12);
+  }
+  std::vector<double> got(n);
+  TacsScalar *ra = NULL, *ya = NULL;
+  res->getArray(&ra);
+  y->getArray(&ya);
+  dres->getValues(got.data());
+  check("residual", relerr(got, ra, n), 1e-12);
+  dy->getValues(got.data());
+  check("A*x", relerr(got, ya, n), 1e-12);
+  // the reference's host vectors through the device matrix (copies in and out)
+  TACSBVec *y2 = assembler->createVec();
+  y2->incref();
+  Adev->mult(x, y2);
+  TacsScalar *y2a = NULL;
+  y2->getArray(&y2a);
+  check("A*x through host TACSBVec arguments", relerr(std::vector<double>(y2a, y2a + n), ya, n), 1e-12);
+
+  if (with_solve) {
+    // linear static solve, boundary conditions applied to the load (plate.cpp:158-164); the load excites every dof
+    // (a Chebyshev-preconditioned GMRES needs it to converge on the thin plate within the restarts allowed here)
+    TACSBVec *f = assembler->createVec(), *ans = assembler->createVec();
+    f->incref(); ans->incref();
+    TacsScalar *fa = NULL;
+    f->getArray(&fa);
+    for (int i = 0; i < n; i++) fa[i] = hash_entry(i) - 0.4e-3;
+    (void)vpn;
+    assembler->applyBCs(f);
+    const int m = 30, nrestart = 8, flexible = 1, degree = 5, iters = 2;
+    const double rtol = 1e-12, atol = 1e-30;
+    // (1) everything of the reference
+    TACSChebyshevSmoother *pc_ref = new TACSChebyshevSmoother(Aref, degree, 1.0 / 30.0, 1.1, iters);
+    pc_ref->incref();
+    pc_ref->factor();
+    GMRES *ksm_ref = new GMRES(Aref, pc_ref, m, nrestart, flexible);
+    ksm_ref->incref();
+    ksm_ref->setTolerances(rtol, atol);
+    ksm_ref->solve(f, ans);
+    TacsScalar *aa = NULL;
+    ans->getArray(&aa);
+    // (2) the reference's GMRES class, unchanged, on the device matrix / vectors / preconditioner
+    TACSB200ChebyshevPc *pc_dev = new TACSB200ChebyshevPc(Adev, degree, 1.0 / 30.0, 1.1, iters);
+    pc_dev->incref();
+    pc_dev->factor();
+    TACSB200Vec *df = dev->createVec(), *dans = dev->createVec();
+    df->incref(); dans->incref();
+    df->copyValues(f);
+    GMRES *ksm_mixed = new GMRES(Adev, pc_dev, m, nrestart, flexible);
+    ksm_mixed->incref();
+    ksm_mixed->setTolerances(rtol, atol);
+    ksm_mixed->solve(df, dans);
+    dans->getValues(got.data());
+    printf("  iterations: reference %d, reference GMRES on device objects %d", ksm_ref->getIterCount(),
+           ksm_mixed->getIterCount());
+    check("\n  displacements, reference GMRES on device objects", relerr(got, aa, n), 1e-10);
+    // (3) the device solver behind TACSKsm
+    TACSB200ChebyshevPc *pc_dev2 = new TACSB200ChebyshevPc(Adev, degree, 1.0 / 30.0, 1.1, iters);
+    pc_dev2->incref();
+    pc_dev2->factor();
+    TACSB200GMRES *ksm_dev = new TACSB200GMRES(Adev, pc_dev2, m, nrestart, flexible);
+    ksm_dev->incref();
+    ksm_dev->setTolerances(rtol, atol);
+    dans->zeroEntries();
+    ksm_dev->solve(df, dans);
+    dans->getValues(got.data());
+    printf("  iterations: device GMRES %d\n", ksm_dev->getIterCount());
+    check("displacements, device GMRES", relerr(got, aa, n), 1e-10);
+    ksm_dev->decref(); pc_dev2->decref(); ksm_mixed->decref(); pc_dev->decref(); ksm_ref->decref(); pc_ref->decref();
+    df->decref(); dans->decref(); f->decref(); ans->decref();
+  }
+  delete[] drowp;
+  delete[] dcols;
+  delete[] dvals;
+  y2->decref();
+  dres->decref(); dx->decref(); dy->decref();
+  Adev->decref();
+  dev->decref();
+  u->decref(); x->decref(); res->decref(); y->decref();
+  Aref->decref();
+}
+
+int main(int argc, char **argv) {
+  MPI_Init(&argc, &argv);
+  const char *which = argc > 1 ? argv[1] : "all";
+  const bool all = strcmp(which, "all") == 0;
+  if (all || !strcmp(which, "plate")) {
+    TACSAssembler *a = shell_plate(2, 13, 9);
+    run_case("plate (Quad4, TACSCreator)", a, 1);
+    a->decref();
+  }
+  if (all || !strcmp(which, "plate9")) {
+    TACSAssembler *a = shell_plate(3, 7, 5);
+    run_case("plate9 (Quad9, TACSCreator)", a, 0);
+    a->decref();
+  }
+  if (all || !strcmp(which, "direct")) {
+    TACSAssembler *a = direct_plate(11, 8);
+    run_case("direct (Quad4, hand-built TACSAssembler, two element objects, partial BCs)", a, 0);
+    a->decref();
+  }
+  if (all || !strcmp(which, "cube")) {
+    TACSAssembler *a = solid_cube(2, 5);
+    run_case("cube (hex8, TACSCreator)", a, 1);
+    a->decref();
+  }
+  if (all || !strcmp(which, "cube27")) {
+    TACSAssembler *a = solid_cube(3, 3);
+    run_case("cube27 (hex27, TACSCreator)", a, 0);
+    a->decref();
+  }
+  MPI_Finalize();
+  printf("%s (%d failed checks)\n", failures ? "FAILED" : "ALL OK", failures);
+  return failures ? 1 : 0;
+}
