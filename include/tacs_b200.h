@@ -212,6 +212,20 @@ int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y); 
 int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y);
 tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m); /* TACSMat::createVec KSM.h */
 
+/* ---- TACSSchurMat: src/bpmat/TACSSchurMat.h:58-125, TACSSchurMat.cpp:453-552 (addValues), 883-938 (mult) ------
+   The four blocks [B E; F C] in the reference's local ordering (interior unknowns b, interface unknowns c), as a view
+   of an assembled matrix: b_nodes[nb] / c_nodes[nc] give the owned node of every local index (TACSSchurMat::
+   getLocalMap / getSchurMap ->getIndices), the rowp / cols arrays are the patterns of the live reference object
+   (getBCSRMat -> getArrays). update() gathers the values of the source matrix (after assembleJacobian) into the four
+   blocks on the device; get_values(which = 0 B, 1 E, 2 F, 3 C) copies one block's values to the host so that
+   TACSSchurPc::factor runs on them; mult is TACSSchurMat::mult on the device. One rank. */
+tacsb200_handle tacsb200_schur_mat_create(tacsb200_handle mat, int nb, const int *b_nodes, int nc, const int *c_nodes,
+                                          const int *Browp, const int *Bcols, const int *Erowp, const int *Ecols,
+                                          const int *Frowp, const int *Fcols, const int *Crowp, const int *Ccols);
+int tacsb200_schur_mat_update(tacsb200_handle schur);
+int tacsb200_schur_mat_get_values(tacsb200_handle schur, int which, double *vals);
+int tacsb200_schur_mat_mult(tacsb200_handle schur, tacsb200_handle x, tacsb200_handle y);
+
 /* ---- TACSChebyshevSmoother: src/bpmat/TACSParallelMat.h:180-217, TACSParallelMat.cpp:871-1113 ---- */
 /* TACSChebyshevSmoother(mat, degree, lower_factor = 1/30, upper_factor = 1.1, iters = 1) */
 tacsb200_handle tacsb200_chebyshev_create(tacsb200_handle mat, int degree, double lower_factor,

@@ -244,6 +244,52 @@ void TACSB200Mat::getArrays(int *bsize, int *nrows, int *nnzb, int **rowp, int *
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// TACSB200SchurMat
+// ---------------------------------------------------------------------------------------------------------------
+TACSB200SchurMat::TACSB200SchurMat(TACSB200Mat *src, TACSSchurMat *pattern) : source(src), handle(NULL) {
+  source->incref();
+  BCSRMat *blk[4] = {NULL, NULL, NULL, NULL};
+  pattern->getBCSRMat(&blk[0], &blk[1], &blk[2], &blk[3]);
+  const int *rowp[4], *cols[4];
+  for (int k = 0; k < 4; k++) {
+    int bs, nr, ncol;
+    TacsScalar *vals;
+    blk[k]->getArrays(&bs, &nr, &ncol, &rowp[k], &cols[k], &vals);
+  }
+  // local index -> global node of the interior (b) and interface (c) unknowns
+  const int *b_nodes = NULL, *c_nodes = NULL;
+  const int nb = pattern->getLocalMap()->getIndices()->getIndices(&b_nodes);
+  const int nc = pattern->getSchurMap()->getIndices()->getIndices(&c_nodes);
+  handle = tacsb200_schur_mat_create(source->getHandle(), nb, b_nodes, nc, c_nodes, rowp[0], cols[0], rowp[1], cols[1],
+                                     rowp[2], cols[2], rowp[3], cols[3]);
+  if (!handle) fprintf(stderr, "TACSB200SchurMat: the device view could not be created\n");
+}
+TACSB200SchurMat::~TACSB200SchurMat() {
+  if (handle) tacsb200_release(handle);
+  source->decref();
+}
+int TACSB200SchurMat::update() { return handle ? tacsb200_schur_mat_update(handle) : 1; }
+void TACSB200SchurMat::copyValuesTo(TACSSchurMat *host) {
+  if (!handle) return;
+  BCSRMat *blk[4] = {NULL, NULL, NULL, NULL};
+  host->getBCSRMat(&blk[0], &blk[1], &blk[2], &blk[3]);
+  for (int k = 0; k < 4; k++) {
+    int bs, nr, ncol;
+    const int *rowp, *cols;
+    TacsScalar *vals = NULL;
+    blk[k]->getArrays(&bs, &nr, &ncol, &rowp, &cols, &vals);
+    if (rowp[nr] > 0) tacsb200_schur_mat_get_values(handle, k, vals);
+  }
+}
+TACSVec *TACSB200SchurMat::createVec() { return source->createVec(); }
+void TACSB200SchurMat::getSize(int *nr, int *nc) { source->getSize(nr, nc); }
+void TACSB200SchurMat::mult(TACSVec *x, TACSVec *y) {
+  TACSB200Vec *xv = device_vec(x), *yv = device_vec(y);
+  if (xv && yv && handle) tacsb200_schur_mat_mult(handle, xv->getHandle(), yv->getHandle());
+  else fprintf(stderr, "TACSB200SchurMat::mult: device vectors required\n");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // preconditioner and Krylov solver
 // ---------------------------------------------------------------------------------------------------------------
 TACSB200ChebyshevPc::TACSB200ChebyshevPc(TACSB200Mat *m, int degree, double lower_factor, double upper_factor,
@@ -364,7 +410,6 @@ TACSB200Assembler *TACSB200Assembler::create(TACSAssembler *assembler) {
     assembler->incref();
     self->num_nodes = nnodes;
     self->vars_per_node = vpn;
-    self->scratch_q = self->scratch_qd = self->scratch_qdd = NULL;
     tacsb200_handle cr = tacsb200_creator_create(vpn);
     self->creator = cr;
     ok = cr && tacsb200_creator_set_keep_numbering(cr, 1) == 0 &&
@@ -409,7 +454,28 @@ TACSB200Assembler *TACSB200Assembler::create(TACSAssembler *assembler) {
   return self;
 }
 
+int TACSB200Assembler::assembleJacobian(TacsScalar alpha, TacsScalar beta, TacsScalar gamma, TACSBVec *res,
+                                        TACSSchurMat *mat) {
+  if (!schur_view) {
+    schur_source = createMat();
+    schur_source->incref();
+    schur_view = new TACSB200SchurMat(schur_source, mat);
+    schur_view->incref();
+    schur_res = createVec();
+    schur_res->incref();
+  }
+  if (!schur_view->valid()) return 1;
+  assembleJacobian(alpha, beta, gamma, schur_res, schur_source);
+  if (schur_view->update()) return 1;
+  schur_view->copyValuesTo(mat);
+  if (res) schur_res->copyTo(res);
+  return 0;
+}
+
 TACSB200Assembler::~TACSB200Assembler() {
+  if (schur_res) schur_res->decref();
+  if (schur_view) schur_view->decref();
+  if (schur_source) schur_source->decref();
   if (scratch_q) scratch_q->decref();
   if (scratch_qd) scratch_qd->decref();
   if (scratch_qdd) scratch_qdd->decref();

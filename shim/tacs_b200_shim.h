@@ -20,6 +20,7 @@
 
 #include "KSM.h"
 #include "TACSAssembler.h"
+#include "TACSSchurMat.h"
 #include "tacs_b200.h"
 
 class TACSB200Assembler;
@@ -81,6 +82,30 @@ class TACSB200Mat : public TACSMat {
   tacsb200_handle handle;
 };
 
+// TACSSchurMat (src/bpmat/TACSSchurMat.h:58) on the device: the blocks [B E; F C] of a live reference TACSSchurMat --
+// its non-zero patterns and its local ordering (AMD / nested dissection, interior before interface unknowns) are read
+// from the object the application created with assembler->createSchurMat() -- filled from a device-assembled matrix.
+// update() after TACSB200Assembler::assembleJacobian; mult on the device; copyValuesTo writes the device-assembled
+// values into a reference TACSSchurMat of the same pattern so that TACSSchurPc::factor / applyFactor run unchanged
+// (the assembly the reference spends its time in is replaced, its direct solver is kept).
+class TACSB200SchurMat : public TACSMat {
+ public:
+  TACSB200SchurMat(TACSB200Mat *source, TACSSchurMat *pattern);
+  ~TACSB200SchurMat();
+  bool valid() { return handle != NULL; }
+  int update();
+  void copyValuesTo(TACSSchurMat *host);
+  TACSVec *createVec();
+  void mult(TACSVec *x, TACSVec *y);
+  void getSize(int *nr, int *nc);
+  tacsb200_handle getHandle() { return handle; }
+  const char *getObjectName() { return "TACSB200SchurMat"; }
+
+ private:
+  TACSB200Mat *source;
+  tacsb200_handle handle;
+};
+
 class TACSB200ChebyshevPc : public TACSPc {
  public:
   // TACSChebyshevSmoother(mat, degree, lower_factor, upper_factor, iters) (src/bpmat/TACSParallelMat.h:180-217)
@@ -133,6 +158,10 @@ class TACSB200Assembler : public TACSObject {
   void assembleRes(TACSB200Vec *res);
   void assembleJacobian(TacsScalar alpha, TacsScalar beta, TacsScalar gamma, TACSB200Vec *res, TACSB200Mat *A);
   int assembleMatType(ElementMatrixType matType, TACSB200Mat *A);
+  // The drop-in for drivers that assemble into a TACSSchurMat (examples/plate/plate.cpp:133-146, pyTACS
+  // StaticProblem): element loop, scatter and boundary conditions on the device, then the values land in the blocks
+  // of `mat`; `res` (host vector, may be NULL) receives the residual.
+  int assembleJacobian(TacsScalar alpha, TacsScalar beta, TacsScalar gamma, TACSBVec *res, TACSSchurMat *mat);
   void applyBCs(TACSVec *vec);
   void setBCs(TACSVec *vec);
 
@@ -143,12 +172,18 @@ class TACSB200Assembler : public TACSObject {
   const char *getObjectName() { return "TACSB200Assembler"; }
 
  private:
-  TACSB200Assembler() : assembler(NULL), handle(NULL), creator(NULL), num_nodes(0), vars_per_node(0) {}
+  TACSB200Assembler()
+      : assembler(NULL), handle(NULL), creator(NULL), num_nodes(0), vars_per_node(0), scratch_q(NULL), scratch_qd(NULL),
+        scratch_qdd(NULL), schur_source(NULL), schur_view(NULL), schur_res(NULL) {}
   TACSB200Vec *stage(TACSVec *v, TACSB200Vec **scratch);
   TACSAssembler *assembler;
   tacsb200_handle handle, creator;
   int num_nodes, vars_per_node;
   TACSB200Vec *scratch_q, *scratch_qd, *scratch_qdd;
+  // device objects behind assembleJacobian(..., TACSSchurMat *): created on first use, keyed by the Schur ordering
+  TACSB200Mat *schur_source;
+  TACSB200SchurMat *schur_view;
+  TACSB200Vec *schur_res;
 };
 
 #endif  // TACS_B200_SHIM_H

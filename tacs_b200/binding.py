@@ -134,6 +134,10 @@ PRODUCT_ONLY = {
     "shell_constitutive_create_raw": (H, [DP, DP]),
     "solid_constitutive_create_raw": (H, [DP, D]),
     "creator_set_keep_numbering": (I, [H, I]),
+    "schur_mat_create": (H, [H, I, IP, I, IP, IP, IP, IP, IP, IP, IP, IP, IP]),
+    "schur_mat_update": (I, [H]),
+    "schur_mat_get_values": (I, [H, I, DP]),
+    "schur_mat_mult": (I, [H, H, H]),
     "gmres_set_ortho_type": (I, [H, I]),
     "gmres_set_monitor": (I, [H, C.c_char_p, I]),
     "gmres_set_time_monitor": (I, [H]),

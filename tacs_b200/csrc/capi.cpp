@@ -568,6 +568,44 @@ tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m) {
   return keep_vec(A->createVec());
 }
 
+/* ---- TACSSchurMat view ------------------------------------------------------------------------------- */
+tacsb200_handle tacsb200_schur_mat_create(tacsb200_handle mat, int nb, const int *b_nodes, int nc, const int *c_nodes,
+                                          const int *Browp, const int *Bcols, const int *Erowp, const int *Ecols,
+                                          const int *Frowp, const int *Fcols, const int *Crowp, const int *Ccols) {
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE_H(A, "matrix");
+  const int *rowp[4] = {Browp, Erowp, Frowp, Crowp}, *cols[4] = {Bcols, Ecols, Fcols, Ccols};
+  for (int k = 0; k < 4; k++)
+    if (!rowp[k]) {
+      fprintf(stderr, "tacs_b200: schur_mat_create: row pointers of all four blocks are required\n");
+      return nullptr;
+    }
+  TACSSchurMat *S = new TACSSchurMat(A, nb, b_nodes, nc, c_nodes, rowp, cols);
+  if (!S->ok) {
+    S->incref();
+    S->decref();
+    return nullptr;
+  }
+  return keep(S);
+}
+int tacsb200_schur_mat_update(tacsb200_handle s) {
+  TACSSchurMat *S = as<TACSSchurMat>(s);
+  REQUIRE(S, "Schur matrix");
+  return S->update();
+}
+int tacsb200_schur_mat_get_values(tacsb200_handle s, int which, double *vals) {
+  TACSSchurMat *S = as<TACSSchurMat>(s);
+  REQUIRE(S, "Schur matrix");
+  return S->getValues(which, vals);
+}
+int tacsb200_schur_mat_mult(tacsb200_handle s, tacsb200_handle xv, tacsb200_handle yv) {
+  TACSSchurMat *S = as<TACSSchurMat>(s);
+  REQUIRE(S, "Schur matrix");
+  VEC(xv, x); VEC(yv, y);
+  if (S->mult(x, y)) return 1;
+  return tacsb200_synchronize();
+}
+
 /* ---- GMRES --------------------------------------------------------------------------------------- */
 tacsb200_handle tacsb200_gmres_create(tacsb200_handle mat, int m, int nrestart) {
   TACSParallelMat *A = as<TACSParallelMat>(mat);

@@ -2056,6 +2056,23 @@ cudaError_t launch_unpack_blocks(int bs, long count, const int *idx, const doubl
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) permute_blocks_kernel(int b2, long nblocks, const int *__restrict__ src,
+                                                            const double *__restrict__ in, double *__restrict__ out) {
+  const long total = nblocks * b2;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long k = g / b2;
+    const int s = __ldg(src + k);
+    out[g] = s >= 0 ? __ldg(in + (long)s * b2 + (g - k * b2)) : 0.0;
+  }
+}
+
+cudaError_t launch_permute_blocks(int b2, long nblocks, const int *src, const double *in, double *out, int num_sms,
+                                  cudaStream_t s) {
+  if (nblocks <= 0) return cudaSuccess;
+  permute_blocks_kernel<<<grid_for(nblocks * b2, 256, num_sms), 256, 0, s>>>(b2, nblocks, src, in, out);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // roofline denominators measured live: dependent-chain-free DFMA stream and a device copy
 // ------------------------------------------------------------------------------------------

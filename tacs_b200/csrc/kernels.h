@@ -113,6 +113,10 @@ cudaError_t launch_pack_blocks(int bs, long count, const int *idx, const double 
 cudaError_t launch_unpack_blocks(int bs, long count, const int *idx, const double *buf, double *x, int add,
                                  int num_sms, cudaStream_t s);
 
+// out[k] = src[k] >= 0 ? in[src[k]] : 0 for blocks of b2 doubles (values of a matrix view in another block order)
+cudaError_t launch_permute_blocks(int b2, long nblocks, const int *src, const double *in, double *out, int num_sms,
+                                  cudaStream_t s);
+
 cudaError_t launch_dfma_peak(double *out, int iters, int blocks, cudaStream_t s);
 cudaError_t launch_copy(long n, const double *src, double *dst, int num_sms, cudaStream_t s);
 

@@ -1287,6 +1287,129 @@ int TACSParallelMat::axpy(double alpha, TACSParallelMat *o) {
                  "axpy") ? 0 : 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TACSSchurMat: [B E; F C] view of an assembled matrix in the reference's local ordering
+// ---------------------------------------------------------------------------------------------
+TACSSchurMat::TACSSchurMat(TACSParallelMat *src, int _nb, const int *b_nodes, int _nc, const int *c_nodes,
+                           const int *const rowp[4], const int *const cols[4]) {
+  source = src;
+  source->incref();
+  nb = _nb;
+  nc = _nc;
+  bsize = src->Aloc.bsize;
+  TACSAssembler *a = src->assembler;
+  if (a->size != 1) {
+    fprintf(stderr, "tacs_b200: the TACSSchurMat view is implemented for one rank\n");
+    return;
+  }
+  const int nrows[4] = {nb, nb, nc, nc}, ncols[4] = {nb, nc, nb, nc};
+  const int *rnodes[4] = {b_nodes, b_nodes, c_nodes, c_nodes}, *cnodes[4] = {b_nodes, c_nodes, b_nodes, c_nodes};
+  const BCSRPattern &A = src->Aloc;
+  std::vector<char> used(A.nnzb(), 0);
+  for (int k = 0; k < 4; k++) {
+    BCSRPattern &P = blk[k];
+    P.bsize = bsize;
+    P.nrows = nrows[k];
+    P.ncols = ncols[k];
+    P.rowp.assign(rowp[k], rowp[k] + nrows[k] + 1);
+    P.cols.assign(cols[k], cols[k] + P.rowp[nrows[k]]);
+    std::vector<int> srcv(P.nnzb(), -1);
+    for (int i = 0; i < nrows[k]; i++) {
+      const int gr = rnodes[k][i];
+      if (gr < 0 || gr >= A.nrows) continue;
+      const int *cb = A.cols.data() + A.rowp[gr], *ce = A.cols.data() + A.rowp[gr + 1];
+      for (int p = P.rowp[i]; p < P.rowp[i + 1]; p++) {
+        const int gc = cnodes[k][P.cols[p]];
+        const int *it = std::lower_bound(cb, ce, gc);
+        if (it != ce && *it == gc) {
+          srcv[p] = (int)(it - A.cols.data());
+          used[srcv[p]] = 1;
+        }
+      }
+    }
+    const size_t b2 = (size_t)bsize * bsize;
+    if (!P.d_rowp.upload(P.rowp) || !P.d_cols.upload(P.cols) || !src_blk[k].upload(srcv) ||
+        !vals[k].alloc(b2 * P.nnzb()))
+      return;
+    P.d_vals.ptr = vals[k].ptr;
+    P.d_vals.count = vals[k].count;
+  }
+  for (char u : used)
+    if (!u) missing++;
+  if (missing) {
+    fprintf(stderr, "tacs_b200: TACSSchurMat view: %ld blocks of the assembled matrix have no place in [B E; F C]\n",
+            missing);
+    return;
+  }
+  std::vector<int> bn(b_nodes, b_nodes + nb), cn(c_nodes, c_nodes + nc);
+  if (!d_bnodes.upload(bn) || !d_cnodes.upload(cn)) return;
+  xb = new TACSBVec(bsize, nb, 0, 0);
+  yb = new TACSBVec(bsize, nb, 0, 0);
+  xc = new TACSBVec(bsize, nc, 0, 0);
+  yc = new TACSBVec(bsize, nc, 0, 0);
+  xb->incref(); yb->incref(); xc->incref(); yc->incref();
+  ok = true;
+}
+
+TACSSchurMat::~TACSSchurMat() {
+  if (xb) xb->decref();
+  if (yb) yb->decref();
+  if (xc) xc->decref();
+  if (yc) yc->decref();
+  source->decref();
+}
+
+int TACSSchurMat::update() {
+  if (!ok) return 1;
+  for (int k = 0; k < 4; k++) {
+    KernelTimer kt(K_GATHER_MAT, "permute_blocks_kernel");
+    if (!cuda_ok(launch_permute_blocks(bsize * bsize, blk[k].nnzb(), src_blk[k].ptr, source->vals_all.ptr, vals[k].ptr,
+                                       ctx().num_sms, ctx().stream), "schur view update")) return 1;
+  }
+  return 0;
+}
+
+int TACSSchurMat::getValues(int which, double *host) {
+  if (!ok || which < 0 || which > 3) return 1;
+  return blk[which].d_vals.download(host, blk[which].d_vals.count) ? 0 : 1;
+}
+
+int TACSSchurMat::mult(TACSBVec *x, TACSBVec *y) {
+  if (!ok) return 1;
+  Context &c = ctx();
+  bool good = true;
+  auto spmv = [&](int k, TACSBVec *in, TACSBVec *out, int add) {
+    if (blk[k].nrows == 0) return;
+    if (blk[k].nnzb() == 0 && add) return;
+    KernelTimer kt(K_SPMV, spmv_kernel_name(bsize, add));
+    good = good && cuda_ok(launch_spmv(bsize, blk[k].nrows, blk[k].d_rowp.ptr, blk[k].d_cols.ptr, blk[k].d_vals.ptr,
+                                       in->owned(), out->owned(), add, c.num_sms, c.stream), "schur spmv");
+  };
+  {
+    KernelTimer kt(K_HALO, "pack_blocks_kernel");
+    good = good && cuda_ok(launch_pack_blocks(bsize, nb, d_bnodes.ptr, x->owned(), xb->owned(), c.num_sms, c.stream), "x_b");
+  }
+  if (nc > 0) {
+    KernelTimer kt(K_HALO, "pack_blocks_kernel");
+    good = good && cuda_ok(launch_pack_blocks(bsize, nc, d_cnodes.ptr, x->owned(), xc->owned(), c.num_sms, c.stream), "x_c");
+  }
+  spmv(0, xb, yb, 0);  // y_b = B x_b
+  spmv(2, xb, yc, 0);  // y_c = F x_b
+  spmv(3, xc, yc, 1);  // y_c += C x_c
+  spmv(1, xc, yb, 1);  // y_b += E x_c
+  {
+    KernelTimer kt(K_HALO, "unpack_blocks_kernel");
+    good = good && cuda_ok(launch_unpack_blocks(bsize, nb, d_bnodes.ptr, yb->owned(), y->owned(), 0, c.num_sms, c.stream),
+                           "y_b");
+  }
+  if (nc > 0) {
+    KernelTimer kt(K_HALO, "unpack_blocks_kernel");
+    good = good && cuda_ok(launch_unpack_blocks(bsize, nc, d_cnodes.ptr, yc->owned(), y->owned(), 0, c.num_sms, c.stream),
+                           "y_c");
+  }
+  return good ? 0 : 1;
+}
+
 bool BCSRPattern::ValuesView::download(double *host, size_t n) const {
   if (n == 0) return true;
   return cuda_ok(cudaMemcpyAsync(host, ptr, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream), "D2H") &&

@@ -534,6 +534,31 @@ class TACSAssembler : public Object {
                      const double *ddvars_override = nullptr, bool use_override = false);
 };
 
+// Device mirror of TACSSchurMat (src/bpmat/TACSSchurMat.h:58-125): the four blocks [B E; F C] in the reference's own
+// local ordering -- interior unknowns "b" first, interface unknowns "c" -- with the non-zero patterns and the
+// node -> local index maps read from a live reference TACSSchurMat (the shim does that). The values are not
+// assembled a second time: update() gathers them from the value array of an assembled TACSParallelMat through a
+// block permutation computed once, so the matrix carries the boundary conditions of the source. mult follows
+// TACSSchurMat::mult (TACSSchurMat.cpp:883-938): y_b = B x_b + E x_c, y_c = F x_b + C x_c on permuted copies of x.
+class TACSSchurMat : public Object {
+ public:
+  TACSSchurMat(TACSParallelMat *src, int nb, const int *b_nodes, int nc, const int *c_nodes,
+               const int *const rowp[4], const int *const cols[4]);
+  ~TACSSchurMat();
+  bool ok = false;
+  TACSParallelMat *source;
+  int nb = 0, nc = 0, bsize = 0;
+  BCSRPattern blk[4];           // B (nb x nb), E (nb x nc), F (nc x nb), C (nc x nc)
+  DeviceArray<double> vals[4];
+  DeviceArray<int> src_blk[4];  // per block: index into the source's [Aloc | Bext] value array, or -1 (stays zero)
+  long missing = 0;             // blocks of the source pattern that have no place in the four blocks (must be 0)
+  DeviceArray<int> d_bnodes, d_cnodes;
+  TACSBVec *xb = nullptr, *xc = nullptr, *yb = nullptr, *yc = nullptr;
+  int update();
+  int mult(TACSBVec *x, TACSBVec *y);
+  int getValues(int which, double *host);
+};
+
 // reduction scratch shared by the vector kernels (tb2_host.cpp)
 extern double *g_dot_partial, *g_dot_out, *g_dot_host;
 bool dot_buffers();

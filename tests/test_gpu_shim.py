@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "tests", "shim", "_build", "shim_driver")
 
 
-@pytest.mark.parametrize("case", ["plate", "plate9", "direct", "cube", "cube27"])
+@pytest.mark.parametrize("case", ["plate", "plate9", "direct", "cube", "cube27", "schur"])
 def test_reference_driver_on_device_objects(lib, case):
     if not os.path.exists(DRIVER):
         pytest.skip("tests/shim/_build/shim_driver not built (needs /root/reference at build time)")
