@@ -206,6 +206,8 @@ int tacsb200_mat_get_ext_col_nodes(tacsb200_handle m, int *nodes); /* getExtColM
 int tacsb200_mat_copy_values(tacsb200_handle mat, tacsb200_handle other);
 int tacsb200_mat_scale(tacsb200_handle mat, double alpha);
 int tacsb200_mat_axpy(tacsb200_handle mat, double alpha, tacsb200_handle other);
+/* TACSParallelMat::multTranspose (src/bpmat/TACSParallelMat.cpp:267-290): y = A^T x (one rank) */
+int tacsb200_mat_mult_transpose(tacsb200_handle mat, tacsb200_handle x, tacsb200_handle y);
 int tacsb200_mat_zero_entries(tacsb200_handle m);
 int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y); /* mult :248 */
 /* asynchronous variant for benchmarking: enqueue only, pair with tacsb200_synchronize */

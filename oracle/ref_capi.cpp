@@ -477,6 +477,11 @@ int ref_mat_mult(ref_handle m, ref_handle x, ref_handle y) {
   return 0;
 }
 
+int ref_mat_mult_transpose(ref_handle m, ref_handle x, ref_handle y) {
+  as<TACSMat>(m)->multTranspose(as<TACSBVec>(x), as<TACSBVec>(y));
+  return 0;
+}
+
 /* ---- Chebyshev smoother ---------------------------------------------------- */
 ref_handle ref_chebyshev_create(ref_handle mat, int degree, double lower_factor, double upper_factor, int iters) {
   return keep(new TACSChebyshevSmoother(as<TACSMat>(mat), degree, lower_factor, upper_factor, iters));

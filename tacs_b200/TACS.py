@@ -253,6 +253,9 @@ class Mat(_Obj):
     def mult(self, x, y):
         _check(self.lib.mat_mult(self.h, x.h, y.h), "mat_mult")
 
+    def multTranspose(self, x, y):
+        _check(self.lib.mat_mult_transpose(self.h, x.h, y.h), "mat_mult_transpose")
+
     def createVec(self):
         if self.lib.is_product:
             return Vec(self.lib, self.lib.mat_create_vec(self.h))

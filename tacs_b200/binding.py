@@ -96,6 +96,7 @@ SIGNATURES = {
     "mat_get_ext_col_nodes": (I, [H, IP]),
     "mat_zero_entries": (I, [H]),
     "mat_mult": (I, [H, H, H]),
+    "mat_mult_transpose": (I, [H, H, H]),
     "chebyshev_create": (H, [H, I, D, D, I]),
     "chebyshev_factor": (I, [H]),
     "chebyshev_apply_factor": (I, [H, H, H]),

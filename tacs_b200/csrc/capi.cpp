@@ -558,6 +558,12 @@ int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle xv, tacsb200_hand
   VEC(xv, x); VEC(yv, y);
   return A->mult(x, y);
 }
+int tacsb200_mat_mult_transpose(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
+  MAT(m);
+  VEC(xv, x); VEC(yv, y);
+  if (A->multTranspose(x, y)) return 1;
+  return tacsb200_synchronize();
+}
 int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle xv, tacsb200_handle yv) {
   if (tacsb200_mat_mult_async(m, xv, yv)) return 1;
   return tacsb200_synchronize();

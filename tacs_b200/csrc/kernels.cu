@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "elem_phases.cuh"
 #include "kernels.h"
@@ -1640,6 +1641,96 @@ __global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__rest
   }
 }
 
+// 3x3 blocks, one warp per block row: the 9 nnz doubles of a row are contiguous, so the warp streams them with
+// fully coalesced loads (lane l takes entries l, l+32, ... of the row, four in flight), multiplies each by its x entry
+// and the three row sums are formed by a shuffle reduction. (One thread per scalar row reached 0.65-0.75 of the HBM
+// peak on the hexahedral meshes: three lanes per 72-byte block and a dependent cols -> x chain per block.) The sum of
+// a row is formed in a different order than BCSRMatVecMult3's; the parity bound is 1e-12 relative.
+template <int ADD>
+__global__ void __launch_bounds__(256) spmv3_warp_kernel(int nrows, const int *__restrict__ rowp,
+                                                        const int *__restrict__ cols, const double *__restrict__ A,
+                                                        const double *__restrict__ x, double *__restrict__ y,
+                                                        double sign, double zs, const double *__restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long row = warp; row < nrows; row += nwarps) {
+    const int k0 = __ldg(rowp + row), k1 = __ldg(rowp + row + 1);
+    const double *a = A + (long)9 * k0;
+    const int n = 9 * (k1 - k0);
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    auto term = [&](int e, double v) {
+      const int b = e / 9, rem = e - 9 * b, r = rem / 3, c = rem - 3 * r;
+      const double p = v * __ldg(x + (long)3 * __ldg(cols + k0 + b) + c);
+      acc0 += r == 0 ? p : 0.0;
+      acc1 += r == 1 ? p : 0.0;
+      acc2 += r == 2 ? p : 0.0;
+    };
+    int e = lane;
+    for (; e + 96 < n; e += 128) {
+      const double v0 = __ldg(a + e), v1 = __ldg(a + e + 32), v2 = __ldg(a + e + 64), v3 = __ldg(a + e + 96);
+      term(e, v0);
+      term(e + 32, v1);
+      term(e + 64, v2);
+      term(e + 96, v3);
+    }
+    for (; e < n; e += 32) term(e, __ldg(a + e));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc0 += __shfl_down_sync(0xffffffffu, acc0, off);
+      acc1 += __shfl_down_sync(0xffffffffu, acc1, off);
+      acc2 += __shfl_down_sync(0xffffffffu, acc2, off);
+    }
+    const double t0 = __shfl_sync(0xffffffffu, acc0, 0), t1 = __shfl_sync(0xffffffffu, acc1, 0),
+                 t2 = __shfl_sync(0xffffffffu, acc2, 0);
+    if (lane < 3) {
+      double acc = lane == 0 ? t0 : (lane == 1 ? t1 : t2);
+      const long g = 3 * row + lane;
+      if (ADD == 1) acc = y[g] + acc;
+      if (ADD == 2) acc = zs * z[g] + sign * acc;
+      if (ADD == 3) acc = y[g] + sign * acc;
+      y[g] = acc;
+    }
+  }
+}
+
+// y = A^T x for a structurally symmetric pattern: tidx[k] is the position of the mirror (cols[k], row) of block k, so
+// row i of A^T is sum_k (A_tidx[k])^T x_cols[k] -- a gather like the forward product, no atomics. One thread per scalar
+// row reads column r of every mirror block.
+template <int BS>
+__global__ void __launch_bounds__(256) spmv_transpose_kernel(int nrows, const int *__restrict__ rowp,
+                                                            const int *__restrict__ cols,
+                                                            const int *__restrict__ tidx, const double *__restrict__ A,
+                                                            const double *__restrict__ x, double *__restrict__ y) {
+  const long total = (long)nrows * BS;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(g / BS), r = (int)(g - (long)row * BS);
+    const int beg = rowp[row], end = rowp[row + 1];
+    double acc = 0.0;
+    for (int k = beg; k < end; k++) {
+      const double *a = A + (long)(BS * BS) * __ldg(tidx + k) + r;
+      const double *xp = x + (long)BS * __ldg(cols + k);
+      double s = __ldg(a) * __ldg(xp);
+#pragma unroll
+      for (int c = 1; c < BS; c++) s += __ldg(a + BS * c) * __ldg(xp + c);
+      acc += s;
+    }
+    y[g] = acc;
+  }
+}
+
+cudaError_t launch_spmv_transpose(int bs, int nrows, const int *rowp, const int *cols, const int *tidx, const double *A,
+                                  const double *x, double *y, int num_sms, cudaStream_t s) {
+  if (nrows <= 0) return cudaSuccess;
+  const int block = 256;
+  long want = ((long)nrows * bs + block - 1) / block;
+  long cap = (long)num_sms * 8 * 64;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (bs == 6) spmv_transpose_kernel<6><<<grid, block, 0, s>>>(nrows, rowp, cols, tidx, A, x, y);
+  else if (bs == 3) spmv_transpose_kernel<3><<<grid, block, 0, s>>>(nrows, rowp, cols, tidx, A, x, y);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
                               double *y, int mode, double sign, double zs, const double *z, int num_sms,
                               cudaStream_t s) {
@@ -1658,12 +1749,25 @@ cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *col
       default: return cudaErrorInvalidValue;
     }
   } else if (bs == 3) {
-    switch (mode) {
-      case 0: TB2_SPMV(spmv3_kernel, 0); break;
-      case 1: TB2_SPMV(spmv3_kernel, 1); break;
-      case 2: TB2_SPMV(spmv3_kernel, 2); break;
-      case 3: TB2_SPMV(spmv3_kernel, 3); break;
-      default: return cudaErrorInvalidValue;
+    static const bool per_thread = getenv("TACSB200_SPMV3_THREAD") != nullptr;  // measurement switch
+    if (per_thread) {
+      switch (mode) {
+        case 0: TB2_SPMV(spmv3_kernel, 0); break;
+        case 1: TB2_SPMV(spmv3_kernel, 1); break;
+        case 2: TB2_SPMV(spmv3_kernel, 2); break;
+        case 3: TB2_SPMV(spmv3_kernel, 3); break;
+        default: return cudaErrorInvalidValue;
+      }
+    } else {
+      want = ((long)nrows * 32 + block - 1) / block;  // one warp per block row
+      grid = (unsigned)(want < cap ? want : cap);
+      switch (mode) {
+        case 0: TB2_SPMV(spmv3_warp_kernel, 0); break;
+        case 1: TB2_SPMV(spmv3_warp_kernel, 1); break;
+        case 2: TB2_SPMV(spmv3_warp_kernel, 2); break;
+        case 3: TB2_SPMV(spmv3_warp_kernel, 3); break;
+        default: return cudaErrorInvalidValue;
+      }
     }
   } else {
     return cudaErrorInvalidValue;

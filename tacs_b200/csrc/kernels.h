@@ -58,7 +58,7 @@ const char *element_kernel_name(const ElemGroupArgs &g);
 inline const char *gather_blocks_kernel_name(int bs) { return bs == 6 ? "gather_blocks36_kernel" : "gather_blocks9_kernel"; }
 inline const char *gather_residual_kernel_name(int bs) { return bs == 6 ? "gather_residual_kernel<6>" : "gather_residual_kernel<3>"; }
 inline const char *spmv_kernel_name(int bs, int add) {
-  return bs == 6 ? (add ? "spmv6_kernel<1>" : "spmv6_kernel<0>") : (add ? "spmv3_kernel<1>" : "spmv3_kernel<0>");
+  return bs == 6 ? (add ? "spmv6_kernel<1>" : "spmv6_kernel<0>") : (add ? "spmv3_warp_kernel<1>" : "spmv3_warp_kernel<0>");
 }
 
 // blocks gb_blk[0..nblocks) of A sum their staging sources src[ptr[g]..ptr[g+1]) (2*slot + transposed flag)
@@ -82,6 +82,10 @@ cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, con
 cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
                               double *y, int mode, double sign, double zs, const double *z, int num_sms,
                               cudaStream_t s);
+
+// y = A^T x; tidx[k] = position of the mirror block of block k (structurally symmetric pattern)
+cudaError_t launch_spmv_transpose(int bs, int nrows, const int *rowp, const int *cols, const int *tidx, const double *A,
+                                  const double *x, double *y, int num_sms, cudaStream_t s);
 
 // Krylov building blocks with device-resident scalars (kernels.cu): see the kernels for the contracts
 cudaError_t launch_orth_step(long n, double *w, const double *vprev, const double *coef, const double *vnext,

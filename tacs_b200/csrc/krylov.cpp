@@ -99,6 +99,7 @@ int TACSChebyshevSmoother::factor() {
 // y enters as the initial guess (TACSParallelMat.cpp:981-1014). Horner's rule on s(A) r with the updates fused into
 // the products: r = x - A y;  h = -c0 r;  h <- A h - c_k r (k = 1 .. d-1);  y += h.
 int TACSChebyshevSmoother::applyFactor(TACSBVec *x, TACSBVec *y) {
+  NvtxRange nvtx_range("tacs_b200::TACSChebyshevSmoother::applyFactor");
   int rc = 0;
   for (int it = 0; it < iters; it++) {
     rc |= mat->multFused(y, res, -1.0, 1.0, x);  // res = x - A y
@@ -289,6 +290,7 @@ int GMRES::runIteration(int i) {
 }
 
 int GMRES::solve(TACSBVec *b, TACSBVec *x, int zero_guess) {
+  NvtxRange nvtx_range("tacs_b200::GMRES::solve");
   Context &c = ctx();
   if (!d_hcol || !h_res || !dot_buffers()) return 0;
   const auto t_begin = std::chrono::steady_clock::now();

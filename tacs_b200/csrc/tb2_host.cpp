@@ -1074,6 +1074,7 @@ int staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank
 
 // TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
+  NvtxRange nvtx_range("tacs_b200::assembleRes");
   if (launchElements(1.0, 0.0, nullptr)) return 1;
   if (size > 1 && staging_exchange(this, false)) return 1;
   {
@@ -1100,6 +1101,7 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
                                     double lambda, bool apply_bcs) {
   (void)beta;
   Context &c = ctx();
+  NvtxRange nvtx_range("tacs_b200::assembleJacobian");
   if (Ke.count < (size_t)total_blocks * bs * bs && !Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
   const double *vp = vars_zero ? nullptr : vars->local(), *ap = ddvars_zero ? nullptr : ddvars->local();
   auto gather = [&](long g0, long g1, cudaStream_t st) -> int {
@@ -1173,6 +1175,7 @@ int TACSAssembler::assembleMatType(int matType, TACSParallelMat *A, bool apply_b
 int TACSAssembler::addJacobianVecProduct(double scale, double alpha, double beta, double gamma, TACSBVec *x,
                                          TACSBVec *y, bool apply_bcs) {
   (void)beta;
+  NvtxRange nvtx_range("tacs_b200::addJacobianVecProduct");
   if (!jvp_x) {
     jvp_x = createVec();
     jvp_a = createVec();
@@ -1474,6 +1477,32 @@ void TACSParallelMat::applyBCs() {
 int spmv_halo_begin(TACSParallelMat *A, TACSBVec *x);  // comm.cpp
 void spmv_halo_end(TACSParallelMat *A);
 
+int TACSParallelMat::multTranspose(TACSBVec *x, TACSBVec *y) {
+  if (assembler->size > 1) {
+    fprintf(stderr, "tacs_b200: multTranspose is implemented for one rank\n");
+    return 1;
+  }
+  if (!d_tidx.ptr) {
+    std::vector<int> tidx(Aloc.nnzb(), -1);
+    for (int i = 0; i < Aloc.nrows; i++)
+      for (int k = Aloc.rowp[i]; k < Aloc.rowp[i + 1]; k++) {
+        const int j = Aloc.cols[k];
+        const int *b = Aloc.cols.data() + Aloc.rowp[j], *e = Aloc.cols.data() + Aloc.rowp[j + 1];
+        const int *it = std::lower_bound(b, e, i);
+        if (it == e || *it != i) {
+          fprintf(stderr, "tacs_b200: multTranspose: the pattern is not structurally symmetric at (%d, %d)\n", i, j);
+          return 1;
+        }
+        tidx[k] = (int)(it - Aloc.cols.data());
+      }
+    if (!d_tidx.upload(tidx)) return 1;
+  }
+  KernelTimer kt(K_SPMV, Aloc.bsize == 6 ? "spmv_transpose_kernel<6>" : "spmv_transpose_kernel<3>");
+  return cuda_ok(launch_spmv_transpose(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, d_tidx.ptr,
+                                       Aloc.d_vals.ptr, x->owned(), y->owned(), ctx().num_sms, ctx().stream),
+                 "spmv transpose") ? 0 : 1;
+}
+
 // y = zs z + sign (A x): the product with the vector update in its epilogue (smoother steps, Krylov residuals)
 int TACSParallelMat::multFused(TACSBVec *x, TACSBVec *y, double sign, double zs, TACSBVec *z) {
   const bool dist = assembler->size > 1;
@@ -1499,6 +1528,7 @@ int TACSParallelMat::multFused(TACSBVec *x, TACSBVec *y, double sign, double zs,
 
 // TACSParallelMat::mult (TACSParallelMat.cpp:248-265): y = Aloc x + Bext x_ext, halo overlapped
 int TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
+  NvtxRange nvtx_range("tacs_b200::TACSParallelMat::mult");
   const bool dist = assembler->size > 1;
   int rc = 0;
   // every rank takes part in the column halo (a rank without external columns may still have to send)

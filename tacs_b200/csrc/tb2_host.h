@@ -34,7 +34,16 @@
 #include "kernels.h"
 #include "plan.h"
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: a no-op unless a profiler is attached
+
 namespace tb2 {
+
+// NVTX range around a host-side phase (assembleJacobian, assembleRes, mult, GMRES::solve ...): what Nsight Systems /
+// ncu --nvtx show instead of the reference's MPI_Wtime monitors (KSM.cpp:765, TACSAssembler timing prints)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // runtime context: one process drives one GPU
@@ -405,6 +414,9 @@ class TACSParallelMat : public Object {
   int axpy(double alpha, TACSParallelMat *other);
   int mult(TACSBVec *x, TACSBVec *y);
   int multFused(TACSBVec *x, TACSBVec *y, double sign, double zs, TACSBVec *z);  // y = zs z + sign (A x)
+  // TACSParallelMat::multTranspose (TACSParallelMat.cpp:267-290), one rank: the mirror-block index is built on first use
+  int multTranspose(TACSBVec *x, TACSBVec *y);
+  DeviceArray<int> d_tidx;
   void applyBCs();
   TACSBVec *createVec();
 };

@@ -435,3 +435,23 @@ def test_gmres_device_design_variants(lib, ref, capfd):
     out = capfd.readouterr().out
     assert "GMRES[  0]:" in out and "GMRES[  5]:" in out
     assert relerr(x.getArray(), xr) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["quad4_plate", "hex8_cube"])
+def test_mult_transpose_matches_reference(lib, ref, name):
+    """TACSParallelMat::multTranspose (TACSParallelMat.cpp:267-290): the boundary-condition rows make the assembled
+    matrix unsymmetric, so A^T x differs from A x; both against the compiled reference."""
+    mesh_f, kind, elem_f = common.SMALL_MODELS[name]
+    mesh = mesh_f()
+    out = {}
+    for tag, L in (("b200", lib), ("ref", ref)):
+        creator, asm = meshgen.build_model(T, L, mesh, [elem_f(L)])
+        A, res, x, y, yt = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec(), asm.createVec()
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+        x.setArray(meshgen.hash_vector(x.getSize()) - 0.3e-3)   # not zero on the constrained dofs
+        A.mult(x, y)
+        A.multTranspose(x, yt)
+        out[tag] = (y.getArray(), yt.getArray())
+    assert relerr(out["b200"][0], out["ref"][0]) < TOL
+    assert relerr(out["b200"][1], out["ref"][1]) < TOL
+    assert relerr(out["ref"][1], out["ref"][0]) > 1e-6  # the two products really differ
