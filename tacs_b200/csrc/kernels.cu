@@ -1578,10 +1578,14 @@ template <int ADD>
 __global__ void __launch_bounds__(256) spmv6_kernel(int nrows, const int *__restrict__ rowp,
                                                    const int *__restrict__ cols, const double *__restrict__ A,
                                                    const double *__restrict__ x, double *__restrict__ y,
-                                                   double sign, double zs, const double *__restrict__ z) {
+                                                   double sign, double zs, const double *__restrict__ z,
+                                                   const int *__restrict__ order) {
   const long total = (long)nrows * 6;
-  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const int row = (int)(g / 6), r = (int)(g - (long)row * 6);
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    // `order` (optional) lists the rows by length class so that the lanes of a warp run the same number of steps
+    const int slot = (int)(t / 6), r = (int)(t - (long)slot * 6);
+    const int row = order ? __ldg(order + slot) : slot;
+    const long g = (long)row * 6 + r;
     const int beg = rowp[row], end = rowp[row + 1];
     double acc = ADD == 1 ? y[g] : 0.0;
     const double *a = A + (long)36 * beg + 6 * r;
@@ -1619,10 +1623,13 @@ template <int ADD>
 __global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__restrict__ rowp,
                                                    const int *__restrict__ cols, const double *__restrict__ A,
                                                    const double *__restrict__ x, double *__restrict__ y,
-                                                   double sign, double zs, const double *__restrict__ z) {
+                                                   double sign, double zs, const double *__restrict__ z,
+                                                   const int *__restrict__ order) {
   const long total = (long)nrows * 3;
-  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const int row = (int)(g / 3), r = (int)(g - (long)row * 3);
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int slot = (int)(t / 3), r = (int)(t - (long)slot * 3);
+    const int row = order ? __ldg(order + slot) : slot;
+    const long g = (long)row * 3 + r;
     const int beg = rowp[row], end = rowp[row + 1];
     double acc = ADD == 1 ? y[g] : 0.0;
     const double *a = A + (long)9 * beg + 3 * r;
@@ -1638,58 +1645,6 @@ __global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__rest
     if (ADD == 2) acc = zs * z[g] + sign * acc;
     if (ADD == 3) acc = y[g] + sign * acc;
     y[g] = acc;
-  }
-}
-
-// 3x3 blocks, one warp per block row: the 9 nnz doubles of a row are contiguous, so the warp streams them with
-// fully coalesced loads (lane l takes entries l, l+32, ... of the row, four in flight), multiplies each by its x entry
-// and the three row sums are formed by a shuffle reduction. (One thread per scalar row reached 0.65-0.75 of the HBM
-// peak on the hexahedral meshes: three lanes per 72-byte block and a dependent cols -> x chain per block.) The sum of
-// a row is formed in a different order than BCSRMatVecMult3's; the parity bound is 1e-12 relative.
-template <int ADD>
-__global__ void __launch_bounds__(256) spmv3_warp_kernel(int nrows, const int *__restrict__ rowp,
-                                                        const int *__restrict__ cols, const double *__restrict__ A,
-                                                        const double *__restrict__ x, double *__restrict__ y,
-                                                        double sign, double zs, const double *__restrict__ z) {
-  const int lane = threadIdx.x & 31;
-  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long row = warp; row < nrows; row += nwarps) {
-    const int k0 = __ldg(rowp + row), k1 = __ldg(rowp + row + 1);
-    const double *a = A + (long)9 * k0;
-    const int n = 9 * (k1 - k0);
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    auto term = [&](int e, double v) {
-      const int b = e / 9, rem = e - 9 * b, r = rem / 3, c = rem - 3 * r;
-      const double p = v * __ldg(x + (long)3 * __ldg(cols + k0 + b) + c);
-      acc0 += r == 0 ? p : 0.0;
-      acc1 += r == 1 ? p : 0.0;
-      acc2 += r == 2 ? p : 0.0;
-    };
-    int e = lane;
-    for (; e + 96 < n; e += 128) {
-      const double v0 = __ldg(a + e), v1 = __ldg(a + e + 32), v2 = __ldg(a + e + 64), v3 = __ldg(a + e + 96);
-      term(e, v0);
-      term(e + 32, v1);
-      term(e + 64, v2);
-      term(e + 96, v3);
-    }
-    for (; e < n; e += 32) term(e, __ldg(a + e));
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      acc0 += __shfl_down_sync(0xffffffffu, acc0, off);
-      acc1 += __shfl_down_sync(0xffffffffu, acc1, off);
-      acc2 += __shfl_down_sync(0xffffffffu, acc2, off);
-    }
-    const double t0 = __shfl_sync(0xffffffffu, acc0, 0), t1 = __shfl_sync(0xffffffffu, acc1, 0),
-                 t2 = __shfl_sync(0xffffffffu, acc2, 0);
-    if (lane < 3) {
-      double acc = lane == 0 ? t0 : (lane == 1 ? t1 : t2);
-      const long g = 3 * row + lane;
-      if (ADD == 1) acc = y[g] + acc;
-      if (ADD == 2) acc = zs * z[g] + sign * acc;
-      if (ADD == 3) acc = y[g] + sign * acc;
-      y[g] = acc;
-    }
   }
 }
 
@@ -1731,15 +1686,18 @@ cudaError_t launch_spmv_transpose(int bs, int nrows, const int *rowp, const int 
   return cudaGetLastError();
 }
 
+// (A warp-per-block-row form of the 3x3 product -- lane l streams entries l, l+32, ... of the row's contiguous values,
+// shuffle reduction of the three row sums -- was measured and dropped: 5.65 ms against 3.40 ms on the 200^3 hex8
+// matrix, 12.4 against 9.3 ms on the 100^3 hex27 one; the per-entry cols -> x chain costs more than it saves.)
 cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
-                              double *y, int mode, double sign, double zs, const double *z, int num_sms,
-                              cudaStream_t s) {
+                              double *y, int mode, double sign, double zs, const double *z, const int *order,
+                              int num_sms, cudaStream_t s) {
   if (nrows <= 0) return cudaSuccess;
   const int block = 256;
   long want = ((long)nrows * bs + block - 1) / block;
   long cap = (long)num_sms * 8 * 64;
   unsigned grid = (unsigned)(want < cap ? want : cap);
-#define TB2_SPMV(K, M) K<M><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y, sign, zs, z)
+#define TB2_SPMV(K, M) K<M><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y, sign, zs, z, order)
   if (bs == 6) {
     switch (mode) {
       case 0: TB2_SPMV(spmv6_kernel, 0); break;
@@ -1749,25 +1707,12 @@ cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *col
       default: return cudaErrorInvalidValue;
     }
   } else if (bs == 3) {
-    static const bool per_thread = getenv("TACSB200_SPMV3_THREAD") != nullptr;  // measurement switch
-    if (per_thread) {
-      switch (mode) {
-        case 0: TB2_SPMV(spmv3_kernel, 0); break;
-        case 1: TB2_SPMV(spmv3_kernel, 1); break;
-        case 2: TB2_SPMV(spmv3_kernel, 2); break;
-        case 3: TB2_SPMV(spmv3_kernel, 3); break;
-        default: return cudaErrorInvalidValue;
-      }
-    } else {
-      want = ((long)nrows * 32 + block - 1) / block;  // one warp per block row
-      grid = (unsigned)(want < cap ? want : cap);
-      switch (mode) {
-        case 0: TB2_SPMV(spmv3_warp_kernel, 0); break;
-        case 1: TB2_SPMV(spmv3_warp_kernel, 1); break;
-        case 2: TB2_SPMV(spmv3_warp_kernel, 2); break;
-        case 3: TB2_SPMV(spmv3_warp_kernel, 3); break;
-        default: return cudaErrorInvalidValue;
-      }
+    switch (mode) {
+      case 0: TB2_SPMV(spmv3_kernel, 0); break;
+      case 1: TB2_SPMV(spmv3_kernel, 1); break;
+      case 2: TB2_SPMV(spmv3_kernel, 2); break;
+      case 3: TB2_SPMV(spmv3_kernel, 3); break;
+      default: return cudaErrorInvalidValue;
     }
   } else {
     return cudaErrorInvalidValue;
@@ -1778,7 +1723,7 @@ cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *col
 
 cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
                         double *y, int add, int num_sms, cudaStream_t s) {
-  return launch_spmv_fused(bs, nrows, rowp, cols, A, x, y, add ? 1 : 0, 1.0, 0.0, nullptr, num_sms, s);
+  return launch_spmv_fused(bs, nrows, rowp, cols, A, x, y, add ? 1 : 0, 1.0, 0.0, nullptr, nullptr, num_sms, s);
 }
 
 // ------------------------------------------------------------------------------------------

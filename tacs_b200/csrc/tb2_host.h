@@ -360,6 +360,10 @@ struct BCSRPattern {
   int bsize = 0, nrows = 0, ncols = 0;
   std::vector<int> rowp, cols;  // host copies (bit-exact parity target)
   DeviceArray<int> d_rowp, d_cols;
+  // rows listed by descending length (stable), built when the row lengths differ much: the SpMV then hands the lanes
+  // of a warp rows of (nearly) equal length. Null pointer: natural order.
+  DeviceArray<int> d_order;
+  bool buildRowOrder();
   // bsize^2 * nnzb values, 64-bit offsets: a view into the owning matrix's single value array [Aloc | Bext]
   struct ValuesView {
     double *ptr = nullptr;
