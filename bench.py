@@ -671,6 +671,28 @@ def run_b200(args):
     e2e_s = D.max((time.perf_counter() - t0) / args.steps)
     e2e_value = nelem_total / e2e_s
     clocks.__exit__()
+    # where an end-to-end step spends its time on this rank's host thread (outside the timed region): the pinned
+    # H2D copy of the state, the enqueue of setVariables + assembleJacobian, the wait for the residual (D2H), the rest
+    # of the device work. Max over ranks: the ranks of one node share the host's copy engines and memory channels.
+    phases = np.zeros(4)
+    for _ in range(args.steps):
+        t_a = time.perf_counter()
+        x.setArray(state_np)
+        t_b = time.perf_counter()
+        asm.setVariables(x)
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A, wait=False)
+        t_c = time.perf_counter()
+        lib.vec_get_array(res.h, tacs_b200.binding.dptr(out_np))
+        t_d = time.perf_counter()
+        lib.synchronize()
+        t_e = time.perf_counter()
+        phases += [t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d]
+    e2e_breakdown = {k: D.max(float(v) / args.steps * 1e3) for k, v in
+                     zip(("h2d_state_ms", "enqueue_ms", "residual_d2h_wait_ms", "matrix_tail_ms"), phases)}
+    try:
+        e2e_breakdown["host_cpus_visible_to_this_rank"] = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
 
     fullsize = None
     if default_workload:
@@ -734,7 +756,7 @@ def run_b200(args):
                          "note": "assembleRes alone (SURVEY 8d metric i), same mesh and state"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8),
-                "ms_per_step": e2e_s * 1e3,
+                "ms_per_step": e2e_s * 1e3, "breakdown": e2e_breakdown,
                 "note": "state vector from pinned host memory -> setVariables -> assembleJacobian (enqueue-only C ABI "
                         "entry) -> residual to pinned host memory on the copy stream while the block gather still runs; "
                         "the region ends with a device synchronize; the BCSR matrix stays in HBM for the device-side "

@@ -15,6 +15,7 @@
 //   halo pack/unpack  TACSBVecDistribute forward gather / reverse add
 //                     (/root/reference/src/bpmat/TACSBVecDistribute.cpp:543-743, 980-1326)
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -363,40 +364,33 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
   for (int m = 0; m < NSA; m++) stri[m] = (tid + m * TEAM < NTRI) ? shell_unc_tri<O>(tid + m * TEAM) : 0;
   // staging offsets of this lane's C fragments: rows 8 mt + gq, column pairs 8 nt + 2 tq (node-pair-major 6x6 blocks)
   const int fo = (tq >> 1) * Work::HS + 2 * gq + (tq & 1);  // this lane's fragment inside a half-split row panel
-  // Store plan of a lane's nine C fragments (row tile mt: rows 8 mt + gq, column tile nt: column pair 8 nt + 2 tq).
-  // A fragment lies inside one node pair (i, j) = (row / 6, col / 6). Its offset in the element's staging image is
-  // separable, rowS[mt] + colS[nt]: the upper layout puts pair (i <= j) at slot f(i) + j (plan.h upper_index), the
-  // element-level layout at 4 i + j. upmask: fragments that are staged at all (i <= j; all of them for the
-  // element-level layout). Direct targets are looked up for the diagonal pairs i + j = 3 only -- the plan offers no
-  // others for this family (plan.h direct_candidate) -- at dmap[16 e + dmo[mt]]; candmask marks those fragments.
-  // The plan depends on the lane alone: it lives in shared memory (17 words per lane) and is read back at the store
-  // phase, where the 72 accumulator registers leave no room for it.
-  __shared__ int4 stplan[5][32];
+  // Where the tangent goes. A C fragment (row tile mt: rows 8 mt + gq, column tile nt: column pair 8 nt + 2 tq) lies
+  // inside one node pair (i, j) = (row / 6, col / 6). At the top of every element the sixteen lanes of its team work
+  // out the destination of the sixteen pairs once -- byte offset from g.Ke of the 6x6 block: its staging slot (upper
+  // layout: pairs i <= j, plan.h upper_index; element-level layout: every pair), the block of the matrix when the
+  // plan gives the pair a direct target (the difference of the two base pointers is folded in), or kSkip for a lower
+  // pair without one -- and leave it in shared memory. The store phase then needs one 8-byte load per fragment instead
+  // of a chain of selects on 64-bit pointers (the compiler had turned those into both address computations, 25
+  // instructions per fragment). stplan: the lane's static part, pair index 4 i + j and offset inside the block, both
+  // separable into a row-tile and a column-tile term.
+  constexpr long long kSkip = LLONG_MIN;
+  __shared__ long long dsttab[TEAMS][16];
+  __shared__ int4 stplan[4][32];
   if (threadIdx.x < 32) {
-    int rowS[3], colS[3], rowD[3], colD[3], dmo[3];
-    unsigned upmask = 0, candmask = 0;
+    int prow[3], pcol[3], drow[3], dcol[3];
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-      const int R = 8 * t + gq, C = 8 * t + 2 * tq, i = R / 6, j = C / 6;
-      rowD[t] = (R % 6) * 6;
-      colD[t] = C % 6;
-      rowS[t] = (g.upper ? (i * n - ((i * (i - 1)) >> 1) - i) : i * n) * 36 + rowD[t];
-      colS[t] = j * 36 + colD[t];
-      dmo[t] = i * n + (n - 1 - i);
+      const int R = 8 * t + gq, C = 8 * t + 2 * tq;
+      prow[t] = 4 * (R / 6);
+      pcol[t] = C / 6;
+      drow[t] = (R % 6) * 6;
+      dcol[t] = C % 6;
     }
-#pragma unroll
-    for (int mt = 0; mt < 3; mt++)
-#pragma unroll
-      for (int nt = 0; nt < 3; nt++) {
-        const int i = (8 * mt + gq) / 6, j = (8 * nt + 2 * tq) / 6;
-        if (i <= j || !g.upper) upmask |= 1u << (3 * mt + nt);
-        if (i + j == n - 1) candmask |= 1u << (3 * mt + nt);
-      }
-    stplan[0][lane] = make_int4(rowS[0], rowS[1], rowS[2], (int)upmask);
-    stplan[1][lane] = make_int4(colS[0], colS[1], colS[2], (int)candmask);
-    stplan[2][lane] = make_int4(rowD[0], rowD[1], rowD[2], 0);
-    stplan[3][lane] = make_int4(colD[0], colD[1], colD[2], 0);
-    stplan[4][lane] = make_int4(dmo[0], dmo[1], dmo[2], 0);
+    // byte offsets: pair index * 8 (into dsttab), in-block offset * 8
+    stplan[0][lane] = make_int4(8 * prow[0], 8 * prow[1], 8 * prow[2], 0);
+    stplan[1][lane] = make_int4(8 * drow[0], 8 * drow[1], 8 * drow[2], 0);
+    stplan[2][lane] = make_int4(8 * pcol[0], 8 * pcol[1], 8 * pcol[2], 0);
+    stplan[3][lane] = make_int4(8 * dcol[0], 8 * dcol[1], 8 * dcol[2], 0);
   }
   __syncthreads();
 
@@ -416,8 +410,17 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
     __syncwarp();
     prefetch_data();                                            // next element (ids already here)
     prefetch_ids(clamp_elem(base + 2 * nteams + team_in_cta));  // element after next
-    if (g.dmap && g.Ke && tid == 15)  // the 64-byte direct-map row of the next element (read at its store phase)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(g.dmap + clamp_elem(base + nteams + team_in_cta) * (n * n)));
+    if (g.Ke) {
+      // destination of node pair tid = 4 i + j of this team's element (see dsttab above)
+      const int i = tid >> 2, j = tid & 3;
+      const int dm = g.dmap ? __ldg(g.dmap + e * (n * n) + tid) : -1;
+      long long off;
+      if (!g.upper) off = (e * (n * n) + tid) * 288;
+      else if (dm >= 0) off = (reinterpret_cast<const char *>(g.direct) - reinterpret_cast<const char *>(g.Ke)) + (long long)dm * 288;
+      else if (i <= j) off = (e * (n * (n + 1) / 2) + (i * n - ((i * (i - 1)) >> 1) + (j - i))) * 288;
+      else off = kSkip;
+      dsttab[team_in_cta][tid] = live ? off : kSkip;
+    }
     if (tid < n) shell_p1_node<O>(tid, w, tab, desc);
     __syncwarp();
     if (tid < nty) shell_p2_tying<O>(tid, w, tab);
@@ -566,8 +569,6 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
 #pragma unroll
     for (int el = 0; el < 2; el++) {
       Work &x = *we[el];
-      const long eo = base + (team_in_cta & ~1) + el;
-      const bool live_o = eo < nelem;
       double2 up[3];
 #pragma unroll
       for (int nt = 0; nt < 3; nt++) up[nt] = *reinterpret_cast<const double2 *>(x.uvec() + 8 * nt + 2 * tq);
@@ -580,28 +581,21 @@ __global__ void __launch_bounds__(ShellQ4MmaFamily::TEAM *ShellQ4MmaFamily::TEAM
         r += __shfl_xor_sync(0xffffffffu, r, 2);
         if (tq == 0) x.scr[Work::oRes + 8 * mt + gq] = r;
       }
-      if (live_o) {
-        double *const kbase = g.Ke + eo * (g.upper ? (n * (n + 1) / 2) * 36 : n * n * 36);
-        const int4 pRS = stplan[0][lane], pCS = stplan[1][lane], pRD = stplan[2][lane], pCD = stplan[3][lane],
-                   pDM = stplan[4][lane];
-        const unsigned upmask = (unsigned)pRS.w, candmask = (unsigned)pCS.w;
-        const int rowS[3] = {pRS.x, pRS.y, pRS.z}, colS[3] = {pCS.x, pCS.y, pCS.z};
-        const int rowD[3] = {pRD.x, pRD.y, pRD.z}, colD[3] = {pCD.x, pCD.y, pCD.z}, dmo[3] = {pDM.x, pDM.y, pDM.z};
+      {
+        const char *const tab = reinterpret_cast<const char *>(dsttab[(team_in_cta & ~1) + el]);
+        char *const kbytes = reinterpret_cast<char *>(g.Ke);
+        const int4 pP = stplan[0][lane], pD = stplan[1][lane], cP = stplan[2][lane], cD = stplan[3][lane];
+        const int rowP[3] = {pP.x, pP.y, pP.z}, rowD[3] = {pD.x, pD.y, pD.z};
+        const int colP[3] = {cP.x, cP.y, cP.z}, colD[3] = {cD.x, cD.y, cD.z};
 #pragma unroll
-        for (int mt = 0; mt < 3; mt++) {
-          const int dmi = g.dmap ? __ldg(g.dmap + eo * (n * n) + dmo[mt]) : -1;
-          double *const drow = g.direct + (long)dmi * 36 + rowD[mt];
-          double *const srow = kbase + rowS[mt];
+        for (int mt = 0; mt < 3; mt++)
 #pragma unroll
           for (int nt = 0; nt < 3; nt++) {
-            const unsigned bit = 1u << (3 * mt + nt);
-            const bool direct = (candmask & bit) && dmi >= 0;
-            double *dst = direct ? drow + colD[nt] : srow + colS[nt];
-            if (direct || (upmask & bit))
-              *reinterpret_cast<double2 *>(dst) =
+            const long long off = *reinterpret_cast<const long long *>(tab + rowP[mt] + colP[nt]);
+            if (off != kSkip)
+              *reinterpret_cast<double2 *>(kbytes + off + (rowD[mt] + colD[nt])) =
                   make_double2(g.alpha * kacc[el][mt][nt][0], g.alpha * kacc[el][mt][nt][1]);
           }
-        }
       }
     }
     __syncwarp();
