@@ -299,6 +299,55 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # tacs_b200 arm
 # ------------------------------------------------------------------------------------------------------------
+def gpu_numa_node(device):
+    """NUMA node of a GPU from its PCI address (sysfs), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        with open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+class PreferNumaNode:
+    """Allocate host memory on the NUMA node of this rank's GPU while the block is active (set_mempolicy
+    MPOL_PREFERRED): the pinned state / residual buffers of the end-to-end step then sit next to the GPU's PCIe root
+    even when the process itself may only run on the CPUs of another socket."""
+
+    SYS_SET_MEMPOLICY, MPOL_DEFAULT, MPOL_PREFERRED = 238, 0, 1  # x86_64
+
+    def __init__(self, node):
+        self.node, self.ok = node, False
+
+    def _call(self, mode, node):
+        libc = C.CDLL(None, use_errno=True)
+        if node is None:
+            return libc.syscall(self.SYS_SET_MEMPOLICY, mode, None, 0) == 0
+        mask = (C.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        return libc.syscall(self.SYS_SET_MEMPOLICY, mode, mask, 16 * 64) == 0
+
+    def __enter__(self):
+        if self.node is not None:
+            try:
+                self.ok = self._call(self.MPOL_PREFERRED, self.node)
+            except Exception:
+                self.ok = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.ok:
+            try:
+                self._call(self.MPOL_DEFAULT, None)
+            except Exception:
+                pass
+
+
 class Dist:
     """torch.distributed is the bootstrap only (broadcasts of the ncclUniqueId and of rank 0's METIS partition,
     the closing max-over-ranks); the data path of the library uses its own NCCL communicator."""
@@ -631,8 +680,10 @@ def run_b200(args):
     creator, asm, setup = build_partitioned(D, T, meshgen, lib, mesh, [meshgen.iso_shell_element(T, lib, 2)])
     A, res, x, y, xr = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec(), asm.createVec()
     n = x.getSize()
-    state = torch.empty(n, dtype=torch.float64).pin_memory()
-    out = torch.empty(n, dtype=torch.float64).pin_memory()
+    numa = PreferNumaNode(gpu_numa_node(D.local_rank))
+    with numa:
+        state = torch.empty(n, dtype=torch.float64).pin_memory()
+        out = torch.empty(n, dtype=torch.float64).pin_memory()
     state_np, out_np = state.numpy(), out.numpy()
     lo, hi = asm.getOwnerRange()
     h = meshgen.hash_vector(6 * creator.num_nodes)
@@ -689,6 +740,7 @@ def run_b200(args):
         phases += [t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d]
     e2e_breakdown = {k: D.max(float(v) / args.steps * 1e3) for k, v in
                      zip(("h2d_state_ms", "enqueue_ms", "residual_d2h_wait_ms", "matrix_tail_ms"), phases)}
+    e2e_breakdown["pinned_buffers_numa_node"] = numa.node if numa.ok else None
     try:
         e2e_breakdown["host_cpus_visible_to_this_rank"] = len(os.sched_getaffinity(0))
     except AttributeError:

@@ -1000,6 +1000,65 @@ TB2_HD void solid_tile_accumulate(const double *G, const double *CB, int row0, i
   }
 }
 
+// ---- geometric stiffness (TACSElement3D::getMatType(TACS_GEOMETRIC_STIFFNESS_MATRIX), TACSElement3D.cpp:316-360 with
+// TACSLinearElasticity3D::evalWeakMatrix, TACSLinearElasticity.cpp:1704-1800): with the stress s = C e(u) of the
+// current state, K_G[3a+i][3b+j] = delta_ij sum_q w det (grad N_a . S grad N_b), S the symmetric stress tensor.
+// task (ql, a): gradients only
+template <int O, int QC>
+TB2_HD void solid_geo_grad(int task, int q0, SolidWork<O, QC> &w, const SolidTables<O> &tab) {
+  constexpr int n = SolidDims<O>::n;
+  const int a = task % n, ql = task / n, q = q0 + ql;
+  const double *J = w.J[q];
+  const double x0 = tab.dNq[q][a][0], x1 = tab.dNq[q][a][1], x2 = tab.dNq[q][a][2];
+  w.G[ql][3 * a] = x0 * J[0] + x1 * J[3] + x2 * J[6];
+  w.G[ql][3 * a + 1] = x0 * J[1] + x1 * J[4] + x2 * J[7];
+  w.G[ql][3 * a + 2] = x0 * J[2] + x1 * J[5] + x2 * J[8];
+}
+// task ql: strains (left in rpart by solid_res_strain) -> stresses, in place
+template <int O, int QC>
+TB2_HD void solid_geo_stress(int ql, SolidWork<O, QC> &w) {
+  double *e = &w.rpart[0][0] + 6 * ql;
+  const double *C = w.desc;
+  const int idx[6][6] = {{0, 1, 2, 3, 4, 5},     {1, 6, 7, 8, 9, 10},    {2, 7, 11, 12, 13, 14},
+                         {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
+  double s[6];
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    s[r] = C[idx[r][0]] * e[0] + C[idx[r][1]] * e[1] + C[idx[r][2]] * e[2] + C[idx[r][3]] * e[3] + C[idx[r][4]] * e[4] +
+           C[idx[r][5]] * e[5];
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++) e[r] = s[r];
+}
+// task (ql, b): T_b = w det S grad N_b into the first three rows' worth of the CB slab, CB[ql][3b + dir]
+template <int O, int QC>
+TB2_HD void solid_geo_sgrad(int task, int q0, SolidWork<O, QC> &w) {
+  constexpr int n = SolidDims<O>::n;
+  const int b = task % n, ql = task / n;
+  const double *s = &w.rpart[0][0] + 6 * ql;  // xx yy zz yz xz xy
+  const double gx = w.G[ql][3 * b], gy = w.G[ql][3 * b + 1], gz = w.G[ql][3 * b + 2], wd = w.wdet[q0 + ql];
+  double *t = &w.CB[ql][3 * b];
+  t[0] = wd * (s[0] * gx + s[5] * gy + s[4] * gz);
+  t[1] = wd * (s[5] * gx + s[1] * gy + s[3] * gz);
+  t[2] = wd * (s[4] * gx + s[3] * gy + s[2] * gz);
+}
+// tile accumulation: the same scalar on the three diagonal entries of every node pair of the tile
+template <int QC, int ND, int TR, int TC>
+TB2_HD void solid_geo_accumulate(const double *G, const double *CB, int row0, int col0, double *acc) {
+  for (int ql = 0; ql < QC; ql++) {
+    const double *g = G + ql * ND + row0;
+    const double *t = CB + ql * (6 * ND + 8) + col0;  // SolidWork::CBQ
+#pragma unroll
+    for (int an = 0; an < TR / 3; an++)
+#pragma unroll
+      for (int bn = 0; bn < TC / 3; bn++) {
+        const double k = g[3 * an] * t[3 * bn] + g[3 * an + 1] * t[3 * bn + 1] + g[3 * an + 2] * t[3 * bn + 2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) acc[(3 * an + c) * TC + 3 * bn + c] += k;
+      }
+  }
+}
+
 // phase 6, task tile: residual partials, consistent mass block (only when `inertia`);
 // acc <- alpha*acc + gamma*M
 template <int O, int QC>

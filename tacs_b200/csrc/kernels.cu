@@ -1058,6 +1058,20 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS, S
     const int ti = tid / ntc, tj = tid % ntc;
     if (g.Ke) {
       for (int q0 = 0; q0 < nq; q0 += QC) {
+        if (g.geometric) {
+          // geometric stiffness of the current state: gradients, strains, stresses, S grad N, diagonal tiles
+          for (int t = tid; t < QC * n; t += TEAM) solid_geo_grad<O, QC>(t, q0, w, tab);
+          team_sync<TEAM>();
+          for (int t = tid; t < QC * 6; t += TEAM) solid_res_strain<O, QC>(t, w);
+          team_sync<TEAM>();
+          for (int t = tid; t < QC; t += TEAM) solid_geo_stress<O, QC>(t, w);
+          team_sync<TEAM>();
+          for (int t = tid; t < QC * n; t += TEAM) solid_geo_sgrad<O, QC>(t, q0, w);
+          team_sync<TEAM>();
+          if (has_tile) solid_geo_accumulate<QC, nd, TR, TC>(&w.G[0][0], &w.CB[0][0], TR * ti, TC * tj, acc);
+          team_sync<TEAM>();
+          continue;
+        }
         for (int t = tid; t < QC * n; t += TEAM) solid_p3_bcols<O, QC>(t, q0, w, tab);
         team_sync<TEAM>();
         if (has_tile)

@@ -38,6 +38,8 @@ struct ElemGroupArgs {
   //            whose dmap entry is >= 0 is written to block dmap[..] of `direct` instead (the BCSR value array) and
   //            pairs i > j without a direct target are not written at all: the gather reads the mirror transposed.
   int upper;
+  // 1: the tangent is the geometric stiffness of the current state (solids only; TACS_GEOMETRIC_STIFFNESS_MATRIX)
+  int geometric;
   const int *dmap;           // [nelem][nn*nn] or null (no direct targets)
   double *direct;            // value array of the matrix being assembled
 };

@@ -462,6 +462,7 @@ int TACSElement::addJacobianBatch(int count, double alpha, double beta, double g
   g.tables = d_tab.ptr; g.Xpts = d_X.ptr; g.vars = d_u.ptr; g.ddvars = ddvars ? d_a.ptr : nullptr;
   g.alpha = alpha; g.gamma = gamma; g.Ke = mat ? d_Ke.ptr : nullptr; g.Re = d_Re.ptr;
   g.upper = 0; g.dmap = nullptr; g.direct = nullptr;  // element-level interface: every node pair is returned
+  g.geometric = 0;
   g.uncoupled = (kind == ELEM_QUAD4_SHELL || kind == ELEM_QUAD9_SHELL) && shell_desc_uncoupled(drow) ? 1 : 0;
   if (!cuda_ok(launch_element_group(g, ctx().num_sms, ctx().stream), "element kernel")) return 1;
   ctx().kernel_launches++;
@@ -1052,6 +1053,7 @@ int TACSAssembler::launchGroupRange(const ElemGroup &g, long e0, long e1, double
   a.Ke = want_mat ? Ke.ptr + ((size_t)g.block_base + (size_t)e0 * nu) * b2 : nullptr;
   a.Re = Re.ptr + ((size_t)g.node_base + (size_t)e0 * g.nn) * bs;
   a.upper = 1;
+  a.geometric = geometric_pass ? 1 : 0;
   a.dmap = want_mat ? g.d_dmap.ptr + e0 * g.nn * g.nn : nullptr;
   a.direct = want_mat ? mat->vals_all.ptr : nullptr;
   KernelTimer kt(K_ELEMENT, element_kernel_name(a));
@@ -1161,9 +1163,24 @@ int TACSAssembler::assembleMatType(int matType, TACSParallelMat *A, bool apply_b
     alpha = 1.0;
   } else if (matType == 2) {
     gamma = 1.0;
+  } else if (matType == 3) {
+    // TACS_GEOMETRIC_STIFFNESS_MATRIX: solids evaluate it from the stress of the current state (elem_phases.cuh
+    // solid_geo_*). The shell's (a directional derivative of the tangent of its nonlinear model,
+    // TACSShellElement.h:643-760) is not on the device path.
+    for (auto &g : groups)
+      if (g.kind != ELEM_HEX8 && g.kind != ELEM_HEX27) {
+        fprintf(stderr, "tacs_b200: assembleMatType(TACS_GEOMETRIC_STIFFNESS_MATRIX) is evaluated on the device for "
+                        "solid elements only\n");
+        return 1;
+      }
+    alpha = 1.0;
+    geometric_pass = true;
+    const int rc = assembleJacobian(alpha, 0.0, 0.0, nullptr, A, 1.0, apply_bcs);
+    geometric_pass = false;
+    return rc;
   } else {
-    fprintf(stderr, "tacs_b200: assembleMatType(%d): only TACS_STIFFNESS_MATRIX (1) and TACS_MASS_MATRIX (2) "
-                    "are evaluated on the device\n", matType);
+    fprintf(stderr, "tacs_b200: assembleMatType(%d): stiffness (1), mass (2) and geometric stiffness (3) matrices are "
+                    "evaluated on the device\n", matType);
     return 1;
   }
   return assembleJacobian(alpha, 0.0, gamma, nullptr, A, 1.0, apply_bcs);

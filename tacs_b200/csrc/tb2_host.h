@@ -539,6 +539,7 @@ class TACSAssembler : public Object {
   struct ElemChunk { int group; long e0, e1, gather_end; };
   std::vector<ElemChunk> chunks;
   bool overlap_gather = false;
+  bool geometric_pass = false;  // set by assembleMatType(TACS_GEOMETRIC_STIFFNESS_MATRIX) around its element launches
   int launchGroupRange(const ElemGroup &g, long e0, long e1, double alpha, double gamma, TACSParallelMat *mat,
                        const double *vars_p, const double *ddvars_p);
   int uploadMatPlan();

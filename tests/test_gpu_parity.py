@@ -169,11 +169,33 @@ def test_chebyshev_preconditioned_gmres_matches_reference(lib, ref, name, flexib
     assert relerr(out["b200"]["x"], out["ref"]["x"]) < 1e-10  # north_star: displacements within 1e-10
 
 
-def test_geometric_stiffness_is_refused(lib):
+def test_shell_geometric_stiffness_is_refused(lib):
+    """The shell's geometric stiffness (directional derivative of the nonlinear model's tangent) is not on the device
+    path: non-zero return, the caller keeps the reference for it."""
     creator, asm = meshgen.build_model(T, lib, meshgen.plate(2, 3, 3), [meshgen.iso_shell_element(T, lib, 2)])
     A = asm.createMat()
     with pytest.raises(Exception):
         asm.assembleMatType(T.GEOMETRIC_STIFFNESS_MATRIX, A)
+
+
+@pytest.mark.parametrize("name", ["hex8_cube", "hex27_cube"])
+def test_solid_geometric_stiffness_matches_reference(lib, ref, name):
+    """assembleMatType(TACS_GEOMETRIC_STIFFNESS_MATRIX) for TACSElement3D (TACSElement3D.cpp:316-360,
+    TACSLinearElasticity.cpp:1704-1800): stress of the current state contracted with the shape-function gradients."""
+    mesh_f, kind, elem_f = common.SMALL_MODELS[name]
+    mesh = mesh_f()
+    out = {}
+    for tag, L in (("b200", lib), ("ref", ref)):
+        creator, asm = meshgen.build_model(T, L, mesh, [elem_f(L)])
+        G, u = asm.createMat(), asm.createVec()
+        u.setArray(meshgen.hash_vector(u.getSize()))
+        asm.applyBCs(u)
+        asm.setVariables(u)
+        asm.assembleMatType(T.GEOMETRIC_STIFFNESS_MATRIX, G)
+        out[tag] = G.getValues()
+        keep = (creator, asm)
+    assert np.abs(out["ref"]).max() > 0.0
+    assert relerr(out["b200"], out["ref"]) < TOL
 
 
 def test_host_copies_overlap_the_matrix_gather(lib):
