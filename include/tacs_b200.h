@@ -214,6 +214,18 @@ int tacsb200_mat_mult(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y); 
 int tacsb200_mat_mult_async(tacsb200_handle m, tacsb200_handle x, tacsb200_handle y);
 tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m); /* TACSMat::createVec KSM.h */
 
+/* ---- TACSAuxElements: src/TACSAuxElements.h:52-100, TACSAssembler::setAuxElements src/TACSAssembler.h:158 ------
+   State-independent loads bound to an element number of the creator's global numbering and added, scaled by the load
+   factor, to that element's residual in assembleRes / assembleJacobian (TACSAssembler.cpp:4207-4223):
+   TACSShellTraction(t, useConstTrac) src/elements/shell/TACSShellTraction.h:17-33 (t[3], or t[3 nn] node by node),
+   TACSShellPressure(p) src/elements/shell/TACSShellPressure.h:17-29 (p[1] or p[nn]). order = 2 Quad4, 3 Quad9. */
+tacsb200_handle tacsb200_aux_elements_create(void);
+int tacsb200_aux_elements_add_shell_traction(tacsb200_handle aux, int elem_num, int order, const double *t,
+                                             int use_const_trac);
+int tacsb200_aux_elements_add_shell_pressure(tacsb200_handle aux, int elem_num, int order, const double *p,
+                                             int use_const_pressure);
+int tacsb200_assembler_set_aux_elements(tacsb200_handle assembler, tacsb200_handle aux);
+
 /* ---- TACSSchurMat: src/bpmat/TACSSchurMat.h:58-125, TACSSchurMat.cpp:453-552 (addValues), 883-938 (mult) ------
    The four blocks [B E; F C] in the reference's local ordering (interior unknowns b, interface unknowns c), as a view
    of an assembled matrix: b_nodes[nb] / c_nodes[nc] give the owned node of every local index (TACSSchurMat::

@@ -28,6 +28,9 @@
 #include "TACSLinearElasticity.h"
 #include "TACSMaterialProperties.h"
 #include "TACSShellElementDefs.h"
+#include "TACSAuxElements.h"
+#include "TACSShellPressure.h"
+#include "TACSShellTraction.h"
 #include "TACSSolidConstitutive.h"
 
 typedef void *ref_handle;
@@ -479,6 +482,32 @@ int ref_mat_mult(ref_handle m, ref_handle x, ref_handle y) {
 
 int ref_mat_mult_transpose(ref_handle m, ref_handle x, ref_handle y) {
   as<TACSMat>(m)->multTranspose(as<TACSBVec>(x), as<TACSBVec>(y));
+  return 0;
+}
+
+/* ---- auxiliary load elements -------------------------------------------------- */
+ref_handle ref_aux_elements_create(void) { return keep(new TACSAuxElements()); }
+int ref_aux_elements_add_shell_traction(ref_handle aux, int elem_num, int order, const double *t, int use_const) {
+  TACSElement *e = NULL;
+  if (order == 2) e = new TACSShellTraction<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> >(t, use_const);
+  else e = new TACSShellTraction<6, TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3> >(t, use_const);
+  as<TACSAuxElements>(aux)->addElement(elem_num, e);
+  return 0;
+}
+int ref_aux_elements_add_shell_pressure(ref_handle aux, int elem_num, int order, const double *p, int use_const) {
+  TACSElement *e = NULL;
+  if (order == 2) {
+    if (use_const) e = new TACSShellPressure<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> >(p[0]);
+    else e = new TACSShellPressure<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> >(p);
+  } else {
+    if (use_const) e = new TACSShellPressure<6, TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3> >(p[0]);
+    else e = new TACSShellPressure<6, TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3> >(p);
+  }
+  as<TACSAuxElements>(aux)->addElement(elem_num, e);
+  return 0;
+}
+int ref_assembler_set_aux_elements(ref_handle a, ref_handle aux) {
+  as<TACSAssembler>(a)->setAuxElements(aux ? as<TACSAuxElements>(aux) : NULL);
   return 0;
 }
 

@@ -370,6 +370,10 @@ class Assembler(_Obj):
     def zeroVariables(self):
         _check(self.lib.assembler_zero_variables(self.h), "zeroVariables")
 
+    def setAuxElements(self, aux):
+        self._aux = aux
+        _check(self.lib.assembler_set_aux_elements(self.h, aux.h if aux is not None else None), "setAuxElements")
+
     def applyBCs(self, vec):
         _check(self.lib.assembler_apply_bcs_vec(self.h, vec.h), "applyBCs")
 
@@ -403,6 +407,24 @@ class Assembler(_Obj):
 
 
 JACOBIAN_MATRIX, STIFFNESS_MATRIX, MASS_MATRIX, GEOMETRIC_STIFFNESS_MATRIX = 0, 1, 2, 3
+
+
+class AuxElements(_Obj):
+    """tacs.TACS.AuxElements restricted to the shell load elements of the path: addElement(num, ShellTraction(...)) /
+    addElement(num, ShellPressure(...)) become addShellTraction / addShellPressure."""
+
+    def __init__(self, lib):
+        super().__init__(lib, lib.aux_elements_create(), "aux_elements_create")
+
+    def addShellTraction(self, num, order, t):
+        t = B.as_f64(t).ravel()
+        _check(self.lib.aux_elements_add_shell_traction(self.h, int(num), order, B.dptr(t), 1 if t.size == 3 else 0),
+               "addShellTraction")
+
+    def addShellPressure(self, num, order, p):
+        p = B.as_f64(np.atleast_1d(p)).ravel()
+        _check(self.lib.aux_elements_add_shell_pressure(self.h, int(num), order, B.dptr(p), 1 if p.size == 1 else 0),
+               "addShellPressure")
 
 
 class Creator(_Obj):

@@ -101,6 +101,10 @@ SIGNATURES = {
     "chebyshev_factor": (I, [H]),
     "chebyshev_apply_factor": (I, [H, H, H]),
     "chebyshev_get_spectral_radius": (D, [H]),
+    "aux_elements_create": (H, []),
+    "aux_elements_add_shell_traction": (I, [H, I, I, DP, I]),
+    "aux_elements_add_shell_pressure": (I, [H, I, I, DP, I]),
+    "assembler_set_aux_elements": (I, [H, H]),
     "gmres_create": (H, [H, I, I]),
     "gmres_create_pc": (H, [H, H, I, I, I]),
     "gmres_set_tolerances": (I, [H, D, D]),

@@ -574,6 +574,29 @@ tacsb200_handle tacsb200_mat_create_vec(tacsb200_handle m) {
   return keep_vec(A->createVec());
 }
 
+/* ---- auxiliary load elements ------------------------------------------------------------------------ */
+tacsb200_handle tacsb200_aux_elements_create(void) { return keep(new TACSAuxElements()); }
+int tacsb200_aux_elements_add_shell_traction(tacsb200_handle aux, int elem_num, int order, const double *t,
+                                             int use_const_trac) {
+  TACSAuxElements *a = as<TACSAuxElements>(aux);
+  REQUIRE(a, "auxiliary elements");
+  if ((order != 2 && order != 3) || !t) return 1;
+  a->addShellTraction(elem_num, order, t, use_const_trac != 0);
+  return 0;
+}
+int tacsb200_aux_elements_add_shell_pressure(tacsb200_handle aux, int elem_num, int order, const double *p,
+                                             int use_const_pressure) {
+  TACSAuxElements *a = as<TACSAuxElements>(aux);
+  REQUIRE(a, "auxiliary elements");
+  if ((order != 2 && order != 3) || !p) return 1;
+  a->addShellPressure(elem_num, order, p, use_const_pressure != 0);
+  return 0;
+}
+int tacsb200_assembler_set_aux_elements(tacsb200_handle asmb, tacsb200_handle aux) {
+  ASM(asmb);
+  return t->setAuxElements(as<TACSAuxElements>(aux));
+}
+
 /* ---- TACSSchurMat view ------------------------------------------------------------------------------- */
 tacsb200_handle tacsb200_schur_mat_create(tacsb200_handle mat, int nb, const int *b_nodes, int nc, const int *c_nodes,
                                           const int *Browp, const int *Bcols, const int *Erowp, const int *Ecols,

@@ -1216,6 +1216,110 @@ __global__ void __launch_bounds__(SolidFamily<O>::TEAM *SolidFamily<O>::TEAMS, S
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// auxiliary load elements on shells: TACSShellTraction / TACSShellPressure
+// (/root/reference/src/elements/shell/TACSShellTraction.h:50-88, TACSShellPressure.h:56-96)
+// ------------------------------------------------------------------------------------------
+// These elements add a state-independent load to the residual of the element they sit on:
+//   traction: res[6a + c] -= sum_q w det N_a(q) t_c(q)          t interpolated from nodal values
+//   pressure: res[6a + c] -= sum_q w det N_a(q) p(q) n_c(q)      n = interpolated node normals (not normalised)
+// with det = det[X,xi1 | X,xi2 | n]. One thread evaluates one load into loads[k][3 nn] (displacement dofs only); the
+// assembler adds lambda * loads to the element's residual staging slots after the element kernel, so the sum reaches
+// the residual in the reference's order (element residual, then its auxiliary elements, then the scatter).
+template <int O>
+__global__ void shell_aux_loads_kernel(int nloads, const int *__restrict__ conn, const int *__restrict__ elem,
+                                       const int *__restrict__ type, const double *__restrict__ data,
+                                       const ShellTables<O> *__restrict__ tabp, const double *__restrict__ Xpts,
+                                       double *__restrict__ loads) {
+  constexpr int n = ShellDims<O>::n, nq = ShellDims<O>::nq;
+  const ShellTables<O> &tab = *tabp;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nloads; k += gridDim.x * blockDim.x) {
+    const int *nodes = conn + (long)elem[k] * n;
+    const double *d = data + (long)k * 3 * n;  // traction: t[3 nn]; pressure: p[nn] in the first nn entries
+    double X[3 * n], fn[3 * n], f[3 * n];
+    for (int j = 0; j < n; j++)
+      for (int c = 0; c < 3; c++) {
+        X[3 * j + c] = Xpts[3 * (long)nodes[j] + c];
+        f[3 * j + c] = 0.0;
+      }
+    for (int i = 0; i < n; i++) {  // node normals (TacsShellComputeNodeNormals)
+      double a[3] = {0.0, 0.0, 0.0}, b[3] = {0.0, 0.0, 0.0}, nrm[3];
+      for (int j = 0; j < n; j++)
+        for (int c = 0; c < 3; c++) {
+          a[c] += tab.dNn_T[j][0][i] * X[3 * j + c];
+          b[c] += tab.dNn_T[j][1][i] * X[3 * j + c];
+        }
+      cross3(a, b, nrm);
+      const double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+      const double inv = len != 0.0 ? 1.0 / len : 0.0;
+      for (int c = 0; c < 3; c++) fn[3 * i + c] = len != 0.0 ? nrm[c] * inv : nrm[c];
+    }
+    for (int q = 0; q < nq; q++) {
+      double x1[3] = {0.0, 0.0, 0.0}, x2[3] = {0.0, 0.0, 0.0}, nv[3] = {0.0, 0.0, 0.0}, tr[3] = {0.0, 0.0, 0.0};
+      double pq = 0.0;
+      for (int j = 0; j < n; j++) {
+        const double N = tab.Nq[q][j];
+        for (int c = 0; c < 3; c++) {
+          x1[c] += tab.dNq[q][j][0] * X[3 * j + c];
+          x2[c] += tab.dNq[q][j][1] * X[3 * j + c];
+          nv[c] += N * fn[3 * j + c];
+        }
+        if (type[k] == 0) {
+          for (int c = 0; c < 3; c++) tr[c] += N * d[3 * j + c];
+        } else {
+          pq += N * d[j];
+        }
+      }
+      const double Xd[9] = {x1[0], x2[0], nv[0], x1[1], x2[1], nv[1], x1[2], x2[2], nv[2]};
+      const double det = (Xd[8] * (Xd[0] * Xd[4] - Xd[3] * Xd[1]) - Xd[7] * (Xd[0] * Xd[5] - Xd[3] * Xd[2]) +
+                          Xd[6] * (Xd[1] * Xd[5] - Xd[2] * Xd[4])) * tab.wq[q];
+      double fq[3];
+      for (int c = 0; c < 3; c++) fq[c] = type[k] == 0 ? tr[c] * -det : pq * -det * nv[c];
+      for (int j = 0; j < n; j++)
+        for (int c = 0; c < 3; c++) f[3 * j + c] += tab.Nq[q][j] * fq[c];
+    }
+    for (int j = 0; j < 3 * n; j++) loads[(long)k * 3 * n + j] = f[j];
+  }
+}
+
+cudaError_t launch_shell_aux_loads(int order, int nloads, const int *conn, const int *elem, const int *type,
+                                   const double *data, const void *tables, const double *Xpts, double *loads,
+                                   cudaStream_t s) {
+  if (nloads <= 0) return cudaSuccess;
+  const int grid = (nloads + 63) / 64;
+  if (order == 2)
+    shell_aux_loads_kernel<2><<<grid, 64, 0, s>>>(nloads, conn, elem, type, data,
+                                                  static_cast<const ShellTables<2> *>(tables), Xpts, loads);
+  else if (order == 3)
+    shell_aux_loads_kernel<3><<<grid, 64, 0, s>>>(nloads, conn, elem, type, data,
+                                                  static_cast<const ShellTables<3> *>(tables), Xpts, loads);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// Re[slot[k] .. + 6 nn] += lambda * loads[k] on the displacement dofs (one thread per entry; several loads on one
+// element are added one after the other: the list is sorted by element and a thread walks its element's run)
+__global__ void aux_add_kernel(int nruns, int nn, const int *__restrict__ run_ptr, const long *__restrict__ slot,
+                               const double *__restrict__ loads, double lambda, double *__restrict__ Re) {
+  const int total = nruns * 3 * nn;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int r = g / (3 * nn), j = g - r * 3 * nn, a = j / 3, c = j - 3 * a;
+    double *dst = Re + slot[r] + 6 * a + c;
+    double v = *dst;
+    for (int k = run_ptr[r]; k < run_ptr[r + 1]; k++) v += lambda * loads[(long)k * 3 * nn + j];
+    *dst = v;
+  }
+}
+
+cudaError_t launch_aux_add(int nruns, int nn, const int *run_ptr, const long *slot, const double *loads, double lambda,
+                           double *Re, cudaStream_t s) {
+  if (nruns <= 0) return cudaSuccess;
+  const int total = nruns * 3 * nn;
+  aux_add_kernel<<<(total + 255) / 256, 256, 0, s>>>(nruns, nn, run_ptr, slot, loads, lambda, Re);
+  return cudaGetLastError();
+}
+
 template <class F>
 static size_t family_smem() {
   return sizeof(typename F::Tables) + 16 + F::WORK_STRIDE * F::TEAMS;

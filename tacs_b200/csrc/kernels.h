@@ -66,6 +66,13 @@ inline const char *spmv_kernel_name(int bs, int add) {
 // blocks gb_blk[0..nblocks) of A sum their staging sources src[ptr[g]..ptr[g+1]) (2*slot + transposed flag)
 cudaError_t launch_gather_blocks(int bs, long nblocks, const int *blk, const int *ptr, const int *src,
                                  const double *Ke, double *A, int num_sms, cudaStream_t s);
+// auxiliary shell loads (traction type 0: data = t[3 nn]; pressure type 1: data[0..nn) = p): loads[k][3 nn]
+cudaError_t launch_shell_aux_loads(int order, int nloads, const int *conn, const int *elem, const int *type,
+                                   const double *data, const void *tables, const double *Xpts, double *loads,
+                                   cudaStream_t s);
+// Re[slot[r] + 6 a + c] += lambda * sum of the loads run_ptr[r] .. run_ptr[r+1]) of one element
+cudaError_t launch_aux_add(int nruns, int nn, const int *run_ptr, const long *slot, const double *loads, double lambda,
+                           double *Re, cudaStream_t s);
 cudaError_t launch_gather_residual(int bs, long nnodes, const int *ptr, const int *src, const double *Re,
                                    double *res, int num_sms, cudaStream_t s);
 

@@ -882,6 +882,7 @@ TACSAssembler::~TACSAssembler() {
   if (jvp_x) jvp_x->decref();
   if (jvp_a) jvp_a->decref();
   if (jvp_t) jvp_t->decref();
+  if (aux_elements) aux_elements->decref();
 }
 
 int TACSAssembler::localNode(int g) const { return plan->localNode(g); }
@@ -1018,7 +1019,117 @@ void TACSAssembler::zeroVariables() {
 void TACSAssembler::getNodes(TACSBVec *X) { X->copyValues(xpts); }
 int TACSAssembler::setNodes(TACSBVec *X) {
   xpts->copyValues(X);
-  return size > 1 ? halo_forward(this, xpts) : 0;
+  if (size > 1 && halo_forward(this, xpts)) return 1;
+  return evaluateAuxLoads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// auxiliary load elements
+// ---------------------------------------------------------------------------------------------
+void TACSAuxElements::addShellTraction(int elem_num, int order, const double *t, bool constant) {
+  Load l;
+  l.elem_num = elem_num;
+  l.type = 0;
+  l.order = order;
+  const int nn = order * order;
+  l.data.resize(3 * nn);
+  for (int i = 0; i < nn; i++)
+    for (int c = 0; c < 3; c++) l.data[3 * i + c] = constant ? t[c] : t[3 * i + c];
+  loads.push_back(l);
+}
+void TACSAuxElements::addShellPressure(int elem_num, int order, const double *p, bool constant) {
+  Load l;
+  l.elem_num = elem_num;
+  l.type = 1;
+  l.order = order;
+  const int nn = order * order;
+  l.data.assign(3 * nn, 0.0);
+  for (int i = 0; i < nn; i++) l.data[i] = constant ? p[0] : p[i];
+  loads.push_back(l);
+}
+
+int TACSAssembler::setAuxElements(TACSAuxElements *aux) {
+  if (aux) aux->incref();
+  if (aux_elements) aux_elements->decref();
+  aux_elements = aux;
+  aux_groups.clear();
+  if (!aux) return 0;
+  HostPlan &P = *plan;
+  // global element number -> local element, then (group, index inside the group)
+  std::map<int, int> local_of;
+  for (int e = 0; e < P.nelems; e++) local_of[P.elem_global[e]] = e;
+  std::vector<std::pair<int, long>> where(P.nelems);  // local element -> (group, index in group)
+  for (size_t gi = 0; gi < groups.size(); gi++)
+    for (long k = 0; k < groups[gi].nelem; k++) where[groups[gi].local_elems[k]] = {(int)gi, k};
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const ElemGroup &g = groups[gi];
+    if (g.kind != ELEM_QUAD4_SHELL && g.kind != ELEM_QUAD9_SHELL) continue;
+    const int order = g.kind == ELEM_QUAD4_SHELL ? 2 : 3;
+    // loads of this group sorted by element (stable: insertion order inside an element, TACSAuxElements::sort)
+    std::vector<std::pair<long, const TACSAuxElements::Load *>> mine;
+    for (const auto &l : aux->loads) {
+      auto it = local_of.find(l.elem_num);
+      if (it == local_of.end() || where[it->second].first != (int)gi) continue;
+      if (l.order != order) {
+        fprintf(stderr, "tacs_b200: auxiliary load on element %d does not match the element's order\n", l.elem_num);
+        return 1;
+      }
+      mine.emplace_back(where[it->second].second, &l);
+    }
+    if (mine.empty()) continue;
+    std::stable_sort(mine.begin(), mine.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    std::unique_ptr<AuxGroup> ag(new AuxGroup());
+    ag->group = (int)gi;
+    ag->nloads = (int)mine.size();
+    std::vector<int> elem, type, run_ptr;
+    std::vector<long> slot;
+    std::vector<double> data;
+    for (size_t k = 0; k < mine.size(); k++) {
+      if (k == 0 || mine[k].first != mine[k - 1].first) {
+        run_ptr.push_back((int)k);
+        slot.push_back(((long)g.node_base + mine[k].first * g.nn) * bs);
+      }
+      elem.push_back((int)mine[k].first);
+      type.push_back(mine[k].second->type);
+      data.insert(data.end(), mine[k].second->data.begin(), mine[k].second->data.end());
+    }
+    run_ptr.push_back((int)mine.size());
+    ag->nruns = (int)slot.size();
+    if (!ag->d_elem.upload(elem) || !ag->d_type.upload(type) || !ag->d_run_ptr.upload(run_ptr) ||
+        !ag->d_slot.upload(slot) || !ag->d_data.upload(data) || !ag->d_loads.alloc((size_t)ag->nloads * 3 * g.nn))
+      return 1;
+    aux_groups.push_back(std::move(ag));
+  }
+  // every load must sit on a shell element of some rank; a load on a solid / unknown element is an error here
+  for (const auto &l : aux->loads) {
+    if (l.elem_num < 0 || l.elem_num >= (int)plan->gm->num_elements) {
+      fprintf(stderr, "tacs_b200: auxiliary load on element %d: no such element\n", l.elem_num);
+      return 1;
+    }
+  }
+  return evaluateAuxLoads();
+}
+
+// the loads depend on the node locations only: evaluated when they are set and when the nodes change
+int TACSAssembler::evaluateAuxLoads() {
+  for (auto &ag : aux_groups) {
+    const ElemGroup &g = groups[ag->group];
+    KernelTimer kt(K_ELEMENT, g.nn == 4 ? "shell_aux_loads_kernel<2>" : "shell_aux_loads_kernel<3>");
+    if (!cuda_ok(launch_shell_aux_loads(g.nn == 4 ? 2 : 3, ag->nloads, g.d_conn.ptr, ag->d_elem.ptr, ag->d_type.ptr,
+                                        ag->d_data.ptr, g.d_tables.ptr, xpts->local(), ag->d_loads.ptr, ctx().stream),
+                 "auxiliary loads")) return 1;
+  }
+  return 0;
+}
+
+// after the element kernels: lambda * load added to the residual staging slots of the loaded elements
+int TACSAssembler::addAuxLoads(double lambda) {
+  for (auto &ag : aux_groups) {
+    KernelTimer kt(K_ELEMENT, "aux_add_kernel");
+    if (!cuda_ok(launch_aux_add(ag->nruns, groups[ag->group].nn, ag->d_run_ptr.ptr, ag->d_slot.ptr, ag->d_loads.ptr,
+                                lambda, Re.ptr, ctx().stream), "auxiliary loads")) return 1;
+  }
+  return 0;
 }
 
 void TACSAssembler::applyBCs(TACSBVec *v) {
@@ -1078,6 +1189,7 @@ int staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
   NvtxRange nvtx_range("tacs_b200::assembleRes");
   if (launchElements(1.0, 0.0, nullptr)) return 1;
+  if (addAuxLoads(lambda)) return 1;
   if (size > 1 && staging_exchange(this, false)) return 1;
   {
     KernelTimer kt(K_GATHER_RES, gather_residual_kernel_name(bs));
@@ -1130,6 +1242,7 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
       forked = true;
     }
   }
+  if (res && addAuxLoads(lambda)) return 1;
   if (size > 1 && staging_exchange(this, true)) return 1;
   if (res) {
     {

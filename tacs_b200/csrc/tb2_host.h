@@ -476,6 +476,22 @@ struct ElemGroup {
   long node_base = 0;   // first residual staging slot (units of one node block)
 };
 
+// TACSAuxElements (src/TACSAuxElements.h:52-100) restricted to the state-independent shell loads of the reference:
+// TACSShellTraction and TACSShellPressure (src/elements/shell/TACSShellTraction.h, TACSShellPressure.h), each bound to
+// an element number of the creator's global numbering.
+class TACSAuxElements : public Object {
+ public:
+  struct Load {
+    int elem_num;   // global element number (TACSAuxElements::addElement(num, elem))
+    int type;       // 0 traction, 1 pressure
+    int order;      // 2 Quad4, 3 Quad9
+    std::vector<double> data;  // 3 nn tractions (node by node) or nn pressures
+  };
+  std::vector<Load> loads;
+  void addShellTraction(int elem_num, int order, const double *t, bool constant);
+  void addShellPressure(int elem_num, int order, const double *p, bool constant);
+};
+
 class TACSAssembler : public Object {
  public:
   TACSAssembler();
@@ -491,6 +507,9 @@ class TACSAssembler : public Object {
   void zeroVariables();
   void getNodes(TACSBVec *X);
   int setNodes(TACSBVec *X);
+  // TACSAssembler::setAuxElements (src/TACSAssembler.h:158): loads added to the residual of assembleRes /
+  // assembleJacobian, scaled by the load factor lambda
+  int setAuxElements(TACSAuxElements *aux);
   void applyBCs(TACSBVec *v);
   void applyBCs(TACSParallelMat *m);
   void setBCs(TACSBVec *v);
@@ -539,7 +558,18 @@ class TACSAssembler : public Object {
   struct ElemChunk { int group; long e0, e1, gather_end; };
   std::vector<ElemChunk> chunks;
   bool overlap_gather = false;
-  bool geometric_pass = false;  // set by assembleMatType(TACS_GEOMETRIC_STIFFNESS_MATRIX) around its element launches
+  bool geometric_pass = false;
+  // auxiliary loads of the local elements, per shell group: sorted by element, one run of loads per loaded element
+  TACSAuxElements *aux_elements = nullptr;
+  struct AuxGroup {
+    int group = 0, nloads = 0, nruns = 0;
+    DeviceArray<int> d_elem, d_type, d_run_ptr;
+    DeviceArray<long> d_slot;
+    DeviceArray<double> d_data, d_loads;
+  };
+  std::vector<std::unique_ptr<AuxGroup>> aux_groups;
+  int evaluateAuxLoads();
+  int addAuxLoads(double lambda);  // set by assembleMatType(TACS_GEOMETRIC_STIFFNESS_MATRIX) around its element launches
   int launchGroupRange(const ElemGroup &g, long e0, long e1, double alpha, double gamma, TACSParallelMat *mat,
                        const double *vars_p, const double *ddvars_p);
   int uploadMatPlan();

@@ -477,3 +477,46 @@ def test_mult_transpose_matches_reference(lib, ref, name):
     assert relerr(out["b200"][0], out["ref"][0]) < TOL
     assert relerr(out["b200"][1], out["ref"][1]) < TOL
     assert relerr(out["ref"][1], out["ref"][0]) > 1e-6  # the two products really differ
+
+
+@pytest.mark.parametrize("name,order", [("quad4_cylinder", 2), ("quad9_cylinder", 3)])
+def test_aux_shell_loads_match_reference(lib, ref, name, order):
+    """TACSAuxElements with TACSShellTraction / TACSShellPressure (constant and nodal values, two loads on one
+    element) added to the residual of assembleRes and assembleJacobian (TACSAssembler.cpp:4207-4223) on a curved
+    shell, against the compiled reference."""
+    mesh_f, kind, elem_f = common.SMALL_MODELS[name]
+    mesh = mesh_f()
+    ne = mesh["elem_ids"].size
+    nn = order * order
+    rng = np.random.default_rng(7)
+    tr_nodal = rng.standard_normal(3 * nn)
+    pr_nodal = rng.standard_normal(nn)
+    out = {}
+    for tag, L in (("b200", lib), ("ref", ref)):
+        creator, asm = meshgen.build_model(T, L, mesh, [elem_f(L)])
+        aux = T.AuxElements(L)
+        for e in range(0, ne, 3):
+            aux.addShellPressure(e, order, 2.5)
+        for e in range(1, ne, 4):
+            aux.addShellTraction(e, order, [0.3, -1.0, 2.0])
+        aux.addShellTraction(5, order, tr_nodal)
+        aux.addShellPressure(5, order, pr_nodal)
+        aux.addShellPressure(0, order, pr_nodal[::-1].copy())
+        asm.setAuxElements(aux)
+        A, res, res2, u = asm.createMat(), asm.createVec(), asm.createVec(), asm.createVec()
+        u.setArray(meshgen.hash_vector(u.getSize()))
+        asm.applyBCs(u)
+        asm.setVariables(u)
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+        asm.assembleRes(res2)
+        r_with = res.getArray()
+        asm.setAuxElements(None)
+        asm.assembleRes(res)
+        out[tag] = (r_with, res2.getArray(), res.getArray(), A.getValues())
+        keep = (creator, asm, aux)
+    b, r = out["b200"], out["ref"]
+    assert relerr(r[0] - r[2], 0 * r[0]) > 0.0  # the loads contribute
+    load_scale = np.abs(r[0] - r[2]).max()
+    assert np.abs((b[0] - b[2]) - (r[0] - r[2])).max() < TOL * load_scale  # the load vector itself
+    assert relerr(b[0], r[0]) < TOL and relerr(b[1], r[1]) < TOL and relerr(b[2], r[2]) < TOL
+    assert relerr(b[3], r[3]) < TOL
