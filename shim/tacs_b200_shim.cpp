@@ -11,7 +11,10 @@
 #include "TACSElement3D.h"
 #include "TACSHexaBasis.h"
 #include "TACSLinearElasticity.h"
+#include "TACSAuxElements.h"
 #include "TACSShellElementDefs.h"
+#include "TACSShellPressure.h"
+#include "TACSShellTraction.h"
 #include "TACSSolidConstitutive.h"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -36,6 +39,44 @@ TB2_PRIVATE_MEMBER(Quad4Transform, TACSQuad4Shell, TACSShellTransform *, transfo
 TB2_PRIVATE_MEMBER(Quad9Con, TACSQuad9Shell, TACSShellConstitutive *, con)
 TB2_PRIVATE_MEMBER(Quad9Transform, TACSQuad9Shell, TACSShellTransform *, transform)
 TB2_PRIVATE_MEMBER(ElasticityStrainType, TACSLinearElasticity3D, ElementStrainType, strain_type)
+
+// the nodal traction / pressure arrays of the shell load elements are private as well
+typedef TACSShellTraction<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> > Quad4TractionElem;
+typedef TACSShellTraction<6, TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3> > Quad9TractionElem;
+typedef TACSShellPressure<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> > Quad4PressureElem;
+typedef TACSShellPressure<6, TACSQuadQuadraticQuadrature, TACSShellQuadBasis<3> > Quad9PressureElem;
+typedef TacsScalar TractionArray4[12];
+typedef TacsScalar TractionArray9[27];
+typedef TacsScalar PressureArray4[4];
+typedef TacsScalar PressureArray9[9];
+TB2_PRIVATE_MEMBER(Quad4TractionT, Quad4TractionElem, TractionArray4, t)
+TB2_PRIVATE_MEMBER(Quad9TractionT, Quad9TractionElem, TractionArray9, t)
+TB2_PRIVATE_MEMBER(Quad4PressureP, Quad4PressureElem, PressureArray4, p)
+TB2_PRIVATE_MEMBER(Quad9PressureP, Quad9PressureElem, PressureArray9, p)
+
+// device-side copy of the application's auxiliary elements, or NULL when one of them is not a shell load of the path
+tacsb200_handle convert_aux_elements(TACSAuxElements *aux) {
+  TACSAuxElem *list = NULL;
+  const int naux = aux->getAuxElements(&list);
+  tacsb200_handle out = tacsb200_aux_elements_create();
+  for (int k = 0; k < naux && out; k++) {
+    TACSElement *e = list[k].elem;
+    int rc = 1;
+    if (Quad4TractionElem *q = dynamic_cast<Quad4TractionElem *>(e))
+      rc = tacsb200_aux_elements_add_shell_traction(out, list[k].num, 2, q->*get(Quad4TractionT()), 0);
+    else if (Quad9TractionElem *q = dynamic_cast<Quad9TractionElem *>(e))
+      rc = tacsb200_aux_elements_add_shell_traction(out, list[k].num, 3, q->*get(Quad9TractionT()), 0);
+    else if (Quad4PressureElem *q = dynamic_cast<Quad4PressureElem *>(e))
+      rc = tacsb200_aux_elements_add_shell_pressure(out, list[k].num, 2, q->*get(Quad4PressureP()), 0);
+    else if (Quad9PressureElem *q = dynamic_cast<Quad9PressureElem *>(e))
+      rc = tacsb200_aux_elements_add_shell_pressure(out, list[k].num, 3, q->*get(Quad9PressureP()), 0);
+    if (rc) {
+      tacsb200_release(out);
+      out = NULL;
+    }
+  }
+  return out;
+}
 
 void fail(const char *what) { fprintf(stderr, "TACSB200Assembler: %s; the reference path stays in charge\n", what); }
 
@@ -366,13 +407,18 @@ TACSB200Assembler *TACSB200Assembler::create(TACSAssembler *assembler) {
     fail("dependent nodes are not on the device path");
     return NULL;
   }
-  if (assembler->getAuxElements()) {
-    fail("auxiliary elements are not on the device path");
-    return NULL;
-  }
   if (tacsb200_init(0) != 0) {
     fail("no usable B200");
     return NULL;
+  }
+  // auxiliary elements: the shell traction / pressure loads are carried over, anything else keeps the reference path
+  tacsb200_handle dev_aux = NULL;
+  if (assembler->getAuxElements()) {
+    dev_aux = convert_aux_elements(assembler->getAuxElements());
+    if (!dev_aux) {
+      fail("an auxiliary element is not a TACSShellTraction / TACSShellPressure");
+      return NULL;
+    }
   }
   const int vpn = assembler->getVarsPerNode(), nnodes = assembler->getNumNodes(), nelems = assembler->getNumElements();
   const int *ptr = NULL, *conn = NULL;
@@ -443,6 +489,7 @@ TACSB200Assembler *TACSB200Assembler::create(TACSAssembler *assembler) {
       self->handle = tacsb200_creator_create_tacs(cr);
       ok = self->handle != NULL;
     }
+    if (ok && dev_aux) ok = tacsb200_assembler_set_aux_elements(self->handle, dev_aux) == 0;
     if (!ok) {
       fail("the device assembler could not be created");
       self->incref();
@@ -451,6 +498,7 @@ TACSB200Assembler *TACSB200Assembler::create(TACSAssembler *assembler) {
     }
   }
   for (size_t k = 0; k < dev_elems.size(); k++) tacsb200_release(dev_elems[k]);
+  if (dev_aux) tacsb200_release(dev_aux);
   return self;
 }
 

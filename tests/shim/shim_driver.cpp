@@ -25,7 +25,10 @@
 #include "TACSIsoShellConstitutive.h"
 #include "TACSLinearElasticity.h"
 #include "TACSShellElementDefs.h"
+#include "TACSAuxElements.h"
 #include "TACSSchurMat.h"
+#include "TACSShellPressure.h"
+#include "TACSShellTraction.h"
 #include "TACSSolidConstitutive.h"
 #include "tacs_b200_shim.h"
 
@@ -447,6 +450,15 @@ int main(int argc, char **argv) {
   }
   if (all || !strcmp(which, "direct")) {
     TACSAssembler *a = direct_plate(11, 8);
+    // pressure on every element, a nodal traction on a few (TACSAuxElements, TACSAssembler::setAuxElements)
+    TACSAuxElements *aux = new TACSAuxElements();
+    for (int e = 0; e < a->getNumElements(); e++)
+      aux->addElement(e, new TACSShellPressure<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> >(1.5));
+    TacsScalar tr[12];
+    for (int i = 0; i < 12; i++) tr[i] = 0.1 * (i + 1) - 0.4;
+    for (int e = 3; e < a->getNumElements(); e += 7)
+      aux->addElement(e, new TACSShellTraction<6, TACSQuadLinearQuadrature, TACSShellQuadBasis<2> >(tr, 0));
+    a->setAuxElements(aux);
     run_case("direct (Quad4, hand-built TACSAssembler, two element objects, partial BCs)", a, 0);
     a->decref();
   }
