@@ -227,6 +227,7 @@ void TACSOrthotropicPly::calculateAbar(double angle, double Abar[3]) const {
 }
 
 double TACSShellConstitutive::DRILLING_REGULARIZATION = 0.1;  // TACSShellConstitutive.cpp:61
+long TACSShellConstitutive::drill_version = 0;
 
 void TACSShellConstitutive::fillDescriptor(double d[]) {
   evalTangentStiffness(d);
@@ -901,7 +902,6 @@ int TACSAssembler::finalize() {
   // distinct descriptors -> device table
   std::map<TACSElement *, int> index;
   elem_desc.resize(nelems);
-  std::vector<double> table;
   for (int e = 0; e < nelems; e++) {
     TACSElement *el = elems[e];
     auto it = index.find(el);
@@ -909,21 +909,12 @@ int TACSAssembler::finalize() {
       int row = (int)distinct.size();
       index[el] = row;
       distinct.push_back(el);
-      table.resize((size_t)32 * (row + 1));
-      el->fillDescriptor(&table[(size_t)32 * row]);
       elem_desc[e] = row;
     } else {
       elem_desc[e] = it->second;
     }
   }
-  if (!d_desc_table.upload(table)) return 1;
-  // shells whose constitutive B block (entries 6..11) vanishes take the cheaper uncoupled kernel path
-  shells_uncoupled = true;
-  for (size_t row = 0; row < distinct.size(); row++) {
-    const int k = distinct[row]->kernelKind();
-    if ((k == ELEM_QUAD4_SHELL || k == ELEM_QUAD9_SHELL) && !shell_desc_uncoupled(&table[32 * row]))
-      shells_uncoupled = false;
-  }
+  if (buildDescriptorTable()) return 1;
   // element groups by kernel family (local order preserved inside a group)
   groups.clear();
   for (size_t gi = 0; gi < P.group_kinds.size(); gi++) {
@@ -989,6 +980,28 @@ int TACSAssembler::finalize() {
       return 1;
   }
   return 0;
+}
+
+int TACSAssembler::buildDescriptorTable() {
+  std::vector<double> table((size_t)32 * distinct.size(), 0.0);
+  for (size_t row = 0; row < distinct.size(); row++) distinct[row]->fillDescriptor(&table[32 * row]);
+  if (!d_desc_table.upload(table)) return 1;
+  // shells whose constitutive B block (entries 6..11) vanishes take the cheaper uncoupled kernel path
+  shells_uncoupled = true;
+  for (size_t row = 0; row < distinct.size(); row++) {
+    const int k = distinct[row]->kernelKind();
+    if ((k == ELEM_QUAD4_SHELL || k == ELEM_QUAD9_SHELL) && !shell_desc_uncoupled(&table[32 * row]))
+      shells_uncoupled = false;
+  }
+  desc_version = TACSShellConstitutive::drill_version;
+  return 0;
+}
+
+int TACSAssembler::refreshDescriptors() {
+  if (desc_version == TACSShellConstitutive::drill_version) return 0;
+  // the table may still be read by kernels in flight
+  if (!cuda_ok(cudaStreamSynchronize(ctx().stream.s), "descriptor refresh")) return 1;
+  return buildDescriptorTable();
 }
 
 TACSBVec *TACSAssembler::createVec() { return new TACSBVec(bs, nowned, ext_before, ext_after); }
@@ -1188,6 +1201,7 @@ int staging_exchange(TACSAssembler *a, bool with_blocks);  // comm.cpp: off-rank
 // TACSAssembler::assembleRes (TACSAssembler.cpp:4133-4242)
 int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
   NvtxRange nvtx_range("tacs_b200::assembleRes");
+  if (refreshDescriptors()) return 1;
   if (launchElements(1.0, 0.0, nullptr)) return 1;
   if (addAuxLoads(lambda)) return 1;
   if (size > 1 && staging_exchange(this, false)) return 1;
@@ -1216,6 +1230,7 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
   (void)beta;
   Context &c = ctx();
   NvtxRange nvtx_range("tacs_b200::assembleJacobian");
+  if (refreshDescriptors()) return 1;
   if (Ke.count < (size_t)total_blocks * bs * bs && !Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
   const double *vp = vars_zero ? nullptr : vars->local(), *ap = ddvars_zero ? nullptr : ddvars->local();
   auto gather = [&](long g0, long g1, cudaStream_t st) -> int {
@@ -1306,6 +1321,7 @@ int TACSAssembler::addJacobianVecProduct(double scale, double alpha, double beta
                                          TACSBVec *y, bool apply_bcs) {
   (void)beta;
   NvtxRange nvtx_range("tacs_b200::addJacobianVecProduct");
+  if (refreshDescriptors()) return 1;
   if (!jvp_x) {
     jvp_x = createVec();
     jvp_a = createVec();

@@ -219,7 +219,14 @@ class TACSShellConstitutive : public TACSConstitutive {
   int getNumStresses() { return 9; }
   virtual void evalMassMoments(double moments[3]) = 0;
   void fillDescriptor(double d[]);
-  static void setDrillingRegularization(double k) { DRILLING_REGULARIZATION = k; }
+  // The reference evaluates the tangent stiffness (drill entry included) on every assembly, so a change takes effect
+  // at once (TACSShellConstitutive.cpp:57-73). Here the constants live in a device table: the version counter lets
+  // every assembler rebuild its table at the start of the next assembly.
+  static void setDrillingRegularization(double k) {
+    DRILLING_REGULARIZATION = k;
+    drill_version++;
+  }
+  static long drill_version;
   static double getDrillingRegularization() { return DRILLING_REGULARIZATION; }
   static double DRILLING_REGULARIZATION;
 };
@@ -577,6 +584,9 @@ class TACSAssembler : public Object {
   DeviceExchange x_state, x_rows, x_blocks;
   int localNode(int global) const;
   int finalize();  // build device data after the creator filled the host arrays
+  int buildDescriptorTable();   // constitutive / transform constants of the distinct element objects -> device
+  int refreshDescriptors();     // rebuilds the table when setDrillingRegularization was called since
+  long desc_version = -1;
   int launchElements(double alpha, double gamma, TACSParallelMat *mat, const double *vars_override = nullptr,
                      const double *ddvars_override = nullptr, bool use_override = false);
 };

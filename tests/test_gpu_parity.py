@@ -520,3 +520,58 @@ def test_aux_shell_loads_match_reference(lib, ref, name, order):
     assert np.abs((b[0] - b[2]) - (r[0] - r[2])).max() < TOL * load_scale  # the load vector itself
     assert relerr(b[0], r[0]) < TOL and relerr(b[1], r[1]) < TOL and relerr(b[2], r[2]) < TOL
     assert relerr(b[3], r[3]) < TOL
+
+
+@pytest.mark.parametrize("ratio", [0.5, 2.0, 1e4])
+def test_laminate_at_the_uncoupled_threshold(lib, ref, ratio):
+    """shell_desc_uncoupled (tb2_host.h) sends a shell descriptor to the tensor-core kernels when its membrane-bending
+    block B vanishes against 1e-14 sqrt(|A||D|). Laminates whose |B| sits just below (dropped: ratio 0.5), just above
+    (kept: ratio 2) and far above the threshold must all match the reference to 1e-12 -- dropping a B of that size
+    changes no tangent entry at double precision, and the general kernel carries every larger one. The offset of an
+    isotropic shell tunes |B| = |tOffset| t |A| continuously."""
+    mesh = meshgen.cylinder(2, 5, 8, defect=0.1)
+    t = 0.01
+    # iso shell: B = -tOffset * t * A, D ~ t^2/12 A  =>  |B| / sqrt(|A||D|) = |tOffset| * sqrt(12)
+    tOffset = ratio * 1e-14 / np.sqrt(12.0)
+    out = {}
+    for tag, L in (("b200", lib), ("ref", ref)):
+        props = T.MaterialProperties(L, rho=2700.0, specific_heat=921.096, E=70e3, nu=0.3, ys=270.0, alpha=24e-6,
+                                     kappa=230.0)
+        con = T.IsoShellConstitutive(L, props, t=t, tOffset=tOffset)
+        elem = T.Quad4Shell(L, T.ShellRefAxisTransform(L, (1.0, 0.0, 0.0)), con)
+        creator, asm = meshgen.build_model(T, L, mesh, [elem])
+        A, res, u = asm.createMat(), asm.createVec(), asm.createVec()
+        u.setArray(meshgen.hash_vector(u.getSize()))
+        asm.applyBCs(u)
+        asm.setVariables(u)
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+        out[tag] = (A.getValues(), res.getArray(), con.evalTangentStiffness())
+        keep = (creator, asm, elem)
+    C = out["ref"][2]
+    bmax, amax, dmax = np.abs(C[6:12]).max(), np.abs(C[0:6]).max(), np.abs(C[12:18]).max()
+    assert (bmax <= 1e-14 * np.sqrt(amax * dmax)) == (ratio < 1.0)  # the case sits on the intended side
+    assert np.array_equal(out["b200"][2], C)
+    assert relerr(out["b200"][0], out["ref"][0]) < TOL and relerr(out["b200"][1], out["ref"][1]) < TOL
+
+
+def test_drilling_regularization_changed_after_create(lib, ref):
+    """TACSShellConstitutive::setDrillingRegularization after createTACS: the reference evaluates the tangent
+    stiffness on every assembly, so the new value takes effect at once; the device descriptor table follows."""
+    mesh = meshgen.plate(2, 6, 5)
+    out = {}
+    try:
+        for tag, L in (("b200", lib), ("ref", ref)):
+            L.shell_set_drilling_regularization(0.1)
+            creator, asm = meshgen.build_model(T, L, mesh, [meshgen.iso_shell_element(T, L, 2)])
+            A, res = asm.createMat(), asm.createVec()
+            asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+            before = A.getValues()
+            L.shell_set_drilling_regularization(7.5)
+            asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
+            out[tag] = (before, A.getValues())
+            keep = (creator, asm)
+    finally:
+        lib.shell_set_drilling_regularization(0.1)
+        ref.shell_set_drilling_regularization(0.1)
+    assert relerr(out["ref"][1], out["ref"][0]) > 1e-6       # the setting matters
+    assert relerr(out["b200"][0], out["ref"][0]) < TOL and relerr(out["b200"][1], out["ref"][1]) < TOL
