@@ -670,11 +670,13 @@ def run_b200(args):
         worst = {k: D.max(v) for k, v in errs["max"].items()}
         exact = D.max(0.0 if errs["pattern_exact"] else 1.0) == 0.0
         parity = {"A": worst["A"], "res": worst["res"], "y": worst["y"], "res_only": worst["res_only"],
-                  "norm": worst["norm"], "dot": worst["dot"], "pattern_exact": exact, "tol": PARITY_TOL,
+                  "norm": worst["norm"], "dot": worst["dot"], "gmres_displacements": worst["gmres"],
+                  "gmres_tol": 1e-10, "pattern_exact": exact, "tol": PARITY_TOL,
                   "cases": sorted(k for k in errs if k not in ("max", "pattern_exact")),
                   "what": "every owned row of the METIS-partitioned matrix / residual / A*x on every rank (NCCL halo and "
                           "off-rank staging rows included) vs the serial oracle in the same numbering; max over ranks"}
-        parity["ok"] = bool(exact and all(worst[k] < PARITY_TOL for k in ("A", "res", "y", "res_only", "norm")))
+        parity["ok"] = bool(exact and all(worst[k] < PARITY_TOL for k in ("A", "res", "y", "res_only", "norm")) and
+                            worst["gmres"] < 1e-10 and D.max(0.0 if errs["gmres_converged"] else 1.0) == 0.0)
         if not parity["ok"]:
             if rank == 0:
                 emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity": parity,

@@ -9,7 +9,10 @@
 // dependency and a torch process shares the copy torch already mapped.
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "tb2_host.h"
 
@@ -22,6 +25,7 @@ typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cuda
 typedef int (*fn_send)(const void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_recv)(void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_group)(void);
+typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef const char *(*fn_errstr)(int);
 
 static struct {
@@ -32,6 +36,7 @@ static struct {
   fn_send send = nullptr;
   fn_recv recv = nullptr;
   fn_group group_start = nullptr, group_end = nullptr;
+  fn_allgather allgather = nullptr;
   fn_errstr errstr = nullptr;
 } nccl;
 
@@ -56,6 +61,7 @@ static int load_nccl() {
   nccl.group_start = (fn_group)dlsym(nccl.lib, "ncclGroupStart");
   nccl.group_end = (fn_group)dlsym(nccl.lib, "ncclGroupEnd");
   nccl.errstr = (fn_errstr)dlsym(nccl.lib, "ncclGetErrorString");
+  nccl.allgather = (fn_allgather)dlsym(nccl.lib, "ncclAllGather");
   if (!nccl.get_uid || !nccl.init_rank || !nccl.allreduce || !nccl.send || !nccl.recv || !nccl.group_start ||
       !nccl.group_end) {
     fprintf(stderr, "tacs_b200: libnccl is missing required symbols\n");
@@ -78,6 +84,9 @@ int comm_unique_id(unsigned char id[128]) {
   return 0;
 }
 
+int comm_peer_init();
+int comm_allreduce_sum(double *dev_buf, int n);
+
 int comm_init(int rank, int size, const unsigned char id[128]) {
   Context &c = ctx();
   if (c.device < 0) {
@@ -90,7 +99,77 @@ int comm_init(int rank, int size, const unsigned char id[128]) {
   if (load_nccl()) return 1;
   nccl_uid uid;
   memcpy(uid.internal, id, 128);
-  return nccl_ok(nccl.init_rank(&c.nccl_comm, size, uid, rank), "ncclCommInitRank") ? 0 : 1;
+  if (!nccl_ok(nccl.init_rank(&c.nccl_comm, size, uid, rank), "ncclCommInitRank")) return 1;
+  comm_peer_init();  // optional: failure leaves the NCCL reductions in place
+  return 0;
+}
+
+// Peer-mapped exchange buffers for the fused scalar all-reduce (kernels.h PeerExchange): every rank allocates a small
+// buffer, the CUDA IPC handles travel through one ncclAllGather, and each rank maps the buffers of all the others
+// (NVLink / NVSwitch peer access within the node). TACSB200_NO_PEER=1 keeps the NCCL path.
+int comm_peer_init() {
+  Context &c = ctx();
+  if (c.size <= 1 || c.size > PeerExchange::kMaxRanks || c.d_peer || !nccl.allgather || getenv("TACSB200_NO_PEER"))
+    return 1;
+  const size_t nval = (size_t)PeerExchange::kSlots * c.size;
+  // layout of a rank's buffer: vals[kSlots * size] doubles | flags[kSlots * size] u64 | produced | consumed
+  const size_t bytes = nval * 8 + nval * 8 + 16;
+  unsigned char *mine = nullptr;
+  if (cudaMalloc(&mine, bytes) != cudaSuccess) { cudaGetLastError(); return 1; }
+  cudaMemset(mine, 0, bytes);
+  cudaIpcMemHandle_t handle;
+  if (cudaIpcGetMemHandle(&handle, mine) != cudaSuccess) { cudaGetLastError(); cudaFree(mine); return 1; }
+  unsigned char *d_handles = nullptr;
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  if (cudaMalloc(&d_handles, hb * (c.size + 1)) != cudaSuccess) { cudaGetLastError(); cudaFree(mine); return 1; }
+  cudaMemcpy(d_handles + hb * c.size, &handle, hb, cudaMemcpyHostToDevice);
+  const int kNcclChar = 0;
+  bool ok = nccl_ok(nccl.allgather(d_handles + hb * c.size, d_handles, hb, kNcclChar, c.nccl_comm, c.stream.s),
+                    "ncclAllGather") &&
+            cuda_ok(cudaStreamSynchronize(c.stream.s), "peer handle exchange");
+  std::vector<cudaIpcMemHandle_t> all(c.size);
+  if (ok) cudaMemcpy(all.data(), d_handles, hb * c.size, cudaMemcpyDeviceToHost);
+  cudaFree(d_handles);
+  PeerExchange px;
+  memset(&px, 0, sizeof(px));
+  px.rank = c.rank;
+  px.size = c.size;
+  for (int p = 0; p < c.size && ok; p++) {
+    unsigned char *base = mine;
+    if (p != c.rank) {
+      void *mapped = nullptr;
+      if (cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      base = static_cast<unsigned char *>(mapped);
+    }
+    px.vals[p] = reinterpret_cast<double *>(base);
+    px.flags[p] = reinterpret_cast<unsigned long long *>(base + nval * 8);
+  }
+  // every rank must agree on the outcome: a rank that failed to map a peer would otherwise wait for flags for ever
+  double *d_flag = nullptr;
+  double h_flag = ok ? 0.0 : 1.0;
+  if (cudaMalloc(&d_flag, sizeof(double)) == cudaSuccess) {
+    cudaMemcpy(d_flag, &h_flag, sizeof(double), cudaMemcpyHostToDevice);
+    comm_allreduce_sum(d_flag, 1);
+    cudaStreamSynchronize(c.stream.s);
+    cudaMemcpy(&h_flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_flag);
+  } else {
+    cudaGetLastError();
+    h_flag = 1.0;
+  }
+  if (h_flag != 0.0) {
+    if (c.rank == 0) fprintf(stderr, "tacs_b200: peer-mapped exchange buffers unavailable; reductions stay on NCCL\n");
+    return 1;
+  }
+  px.produced = reinterpret_cast<unsigned long long *>(mine + 2 * nval * 8);
+  px.consumed = px.produced + 1;
+  if (cudaMalloc(&c.d_peer, sizeof(PeerExchange)) != cudaSuccess) { cudaGetLastError(); c.d_peer = nullptr; return 1; }
+  cudaMemcpy(c.d_peer, &px, sizeof(PeerExchange), cudaMemcpyHostToDevice);
+  return 0;
 }
 
 int comm_allreduce_sum(double *dev_buf, int n) {

@@ -2061,6 +2061,111 @@ cudaError_t launch_orth_step(long n, double *w, const double *vprev, const doubl
   return cudaGetLastError();
 }
 
+// ---- the same sweep with the reduction completed over NVLink peer memory (PeerExchange, kernels.h) ----
+__device__ __forceinline__ double peer_wait_sum(const PeerExchange &px, unsigned long long k) {
+  // reduction number k (0-based) lives in slot k % kSlots; its flags read k + 1 once a rank's partial has landed
+  const int slot = (int)(k % PeerExchange::kSlots);
+  const volatile unsigned long long *fl = px.flags[px.rank] + (long)slot * px.size;
+  const volatile double *vl = px.vals[px.rank] + (long)slot * px.size;
+  double s = 0.0;
+  for (int q = 0; q < px.size; q++) {
+    while (fl[q] < k + 1) {
+    }
+  }
+  __threadfence();
+  for (int q = 0; q < px.size; q++) s += vl[q];  // rank order: the same sum on every rank
+  return s;
+}
+__device__ __forceinline__ void peer_push(const PeerExchange &px, unsigned long long k, double v) {
+  const int slot = (int)(k % PeerExchange::kSlots);
+  for (int p = 0; p < px.size; p++) px.vals[p][(long)slot * px.size + px.rank] = v;
+  __threadfence_system();
+  for (int p = 0; p < px.size; p++) {
+    volatile unsigned long long *f = px.flags[p] + (long)slot * px.size + px.rank;
+    *f = k + 1;
+  }
+}
+
+__global__ void __launch_bounds__(kDotBlock) orth_step_peer_kernel(long n, double *__restrict__ w,
+                                                                  const double *__restrict__ vprev,
+                                                                  double *__restrict__ coef_out,
+                                                                  const double *__restrict__ vnext,
+                                                                  double *__restrict__ partial, unsigned *ticket,
+                                                                  const PeerExchange *__restrict__ pxp) {
+  __shared__ double sh[kDotBlock / 32];
+  __shared__ double coef_sh;
+  __shared__ bool last;
+  const PeerExchange &px = *pxp;
+  double c = 0.0;
+  if (vprev) {
+    // the previous sweep's all-rank sum: one thread per block waits for the partials of every rank
+    if (threadIdx.x == 0) {
+      coef_sh = peer_wait_sum(px, *px.consumed);
+      if (blockIdx.x == 0 && coef_out) *coef_out = coef_sh;
+    }
+    __syncthreads();
+    c = coef_sh;
+  }
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    if (vprev) {
+      wi -= c * vprev[i];
+      w[i] = wi;
+    }
+    acc += wi * (vnext ? vnext[i] : wi);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < kDotBlock / 32; k++) t += sh[k];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) t += __ldcg(partial + k);
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int k = 0; k < kDotBlock / 32; k++) r += sh[k];
+      // every block of this kernel has read `consumed` by now (this is the last block to finish)
+      if (vprev) *px.consumed = *px.consumed + 1;
+      const unsigned long long k = *px.produced;
+      peer_push(px, k, r);
+      *px.produced = k + 1;
+      *ticket = 0u;
+    }
+  }
+}
+
+cudaError_t launch_orth_step_peer(long n, double *w, const double *vprev, double *coef_out, const double *vnext,
+                                  double *partial, unsigned *ticket, const PeerExchange *px, int num_sms,
+                                  cudaStream_t s) {
+  orth_step_peer_kernel<<<dot_num_partials(num_sms), kDotBlock, 0, s>>>(n, w, vprev, coef_out, vnext, partial, ticket,
+                                                                      px);
+  return cudaGetLastError();
+}
+
+__global__ void peer_finish_kernel(const PeerExchange *__restrict__ pxp, double *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const PeerExchange &px = *pxp;
+  const unsigned long long k = *px.consumed;
+  out[0] = peer_wait_sum(px, k);
+  *px.consumed = k + 1;
+}
+cudaError_t launch_peer_finish(const PeerExchange *px, double *out, cudaStream_t s) {
+  peer_finish_kernel<<<1, 32, 0, s>>>(px, out);
+  return cudaGetLastError();
+}
+
 // v <- v * (sign / sqrt(*sumsq))   (the reference scales by the reciprocal of the norm, KSM.cpp:804, 849)
 __global__ void scale_rsqrt_kernel(long n, double *__restrict__ v, const double *__restrict__ sumsq, double sign) {
   const double f = sign * (1.0 / sqrt(*sumsq));

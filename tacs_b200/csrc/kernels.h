@@ -98,9 +98,31 @@ cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *col
 cudaError_t launch_spmv_transpose(int bs, int nrows, const int *rowp, const int *cols, const int *tidx, const double *A,
                                   const double *x, double *y, int num_sms, cudaStream_t s);
 
+// Scalar all-reduce over NVLink peer memory, fused into the kernels that produce and consume the scalar (kernels.cu).
+// Every rank owns an exchange buffer that all peers map (CUDA IPC): vals[slot][rank], flags[slot][rank]. The block that
+// finishes a reduction stores its rank's partial into every peer's buffer and then raises the flag there; the kernel
+// that needs the sum spins on its own (local) flags and adds the partials in rank order -- deterministic, no NCCL call,
+// no host round trip. Sequence numbers live in device memory (produced / consumed counters advanced by the kernels), so
+// a captured CUDA graph can be replayed.
+struct PeerExchange {
+  static constexpr int kMaxRanks = 8, kSlots = 4;
+  double *vals[kMaxRanks];                 // vals[p]: rank p's buffer, kSlots x size doubles
+  unsigned long long *flags[kMaxRanks];    // flags[p]: rank p's flags, kSlots x size
+  unsigned long long *produced, *consumed; // local counters
+  int rank, size;
+};
+
 // Krylov building blocks with device-resident scalars (kernels.cu): see the kernels for the contracts
 cudaError_t launch_orth_step(long n, double *w, const double *vprev, const double *coef, const double *vnext,
                              double *partial, unsigned *ticket, double *out, int num_sms, cudaStream_t s);
+// The same sweep on several GPUs: the coefficient is the all-rank sum of the previous sweep's partials (taken from the
+// peer exchange; its value is also written to coef_out for later readers), and this sweep's partial is pushed to the
+// peers instead of being written to `out`.
+cudaError_t launch_orth_step_peer(long n, double *w, const double *vprev, double *coef_out, const double *vnext,
+                                  double *partial, unsigned *ticket, const PeerExchange *px, int num_sms,
+                                  cudaStream_t s);
+// completes the last pending peer reduction: out[0] = sum over ranks (one thread)
+cudaError_t launch_peer_finish(const PeerExchange *px, double *out, cudaStream_t s);
 cudaError_t launch_scale_rsqrt(long n, double *v, const double *sumsq, double sign, int num_sms, cudaStream_t s);
 cudaError_t launch_multi_axpy(long n, double *x, int nv, const double *const *vs, const double *coef, double scale,
                               int num_sms, cudaStream_t s);

@@ -188,8 +188,18 @@ void GMRES::setMonitor(const char *descript, int freq) {
   monitor_freq = freq < 1 ? 1 : freq;
 }
 
-// w . v (or w . w) of the whole distributed vector into *out, optionally after w -= (*coef) vprev
-static int orth_step(TACSBVec *w, TACSBVec *vprev, const double *coef, TACSBVec *vnext, unsigned *ticket, double *out) {
+// w . v (or w . w) of the whole distributed vector into *out, optionally after w -= (*coef) vprev.
+// On several GPUs with peer-mapped exchange buffers the reduction over the ranks is fused into the sweeps themselves
+// (orth_step_peer_kernel): the partial of this sweep goes to the peers over NVLink from its last block, the next sweep
+// picks the all-rank sum up in its prologue (and leaves it in *coef for the rotation kernel), and `out` is written by
+// whoever completes the chain -- orth_finish after the last sweep. Otherwise: one ncclAllReduce per sweep.
+static int orth_step(TACSBVec *w, TACSBVec *vprev, double *coef, TACSBVec *vnext, unsigned *ticket, double *out) {
+  if (ctx().size > 1 && ctx().d_peer) {
+    KernelTimer kt(K_DOT, "orth_step_peer_kernel");
+    return cuda_ok(launch_orth_step_peer(w->ownedSize(), w->owned(), vprev ? vprev->owned() : nullptr, coef,
+                                         vnext ? vnext->owned() : nullptr, g_dot_partial, ticket, ctx().d_peer,
+                                         ctx().num_sms, ctx().stream), "orth step") ? 0 : 1;
+  }
   {
     KernelTimer kt(K_DOT, "orth_step_kernel");
     if (!cuda_ok(launch_orth_step(w->ownedSize(), w->owned(), vprev ? vprev->owned() : nullptr, coef,
@@ -243,6 +253,13 @@ static void l2_window(const void *base, size_t bytes) {
   cudaGetLastError();
 }
 
+// completes the reduction chain of orth_step on the peer path: *out = all-rank sum of the last sweep's partials
+static int orth_finish(double *out) {
+  if (!(ctx().size > 1 && ctx().d_peer)) return 0;
+  KernelTimer kt(K_DOT, "peer_finish_kernel");
+  return cuda_ok(launch_peer_finish(ctx().d_peer, out, ctx().stream), "peer finish") ? 0 : 1;
+}
+
 // Iteration i: w = A M^{-1} v_i, orthogonalised against v_0..v_i, new rotation, v_{i+1} = w / |w|
 int GMRES::iterationBody(int i) {
   int rc = 0;
@@ -262,6 +279,7 @@ int GMRES::iterationBody(int i) {
     rc |= orth_step(w, nullptr, nullptr, W[0], d_ticket.ptr, d_hcol);
     for (int j = 1; j <= i; j++) rc |= orth_step(w, W[j - 1], d_hcol + (j - 1), W[j], d_ticket.ptr, d_hcol + j);
     rc |= orth_step(w, W[i], d_hcol + i, nullptr, d_ticket.ptr, d_hcol + i + 1);
+    rc |= orth_finish(d_hcol + i + 1);
   } else {
     // classical Gram-Schmidt: all projections from one sweep (batches of 8), one sweep to subtract them
     for (int j0 = 0; j0 <= i; j0 += 8) {
@@ -282,6 +300,7 @@ int GMRES::iterationBody(int i) {
                                      ctx().stream), "multi axpy")) rc = 1;
     }
     rc |= orth_step(w, nullptr, nullptr, nullptr, d_ticket.ptr, d_hcol + i + 1);
+    rc |= orth_finish(d_hcol + i + 1);
   }
   {
     KernelTimer kt(K_VEC, "gmres_rotate_kernel");
@@ -359,6 +378,7 @@ int GMRES::solve(TACSBVec *b, TACSBVec *x, int zero_guess) {
       sign = -1.0;
     }
     rc |= orth_step(W[0], nullptr, nullptr, nullptr, d_ticket.ptr, d_sumsq);
+    rc |= orth_finish(d_sumsq);
     {
       KernelTimer kt(K_VEC, "gmres_start_kernel");
       if (!cuda_ok(launch_gmres_start(d_sumsq, d_g, m, c.stream), "gmres start")) rc = 1;

@@ -1391,6 +1391,7 @@ TACSParallelMat::TACSParallelMat(TACSAssembler *a) {
     ok = Bext.d_rowp.upload(Bext.rowp) && Bext.d_cols.upload(Bext.cols) && x_ext.alloc((size_t)Aloc.bsize * Bext.ncols);
   if (ok) ok = a->uploadMatPlan() == 0;
   if (ok && !getenv("TACSB200_SPMV_NATURAL_ORDER")) ok = Aloc.buildRowOrder();
+  if (ok && nnzB > 0) ok = Bext.buildNonEmptyRows();
   if (ok && a->size > 1) ok = comm_setup_exchange(x_cols, P.cols) == 0;
   if (!ok) {
     Aloc.bsize = 0;
@@ -1431,6 +1432,15 @@ bool BCSRPattern::buildRowOrder() {
   std::stable_sort(order.begin(), order.end(),
                    [&](int a, int b) { return rowp[a + 1] - rowp[a] > rowp[b + 1] - rowp[b]; });
   return d_order.upload(order);
+}
+
+bool BCSRPattern::buildNonEmptyRows() {
+  std::vector<int> rows;
+  for (int i = 0; i < nrows; i++)
+    if (rowp[i + 1] > rowp[i]) rows.push_back(i);
+  order_rows = (int)rows.size();
+  if (rows.empty()) return true;
+  return d_order.upload(rows);
 }
 
 int TACSParallelMat::copyValues(TACSParallelMat *o) {
@@ -1683,9 +1693,9 @@ int TACSParallelMat::multFused(TACSBVec *x, TACSBVec *y, double sign, double zs,
     spmv_halo_end(this);
     if (Bext.nnzb() > 0) {
       KernelTimer kt(K_SPMV, Bext.bsize == 6 ? "spmv6_kernel<3>" : "spmv3_kernel<3>");
-      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
-                                     x_ext.ptr, y->owned() + (size_t)Bext.bsize * np, 3, sign, 0.0, nullptr, nullptr,
-                                     ctx().num_sms, ctx().stream), "spmv ext fused")) rc = 1;
+      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.order_rows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
+                                     x_ext.ptr, y->owned() + (size_t)Bext.bsize * np, 3, sign, 0.0, nullptr,
+                                     Bext.d_order.ptr, ctx().num_sms, ctx().stream), "spmv ext fused")) rc = 1;
     }
   }
   return rc;
@@ -1708,8 +1718,10 @@ int TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
     spmv_halo_end(this);
     if (Bext.nnzb() > 0) {
       KernelTimer kt(K_SPMV, spmv_kernel_name(Bext.bsize, 1));
-      if (!cuda_ok(launch_spmv(Bext.bsize, Bext.nrows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr, x_ext.ptr,
-                               y->owned() + (size_t)Bext.bsize * np, 1, ctx().num_sms, ctx().stream), "spmv ext"))
+      // rows with an off-rank column only (Bext.d_order): the others would be read and rewritten for nothing
+      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.order_rows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
+                                     x_ext.ptr, y->owned() + (size_t)Bext.bsize * np, 1, 1.0, 0.0, nullptr,
+                                     Bext.d_order.ptr, ctx().num_sms, ctx().stream), "spmv ext"))
         rc = 1;
     }
   }

@@ -80,6 +80,9 @@ struct Context {
   bool tail_is_matrix_only() const { return tail_seq >= 0 && stream.seq == tail_seq; }
   int rank = 0, size = 1;
   void *nccl_comm = nullptr;  // ncclComm_t when size > 1
+  // scalar all-reduce over NVLink peer memory (kernels.h PeerExchange): device copy of the descriptor, null when the
+  // peers' buffers could not be mapped (the NCCL all-reduce is used then)
+  PeerExchange *d_peer = nullptr;
   long kernel_launches = 0;   // launches of tacs_b200 kernels since the last reset
 };
 Context &ctx();
@@ -370,7 +373,9 @@ struct BCSRPattern {
   // rows listed by descending length (stable), built when the row lengths differ much: the SpMV then hands the lanes
   // of a warp rows of (nearly) equal length. Null pointer: natural order.
   DeviceArray<int> d_order;
+  int order_rows = -1;  // number of rows listed in d_order (-1: none; < nrows: the empty rows are left out)
   bool buildRowOrder();
+  bool buildNonEmptyRows();  // Bext: most rows of a partition have no off-rank column; list the ones that do
   // bsize^2 * nnzb values, 64-bit offsets: a view into the owning matrix's single value array [Aloc | Bext]
   struct ValuesView {
     double *ptr = nullptr;

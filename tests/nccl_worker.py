@@ -38,6 +38,7 @@ def main():
     for key in ("A", "res", "y", "res_only", "norm"):
         assert errs["max"][key] < 1e-12, (key, errs)
     assert errs["max"]["dot"] < 1e-11, errs
+    assert errs["gmres_converged"] and errs["max"]["gmres"] < 1e-10, errs  # north_star: displacements within 1e-10
     dist.barrier()
     print(f"rank {rank} ok {json.dumps(errs['max'])}", flush=True)
     dist.destroy_process_group()
