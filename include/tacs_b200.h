@@ -172,6 +172,14 @@ int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double
    gather of the matrix is still running; pair with tacsb200_synchronize before the matrix is read on the host. */
 int tacsb200_assembler_assemble_jacobian_async(tacsb200_handle a, double alpha, double beta, double gamma,
                                                tacsb200_handle res, tacsb200_handle mat);
+/* setVariables(q) + assembleJacobian(alpha, beta, gamma, res, A) with the state vector taken from and the residual
+   returned to host memory (the owned entries, as getArray / setArray). What a host-resident caller does every Newton /
+   time step, in one call so that the transfers overlap the kernels: the state is uploaded in pieces on a copy stream
+   and each chunk of elements starts as soon as the piece with its last node has arrived; the residual goes back while
+   the matrix is still being gathered. Pinned buffers make the copies asynchronous. Returns when res_host is complete;
+   tacsb200_synchronize before the matrix is used from the host. */
+int tacsb200_assembler_assemble_jacobian_host(tacsb200_handle a, double alpha, double beta, double gamma,
+                                              const double *q_host, double *res_host, tacsb200_handle mat);
 /* assembleMatType(matType, A, TACS_MAT_NORMAL, lambda = 1, applyBCs) :227, src/TACSAssembler.cpp:4418-4504.
    matType follows ElementMatrixType (src/elements/TACSElementTypes.h:113-119): 1 = TACS_STIFFNESS_MATRIX,
    2 = TACS_MASS_MATRIX; any other type returns non-zero (not evaluated on the device). */

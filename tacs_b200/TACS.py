@@ -396,6 +396,14 @@ class Assembler(_Obj):
         _check(f(self.h, alpha, beta, gamma, res.h if res else None, mat.h), "assembleJacobian")
 
 
+    def assembleJacobianHost(self, alpha, beta, gamma, q_host, res_host, mat):
+        """setVariables(q) + assembleJacobian with the state taken from / the residual returned to host arrays
+        (float64, C-contiguous, ideally pinned): transfers pipelined against the kernels. The matrix gather may still
+        be running on return (lib.synchronize())."""
+        assert q_host.dtype == np.float64 and res_host.dtype == np.float64
+        _check(self.lib.assembler_assemble_jacobian_host(self.h, alpha, beta, gamma, B.dptr(q_host), B.dptr(res_host),
+                                                         mat.h), "assembleJacobianHost")
+
     def assembleMatType(self, matType, mat, applyBCs=True):
         """matType: STIFFNESS_MATRIX (1) or MASS_MATRIX (2) (tacs/TACS.pyx ElementMatrixType)."""
         _check(self.lib.assembler_assemble_mat_type(self.h, int(matType), mat.h, 1 if applyBCs else 0),

@@ -133,6 +133,7 @@ PRODUCT_ONLY = {
     "profile_enable": (I, [I]),
     "profile_collect": (I, [DP, C.POINTER(C.c_long)]),
     "profile_named": (C.c_char_p, []),
+    "assembler_assemble_jacobian_host": (I, [H, D, D, D, DP, DP, H]),
     "mat_copy_values": (I, [H, H]),
     "mat_scale": (I, [H, D]),
     "mat_axpy": (I, [H, D, H]),

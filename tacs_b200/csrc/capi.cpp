@@ -441,6 +441,14 @@ int tacsb200_assembler_assemble_jacobian(tacsb200_handle a, double alpha, double
   if (t->assembleJacobian(alpha, beta, gamma, as<TACSBVec>(res), A, 1.0)) return 1;
   return tacsb200_synchronize();
 }
+int tacsb200_assembler_assemble_jacobian_host(tacsb200_handle a, double alpha, double beta, double gamma,
+                                              const double *q_host, double *res_host, tacsb200_handle mat) {
+  ASM(a);
+  TACSParallelMat *A = as<TACSParallelMat>(mat);
+  REQUIRE(A, "matrix");
+  if (!q_host || !res_host) return 1;
+  return t->assembleJacobianHost(alpha, beta, gamma, q_host, res_host, A, 1.0) ? 1 : 0;
+}
 int tacsb200_assembler_assemble_jacobian_async(tacsb200_handle a, double alpha, double beta, double gamma,
                                                tacsb200_handle res, tacsb200_handle mat) {
   ASM(a);

@@ -1227,11 +1227,62 @@ int TACSAssembler::assembleRes(TACSBVec *res, double lambda) {
 // need rows of other ranks are gathered after the exchange.
 int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
                                     double lambda, bool apply_bcs) {
+  return assembleJacobianImpl(alpha, beta, gamma, res, A, lambda, apply_bcs, nullptr);
+}
+
+// setVariables(q) + assembleJacobian + the residual back on the host, with the state vector taken from (pinned) host
+// memory: the upload is pipelined against the element kernels (see host_chunks). Returns when the residual has
+// arrived; the block gather of the matrix may still be running (tacsb200_synchronize before the matrix is read).
+int TACSAssembler::assembleJacobianHost(double alpha, double beta, double gamma, const double *q_host, double *res_host,
+                                        TACSParallelMat *A, double lambda) {
+  Context &c = ctx();
+  if (!jvp_t) {
+    // residual target of this entry point (shares the scratch vectors of addJacobianVecProduct)
+    jvp_x = createVec(); jvp_a = createVec(); jvp_t = createVec();
+    jvp_x->incref(); jvp_a->incref(); jvp_t->incref();
+    if (!jvp_x->data.ptr || !jvp_a->data.ptr || !jvp_t->data.ptr) return 1;
+  }
+  TACSBVec *res = jvp_t;
+  if (size > 1) {
+    // several ranks: the halo needs the whole owned state first -- plain upload, then the usual path
+    if (!cuda_ok(cudaMemcpyAsync(vars->owned(), q_host, vars->ownedSize() * sizeof(double), cudaMemcpyHostToDevice,
+                                 c.stream), "state H2D")) return 1;
+    vars_zero = false;
+    if (halo_forward(this, vars)) return 1;
+    if (assembleJacobianImpl(alpha, beta, gamma, res, A, lambda, true, nullptr)) return 1;
+  } else {
+    if (assembleJacobianImpl(alpha, beta, gamma, res, A, lambda, true, q_host)) return 1;
+  }
+  // residual to the host behind the residual kernels only (tail_evt), while the matrix is still being gathered
+  return cuda_ok(cudaStreamWaitEvent(c.copy_stream, c.tail_evt, 0), "residual D2H") &&
+                 cuda_ok(cudaMemcpyAsync(res_host, res->owned(), res->ownedSize() * sizeof(double),
+                                         cudaMemcpyDeviceToHost, c.copy_stream), "residual D2H") &&
+                 cuda_ok(cudaStreamSynchronize(c.copy_stream), "residual D2H")
+             ? 0 : 1;
+}
+
+int TACSAssembler::assembleJacobianImpl(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A,
+                                        double lambda, bool apply_bcs, const double *q_host) {
   (void)beta;
   Context &c = ctx();
   NvtxRange nvtx_range("tacs_b200::assembleJacobian");
   if (refreshDescriptors()) return 1;
   if (Ke.count < (size_t)total_blocks * bs * bs && !Ke.alloc((size_t)total_blocks * bs * bs)) return 1;
+  if (!elem_done_evt && !cuda_ok(cudaEventCreateWithFlags(&elem_done_evt, cudaEventDisableTiming), "event")) return 1;
+  const std::vector<ElemChunk> &chunks = q_host ? host_chunks : this->chunks;
+  if (q_host) {
+    // state upload in pieces on the copy stream, behind the element kernels of the previous assembly (they read vars)
+    cudaStreamWaitEvent(c.copy_stream, elem_done_evt, 0);
+    const long nb = nowned;
+    for (int k = 0; k < kStateChunks; k++) {
+      if (!state_evt[k] && !cuda_ok(cudaEventCreateWithFlags(&state_evt[k], cudaEventDisableTiming), "event")) return 1;
+      const long n0 = nb * k / kStateChunks * bs, n1 = nb * (k + 1) / kStateChunks * bs;
+      if (n1 > n0 && !cuda_ok(cudaMemcpyAsync(vars->owned() + n0, q_host + n0, (size_t)(n1 - n0) * sizeof(double),
+                                               cudaMemcpyHostToDevice, c.copy_stream), "state H2D")) return 1;
+      cudaEventRecord(state_evt[k], c.copy_stream);
+    }
+    vars_zero = false;
+  }
   const double *vp = vars_zero ? nullptr : vars->local(), *ap = ddvars_zero ? nullptr : ddvars->local();
   auto gather = [&](long g0, long g1, cudaStream_t st) -> int {
     if (g1 <= g0) return 0;
@@ -1241,8 +1292,13 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
   };
   long gdone = 0;
   bool forked = false;
+  int state_waited = -1;
   for (size_t k = 0; k < chunks.size(); k++) {
     const ElemChunk &ch = chunks[k];
+    if (q_host && ch.need_state > state_waited) {
+      cudaStreamWaitEvent(c.stream.s, state_evt[ch.need_state], 0);
+      state_waited = ch.need_state;
+    }
     if (launchGroupRange(groups[ch.group], ch.e0, ch.e1, alpha, gamma, A, vp, ap)) return 1;
     if (overlap_gather && k + 1 < chunks.size() && ch.gather_end > gdone) {
       if (c.chunk_evt.size() <= k) {
@@ -1257,6 +1313,8 @@ int TACSAssembler::assembleJacobian(double alpha, double beta, double gamma, TAC
       forked = true;
     }
   }
+  if (q_host && state_waited < kStateChunks - 1) cudaStreamWaitEvent(c.stream.s, state_evt[kStateChunks - 1], 0);
+  cudaEventRecord(elem_done_evt, c.stream.s);
   if (res && addAuxLoads(lambda)) return 1;
   if (size > 1 && staging_exchange(this, true)) return 1;
   if (res) {
@@ -1629,6 +1687,31 @@ int TACSAssembler::uploadMatPlan() {
       if (ch.e1 > ch.e0) chunks.push_back(ch);
     }
     if (n > 1) overlap_gather = true;
+  }
+  // chunks of the host-state entry point: kStateChunks per group, each knowing the last state piece it reads
+  host_chunks.clear();
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const ElemGroup &g = groups[gi];
+    const long nu = upper_pairs(g.nn);
+    const long n = std::min<long>(kStateChunks, std::max<long>(1, g.nelem / 8192));
+    for (long k = 0; k < n; k++) {
+      ElemChunk ch;
+      ch.group = (int)gi;
+      ch.e0 = g.nelem * k / n;
+      ch.e1 = g.nelem * (k + 1) / n;
+      if (ch.e1 <= ch.e0) continue;
+      ch.gather_end = ((overlap_kinds >> (g.kind - 1)) & 1u) ? P.gatherEnd(g.block_base + ch.e1 * nu) : 0;
+      int max_node = 0;
+      for (long e = ch.e0; e < ch.e1; e++) {
+        const int le = g.local_elems[e];
+        for (int q = P.elem_ptr[le]; q < P.elem_ptr[le + 1]; q++) max_node = std::max(max_node, P.elem_conn_local[q]);
+      }
+      // piece k holds the owned nodes [nowned k / K, nowned (k+1) / K)
+      int piece = 0;
+      while (piece < kStateChunks - 1 && (long)nowned * (piece + 1) / kStateChunks <= max_node) piece++;
+      ch.need_state = piece;
+      host_chunks.push_back(ch);
+    }
   }
   mat_plan_ready = true;
   return 0;

@@ -567,8 +567,19 @@ class TACSAssembler : public Object {
   bool mat_plan_ready = false;
   // element chunks of assembleJacobian: [e0, e1) of group `group`; every gathered block below gather_end is complete
   // once the chunk (and all chunks before it) has been evaluated
-  struct ElemChunk { int group; long e0, e1, gather_end; };
+  struct ElemChunk { int group; long e0, e1, gather_end; int need_state = -1; };
   std::vector<ElemChunk> chunks;
+  // Finer chunks of the host-state entry point (assembleJacobianHost): the state vector arrives from pinned host memory
+  // in kStateChunks pieces on the copy stream, and element chunk k only waits for the piece that holds the last node
+  // it references (need_state), so the upload hides behind the element kernels of the chunks before it.
+  static constexpr int kStateChunks = 8;
+  std::vector<ElemChunk> host_chunks;
+  cudaEvent_t state_evt[kStateChunks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t elem_done_evt = nullptr;
+  int assembleJacobianHost(double alpha, double beta, double gamma, const double *q_host, double *res_host,
+                           TACSParallelMat *A, double lambda);
+  int assembleJacobianImpl(double alpha, double beta, double gamma, TACSBVec *res, TACSParallelMat *A, double lambda,
+                           bool apply_bcs, const double *q_host);
   bool overlap_gather = false;
   bool geometric_pass = false;
   // auxiliary loads of the local elements, per shell group: sorted by element, one run of loads per loaded element

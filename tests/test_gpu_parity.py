@@ -575,3 +575,27 @@ def test_drilling_regularization_changed_after_create(lib, ref):
         ref.shell_set_drilling_regularization(0.1)
     assert relerr(out["ref"][1], out["ref"][0]) > 1e-6       # the setting matters
     assert relerr(out["b200"][0], out["ref"][0]) < TOL and relerr(out["b200"][1], out["ref"][1]) < TOL
+
+
+def test_host_state_entry_point_matches_separate_calls(lib):
+    """tacsb200_assembler_assemble_jacobian_host (state upload pipelined against the element kernels, residual download
+    behind the residual kernels) gives bit-identical results to setArray + setVariables + assembleJacobian + getArray,
+    on a mesh large enough for several state pieces / element chunks, called back to back with changing states."""
+    mesh = meshgen.plate(2, 300, 280)
+    creator, asm = meshgen.build_model(T, lib, mesh, [meshgen.iso_shell_element(T, lib, 2)])
+    A, A2, res, u = asm.createMat(), asm.createMat(), asm.createVec(), asm.createVec()
+    n = u.getSize()
+    out = np.zeros(n)
+    for k in range(3):
+        q = meshgen.hash_vector(n) * (1.0 + 0.5 * k)
+        u.setArray(q)
+        asm.applyBCs(u)
+        q = u.getArray()
+        asm.assembleJacobianHost(1.0, 0.0, 0.0, q, out, A)
+        lib.synchronize()
+        got_res, got_A = out.copy(), A.getValues()
+        u.setArray(q)
+        asm.setVariables(u)
+        asm.assembleJacobian(1.0, 0.0, 0.0, res, A2)
+        assert np.array_equal(got_res, res.getArray())
+        assert np.array_equal(got_A, A2.getValues())
