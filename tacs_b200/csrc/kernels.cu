@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "elem_phases.cuh"
 #include "kernels.h"
@@ -1760,6 +1761,223 @@ __global__ void __launch_bounds__(256) spmv3_kernel(int nrows, const int *__rest
   }
 }
 
+// 3x3 blocks, streamed: every warp owns a contiguous range of block rows holding an equal share of the blocks and pulls
+// its part of `A` and `cols` -- one contiguous span, cut at multiples of CH blocks from the start of the matrix -- through
+// a private ring of shared-memory stages with bulk async copies (TMA, one elected lane; an mbarrier per stage), so that
+// the matrix never passes the L1 tags on its way in. Lane 3 b + c is column c of block b of a step: a step is ten
+// consecutive blocks of one block row, a group is U steps; a lane gathers one entry of x per block and keeps three
+// partial row sums. The loads of a group (ring -> registers, gather of x through L1) are issued before the arithmetic
+// of the group in front of it. At the end of a row the thirty lanes' partial sums are parked in shared memory and
+// added in lane order, RB rows at a time, with coalesced reads / writes of y and z (a fixed order, not the
+// reference's: tests 1e-12). Row ends are handed out by shuffle once per RB rows: a shuffle between the loads of two
+// groups would wait for the gathers in flight. Needs 16-byte aligned A / cols (the launcher checks).
+template <int WARPS_, int CH_, int NS_>
+struct Spmv3Stream {
+  static constexpr int WARPS = WARPS_, CH = CH_, NS = NS_, U = 3, STEP = 10, RB = 4, RED_LD = 34;
+  static constexpr int RING = CH * NS;                 // blocks
+  static constexpr int A_BYTES = RING * 72, C_BYTES = RING * 4, RED_BYTES = RB * 3 * RED_LD * 8;
+  static constexpr int WARP_BYTES = A_BYTES + C_BYTES + RED_BYTES + 16 * ((NS * 8 + 15) / 16);
+  static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
+  static_assert((CH & (CH - 1)) == 0 && (NS & (NS - 1)) == 0 && CH >= STEP * U && NS >= 4, "ring indices are masks");
+  static_assert(RB == 4 && RED_BYTES % 16 == 0, "row ends of a batch live in four registers");
+};
+
+template <int ADD, class F>
+__global__ void __launch_bounds__(F::WARPS * 32, 1) spmv3_stream_kernel(int nrows, const int *__restrict__ rowp,
+                                                                       const int *__restrict__ cols,
+                                                                       const double *__restrict__ A,
+                                                                       const double *__restrict__ x,
+                                                                       double *__restrict__ y, double sign, double zs,
+                                                                       const double *__restrict__ z) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *mine = smem_raw + (size_t)wid * F::WARP_BYTES;
+  const double *ringA = reinterpret_cast<const double *>(mine);
+  const int *ringC = reinterpret_cast<const int *>(mine + F::A_BYTES);
+  double *red = reinterpret_cast<double *>(mine + F::A_BYTES + F::C_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(mine + F::A_BYTES + F::C_BYTES + F::RED_BYTES);
+  // lanes 30, 31 repeat the work of lanes 0, 1; their sums are dropped
+  const int wl = lane < 30 ? lane : lane - 30, b = wl / 3, c = wl - 3 * b;
+
+  // this warp's rows: those whose first block lies in its share [w, w + 1) * nnzb / nwarps of the blocks
+  const long nwarps = (long)gridDim.x * F::WARPS, w = (long)blockIdx.x * F::WARPS + wid;
+  const int nnzb = __ldg(rowp + nrows);
+  int R0, R1;
+  {
+    const long t = (w + (lane & 1)) * (long)nnzb / nwarps;
+    int lo = 0, hi = nrows;   // first row with rowp[row] >= t
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(rowp + mid) < t) lo = mid + 1; else hi = mid;
+    }
+    R0 = __shfl_sync(0xffffffffu, lo, 0);
+    R1 = __shfl_sync(0xffffffffu, lo, 1);
+    if (w == 0) R0 = 0;
+    if (w == nwarps - 1) R1 = nrows;
+  }
+  if (R0 >= R1) return;
+  const int s0 = __ldg(rowp + R0), s1 = __ldg(rowp + R1);
+  const int chunk0 = s0 / F::CH, chunk_end = s1 > s0 ? (s1 - 1) / F::CH + 1 : chunk0;   // chunks [chunk0, chunk_end)
+
+  auto issue = [&](int chunk) {   // lane 0
+    const int stage = chunk & (F::NS - 1), first = chunk * F::CH;
+    const int nb = min(F::CH, nnzb - first);
+    const uint32_t bytes_a = (uint32_t)((72 * nb + 15) & ~15), bytes_c = (uint32_t)((4 * nb + 15) & ~15);
+    const uint32_t bar = smem_addr(bars + stage);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_a + bytes_c) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(ringA + stage * (F::CH * 9))), "l"(A + (long)9 * first), "r"(bytes_a), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(ringC + stage * F::CH)), "l"(cols + first), "r"(bytes_c), "r"(bar) : "memory");
+  };
+  if (lane == 0) {
+    for (int k = 0; k < F::NS; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + k)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int k = 0; k < F::NS && chunk0 + k < chunk_end; k++) issue(chunk0 + k);
+  }
+  __syncwarp();
+
+  int ready = chunk0, released = chunk0;   // chunks known to have landed / chunks handed back to the copy engine
+  // loads of one group (up to U steps of ten blocks of one row, starting at block k): A and cols from the ring, x by
+  // gather
+  auto load_group = [&](int k, int end, double (&av)[3 * F::U], double (&xv)[F::U]) {
+    if (k >= end) {   // a row without blocks
+#pragma unroll
+      for (int u = 0; u < F::U; u++) av[3 * u] = av[3 * u + 1] = av[3 * u + 2] = xv[u] = 0.0;
+      return;
+    }
+    {
+      const int last = min(k + F::STEP * F::U, end) - 1, c_need = last / F::CH, c_gone = k / F::CH;
+      while (released < c_gone) {   // the stream has left these chunks: refill their stages
+        __syncwarp();
+        if (lane == 0 && released + F::NS < chunk_end) issue(released + F::NS);
+        released++;
+      }
+      while (ready <= c_need) {
+        const uint32_t bar = smem_addr(bars + (ready & (F::NS - 1))), parity = (uint32_t)((ready - chunk0) / F::NS) & 1u;
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(done)
+              : "r"(bar), "r"(parity)
+              : "memory");
+        }
+        ready++;
+      }
+    }
+    // past the end of the row a lane re-reads the row's last block (landed, finite) against x = 0: no branches
+    const int stop = end - 1;
+#pragma unroll
+    for (int u = 0; u < F::U; u++) {
+      const int g = k + F::STEP * u + b, gi = min(g, stop) & (F::RING - 1);
+      const double *a = ringA + gi * 9 + c;
+      const int col = ringC[gi];
+      av[3 * u] = a[0]; av[3 * u + 1] = a[3]; av[3 * u + 2] = a[6];
+      xv[u] = 0.0;
+      if (g <= stop) xv[u] = __ldg(x + (long)3 * col + c);
+    }
+  };
+
+  // cursor of the loads: row lrow of the batch of RB rows starting at rb, next block lk of [.., lend). rowp is read 32
+  // rows at a time; the row ends of a batch are pulled out of it together
+  int rp_base = R0, rp_val = (R0 + lane <= nrows) ? __ldg(rowp + R0 + lane) : 0;   // rowp[rp_base + lane]
+  int rb = R0, e1, e2, e3, e4;
+  auto batch_ends = [&]() {
+    if (rb + F::RB - rp_base > 31) {
+      rp_base = rb;
+      rp_val = (rb + lane <= nrows) ? __ldg(rowp + rb + lane) : 0;
+    }
+    const int o = rb - rp_base;
+    e1 = __shfl_sync(0xffffffffu, rp_val, o + 1);
+    e2 = __shfl_sync(0xffffffffu, rp_val, o + 2);
+    e3 = __shfl_sync(0xffffffffu, rp_val, o + 3);
+    e4 = __shfl_sync(0xffffffffu, rp_val, o + 4);
+  };
+  batch_ends();
+  int lrow = R0, lk = s0, lend = e1;
+  auto advance = [&]() {
+    lk += F::STEP * F::U;
+    if (lk >= lend) {
+      lk = lend;   // rows are contiguous: the next one starts where this one ended
+      lrow++;
+      const int q = lrow - rb;
+      if (q == F::RB) {
+        rb = lrow;
+        if (lrow < R1) batch_ends();
+        lend = e1;
+      } else {
+        lend = q == 1 ? e2 : (q == 2 ? e3 : e4);
+      }
+    }
+  };
+  double acc[3] = {0.0, 0.0, 0.0};
+  int parked = 0, park_row = R0;   // rows whose partial sums wait in `red`, the first of them
+  auto flush = [&]() {
+    __syncwarp();
+    if (lane < 3 * parked) {
+      const double2 *p = reinterpret_cast<const double2 *>(red + lane * F::RED_LD);
+      double sum = 0.0;
+#pragma unroll
+      for (int q = 0; q < 3 * F::STEP / 2; q++) {
+        const double2 v = p[q];
+        sum += v.x;
+        sum += v.y;
+      }
+      const long g = (long)park_row * 3 + lane;
+      if (ADD == 1) sum = y[g] + sum;
+      if (ADD == 2) sum = zs * z[g] + sign * sum;
+      if (ADD == 3) sum = y[g] + sign * sum;
+      y[g] = sum;
+    }
+    __syncwarp();
+    park_row += parked;
+    parked = 0;
+  };
+  // arithmetic of one group; at the end of its row the lane sums are parked
+  auto finish_group = [&](const double (&av)[3 * F::U], const double (&xv)[F::U], bool row_done) {
+#pragma unroll
+    for (int u = 0; u < F::U; u++) {
+      acc[0] += av[3 * u] * xv[u];
+      acc[1] += av[3 * u + 1] * xv[u];
+      acc[2] += av[3 * u + 2] * xv[u];
+    }
+    if (row_done) {
+      if (lane < 30) {
+        double *p = red + parked * 3 * F::RED_LD + lane;
+        p[0] = acc[0]; p[F::RED_LD] = acc[1]; p[2 * F::RED_LD] = acc[2];
+      }
+      acc[0] = acc[1] = acc[2] = 0.0;
+      if (++parked == F::RB) flush();
+    }
+  };
+  double av1[3 * F::U], xv1[F::U], av2[3 * F::U], xv2[F::U];
+  bool done1 = lk + F::STEP * F::U >= lend, done2 = false;
+  load_group(lk, lend, av1, xv1);
+  advance();
+  while (true) {   // two groups per trip: the register sets swap roles without moves
+    const bool have2 = lrow < R1;
+    if (have2) {
+      done2 = lk + F::STEP * F::U >= lend;
+      load_group(lk, lend, av2, xv2);
+      advance();
+    }
+    finish_group(av1, xv1, done1);
+    if (!have2) break;
+    const bool have1 = lrow < R1;
+    if (have1) {
+      done1 = lk + F::STEP * F::U >= lend;
+      load_group(lk, lend, av1, xv1);
+      advance();
+    }
+    finish_group(av2, xv2, done2);
+    if (!have1) break;
+  }
+  if (parked) flush();
+}
+
 // y = A^T x for a structurally symmetric pattern: tidx[k] is the position of the mirror (cols[k], row) of block k, so
 // row i of A^T is sum_k (A_tidx[k])^T x_cols[k] -- a gather like the forward product, no atomics. One thread per scalar
 // row reads column r of every mirror block.
@@ -1798,18 +2016,68 @@ cudaError_t launch_spmv_transpose(int bs, int nrows, const int *rowp, const int 
   return cudaGetLastError();
 }
 
-// (A warp-per-block-row form of the 3x3 product -- lane l streams entries l, l+32, ... of the row's contiguous values,
-// shuffle reduction of the three row sums -- was measured and dropped: 5.65 ms against 3.40 ms on the 200^3 hex8
-// matrix, 12.4 against 9.3 ms on the 100^3 hex27 one; the per-entry cols -> x chain costs more than it saves.)
-cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
-                              double *y, int mode, double sign, double zs, const double *z, const int *order,
-                              int num_sms, cudaStream_t s) {
+template <class F>
+static cudaError_t launch_spmv3_stream(int nrows, const int *rowp, const int *cols, const double *A, const double *x,
+                                       double *y, int mode, double sign, double zs, const double *z, int num_sms,
+                                       cudaStream_t s) {
+  long ctas = ((long)nrows + F::WARPS * 16 - 1) / (F::WARPS * 16);
+  if (ctas > (long)num_sms) ctas = num_sms;
+#define TB2_SPMVS(M)                                                                                               \
+  {                                                                                                                \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(spmv3_stream_kernel<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           F::SMEM_BYTES);                                                        \
+      if (e != cudaSuccess) return e;                                                                              \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    spmv3_stream_kernel<M, F><<<(unsigned)ctas, F::WARPS * 32, F::SMEM_BYTES, s>>>(nrows, rowp, cols, A, x, y, sign, \
+                                                                                   zs, z);                       \
+  }
+  switch (mode) {
+    case 0: TB2_SPMVS(0); break;
+    case 1: TB2_SPMVS(1); break;
+    case 2: TB2_SPMVS(2); break;
+    case 3: TB2_SPMVS(3); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef TB2_SPMVS
+  return cudaGetLastError();
+}
+
+// Other forms of the 3x3 product that were measured and dropped (200^3-class hex8 / 100^3-class hex27 matrices):
+// a warp per block row with lane l on entries l, l+32, .. of the row (5.65 against 3.40 ms, 12.4 against 9.3 ms: the
+// per-entry cols -> x chain); nine lanes per block row straight from global memory (4.3 against 5.2 TB/s, 3.1 against
+// 4.3: too few bytes in flight); 128 + 64-bit loads in the thread-per-scalar-row form (3.9 against 5.2 TB/s).
+// Which of the two kept forms runs: the streamed one costs a fixed ~230 instructions per block row (ring bookkeeping,
+// row bookkeeping, parking of the partial sums) and is issue bound below ~40 blocks per row (hex8: 27 -> 4.4 TB/s
+// against 5.2), above it it is the faster one (hex27: 64 on average -> 5.9 against 4.3 TB/s). TACSB200_SPMV3=rows|stream
+// forces one of them (tests run both).
+static bool spmv3_streamed(int nrows, long nnzb, const int *cols, const double *A, const int *order) {
+  static const char *variant = getenv("TACSB200_SPMV3") ? getenv("TACSB200_SPMV3") : "";
+  const bool long_rows = !strcmp(variant, "stream") || (strcmp(variant, "rows") && nnzb >= 40 * (long)nrows);
+  return long_rows && !order && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
+}
+
+const char *spmv_kernel_name(int bs, int nrows, long nnzb, const int *cols, const double *A, int mode, const int *order) {
+  static const char *const names[3][4] = {
+      {"spmv6_kernel<0>", "spmv6_kernel<1>", "spmv6_kernel<2>", "spmv6_kernel<3>"},
+      {"spmv3_kernel<0>", "spmv3_kernel<1>", "spmv3_kernel<2>", "spmv3_kernel<3>"},
+      {"spmv3_stream_kernel<0>", "spmv3_stream_kernel<1>", "spmv3_stream_kernel<2>", "spmv3_stream_kernel<3>"}};
+  return names[bs == 6 ? 0 : (spmv3_streamed(nrows, nnzb, cols, A, order) ? 2 : 1)][mode & 3];
+}
+
+cudaError_t launch_spmv_fused(int bs, int nrows, long nnzb, const int *rowp, const int *cols, const double *A,
+                              const double *x, double *y, int mode, double sign, double zs, const double *z,
+                              const int *order, int num_sms, cudaStream_t s) {
   if (nrows <= 0) return cudaSuccess;
   const int block = 256;
   long want = ((long)nrows * bs + block - 1) / block;
   long cap = (long)num_sms * 8 * 64;
   unsigned grid = (unsigned)(want < cap ? want : cap);
 #define TB2_SPMV(K, M) K<M><<<grid, block, 0, s>>>(nrows, rowp, cols, A, x, y, sign, zs, z, order)
+  if (bs == 3 && spmv3_streamed(nrows, nnzb, cols, A, order))
+    return launch_spmv3_stream<Spmv3Stream<16, 32, 4> >(nrows, rowp, cols, A, x, y, mode, sign, zs, z, num_sms, s);
   if (bs == 6) {
     switch (mode) {
       case 0: TB2_SPMV(spmv6_kernel, 0); break;
@@ -1833,9 +2101,9 @@ cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *col
   return cudaGetLastError();
 }
 
-cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
-                        double *y, int add, int num_sms, cudaStream_t s) {
-  return launch_spmv_fused(bs, nrows, rowp, cols, A, x, y, add ? 1 : 0, 1.0, 0.0, nullptr, nullptr, num_sms, s);
+cudaError_t launch_spmv(int bs, int nrows, long nnzb, const int *rowp, const int *cols, const double *A,
+                        const double *x, double *y, int add, int num_sms, cudaStream_t s) {
+  return launch_spmv_fused(bs, nrows, nnzb, rowp, cols, A, x, y, add ? 1 : 0, 1.0, 0.0, nullptr, nullptr, num_sms, s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -59,9 +59,6 @@ cudaError_t launch_element_group(const ElemGroupArgs &g, int num_sms, cudaStream
 const char *element_kernel_name(const ElemGroupArgs &g);
 inline const char *gather_blocks_kernel_name(int bs) { return bs == 6 ? "gather_blocks36_kernel" : "gather_blocks9_kernel"; }
 inline const char *gather_residual_kernel_name(int bs) { return bs == 6 ? "gather_residual_kernel<6>" : "gather_residual_kernel<3>"; }
-inline const char *spmv_kernel_name(int bs, int add) {
-  return bs == 6 ? (add ? "spmv6_kernel<1>" : "spmv6_kernel<0>") : (add ? "spmv3_kernel<1>" : "spmv3_kernel<0>");
-}
 
 // blocks gb_blk[0..nblocks) of A sum their staging sources src[ptr[g]..ptr[g+1]) (2*slot + transposed flag)
 cudaError_t launch_gather_blocks(int bs, long nblocks, const int *blk, const int *ptr, const int *src,
@@ -84,15 +81,19 @@ cudaError_t launch_vec_apply_bcs(int bs, int nbcs, const int *bc_rows, const int
 cudaError_t launch_vec_set_bcs(int bs, int nbcs, const int *bc_rows, const int *bc_vars, const double *bc_vals,
                                double lambda, double *x, cudaStream_t s);
 
-cudaError_t launch_spmv(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
-                        double *y, int add, int num_sms, cudaStream_t s);
+cudaError_t launch_spmv(int bs, int nrows, long nnzb, const int *rowp, const int *cols, const double *A,
+                        const double *x, double *y, int add, int num_sms, cudaStream_t s);
 
 // mode 0: y = A x; 1: y += A x (block by block, the multAdd order); 2: y = zs z + sign (A x); 3: y = y + sign (A x)
 // order (optional): the rows listed by length class (BCSRPattern::d_order), so that the lanes of a warp run the same
 // number of steps on meshes whose rows differ in length (quadratic elements)
-cudaError_t launch_spmv_fused(int bs, int nrows, const int *rowp, const int *cols, const double *A, const double *x,
-                              double *y, int mode, double sign, double zs, const double *z, const int *order,
-                              int num_sms, cudaStream_t s);
+// nnzb: the number of blocks (picks the 3x3 kernel: rows of 40 blocks and more on average are streamed through shared
+// memory, spmv3_stream_kernel)
+cudaError_t launch_spmv_fused(int bs, int nrows, long nnzb, const int *rowp, const int *cols, const double *A,
+                              const double *x, double *y, int mode, double sign, double zs, const double *z,
+                              const int *order, int num_sms, cudaStream_t s);
+// the name of the kernel launch_spmv_fused picks (profile records)
+const char *spmv_kernel_name(int bs, int nrows, long nnzb, const int *cols, const double *A, int mode, const int *order);
 
 // y = A^T x; tidx[k] = position of the mirror block of block k (structurally symmetric pattern)
 cudaError_t launch_spmv_transpose(int bs, int nrows, const int *rowp, const int *cols, const int *tidx, const double *A,

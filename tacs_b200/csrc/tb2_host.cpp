@@ -1617,8 +1617,8 @@ int TACSSchurMat::mult(TACSBVec *x, TACSBVec *y) {
   auto spmv = [&](int k, TACSBVec *in, TACSBVec *out, int add) {
     if (blk[k].nrows == 0) return;
     if (blk[k].nnzb() == 0 && add) return;
-    KernelTimer kt(K_SPMV, spmv_kernel_name(bsize, add));
-    good = good && cuda_ok(launch_spmv(bsize, blk[k].nrows, blk[k].d_rowp.ptr, blk[k].d_cols.ptr, blk[k].d_vals.ptr,
+    KernelTimer kt(K_SPMV, spmv_kernel_name(bsize, blk[k].nrows, blk[k].nnzb(), blk[k].d_cols.ptr, blk[k].d_vals.ptr, add, nullptr));
+    good = good && cuda_ok(launch_spmv(bsize, blk[k].nrows, blk[k].nnzb(), blk[k].d_rowp.ptr, blk[k].d_cols.ptr, blk[k].d_vals.ptr,
                                        in->owned(), out->owned(), add, c.num_sms, c.stream), "schur spmv");
   };
   {
@@ -1767,16 +1767,16 @@ int TACSParallelMat::multFused(TACSBVec *x, TACSBVec *y, double sign, double zs,
   int rc = 0;
   if (dist) rc = spmv_halo_begin(this, x);
   {
-    KernelTimer kt(K_SPMV, Aloc.bsize == 6 ? "spmv6_kernel<2>" : "spmv3_kernel<2>");
-    if (!cuda_ok(launch_spmv_fused(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr,
+    KernelTimer kt(K_SPMV, spmv_kernel_name(Aloc.bsize, Aloc.nrows, Aloc.nnzb(), Aloc.d_cols.ptr, Aloc.d_vals.ptr, 2, Aloc.d_order.ptr));
+    if (!cuda_ok(launch_spmv_fused(Aloc.bsize, Aloc.nrows, Aloc.nnzb(), Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr,
                                    x->owned(), y->owned(), 2, sign, zs, z->owned(), Aloc.d_order.ptr, ctx().num_sms,
                                    ctx().stream), "spmv fused")) rc = 1;
   }
   if (dist) {
     spmv_halo_end(this);
     if (Bext.nnzb() > 0) {
-      KernelTimer kt(K_SPMV, Bext.bsize == 6 ? "spmv6_kernel<3>" : "spmv3_kernel<3>");
-      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.order_rows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
+      KernelTimer kt(K_SPMV, spmv_kernel_name(Bext.bsize, Bext.order_rows, Bext.nnzb(), Bext.d_cols.ptr, Bext.d_vals.ptr, 3, Bext.d_order.ptr));
+      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.order_rows, Bext.nnzb(), Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
                                      x_ext.ptr, y->owned() + (size_t)Bext.bsize * np, 3, sign, 0.0, nullptr,
                                      Bext.d_order.ptr, ctx().num_sms, ctx().stream), "spmv ext fused")) rc = 1;
     }
@@ -1792,17 +1792,17 @@ int TACSParallelMat::mult(TACSBVec *x, TACSBVec *y) {
   // every rank takes part in the column halo (a rank without external columns may still have to send)
   if (dist) rc = spmv_halo_begin(this, x);
   {
-    KernelTimer kt(K_SPMV, spmv_kernel_name(Aloc.bsize, 0));
-    if (!cuda_ok(launch_spmv_fused(Aloc.bsize, Aloc.nrows, Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr,
+    KernelTimer kt(K_SPMV, spmv_kernel_name(Aloc.bsize, Aloc.nrows, Aloc.nnzb(), Aloc.d_cols.ptr, Aloc.d_vals.ptr, 0, Aloc.d_order.ptr));
+    if (!cuda_ok(launch_spmv_fused(Aloc.bsize, Aloc.nrows, Aloc.nnzb(), Aloc.d_rowp.ptr, Aloc.d_cols.ptr, Aloc.d_vals.ptr,
                                    x->owned(), y->owned(), 0, 1.0, 0.0, nullptr, Aloc.d_order.ptr, ctx().num_sms,
                                    ctx().stream), "spmv")) rc = 1;
   }
   if (dist) {
     spmv_halo_end(this);
     if (Bext.nnzb() > 0) {
-      KernelTimer kt(K_SPMV, spmv_kernel_name(Bext.bsize, 1));
+      KernelTimer kt(K_SPMV, spmv_kernel_name(Bext.bsize, Bext.order_rows, Bext.nnzb(), Bext.d_cols.ptr, Bext.d_vals.ptr, 1, Bext.d_order.ptr));
       // rows with an off-rank column only (Bext.d_order): the others would be read and rewritten for nothing
-      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.order_rows, Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
+      if (!cuda_ok(launch_spmv_fused(Bext.bsize, Bext.order_rows, Bext.nnzb(), Bext.d_rowp.ptr, Bext.d_cols.ptr, Bext.d_vals.ptr,
                                      x_ext.ptr, y->owned() + (size_t)Bext.bsize * np, 1, 1.0, 0.0, nullptr,
                                      Bext.d_order.ptr, ctx().num_sms, ctx().stream), "spmv ext"))
         rc = 1;

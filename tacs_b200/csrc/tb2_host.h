@@ -137,7 +137,8 @@ struct DeviceArray {
     release();
     count = n;
     if (n == 0) return true;
-    return cuda_ok(cudaMalloc(&ptr, n * sizeof(T)), "cudaMalloc");
+    // 16 bytes of slack: bulk copies of spans that start or end off a 16-byte boundary are rounded outwards
+    return cuda_ok(cudaMalloc(&ptr, n * sizeof(T) + 16), "cudaMalloc");
   }
   bool upload(const T *host, size_t n) {
     if (n != count && !alloc(n)) return false;
