@@ -54,8 +54,10 @@ METRIC = "elements/sec for Jacobian+residual assembly (BCSR SpMV GB/s vs HBM pea
 UNIT = "elements/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed `ncu --set full` capture of this
 # same command at the default workload (TRAFFIC_SOURCE); reported only when the run uses that workload on one GPU.
-TRAFFIC_SOURCE = "profiles/r1_n_kernels_ncu.txt"
-NCU_TRAFFIC_BYTES = {"spmv6_kernel<0>": 2.689707e9 + 0.050150e9}
+TRAFFIC_SOURCE = "profiles/r2_v_kernels_ncu.txt"
+NCU_TRAFFIC_BYTES = {"shell4_mma_kernel": 0.197762e9 + 3.599907e9,        # 10 of 16 node-pair blocks staged / direct
+                     "gather_blocks36_kernel": 2.645015e9 + 1.414355e9,   # reads the staged blocks once, writes 5.0 M blocks
+                     "spmv6_kernel<0>": 2.689503e9 + 0.049784e9}
 # minimal-algorithm flops per element used for the FP64 roofline
 FLOPS_PER_ELEMENT = {1: 57e3, 2: 551e3, 3: 69e3, 4: 2.28e6}
 KIND_NN = {1: 4, 2: 9, 3: 8, 4: 27}
