@@ -1,6 +1,11 @@
-"""Every element kernel once on a tiny mesh (for compute-sanitizer racecheck / memcheck runs)."""
+"""Every element / gather / SpMV / Krylov kernel once on a tiny mesh (for compute-sanitizer racecheck / memcheck
+runs; TACSB200_SPMV3=stream|rows selects the 3x3 product)."""
+import os
 import sys
-sys.path.insert(0, '/root/repo')
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tacs_b200
 from tacs_b200 import TACS as T, meshgen
 
@@ -25,4 +30,17 @@ for name, mesh, elem in cases:
     a.assembleJacobian(1.0, 0.0, 0.0, res, A)
     a.assembleRes(res)
     A.mult(x, y)
+    A.multTranspose(x, y)
+    # host-buffer entry point (state pieces / element chunks), smoother with fused SpMV epilogues, device GMRES
+    q, out = x.getArray(), np.zeros(x.getSize())
+    a.assembleJacobianHost(1.0, 0.0, 0.0, q, out, A)
+    lib.synchronize()
+    pc = T.ChebyshevSmoother(lib, A, 3, iters=2)
+    pc.factor()
+    ksm = T.KSM(lib, A, 8, 1, pc=pc, isFlexible=1)
+    ksm.setTolerances(1e-8, 1e-30)
+    for _ in range(3):   # direct launch, graph capture, graph replay
+        ksm.solve(res, y)
+    if name.startswith("hex"):
+        a.assembleMatType(T.GEOMETRIC_STIFFNESS_MATRIX, A)
     print(name, a.getNumElements(), "%.6e" % y.norm(), flush=True)
