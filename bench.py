@@ -191,7 +191,8 @@ def time_reference(nx, ny, steps, warmup, gmres_m=0):
     from tacs_b200 import binding, meshgen
 
     so = os.path.join(ROOT, "oracle", "_ref", "libtacs_ref.so")
-    ref = binding.Lib(so, "ref_")
+    from tests import ref_binding
+    ref = ref_binding.load_reference(so)
     mesh = meshgen.plate(2, nx, ny)
     with _quiet_stdout():
         creator, asm = meshgen.build_model(T, ref, mesh, [meshgen.iso_shell_element(T, ref, 2)])

@@ -257,9 +257,7 @@ class Mat(_Obj):
         _check(self.lib.mat_mult_transpose(self.h, x.h, y.h), "mat_mult_transpose")
 
     def createVec(self):
-        if self.lib.is_product:
-            return Vec(self.lib, self.lib.mat_create_vec(self.h))
-        raise NotImplementedError
+        return Vec(self.lib, self.lib.mat_create_vec(self.h))
 
 
 class ChebyshevSmoother(_Obj):

@@ -152,11 +152,6 @@ PRODUCT_ONLY = {
 }
 
 # entry points that exist only in the reference interface (oracle/ref_capi.cpp)
-REFERENCE_ONLY = {
-    "wtime": (D, []),
-}
-
-
 def iptr(a):
     return None if a is None else a.ctypes.data_as(IP)
 
@@ -174,7 +169,11 @@ def as_f64(a):
 
 
 class Lib:
-    def __init__(self, path, prefix):
+    """A shared library that exports `<prefix><name>` for the entry points of SIGNATURES plus `extra` (name ->
+    (restype, argtypes)): the product library, or -- in the tests -- any other implementation of the same flat
+    interface."""
+
+    def __init__(self, path, prefix, extra=None):
         if not os.path.exists(path):
             raise OSError(
                 f"{path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()'); "
@@ -183,11 +182,11 @@ class Lib:
         self.prefix = prefix
         self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
         self._cache = {}
-        self.is_product = prefix == "tacsb200_"
+        self.extra = dict(extra or {})
 
     def signatures(self):
         sigs = dict(SIGNATURES)
-        sigs.update(PRODUCT_ONLY if self.is_product else REFERENCE_ONLY)
+        sigs.update(self.extra)
         return sigs
 
     def __getattr__(self, name):
@@ -216,5 +215,5 @@ def load():
     """The product library (libtacs_b200.so next to this file)."""
     global _PRODUCT
     if _PRODUCT is None:
-        _PRODUCT = Lib(product_path(), "tacsb200_")
+        _PRODUCT = Lib(product_path(), "tacsb200_", PRODUCT_ONLY)
     return _PRODUCT

@@ -22,7 +22,8 @@ def ref():
 
     if not os.path.exists(REF_SO):
         pytest.skip("oracle/_ref/libtacs_ref.so not built (needs /root/reference)")
-    return binding.Lib(REF_SO, "ref_")
+    from tests import ref_binding
+    return ref_binding.load_reference(REF_SO)
 
 
 @pytest.fixture(scope="session")

@@ -63,7 +63,7 @@ def run(lib, name):
     u.setArray(meshgen.hash_vector(n))
     asm.applyBCs(u)
     asm.setVariables(u)
-    if not lib.is_product:
+    if lib.prefix == "ref_":
         asm.setNumThreads(min(16, len(os.sched_getaffinity(0))))
     t1 = time.time()
     asm.assembleJacobian(1.0, 0.0, 0.0, res, A)
@@ -80,7 +80,8 @@ def run(lib, name):
 
 if __name__ == "__main__":
     names = sys.argv[1:] or ["c2", "c4", "c3max", "c5max"]
-    ref = binding.Lib(os.path.join(ROOT, "oracle", "_ref", "libtacs_ref.so"), "ref_")
+    from tests import ref_binding
+    ref = ref_binding.load_reference()
     data = {}
     if os.path.exists(OUT):
         with open(OUT) as f:

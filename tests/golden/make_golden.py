@@ -17,7 +17,8 @@ from tacs_b200 import binding  # noqa: E402
 from tests import common  # noqa: E402
 
 if __name__ == "__main__":
-    ref = binding.Lib(os.path.join(ROOT, "oracle", "_ref", "libtacs_ref.so"), "ref_")
+    from tests import ref_binding
+    ref = ref_binding.load_reference()
     out = os.path.dirname(os.path.abspath(__file__))
     for name in sorted(common.SMALL_MODELS):
         r = common.run_model(ref, name)
