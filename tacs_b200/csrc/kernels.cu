@@ -1577,6 +1577,8 @@ cudaError_t launch_gather_blocks(int bs, long nblocks, const int *blk, const int
   if (bs == 6)
     gather_blocks36_kernel<<<grid_for(nblocks * 18, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
   else if (bs == 3)
+    // (one thread per entry -- nine threads read one contiguous 72-byte source per step -- measured slower: 1.72
+    // against 1.44 ms on 100^3 hex8, equal on hex27)
     gather_blocks9_kernel<<<grid_for(nblocks * 3, block, num_sms), block, 0, s>>>(nblocks, blk, ptr, src, Ke, A);
   else
     return cudaErrorInvalidValue;
@@ -2048,7 +2050,8 @@ static cudaError_t launch_spmv3_stream(int nrows, const int *rowp, const int *co
 // Other forms of the 3x3 product that were measured and dropped (200^3-class hex8 / 100^3-class hex27 matrices):
 // a warp per block row with lane l on entries l, l+32, .. of the row (5.65 against 3.40 ms, 12.4 against 9.3 ms: the
 // per-entry cols -> x chain); nine lanes per block row straight from global memory (4.3 against 5.2 TB/s, 3.1 against
-// 4.3: too few bytes in flight); 128 + 64-bit loads in the thread-per-scalar-row form (3.9 against 5.2 TB/s).
+// 4.3: too few bytes in flight); 128 + 64-bit loads in the thread-per-scalar-row form (3.9 against 5.2 TB/s); P = 2, 3, 5
+// threads per scalar row, each on every P-th block of the row (5.19, 5.34, 4.66 against 5.19 TB/s on hex8).
 // Which of the two kept forms runs: the streamed one costs a fixed ~230 instructions per block row (ring bookkeeping,
 // row bookkeeping, parking of the partial sums) and is issue bound below ~40 blocks per row (hex8: 27 -> 4.4 TB/s
 // against 5.2), above it it is the faster one (hex27: 64 on average -> 5.9 against 4.3 TB/s). TACSB200_SPMV3=rows|stream
