@@ -657,11 +657,15 @@ struct ShellQ9MmaFamily {
   static constexpr size_t WORK_STRIDE = ((sizeof(Work) + 127) / 128) * 128 + 64;
 };
 
+// The warp index W of the four functions below is a run-time value on purpose: one copy of the code for the three
+// warps (tile rows / columns W + 3 i; the third one exists for warp 0 only and sits behind a warp-uniform test). As
+// templates on W the kernel was 132 KB of SASS and ncu showed 15 % of its stall samples as instruction-cache misses.
+
 // Rty = S Bty: warp W computes the tile columns W + 3 i of all four tile rows (K = 28)
-template <int W>
-__device__ __forceinline__ void q9_sb_product(ShellQ9MmaWork &x, int lane, int gq, int tq) {
+__device__ __forceinline__ void q9_sb_product(const int W, ShellQ9MmaWork &x, int lane, int gq, int tq) {
   using Work = ShellQ9MmaWork;
-  constexpr int NTS = (W == 0) ? 3 : 2, KS = Work::KS, LDP = Work::LDP, LDS_ = Work::LDS_;
+  constexpr int NTS = 3, KS = Work::KS, LDP = Work::LDP, LDS_ = Work::LDS_;
+  const bool third = W == 0;
   double c[4][NTS][2];
 #pragma unroll
   for (int k = 0; k < 8 * NTS; k++) (&c[0][0][0])[k] = 0.0;
@@ -673,9 +677,11 @@ __device__ __forceinline__ void q9_sb_product(ShellQ9MmaWork &x, int lane, int g
     for (int mt = 0; mt < 4; mt++) a[mt] = S[(8 * mt + gq) * LDS_ + 4 * ks + tq];
 #pragma unroll
     for (int i = 0; i < NTS; i++) {
-      const double b = x.Lty[ks][32 * (W + 3 * i) + lane];
+      if (i < 2 || third) {
+        const double b = x.Lty[ks][32 * (W + 3 * i) + lane];
 #pragma unroll
-      for (int mt = 0; mt < 4; mt++) dmma884(c[mt][i][0], c[mt][i][1], a[mt], b);
+        for (int mt = 0; mt < 4; mt++) dmma884(c[mt][i][0], c[mt][i][1], a[mt], b);
+      }
     }
   }
   double *R = x.scr + Work::oRty;
@@ -685,48 +691,54 @@ __device__ __forceinline__ void q9_sb_product(ShellQ9MmaWork &x, int lane, int g
     if (row < Work::nty) {
 #pragma unroll
       for (int i = 0; i < NTS; i++)
+        if (i < 2 || third) {
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int col = 8 * (W + 3 * i) + 2 * tq + h;
-          R[(row >> 2) * LDP + 4 * col + (row & 3)] = c[mt][i][h];
+          for (int h = 0; h < 2; h++) {
+            const int col = 8 * (W + 3 * i) + 2 * tq + h;
+            R[(row >> 2) * LDP + 4 * col + (row & 3)] = c[mt][i][h];
+          }
         }
     }
   }
 }
 
 // K tile rows W + 3 i += L^T R over the KS panels of the tying rows
-template <int W>
-__device__ __forceinline__ void q9_contract_ty(ShellQ9MmaWork &x, int lane, double (&kacc)[3][7][2]) {
+__device__ __forceinline__ void q9_contract_ty(const int W, ShellQ9MmaWork &x, int lane, double (&kacc)[3][7][2]) {
   using Work = ShellQ9MmaWork;
-  constexpr int MTS = (W == 0) ? 3 : 2;
+  const bool third = W == 0;
 #pragma unroll
   for (int ks = 0; ks < Work::KS; ks++) {
-    double a[MTS], b[7];
+    double a[3], b[7];
 #pragma unroll
-    for (int i = 0; i < MTS; i++) a[i] = x.Lty[ks][32 * (W + 3 * i) + lane];
+    for (int i = 0; i < 2; i++) a[i] = x.Lty[ks][32 * (W + 3 * i) + lane];
+    a[2] = third ? x.Lty[ks][32 * 6 + lane] : 0.0;
 #pragma unroll
     for (int nt = 0; nt < 7; nt++) b[nt] = x.scr[Work::oRty + ks * Work::LDP + 32 * nt + lane];
 #pragma unroll
-    for (int i = 0; i < MTS; i++)
+    for (int i = 0; i < 3; i++)
+      if (i < 2 || third) {
 #pragma unroll
-      for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
+        for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
+      }
   }
 }
 
 // ... and over one row buffer (half-split panels; fo = this lane's fragment offset inside a panel)
-template <int W>
-__device__ __forceinline__ void q9_contract_rows(const double *L, int fo, double (&kacc)[3][7][2]) {
+__device__ __forceinline__ void q9_contract_rows(const int W, const double *L, int fo, double (&kacc)[3][7][2]) {
   using Work = ShellQ9MmaWork;
-  constexpr int MTS = (W == 0) ? 3 : 2;
-  double a[MTS], b[7];
+  const bool third = W == 0;
+  double a[3], b[7];
 #pragma unroll
-  for (int i = 0; i < MTS; i++) a[i] = L[fo + 16 * (W + 3 * i)];
+  for (int i = 0; i < 2; i++) a[i] = L[fo + 16 * (W + 3 * i)];
+  a[2] = third ? L[fo + 16 * 6] : 0.0;
 #pragma unroll
   for (int nt = 0; nt < 7; nt++) b[nt] = L[Work::LPAN + fo + 16 * nt];
 #pragma unroll
-  for (int i = 0; i < MTS; i++)
+  for (int i = 0; i < 3; i++)
+    if (i < 2 || third) {
 #pragma unroll
-    for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
+      for (int nt = 0; nt < 7; nt++) dmma884(kacc[i][nt][0], kacc[i][nt][1], a[i], b[nt]);
+    }
 }
 
 // residual rows K u of the warp's tile rows, alpha, tangent fragments to the staging area / the matrix.
@@ -735,11 +747,11 @@ __device__ __forceinline__ void q9_contract_rows(const double *L, int fo, double
 // at 9 i + j -- so the row and column parts are formed once per tile row / tile column. A pair with a direct target
 // (dmap >= 0, one 324-byte row set per element, L1 resident after the prefetch at the top of the element) goes to
 // that block of the matrix instead; lower pairs without one are not stored.
-template <int W>
-__device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, double alpha, const ElemGroupArgs &g,
-                                          long e, double (&kacc)[3][7][2]) {
+__device__ __forceinline__ void q9_finish(const int W, ShellQ9MmaWork &x, int gq, int tq, double alpha,
+                                          const ElemGroupArgs &g, long e, double (&kacc)[3][7][2]) {
   using Work = ShellQ9MmaWork;
-  constexpr int MTS = (W == 0) ? 3 : 2, nd = Work::nd, n = Work::n;
+  constexpr int nd = Work::nd, n = Work::n;
+  const int MTS = (W == 0) ? 3 : 2;
   double2 up[7];
   int nj[7], colS[7];
 #pragma unroll
@@ -752,7 +764,8 @@ __device__ __forceinline__ void q9_finish(ShellQ9MmaWork &x, int gq, int tq, dou
   double *const kbase = g.Ke ? g.Ke + e * (g.upper ? (n * (n + 1) / 2) * 36 : n * n * 36) : nullptr;
   const int *const dme = g.dmap ? g.dmap + e * (n * n) : nullptr;
 #pragma unroll
-  for (int i = 0; i < MTS; i++) {
+  for (int i = 0; i < 3; i++) {
+    if (i >= MTS) break;
     const int R = 8 * (W + 3 * i) + gq;
     double r = 0.0;
 #pragma unroll
@@ -883,37 +896,31 @@ __global__ void __launch_bounds__(ShellQ9MmaFamily::TEAM, ShellQ9MmaFamily::MIN_
     for (int m = 0; m < NSA; m++)
       if (tid + m * TEAM < NTRI) shell_unc_S_entry<O>(stri[m], w, tab);
     __syncthreads();
-    if (warp == 0) q9_sb_product<0>(w, lane, gq, tq);
-    else if (warp == 1) q9_sb_product<1>(w, lane, gq, tq);
-    else q9_sb_product<2>(w, lane, gq, tq);
+    q9_sb_product(warp, w, lane, gq, tq);
     __syncthreads();
     // rows of point 0 go to buffer 0 while the tying rows are contracted; inside the loop the rows of point q+1 are
     // produced in the barrier interval that contracts those of point q
-    if (tid < 3 * n) shell_unc_rows<O>(tid, 0, w, tab, desc, w.buf(0));
+    // (the row tasks run on the third warp: it owns two tile rows of the contraction, the first warp three)
+    const int rtask = tid - 64;
+    if (rtask >= 0 && rtask < 3 * n) shell_unc_rows<O>(rtask, 0, w, tab, desc, w.buf(0));
     double kacc[3][7][2];
 #pragma unroll
     for (int k = 0; k < 42; k++) (&kacc[0][0][0])[k] = 0.0;
-    if (warp == 0) q9_contract_ty<0>(w, lane, kacc);
-    else if (warp == 1) q9_contract_ty<1>(w, lane, kacc);
-    else q9_contract_ty<2>(w, lane, kacc);
+    q9_contract_ty(warp, w, lane, kacc);
     __syncthreads();
 #pragma unroll 1
     for (int q = 0; q < nq; q++) {
       if (q + 1 < nq) {
-        if (tid < 3 * n) shell_unc_rows<O>(tid, q + 1, w, tab, desc, w.buf((q + 1) & 1));
+        if (rtask >= 0 && rtask < 3 * n) shell_unc_rows<O>(rtask, q + 1, w, tab, desc, w.buf((q + 1) & 1));
       } else if (tid < nd) {
         w.uvec()[tid] = cu;  // last interval: the state enters shared memory in the buffer that is no longer read
         w.avec()[tid] = ca;
       }
       const double *L = w.buf(q & 1);
-      if (warp == 0) q9_contract_rows<0>(L, fo, kacc);
-      else if (warp == 1) q9_contract_rows<1>(L, fo, kacc);
-      else q9_contract_rows<2>(L, fo, kacc);
+      q9_contract_rows(warp, L, fo, kacc);
       __syncthreads();
     }
-    if (warp == 0) q9_finish<0>(w, gq, tq, g.alpha, g, e, kacc);
-    else if (warp == 1) q9_finish<1>(w, gq, tq, g.alpha, g, e, kacc);
-    else q9_finish<2>(w, gq, tq, g.alpha, g, e, kacc);
+    q9_finish(warp, w, gq, tq, g.alpha, g, e, kacc);
     __syncthreads();
     if (inertia) {
       if (tid < n * n) {
