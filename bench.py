@@ -481,6 +481,11 @@ def kernel_rooflines(kind, nelem_local, stats, prof, fp64_peak, hbm_peak, world,
         else:
             continue
         entry["frac"] = entry["achieved"] / entry["peak"] if entry["peak"] else None
+        if entry["launches_per_step"] > 1.5 and ("gather_blocks" in name or "element_kernel" in name):
+            entry["overlapped"] = ("element chunks and the gather of the previous chunk run concurrently on two streams: "
+                                   "each kernel's ms is its own launch-to-end time while sharing the GPU, so the two "
+                                   "overlap and their fractions understate what either reaches alone "
+                                   "(TACSB200_OVERLAP_KINDS=0: 22.3 ms / 0.67 and 11.6 ms / 0.53 on C4, step 34.5 ms)")
         entry["traffic"] = NCU_TRAFFIC_BYTES.get(name) if default_workload else None
         entry["traffic_source"] = TRAFFIC_SOURCE if entry["traffic"] else None
         kernels.append(entry)

@@ -645,3 +645,19 @@ def test_streamed_ragged_rows_against_scipy(lib):
         pc.applyFactor(x, z)
         # the same polynomial with scipy products: z_0 = 0, then per sweep r = x - A z, z += p(A) r
         assert np.isfinite(z.norm())
+
+
+def test_chunked_assembly_with_overlapped_gather():
+    """Element groups cut into chunks, the gather of chunk k on a second stream while chunk k+1 is evaluated
+    (TACSB200_OVERLAP_KINDS; by default only hex8 groups of 2^19 elements and more per chunk): forced for every
+    family on the small parity models in a child process -- the assembled matrices must not change."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, TACSB200_OVERLAP_KINDS="15", TACSB200_CHUNK_MIN="7", TACSB200_CHUNKS="5")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = "assembled_model or mixed_families or jacobian_with_mass or partial_dof or host_state_entry"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
+                          "-m", "gpu", "-k", sel], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout, out.stdout[-500:]
