@@ -2566,23 +2566,59 @@ cudaError_t launch_axpbz(long n, double zs, const double *z, double ys, double *
 // ------------------------------------------------------------------------------------------
 // halo pack / unpack (block-size generic: a block is bs doubles)
 // ------------------------------------------------------------------------------------------
-__global__ void pack_blocks_kernel(int bs, long count, const int *__restrict__ idx, const double *__restrict__ x,
-                                   double *__restrict__ buf) {
-  const long total = count * bs;
-  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const long i = g / bs;
-    buf[g] = x[(long)bs * idx[i] + (g - i * bs)];
+// (four independent index -> value chains per thread: with one, the dependent loads left these kernels at ~100 GB/s)
+__global__ void __launch_bounds__(256) pack_blocks_kernel(int bs, long count, const int *__restrict__ idx,
+                                                          const double *__restrict__ x, double *__restrict__ buf) {
+  const long total = count * bs, stride = (long)gridDim.x * blockDim.x;
+  for (long g0 = (long)blockIdx.x * blockDim.x + threadIdx.x; g0 < total; g0 += 4 * stride) {
+    long src[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long g = g0 + u * stride;
+      if (g < total) {
+        const long i = g / bs;
+        src[u] = (long)bs * __ldg(idx + i) + (g - i * bs);
+      } else {
+        src[u] = -1;
+      }
+    }
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = src[u] >= 0 ? __ldg(x + src[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (src[u] >= 0) buf[g0 + u * stride] = v[u];
   }
 }
 
 // add == 0: x[idx] = buf ; add == 1: x[idx] += buf (indices are unique within one call)
-__global__ void unpack_blocks_kernel(int bs, long count, const int *__restrict__ idx, const double *__restrict__ buf,
-                                     double *__restrict__ x, int add) {
-  const long total = count * bs;
-  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-    const long i = g / bs;
-    const long dst = (long)bs * idx[i] + (g - i * bs);
-    x[dst] = add ? x[dst] + buf[g] : buf[g];
+__global__ void __launch_bounds__(256) unpack_blocks_kernel(int bs, long count, const int *__restrict__ idx,
+                                                            const double *__restrict__ buf, double *__restrict__ x,
+                                                            int add) {
+  const long total = count * bs, stride = (long)gridDim.x * blockDim.x;
+  for (long g0 = (long)blockIdx.x * blockDim.x + threadIdx.x; g0 < total; g0 += 4 * stride) {
+    long dst[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long g = g0 + u * stride;
+      if (g < total) {
+        const long i = g / bs;
+        dst[u] = (long)bs * __ldg(idx + i) + (g - i * bs);
+        v[u] = __ldg(buf + g);
+      } else {
+        dst[u] = -1;
+        v[u] = 0.0;
+      }
+    }
+    if (add) {
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (dst[u] >= 0) v[u] += x[dst[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (dst[u] >= 0) x[dst[u]] = v[u];
   }
 }
 

@@ -569,6 +569,7 @@ class TACSAssembler : public Object {
   // element chunks of assembleJacobian: [e0, e1) of group `group`; every gathered block below gather_end is complete
   // once the chunk (and all chunks before it) has been evaluated
   struct ElemChunk { int group; long e0, e1, gather_end; int need_state = -1; };
+  long local_gather_end = 0;  // gathered blocks below it read no received staging slot (multi-rank)
   std::vector<ElemChunk> chunks;
   // Finer chunks of the host-state entry point (assembleJacobianHost): the state vector arrives from pinned host memory
   // in kStateChunks pieces on the copy stream, and element chunk k only waits for the piece that holds the last node
