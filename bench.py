@@ -489,6 +489,10 @@ def kernel_rooflines(kind, nelem_local, stats, prof, fp64_peak, hbm_peak, world,
                                    "each kernel's ms is its own launch-to-end time while sharing the GPU, so the two "
                                    "overlap and their fractions understate what either reaches alone "
                                    "(TACSB200_OVERLAP_KINDS=0: 22.3 ms / 0.67 and 11.6 ms / 0.53 on C4, step 34.5 ms)")
+        elif world > 1 and "gather_blocks" in name:
+            entry["overlapped"] = ("on several ranks the gather of the blocks that read local staging only runs on a "
+                                   "low-priority stream while the off-rank rows are packed, sent and received: its ms "
+                                   "includes the time it shares the GPU with the exchange (one rank: 0.85 ms / 0.90)")
         entry["traffic"] = NCU_TRAFFIC_BYTES.get(name) if default_workload else None
         entry["traffic_source"] = TRAFFIC_SOURCE if entry["traffic"] else None
         kernels.append(entry)
@@ -533,7 +537,8 @@ def time_config(D, lib, asm, A, res, x, y, kind, nelem_total, steps, fp64_peak, 
             "bytes_per_launch": sp_bytes, "note": "aggregate over all ranks; peak = ranks x measured HBM peak"}
     spmv["frac"] = spmv["achieved"] / spmv["peak"]
     # what the kernel list does not explain: NCCL send / recv of the exchanges, launch gaps, and -- the step is the max
-    # over ranks, the kernel times are this rank's -- the imbalance of the partition
+    # over ranks, the kernel times are this rank's -- the imbalance of the partition. Negative when kernels overlap
+    # (the gather on its own stream runs beside the exchange / the next element chunk).
     accounted = sum(k["ms"] for k in kernels if not (k.get("overlapped") and "gather" in k["kernel"]))
     step_rest = {"kernels_ms_this_rank": accounted, "step_minus_kernels_ms": ms - accounted,
                  "step_ms_min_over_ranks": -D.max(-ms_local), "step_ms_max_over_ranks": ms}
