@@ -496,5 +496,5 @@ class Plan(_Obj):
 
     def scalars(self):
         names = ["nelems", "nowned", "nlocal", "ext_before", "ext_after", "np", "local_blocks", "recv_blocks",
-                 "local_node_slots", "recv_node_slots", "direct_blocks"]
+                 "local_node_slots", "recv_node_slots", "direct_blocks", "local_gather_end"]
         return dict(zip(names, (int(v) for v in self.array("scalars"))))

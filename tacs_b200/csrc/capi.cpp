@@ -309,7 +309,8 @@ int tacsb200_plan_get_array(tacsb200_handle plan, const char *name, int *out) {
   else if (n == "r_src") v = &P.r_src;
   else if (n == "scalars") {
     tmp = {P.nelems, P.nowned, P.nlocal, P.ext_before, P.ext_after, P.np, (int)P.local_blocks, (int)P.recv_blocks,
-           (int)P.local_node_slots, (int)P.recv_node_slots, (int)P.direct_blocks};
+           (int)P.local_node_slots, (int)P.recv_node_slots, (int)P.direct_blocks,
+           (int)P.gatherEnd(P.local_blocks)};  // gathered blocks below this index read no received staging slot
     v = &tmp;
   } else if (!(v = ex("state", P.state)) && !(v = ex("cols", P.cols)) && !(v = ex("rows", P.rows)) &&
              !(v = ex("blocks", P.blocks))) {

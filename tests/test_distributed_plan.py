@@ -87,6 +87,38 @@ def test_plans_replay_matches_serial(name, size):
         assert eA < 1e-12 and eR < 1e-12 and eY < 1e-12, (r, eA, eR, eY)
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("size", [2, 4])
+def test_gather_prefix_reads_local_staging_only(name, size):
+    """The multi-GPU assembly gathers the blocks below `local_gather_end` while the off-rank staging rows are still in
+    flight (tb2_host.cpp: assembleJacobianImpl): none of them may read a received slot, the blocks with a received
+    source must all lie behind it, and the prefix has to be most of the plan for the overlap to be worth anything."""
+    import tacs_b200
+
+    lib = tacs_b200.load()
+    mesh, kind, desc, creator, plans, _ = build_plans(lib, name, size)
+    for r in range(size):
+        P = plans[r]
+        s = P.scalars()
+        ptr, src = P.array("gb_ptr"), P.array("gb_src")
+        nblk = P.array("gb_blk").size
+        assert ptr.size == nblk + 1 and 0 <= s["local_gather_end"] <= nblk
+        slots = src[:ptr[-1]] >> 1
+        counts = np.diff(ptr)
+        last = np.maximum.reduceat(slots, ptr[:-1][counts > 0]) if nblk else np.zeros(0, np.int64)
+        last_all = np.full(nblk, -1, np.int64)
+        last_all[counts > 0] = last
+        end = s["local_gather_end"]
+        assert np.all(last_all[:end] < s["local_blocks"]), "a block of the prefix reads a received staging slot"
+        # blocks are ordered by the bucket (64 slots) of their last source
+        assert np.all(np.diff(last_all >> 6) >= 0)
+        if s["recv_blocks"] > 0:
+            local_only = int((last_all < s["local_blocks"]).sum())
+            assert end >= local_only - 64 * 81, (end, local_only)   # at most one bucket of blocks is held back
+        else:
+            assert end >= nblk - 64 * 81
+
+
 def test_single_rank_plan_is_the_serial_pattern():
     import tacs_b200
 
