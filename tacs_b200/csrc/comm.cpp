@@ -114,21 +114,30 @@ int comm_peer_init() {
   const size_t nval = (size_t)PeerExchange::kSlots * c.size;
   // layout of a rank's buffer: vals[kSlots * size] doubles | flags[kSlots * size] u64 | produced | consumed
   const size_t bytes = nval * 8 + nval * 8 + 16;
+  // A rank whose own buffer or handle cannot be made still takes part in the two collectives below (with a zeroed
+  // handle, which its peers fail to open): leaving early on one rank would leave the others waiting in ncclAllGather.
   unsigned char *mine = nullptr;
-  if (cudaMalloc(&mine, bytes) != cudaSuccess) { cudaGetLastError(); return 1; }
-  cudaMemset(mine, 0, bytes);
+  bool ok = true;
+  if (cudaMalloc(&mine, bytes) != cudaSuccess) { cudaGetLastError(); mine = nullptr; ok = false; }
+  if (ok) cudaMemset(mine, 0, bytes);
   cudaIpcMemHandle_t handle;
-  if (cudaIpcGetMemHandle(&handle, mine) != cudaSuccess) { cudaGetLastError(); cudaFree(mine); return 1; }
+  memset(&handle, 0, sizeof(handle));
+  if (ok && cudaIpcGetMemHandle(&handle, mine) != cudaSuccess) { cudaGetLastError(); ok = false; }
   unsigned char *d_handles = nullptr;
   const size_t hb = sizeof(cudaIpcMemHandle_t);
-  if (cudaMalloc(&d_handles, hb * (c.size + 1)) != cudaSuccess) { cudaGetLastError(); cudaFree(mine); return 1; }
+  if (cudaMalloc(&d_handles, hb * (c.size + 1)) != cudaSuccess) {   // nothing else would work on this rank either
+    cudaGetLastError();
+    if (mine) cudaFree(mine);
+    return 1;
+  }
   cudaMemcpy(d_handles + hb * c.size, &handle, hb, cudaMemcpyHostToDevice);
   const int kNcclChar = 0;
-  bool ok = nccl_ok(nccl.allgather(d_handles + hb * c.size, d_handles, hb, kNcclChar, c.nccl_comm, c.stream.s),
-                    "ncclAllGather") &&
-            cuda_ok(cudaStreamSynchronize(c.stream.s), "peer handle exchange");
+  const bool gathered = nccl_ok(nccl.allgather(d_handles + hb * c.size, d_handles, hb, kNcclChar, c.nccl_comm, c.stream.s),
+                                "ncclAllGather") &&
+                        cuda_ok(cudaStreamSynchronize(c.stream.s), "peer handle exchange");
+  ok = ok && gathered;
   std::vector<cudaIpcMemHandle_t> all(c.size);
-  if (ok) cudaMemcpy(all.data(), d_handles, hb * c.size, cudaMemcpyDeviceToHost);
+  if (gathered) cudaMemcpy(all.data(), d_handles, hb * c.size, cudaMemcpyDeviceToHost);
   cudaFree(d_handles);
   PeerExchange px;
   memset(&px, 0, sizeof(px));
