@@ -569,6 +569,13 @@ void TACSB200Assembler::assembleJacobian(TacsScalar alpha, TacsScalar beta, Tacs
                                          TACSB200Mat *A) {
   tacsb200_assembler_assemble_jacobian(handle, alpha, beta, gamma, res ? res->getHandle() : NULL, A->getHandle());
 }
+int TACSB200Assembler::assembleJacobianHost(TacsScalar alpha, TacsScalar beta, TacsScalar gamma, TACSBVec *vars,
+                                            TACSBVec *res, TACSB200Mat *A) {
+  TacsScalar *q = NULL, *r = NULL;
+  vars->getArray(&q);
+  res->getArray(&r);
+  return tacsb200_assembler_assemble_jacobian_host(handle, alpha, beta, gamma, q, r, A->getHandle());
+}
 int TACSB200Assembler::assembleMatType(ElementMatrixType matType, TACSB200Mat *A) {
   return tacsb200_assembler_assemble_mat_type(handle, (int)matType, A->getHandle(), 1);
 }

@@ -158,6 +158,12 @@ class TACSB200Assembler : public TACSObject {
   void assembleRes(TACSB200Vec *res);
   void assembleJacobian(TacsScalar alpha, TacsScalar beta, TacsScalar gamma, TACSB200Vec *res, TACSB200Mat *A);
   int assembleMatType(ElementMatrixType matType, TACSB200Mat *A);
+  // setVariables(vars) + assembleJacobian for drivers whose state and residual are the reference's host vectors
+  // (integrators, Newton loops): one call of tacsb200_assembler_assemble_jacobian_host, transfers pipelined against the
+  // kernels. Returns when `res` is complete; the matrix may still be in flight (device-side consumers are ordered
+  // behind it). Not tested on hardware in round 2 (added after the last GPU run; a forwarding call).
+  int assembleJacobianHost(TacsScalar alpha, TacsScalar beta, TacsScalar gamma, TACSBVec *vars, TACSBVec *res,
+                           TACSB200Mat *A);
   // The drop-in for drivers that assemble into a TACSSchurMat (examples/plate/plate.cpp:133-146, pyTACS
   // StaticProblem): element loop, scatter and boundary conditions on the device, then the values land in the blocks
   // of `mat`; `res` (host vector, may be NULL) receives the residual.
